@@ -1,0 +1,109 @@
+"""ctypes binding of libgraphnics_b200.so (the C ABI declared in include/graphnics_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or a compute entry point is
+called without a CUDA device, this module raises.  The library is built in-tree by
+`make -C graphnics_b200/csrc` (or `__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgraphnics_b200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+
+
+class GnxError(RuntimeError):
+    pass
+
+
+class gnx_network_t(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("E", C.c_int32), ("gdim", C.c_int32), ("n", C.c_int32),
+        ("B", C.c_int32), ("n_bnd", C.c_int32),
+        ("I", C.c_int64),
+        ("pos", C.c_void_p), ("edges", C.c_void_p), ("h", C.c_void_p), ("bix", C.c_void_p),
+        ("bif_nodes", C.c_void_p), ("inc_ptr", C.c_void_p), ("inc_edge", C.c_void_p),
+        ("lam_ptr", C.c_void_p), ("ebif_prefix", C.c_void_p), ("loc", C.c_void_p),
+        ("tloc", C.c_void_p),
+    ]
+
+
+class gnx_mixed_coeffs_t(C.Structure):
+    _fields_ = [("a_edge", C.c_void_p), ("k_edge", C.c_void_p), ("sigma", C.c_double)]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_L = C.c_int64
+_D = C.c_double
+_NET = C.POINTER(gnx_network_t)
+_CO = C.POINTER(gnx_mixed_coeffs_t)
+
+# name -> (restype, argtypes); every symbol of include/graphnics_b200.h
+PROTOTYPES = {
+    "gnx_last_error": (C.c_char_p, []),
+    "gnx_version": (_I, []),
+    "gnx_device_ok": (_I, []),
+    "gnx_refine_1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gnx_edge_tangents": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "gnx_tables_work_ints": (_L, [_I, _I]),
+    "gnx_vertex_tables": (_I, [_P, _I, _I] + [_P] * 13),
+    "gnx_mixed_ndofs": (_L, [_NET]),
+    "gnx_mixed_nnz": (_L, [_NET]),
+    "gnx_build_pattern_mixed": (_I, [_NET, _P, _P, _P]),
+    "gnx_assemble_mixed": (_I, [_NET, _CO, _P, _P, _P]),
+    "gnx_assemble_mass_q_mixed": (_I, [_NET, _D, _P, _P, _P]),
+    "gnx_assemble_rhs_mixed": (_I, [_NET, _P, _P, _P, _P, _P, _P]),
+    "gnx_dof_coordinates_mixed": (_I, [_NET, _P, _P, _P, _P, _P]),
+    "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
+    "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnx_cg_work_doubles": (_L, [_I]),
+    "gnx_cg_create": (_I, [_NET, _P, _P, _P, _P, _P, _P, _I, _I, _P, C.POINTER(_P)]),
+    "gnx_cg_solve": (_I, [_P, _D, _I, c_f64p, c_i32p]),
+    "gnx_cg_destroy": (None, [_P]),
+    "gnx_edge_backsub_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P, _P]),
+    "gnx_spmv_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    "gnx_reduce_work_doubles": (_L, [_L]),
+    "gnx_residual_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnx_axpby_dot": (_I, [_L, _D, _P, _D, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library (no CUDA device needed just to load and list symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GnxError(
+            f"{LIB_PATH} not found: build it with `make -C graphnics_b200/csrc` "
+            "(graphnics_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().gnx_last_error()
+        raise GnxError(f"graphnics_b200 C-ABI call failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def require_device():
+    lib = load()
+    if not lib.gnx_device_ok():
+        raise GnxError("graphnics_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return lib
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None -> NULL)"""
+    return None if t is None else C.c_void_p(t.data_ptr())

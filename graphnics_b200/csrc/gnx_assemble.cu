@@ -1,0 +1,128 @@
+// Sparse assembly of the mixed (q per edge, p, lambda) system: CSR pattern built once in closed
+// form, values and right-hand side by row gather (every CSR slot = fixed-order sum of its <= 2
+// element contributions; deterministic, no atomics).
+// Reference behaviour replaced: graphnics/flowmodels/flow_models.py:200-332 (a_form, L_form,
+// init_a_form) + ii_assemble/ii_convert (:343-344); time_stepping.py:75-101 (mass_matrix_q).
+#include "gnx_common.cuh"
+
+extern "C" int64_t gnx_mixed_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }
+extern "C" int64_t gnx_mixed_nnz(const gnx_network_t* net) { return gnx_mixed_dims(*net).nnz; }
+
+constexpr int MODE_PATTERN = GNX_MODE_PATTERN, MODE_VALUES = GNX_MODE_VALUES;
+
+// One thread per matrix row (row logic in gnx_index.h, shared with the host index self-check).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+mixed_rows_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
+                  const double* __restrict__ k_edge, double a_const, double sg,
+                  int32_t* __restrict__ rowptr, int32_t* __restrict__ colidx,
+                  double* __restrict__ vals) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.N) return;
+  gnx_mixed_row_emit<MODE>(net, d, r, a_edge, k_edge, a_const, sg, rowptr, colidx, vals);
+}
+
+static int check_net(const gnx_network_t* net) {
+  GNX_CHECK_ARG(net != nullptr);
+  GNX_CHECK_ARG(net->V > 0 && net->E > 0 && net->n >= 0 && net->n <= 24 && net->B >= 0);
+  GNX_CHECK_ARG(net->edges && net->bix && net->inc_ptr && net->inc_edge && net->lam_ptr &&
+                net->ebif_prefix && net->loc && net->tloc);
+  GNX_CHECK_ARG(net->B == 0 || net->bif_nodes);
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  GNX_CHECK_ARG(d.N < (1ll << 31) && d.nnz < (1ll << 31));
+  return GNX_OK;
+}
+
+extern "C" int gnx_build_pattern_mixed(const gnx_network_t* net, int32_t* rowptr, int32_t* colidx,
+                                       void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(rowptr && colidx);
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  mixed_rows_kernel<MODE_PATTERN><<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      *net, d, nullptr, nullptr, 1.0, 1.0, rowptr, colidx, nullptr);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+extern "C" int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
+                                  const int32_t* rowptr, double* vals, void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(co && co->a_edge && vals && net->h);
+  (void)rowptr;  // row starts are closed-form; kept in the ABI for pattern-agnostic callers
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  mixed_rows_kernel<MODE_VALUES><<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      *net, d, co->a_edge, co->k_edge, 1.0, co->sigma, nullptr, nullptr, vals);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+extern "C" int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff,
+                                         const int32_t* rowptr, double* vals, void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(vals && net->h);
+  (void)rowptr;
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  mixed_rows_kernel<MODE_VALUES><<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      *net, d, nullptr, nullptr, coeff, 0.0, nullptr, nullptr, vals);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// right-hand side, MixedHydraulicNetwork.L_form (flow_models.py:299-332)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mixed_rhs_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ f_nodal,
+                 const double* __restrict__ g_nodal, const double* __restrict__ pbc_nodal,
+                 const double* __restrict__ pbc_node, double* __restrict__ b) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.N) return;
+  b[r] = gnx_mixed_rhs_row(net, d, r, f_nodal, g_nodal, pbc_nodal, pbc_node);
+}
+
+extern "C" int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_nodal,
+                                      const double* g_nodal, const double* pbc_nodal,
+                                      const double* pbc_node, double* b, void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(b && net->h);
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  mixed_rhs_kernel<<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      *net, d, f_nodal, g_nodal, pbc_nodal, pbc_node, b);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// coordinates of q-dofs and of cell midpoints (inputs of coefficient evaluation)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dof_coords_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ coords,
+                  const int32_t* __restrict__ cells, double* __restrict__ xq, double* __restrict__ xmid) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.lam_off) return;
+  const int32_t m = d.m, gd = net.gdim;
+  if (r < d.p_off) {
+    if (!xq) return;
+    const int32_t e = (int32_t)(r / (m + 1));
+    const int32_t l = (int32_t)(r - (int64_t)e * (m + 1));
+    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+    const int32_t vid = gnx_vertex_id(net.V, net.E, net.n, e, min(u, v), max(u, v), net.tloc[l]);
+    for (int i = 0; i < gd; ++i) xq[r * gd + i] = coords[(int64_t)vid * gd + i];
+  } else {
+    if (!xmid) return;
+    const int64_t c = r - d.p_off;
+    const int32_t va = cells[2 * c], vb = cells[2 * c + 1];
+    for (int i = 0; i < gd; ++i)
+      xmid[c * gd + i] = 0.5 * (coords[(int64_t)va * gd + i] + coords[(int64_t)vb * gd + i]);
+  }
+}
+
+extern "C" int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords,
+                                         const int32_t* cells, double* xq, double* xmid, void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(coords && cells);
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  dof_coords_kernel<<<gnx_blocks(d.lam_off, 256), 256, 0, (cudaStream_t)stream>>>(*net, d, coords, cells, xq, xmid);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}

@@ -1,0 +1,186 @@
+"""Device-resident network state: everything `make_mesh(n)` + `make_submeshes()` leave on a
+FenicsGraph (graphnics/fenics_graph.py:102-156), as CUDA arrays produced by the C-ABI kernels.
+
+torch is used for device memory and streams only (plumbing); all arithmetic happens in
+libgraphnics_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, check
+
+__all__ = ["submesh_numbering", "DeviceNetwork", "current_stream"]
+
+
+def current_stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def submesh_numbering(n):
+    """SubMesh-local vertex numbering pattern for n bisections (same for every edge).
+
+    Positions t = 0..m are counted from the edge's lower-numbered node.  DOLFIN's SubMesh
+    (via xii.EmbeddedMesh, fenics_graph.py:139) numbers vertices by FIRST ENCOUNTER while
+    walking the edge's cells in parent-cell order; a cell's stored vertex pair is ascending in
+    global id, i.e. the coarser (even-t) endpoint first.  Local cell j is the cell with spatial
+    index invgray(j).  Returns (loc[t] -> local id, tloc[local id] -> t) as int32 arrays (m+1).
+    """
+    m = 1 << n
+    j = np.arange(m, dtype=np.int64)
+    s = j.copy()
+    sh = 1
+    while sh < 64:
+        s ^= s >> sh
+        sh <<= 1
+    even = np.where(s % 2 == 0, s, s + 1)
+    odd = np.where(s % 2 == 0, s + 1, s)
+    walk = np.stack([even, odd], axis=1).ravel()
+    uniq, first = np.unique(walk, return_index=True)
+    tloc = uniq[np.argsort(first, kind="stable")]
+    loc = np.empty(m + 1, dtype=np.int64)
+    loc[tloc] = np.arange(m + 1)
+    return loc.astype(np.int32), tloc.astype(np.int32)
+
+
+class DeviceNetwork:
+    """Graph -> mesh on the GPU.  `pos` [V,gdim] float64, `edges` [E,2] ints (host or device)."""
+
+    def __init__(self, pos, edges, n, device=None, with_mf=True):
+        lib = _lib.require_device()
+        self.device = torch.device(device if device is not None else "cuda")
+        dev = self.device
+        pos_t = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64) if not torch.is_tensor(pos) else pos)
+        edg_t = torch.as_tensor(np.ascontiguousarray(edges, dtype=np.int32) if not torch.is_tensor(edges) else edges)
+        self.pos = pos_t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+        self.edges = edg_t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous().reshape(-1, 2)
+        self.V, self.gdim = int(self.pos.shape[0]), int(self.pos.shape[1])
+        self.E = int(self.edges.shape[0])
+        self.n = int(n)
+        self.m = 1 << self.n
+        V, E, m, gd = self.V, self.E, self.m, self.gdim
+        self.num_cells = E * m
+        self.num_vertices = V + E * (m - 1)
+        st = current_stream()
+        with torch.cuda.device(dev):
+            # --- mesh (fenics_graph.py:58-99)
+            self.coords = torch.empty((self.num_vertices, gd), dtype=torch.float64, device=dev)
+            self.cells = torch.empty((self.num_cells, 2), dtype=torch.int32, device=dev)
+            self.mf = torch.empty(self.num_cells, dtype=torch.int32, device=dev) if with_mf else None
+            self.h = torch.empty(self.num_cells, dtype=torch.float64, device=dev)
+            check(lib.gnx_refine_1d(ptr(self.pos), ptr(self.edges), V, E, gd, self.n, ptr(self.coords),
+                                    ptr(self.cells), ptr(self.mf), ptr(self.h), st))
+            # --- tangents (:230-253)
+            self.tangents = torch.empty((E, gd), dtype=torch.float64, device=dev)
+            self.elen = torch.empty(E, dtype=torch.float64, device=dev)
+            check(lib.gnx_edge_tangents(ptr(self.pos), ptr(self.edges), E, gd, ptr(self.tangents),
+                                        ptr(self.elen), st))
+            # --- vertex tables (:161-184, :132-156, :280-311)
+            i32 = dict(dtype=torch.int32, device=dev)
+            self.deg = torch.empty(V, **i32)
+            self.bix = torch.empty(V, **i32)
+            self._bif_nodes = torch.empty(V, **i32)
+            self._bnd_nodes = torch.empty(V, **i32)
+            self.inc_ptr = torch.empty(V + 1, **i32)
+            self.inc_edge = torch.empty(2 * E, **i32)
+            self.lam_ptr = torch.empty(V + 1, **i32)
+            self.ebif_prefix = torch.empty(E + 1, **i32)
+            self.tag_u = torch.empty(E, **i32)
+            self.tag_v = torch.empty(E, **i32)
+            counts = torch.empty(4, **i32)
+            work = torch.empty(int(lib.gnx_tables_work_ints(V, E)), **i32)
+            check(lib.gnx_vertex_tables(ptr(self.edges), V, E, ptr(self.deg), ptr(self.bix),
+                                        ptr(self._bif_nodes), ptr(self._bnd_nodes), ptr(self.inc_ptr),
+                                        ptr(self.inc_edge), ptr(self.lam_ptr), ptr(self.ebif_prefix),
+                                        ptr(self.tag_u), ptr(self.tag_v), ptr(counts), ptr(work), st))
+            loc, tloc = submesh_numbering(self.n)
+            self.loc_host, self.tloc_host = loc, tloc
+            self.loc = torch.from_numpy(loc).to(dev, non_blocking=True)
+            self.tloc = torch.from_numpy(tloc).to(dev, non_blocking=True)
+            cnt = counts.cpu().tolist()          # one small D2H sync: sizes are needed on the host
+        self.B, self.n_bnd, self.I, self.n_lonely = (int(c) for c in cnt)
+        self.bif_nodes = self._bif_nodes[: self.B]
+        self.bnd_nodes = self._bnd_nodes[: self.n_bnd]
+        self._net = None
+        self._keep = work  # keep scratch alive until the stream has consumed it
+
+    # ---- C struct view ------------------------------------------------------------------
+    @property
+    def net(self):
+        if self._net is None:
+            s = _lib.gnx_network_t()
+            s.V, s.E, s.gdim, s.n = self.V, self.E, self.gdim, self.n
+            s.B, s.n_bnd, s.I = self.B, self.n_bnd, self.I
+            for name in ("pos", "edges", "h", "bix", "inc_ptr", "inc_edge", "lam_ptr",
+                         "ebif_prefix", "loc", "tloc"):
+                setattr(s, name, getattr(self, name).data_ptr())
+            s.bif_nodes = self._bif_nodes.data_ptr()
+            self._net = s
+        return self._net
+
+    def net_ref(self):
+        return C.byref(self.net)
+
+    # ---- sizes of the mixed system ---------------------------------------------------------
+    @property
+    def mixed_ndofs(self):
+        return self.E * (self.m + 1) + self.E * self.m + self.B
+
+    @property
+    def mixed_nnz(self):
+        return self.E * (8 * self.m + 1) + 2 * self.I + self.B
+
+    @property
+    def p_off(self):
+        return self.E * (self.m + 1)
+
+    @property
+    def lam_off(self):
+        return self.p_off + self.E * self.m
+
+    # ---- host views (lazy D2H) -----------------------------------------------------------
+    def bifurcation_ixs(self):
+        return self.bif_nodes.cpu().tolist()
+
+    def boundary_ixs(self):
+        return self.bnd_nodes.cpu().tolist()
+
+    def vf_host(self):
+        """vf[E, m+1]: vertex tags of every SubMesh in SubMesh-local numbering
+        (fenics_graph.py:141-156)."""
+        E, m = self.E, self.m
+        edges = self.edges.cpu().numpy()
+        vf = np.zeros((E, m + 1), dtype=np.int64)
+        flip = edges[:, 0] > edges[:, 1]
+        lu = np.where(flip, self.loc_host[m], self.loc_host[0])
+        lv = np.where(flip, self.loc_host[0], self.loc_host[m])
+        ar = np.arange(E)
+        vf[ar, lu] = self.tag_u.cpu().numpy()
+        vf[ar, lv] = self.tag_v.cpu().numpy()
+        return vf
+
+    def parent_vertex_host(self):
+        """parent_vertex[E, m+1]: global vertex id of every SubMesh-local vertex (A5)."""
+        E, m, n, V = self.E, self.m, self.n, self.V
+        edges = self.edges.cpu().numpy().astype(np.int64)
+        lo, hi = edges.min(axis=1), edges.max(axis=1)
+        t = self.tloc_host.astype(np.int64)                # [m+1]
+        out = np.empty((E, m + 1), dtype=np.int64)
+        e = np.arange(E, dtype=np.int64)[:, None]
+        tt = np.broadcast_to(t[None, :], (E, m + 1))
+        interior = (tt > 0) & (tt < m)
+        ts = np.where(interior, tt, 1)
+        ctz = np.zeros_like(ts)
+        tmp = ts.copy()
+        for _ in range(n):
+            z = (tmp & 1) == 0
+            ctz += z
+            tmp = np.where(z, tmp >> 1, tmp)
+        k = n - ctz
+        half = 1 << np.maximum(k - 1, 0)
+        sp = ts >> (n - k + 1)
+        vid = V + E * (half - 1) + e * half + (sp ^ (sp >> 1))
+        out[:] = np.where(tt == 0, lo[:, None], np.where(tt == m, hi[:, None], vid))
+        return out

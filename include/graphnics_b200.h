@@ -1,0 +1,197 @@
+/* graphnics_b200 -- C ABI of the B200-native network-flow hot path.
+ *
+ * The reference (IngeborgGjerde/graphnics) has NO native/FFI boundary: its hot path is Python
+ * calling DOLFIN / fenics_ii / PETSc.  This header is the boundary a maintainer would bind
+ * instead (ctypes stub in INTEGRATION.md); every entry point names the reference call it
+ * replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all buffers (the Python host allocates them as torch CUDA tensors);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs
+ *     unless stated;
+ *   - return value: 0 = ok, <0 = error (message via gnx_last_error());
+ *   - int32 indices: #cells, #dofs and #non-zeros must be < 2^31;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails.
+ *
+ * Numbering (canonical): mesh vertices/cells follow DOLFIN's hierarchical
+ * bisection; mixed dofs W = [q_0..q_{E-1} | p | lambda], q_i numbered like the vertices of
+ * SubMesh i (first encounter), p like global cells, lambda like bifurcation_ixs.
+ */
+#ifndef GRAPHNICS_B200_H
+#define GRAPHNICS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNX_OK 0
+#define GNX_ERR_ARG -1
+#define GNX_ERR_CUDA -2
+#define GNX_ERR_NOCONV -3
+
+/* Marker tags, graphnics/fenics_graph.py:22-25 */
+#define GNX_BIF_IN 1
+#define GNX_BIF_OUT 2
+#define GNX_BOUN_IN 3
+#define GNX_BOUN_OUT 4
+
+/* Network descriptor (host struct holding device pointers).  Filled by the host from the
+ * outputs of gnx_refine_1d / gnx_vertex_tables; read-only for all later calls. */
+typedef struct gnx_network {
+  int32_t V, E, gdim, n;      /* nodes, edges, geometric dim (2|3), refinements (m = 2^n cells/edge) */
+  int32_t B, n_bnd;           /* #bifurcation nodes (degree>=2), #boundary nodes (degree==1) */
+  int64_t I;                  /* #(edge end, bifurcation node) incidences */
+  const double*  pos;         /* [V*gdim]  node positions */
+  const int32_t* edges;       /* [E*2]     (u,v) in G.edges() order */
+  const double*  h;           /* [E*m]     cell lengths, edge-local order u -> v */
+  const int32_t* bix;         /* [V]       bifurcation index of node, or -1 */
+  const int32_t* bif_nodes;   /* [B]       node of bifurcation index (== G.bifurcation_ixs) */
+  const int32_t* inc_ptr;     /* [V+1]     node -> incident edge ends (CSR) */
+  const int32_t* inc_edge;    /* [2E]      (edge<<1)|end, end 0: node==u (out-edge), 1: node==v (in-edge); ascending */
+  const int32_t* lam_ptr;     /* [B+1]     exclusive scan of bifurcation degrees */
+  const int32_t* ebif_prefix; /* [E+1]     exclusive scan over edges of #ends that are bifurcations */
+  const int32_t* loc;         /* [m+1]     SubMesh-local vertex id of position t counted from min(u,v) */
+  const int32_t* tloc;        /* [m+1]     inverse of loc */
+} gnx_network_t;
+
+/* Edge-wise operator coefficients of the (generalised) mixed system
+ *   [ a M + k K   -s B^T   s C^T ] [q]     M = P1 mass, K = P1 stiffness (per edge),
+ *   [ s B          0        0    ] [p]     B = d/ds coupling, C = bifurcation incidence.
+ *   [ s C          0        0    ] [lam]
+ * steady MixedHydraulicNetwork: a = Res_e, k = 0, s = 1      (flow_models.py:233-236)
+ * NetworkStokes:                k = mu/Ainv_e                (flow_models.py:399)
+ * theta-scheme step:            a = Ainv + theta*dt*Res_e, s = theta*dt  (time_stepping.py:184) */
+typedef struct gnx_mixed_coeffs {
+  const double* a_edge;       /* [E] mass coefficient */
+  const double* k_edge;       /* [E] stiffness coefficient, or NULL */
+  double sigma;               /* coupling scale s */
+} gnx_mixed_coeffs_t;
+
+const char* gnx_last_error(void);
+int gnx_version(void);
+/* 1 if a CUDA device is usable, else 0 (never throws) */
+int gnx_device_ok(void);
+
+/* ---------------- graph -> mesh (graphnics/fenics_graph.py) ---------------- */
+
+/* FenicsGraph.get_mesh :58-99 (MeshEditor + n x refine/adapt).  One thread per cell walks the
+ * bisection tree; writes hierarchical vertex coordinates (recursive midpoints, bit-exact),
+ * sorted cell->vertex pairs, the cell->edge marker and the cell lengths.
+ *   coords [ (V+E(m-1))*gdim ], cells [E*m*2], mf [E*m] (may be NULL), h [E*m] */
+int gnx_refine_1d(const double* pos, const int32_t* edges, int32_t V, int32_t E, int32_t gdim,
+                  int32_t n, double* coords, int32_t* cells, int32_t* mf, double* h, void* stream);
+
+/* FenicsGraph.assign_tangents :230-253 (+ compute_edge_lengths :187-198).
+ *   tangents [E*gdim] = (pos[v]-pos[u]) * (1/||.||), elen [E] (may be NULL) */
+int gnx_edge_tangents(const double* pos, const int32_t* edges, int32_t E, int32_t gdim,
+                      double* tangents, double* elen, void* stream);
+
+/* record_bifurcation_and_boundary_nodes :161-184 and the tag logic of make_submeshes /
+ * mark_edge_vfs :132-156,280-311.
+ *   deg[V], bix[V], bif_nodes[V] (first B valid), bnd_nodes[V] (first n_bnd valid),
+ *   inc_ptr[V+1], inc_edge[2E], lam_ptr[V+1] (first B+1 valid), ebif_prefix[E+1],
+ *   tag_u[E], tag_v[E] (vf tag at the u / v end of every edge),
+ *   counts[4] = {B, n_bnd, I, n_lonely}, work[>= gnx_tables_work_ints(V,E)] int32 scratch */
+int64_t gnx_tables_work_ints(int32_t V, int32_t E);
+int gnx_vertex_tables(const int32_t* edges, int32_t V, int32_t E, int32_t* deg, int32_t* bix,
+                      int32_t* bif_nodes, int32_t* bnd_nodes, int32_t* inc_ptr, int32_t* inc_edge,
+                      int32_t* lam_ptr, int32_t* ebif_prefix, int32_t* tag_u, int32_t* tag_v,
+                      int32_t* counts, int32_t* work, void* stream);
+
+/* ---------------- sparse assembly (graphnics/flowmodels/flow_models.py) ---------------- */
+
+/* sizes of the monolithic mixed system (host arithmetic) */
+int64_t gnx_mixed_ndofs(const gnx_network_t* net);
+int64_t gnx_mixed_nnz(const gnx_network_t* net);
+
+/* CSR pattern of MixedHydraulicNetwork.a_form :200-280 after ii_assemble/ii_convert :343-344
+ * (canonical sparsity: structural entries + the explicit-zero p / lambda diagonals of
+ * init_a_form).  Built once; one thread per row, closed form, sorted columns.
+ *   rowptr [N+1], colidx [nnz] */
+int gnx_build_pattern_mixed(const gnx_network_t* net, int32_t* rowptr, int32_t* colidx, void* stream);
+
+/* Values of the same matrix (row gather: every CSR slot is the fixed-order sum of its <=2
+ * element contributions; no atomics).  vals [nnz] */
+int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
+                       const int32_t* rowptr, double* vals, void* stream);
+
+/* TimeDepMixedHydraulicNetwork.mass_matrix_q (time_stepping.py:75-101) on the SAME pattern:
+ * vals = coeff * blockdiag(M_e), zero elsewhere. */
+int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff, const int32_t* rowptr,
+                              double* vals, void* stream);
+
+/* MixedHydraulicNetwork.L_form :299-332.  Nodal data live in q-dof layout [E*(m+1)]:
+ *   g_nodal, f_nodal, pbc_nodal = the per-edge CG1 projections (:315-317) (any may be NULL = 0),
+ *   pbc_node [V] = p_bc evaluated at graph nodes (the un-projected BOUN_IN term :324), NULL = 0.
+ *   b [N] */
+int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_nodal, const double* g_nodal,
+                           const double* pbc_nodal, const double* pbc_node, double* b, void* stream);
+
+/* project(c, CG1(submesh_i)) for all edges (:315-317): consistent-mass L2 projection.
+ *   c_nodal, c_mid: coefficient evaluated at q-dof vertices [E*(m+1)] and at cell midpoints
+ *   [E*m, p-dof order] (c_mid NULL => degree<=1 data).  out [E*(m+1)] q-dof layout.
+ *   work [>= 4*E*(m+1)] doubles */
+int gnx_project_p1_edges(const gnx_network_t* net, const double* c_nodal, const double* c_mid,
+                         double* out, double* work, void* stream);
+
+/* coordinates of the q-dof vertices [E*(m+1)*gdim] and of cell midpoints [E*m*gdim] (p-dof order),
+ * gathered from the mesh coordinates -- inputs of coefficient evaluation. */
+int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords, const int32_t* cells,
+                              double* xq, double* xmid, void* stream);
+
+/* ---------------- saddle-point solve (replaces ii_convert + LUSolver("mumps")) ---------------- */
+
+/* Exact per-edge elimination -> graph-level SPD system on the bifurcation multipliers.
+ * Phase 1: two segmented scans over the cells of every edge.
+ *   b [N] rhs (dof order);  cond[E], rsrc[E], ftot[E] edge scalars out */
+int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
+                             const double* b, double* cond, double* rsrc, double* ftot, void* stream);
+
+/* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics).
+ *   b_lam [B] (lambda rows of b, may be NULL), sdiag [B], soff [2E] (aligned with inc_edge),
+ *   scol [2E] (bifurcation index of the other end, -1 = boundary), srhs [B] */
+int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, const double* rsrc,
+                    const double* ftot, const double* b_lam, double* sdiag, double* soff,
+                    int32_t* scol, double* srhs, void* stream);
+
+/* Jacobi-PCG on the Schur system; 2 fused kernels per iteration (SpMV+<p,Sp> | update+<r,z>,<r,r>),
+ * deterministic two-stage reductions, convergence tested on device, iterations replayed in
+ * batches from a CUDA graph (captured once per handle on an internal stream).
+ *   x [B] in/out (initial guess), work [>= gnx_cg_work_doubles(B)] doubles.
+ * gnx_cg_solve SYNCHRONISES the stream once per batch; resid_host[0] = ||r||/||rhs||,
+ * info_host[3] = {iterations, converged, batches}.  GNX_ERR_NOCONV if max_iter is hit. */
+typedef struct gnx_cg gnx_cg_t;
+int64_t gnx_cg_work_doubles(int32_t B);
+int gnx_cg_create(const gnx_network_t* net, const double* sdiag, const double* soff,
+                  const int32_t* scol, const double* srhs, double* x, double* work, int32_t batch,
+                  int32_t use_graph, void* stream, gnx_cg_t** out);
+int gnx_cg_solve(gnx_cg_t* h, double rtol, int32_t max_iter, double* resid_host, int32_t* info_host);
+void gnx_cg_destroy(gnx_cg_t* h);
+
+/* Phase 2: back-substitution, x [N] (dof order) from the multipliers P [B] (= sigma*lambda). */
+int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
+                           const double* cond, const double* rsrc, const double* P, double* x,
+                           void* stream);
+
+/* ---------------- Krylov building blocks ---------------- */
+
+/* y = A x, fp64 CSR with int32 indices (row-block streaming through shared memory). */
+int gnx_spmv_csr_f64(int32_t nrows, const int32_t* rowptr, const int32_t* colidx,
+                     const double* vals, const double* x, double* y, void* stream);
+/* r = b - A x and out2[0] = ||r||^2, out2[1] = ||b||^2 (deterministic two-stage reduction).
+ * work [>= gnx_reduce_work_doubles(nrows)] */
+int64_t gnx_reduce_work_doubles(int64_t n);
+int gnx_residual_csr_f64(int32_t nrows, const int32_t* rowptr, const int32_t* colidx,
+                         const double* vals, const double* x, const double* b, double* r,
+                         double* out2, double* work, void* stream);
+/* y = alpha*x + beta*y ; out[0] = <x,y> (if out != NULL, computed on the UPDATED y) */
+int gnx_axpby_dot(int64_t n, double alpha, const double* x, double beta, double* y, double* out,
+                  double* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHNICS_B200_H */
