@@ -61,7 +61,7 @@ PROTOTYPES = {
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_cg_work_doubles": (_L, [_I]),
     "gnx_cg_create": (_I, [_NET, _P, _P, _P, _P, _P, _P, _I, _I, _P, C.POINTER(_P)]),
-    "gnx_cg_solve": (_I, [_P, _D, _I, c_f64p, c_i32p]),
+    "gnx_cg_solve": (_I, [_P, _D, _I, c_f64p, c_i32p, _P]),
     "gnx_cg_destroy": (None, [_P]),
     "gnx_edge_backsub_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P, _P]),
     "gnx_spmv_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P]),

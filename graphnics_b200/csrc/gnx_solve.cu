@@ -9,7 +9,9 @@
 //   q-rows :  (a M + k K) q |_j + P_j - P_{j-1} = b_q[j]   (P = sigma p, P_{-1} = P(u), P_m = P(v))
 //   sum    :  q_0 = cond (P(u) - P(v) + rsrc),  cond = 1/(a L),  rsrc = sum b_q - a sum_k h_k (cumF_k+cumF_{k+1})/2
 //   lam-row:  sum_in q_e(m) - sum_out q_e(0) = b_lam / sigma   (Kirchhoff) -> graph Laplacian in P(b)
+#include <cooperative_groups.h>
 #include "gnx_common.cuh"
+namespace cg = cooperative_groups;
 
 // lane-group width for one edge: min(32, m) (m is a power of two)
 static inline int group_width(int32_t n) { return n >= 5 ? 32 : (1 << n); }
@@ -263,10 +265,242 @@ __global__ void __launch_bounds__(CG_T) cg_status_kernel(CgPtrs c, int par) {
   if (threadIdx.x == 0) { c.scal[3] = rr; c.scal[1] = (rr <= c.scal[0]) ? 1.0 : 0.0; }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Persistent PCG: the whole solve is ONE kernel (block / grid barriers instead of launches,
+// convergence decided on device, nothing returns to the host).  Same fused math as the
+// two-kernel version; reductions are fixed-order butterflies, bitwise identical in every
+// thread, so every control decision is grid-uniform.
+// ------------------------------------------------------------------------------------
+constexpr int CGP_T = 1024;
+
+// All-reduce of K values over the block with ONE barrier.  `sh` holds K*32 doubles; callers
+// alternate between two buffers so that a fast warp never overwrites partials still being read.
+template <int K>
+__device__ __forceinline__ void block_allreduce(double (&v)[K], double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(GNX_FULL, v[k], o);
+    if (lane == 0) sh[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = (lane < nw) ? sh[k * 32 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(GNX_FULL, t, o);
+    v[k] = t;
+  }
+}
+
+// Single CTA, B <= ROWS*1024: p lives in shared memory, all per-row state and the first
+// CGS_DEG neighbours of every row in registers; 3 barriers per iteration.
+constexpr int CGS_DEG = 4;
+
+template <int ROWS>
+__global__ void __launch_bounds__(CGP_T)
+cg_small_kernel(CgPtrs c, double rtol, int max_iter) {
+  extern __shared__ double sp[];             // [B] search direction
+  __shared__ double red[2][3 * 32];
+  const int tid = threadIdx.x;
+  int32_t ncol[ROWS][CGS_DEG];
+  double nval[ROWS][CGS_DEG];
+  int32_t k_over0[ROWS], k_over1[ROWS];      // neighbours beyond CGS_DEG stay in global memory
+  double dg[ROWS], xr[ROWS], rr_[ROWS], zr[ROWS], pr[ROWS];
+  bool act[ROWS];
+  double acc[3] = {0.0, 0.0, 0.0};
+  // x must be visible block-wide for the initial residual: stage it in sp
+#pragma unroll
+  for (int q = 0; q < ROWS; ++q) {
+    const int32_t i = tid + q * CGP_T;
+    act[q] = i < c.B;
+    if (act[q]) sp[i] = c.x[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < ROWS; ++q) {
+    const int32_t i = tid + q * CGP_T;
+    dg[q] = 1.0; xr[q] = 0.0; rr_[q] = 0.0; zr[q] = 0.0; pr[q] = 0.0;
+    k_over0[q] = k_over1[q] = 0;
+#pragma unroll
+    for (int d = 0; d < CGS_DEG; ++d) { ncol[q][d] = 0; nval[q][d] = 0.0; }
+    if (act[q]) {
+      const int32_t node = c.bif_nodes[i];
+      const int32_t k0 = c.inc_ptr[node], k1 = c.inc_ptr[node + 1];
+      dg[q] = c.sdiag[i];
+      xr[q] = sp[i];
+      double ax = dg[q] * xr[q];
+#pragma unroll
+      for (int d = 0; d < CGS_DEG; ++d) {
+        if (k0 + d < k1) {
+          const int32_t j = c.scol[k0 + d];
+          if (j >= 0) { ncol[q][d] = j; nval[q][d] = c.soff[k0 + d]; ax += nval[q][d] * sp[j]; }
+        }
+      }
+      k_over0[q] = min(k0 + CGS_DEG, k1); k_over1[q] = k1;
+      for (int32_t k = k_over0[q]; k < k_over1[q]; ++k) {
+        const int32_t j = c.scol[k];
+        if (j >= 0) ax += c.soff[k] * sp[j];
+      }
+      const double bi = c.rhs[i];
+      rr_[q] = bi - ax;
+      zr[q] = rr_[q] / dg[q];
+      acc[0] += rr_[q] * zr[q]; acc[1] += rr_[q] * rr_[q]; acc[2] += bi * bi;
+    }
+  }
+  __syncthreads();                           // everyone is done reading x from sp
+  block_allreduce<3>(acc, red[0]);
+  double rzc = acc[0], rzp = acc[0], rr = acc[1];
+  const double bb = acc[2];
+  const double tol2 = rtol * rtol * bb;
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    if (rr <= tol2) break;
+    const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+      pr[q] = zr[q] + beta * pr[q];
+      if (act[q]) sp[tid + q * CGP_T] = pr[q];
+    }
+    __syncthreads();
+    double pw[1] = {0.0};
+    double wr[ROWS];
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+      double wi = dg[q] * pr[q];
+#pragma unroll
+      for (int d = 0; d < CGS_DEG; ++d) wi += nval[q][d] * sp[ncol[q][d]];
+      for (int32_t k = k_over0[q]; k < k_over1[q]; ++k) {
+        const int32_t j = c.scol[k];
+        if (j >= 0) wi += c.soff[k] * sp[j];
+      }
+      wr[q] = act[q] ? wi : 0.0;
+      pw[0] += pr[q] * wr[q];
+    }
+    block_allreduce<1>(pw, red[1]);          // its barrier also fences the sp reads above
+    const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
+    double a2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+      xr[q] += alpha * pr[q];
+      rr_[q] -= alpha * wr[q];
+      zr[q] = rr_[q] / dg[q];
+      a2[0] += rr_[q] * zr[q]; a2[1] += rr_[q] * rr_[q];
+    }
+    block_allreduce<2>(a2, red[0]);
+    rzp = rzc; rzc = a2[0]; rr = a2[1];
+  }
+#pragma unroll
+  for (int q = 0; q < ROWS; ++q) if (act[q]) c.x[tid + q * CGP_T] = xr[q];
+  if (tid == 0) {
+    c.scal[0] = tol2; c.scal[1] = (rr <= tol2) ? 1.0 : 0.0; c.scal[2] = (double)it;
+    c.scal[3] = rr; c.scal[4] = bb;
+  }
+}
+
+// Multi-CTA cooperative version: vectors stay in global memory (L2 resident), two grid barriers
+// per iteration; partials of every block are re-reduced by every block in the same order.
+template <int K>
+__device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const (&part)[K], int nblk,
+                                               cg::grid_group& grid, double* sh) {
+  block_allreduce<K>(v, sh);
+  if (nblk == 1) return;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) part[k][blockIdx.x] = v[k];
+  }
+  grid.sync();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) t += __ldcg(part[k] + i);
+    v[k] = t;
+  }
+  __syncthreads();                            // sh reuse
+  block_allreduce<K>(v, sh);
+}
+
+__global__ void __launch_bounds__(CGP_T)
+cg_persistent_kernel(CgPtrs c, double rtol, int max_iter) {
+  __shared__ double red[2][3 * 32];
+  cg::grid_group grid = cg::this_grid();
+  const int nblk = gridDim.x;
+  const int32_t stride = nblk * blockDim.x;
+  const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int32_t i = t0; i < c.B; i += stride) {
+    const int32_t node = c.bif_nodes[i];
+    double ax = c.sdiag[i] * c.x[i];
+    for (int32_t k = c.inc_ptr[node]; k < c.inc_ptr[node + 1]; ++k) {
+      const int32_t j = c.scol[k];
+      if (j >= 0) ax += c.soff[k] * c.x[j];
+    }
+    const double bi = c.rhs[i];
+    const double ri = bi - ax;
+    const double zi = ri / c.sdiag[i];
+    c.r[i] = ri; c.z[i] = zi; c.p0[i] = 0.0; c.p1[i] = 0.0;
+    acc[0] += ri * zi; acc[1] += ri * ri; acc[2] += bi * bi;
+  }
+  {
+    double* const part[3] = {c.rz0, c.rr0, c.rz1};
+    grid_allreduce<3>(acc, part, nblk, grid, red[0]);
+  }
+  double rzc = acc[0], rzp = acc[0], rr = acc[1];
+  const double bb = acc[2];
+  const double tol2 = rtol * rtol * bb;
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    if (rr <= tol2) break;
+    const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
+    const double* p_old = (it & 1) ? c.p1 : c.p0;
+    double* p_new = (it & 1) ? c.p0 : c.p1;
+    // ---- phase A: p = z + beta p_old ; w = S p ; <p,w>
+    double pw[1] = {0.0};
+    for (int32_t i = t0; i < c.B; i += stride) {
+      const int32_t node = c.bif_nodes[i];
+      const double pi = c.z[i] + beta * p_old[i];
+      double wi = c.sdiag[i] * pi;
+      for (int32_t k = c.inc_ptr[node]; k < c.inc_ptr[node + 1]; ++k) {
+        const int32_t j = c.scol[k];
+        if (j >= 0) wi += c.soff[k] * (__ldcg(c.z + j) + beta * __ldcg(p_old + j));
+      }
+      p_new[i] = pi;
+      c.w[i] = wi;
+      pw[0] += pi * wi;
+    }
+    {
+      double* const part[1] = {c.pw};
+      grid_allreduce<1>(pw, part, nblk, grid, red[1]);
+    }
+    const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
+    // ---- phase B: x += alpha p ; r -= alpha w ; z = r / diag ; <r,z>, <r,r>
+    double a2[2] = {0.0, 0.0};
+    for (int32_t i = t0; i < c.B; i += stride) {
+      c.x[i] += alpha * p_new[i];
+      const double ri = c.r[i] - alpha * c.w[i];
+      const double zi = ri / c.sdiag[i];
+      c.r[i] = ri; c.z[i] = zi;
+      a2[0] += ri * zi; a2[1] += ri * ri;
+    }
+    {
+      double* const part[2] = {(it & 1) ? c.rz1 : c.rz0, (it & 1) ? c.rr1 : c.rr0};
+      grid_allreduce<2>(a2, part, nblk, grid, red[0]);
+    }
+    rzp = rzc; rzc = a2[0]; rr = a2[1];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c.scal[0] = tol2; c.scal[1] = (rr <= tol2) ? 1.0 : 0.0; c.scal[2] = (double)it;
+    c.scal[3] = rr; c.scal[4] = bb;
+  }
+}
+
 struct gnx_cg {
   CgPtrs c;
-  cudaStream_t st;
   int batch;                 // iterations per graph launch (even)
+  int mode;                  // 0: kernel pairs, 1: CUDA-graph batches, 2: persistent cooperative kernel
+  int pgrid;                 // grid of the persistent kernel
   cudaGraph_t graph;
   cudaGraphExec_t exec;
   double* scal_host;         // pinned [8]
@@ -286,7 +520,7 @@ static void cg_enqueue_iters(const CgPtrs& c, int iters, cudaStream_t st) {
 
 extern "C" int gnx_cg_create(const gnx_network_t* net, const double* sdiag, const double* soff,
                              const int32_t* scol, const double* srhs, double* x, double* work,
-                             int32_t batch, int32_t use_graph, void* stream, gnx_cg** out) {
+                             int32_t batch, int32_t mode, void* stream, gnx_cg** out) {
   GNX_CHECK_ARG(net && sdiag && soff && scol && srhs && x && work && out && net->B > 0);
   gnx_cg* h = new gnx_cg();
   const int32_t B = net->B;
@@ -299,9 +533,23 @@ extern "C" int gnx_cg_create(const gnx_network_t* net, const double* sdiag, cons
   c.r = w; w += B; c.z = w; w += B; c.w = w; w += B; c.p0 = w; w += B; c.p1 = w; w += B;
   c.pw = w; w += nb; c.rz0 = w; w += nb; c.rz1 = w; w += nb; c.rr0 = w; w += nb; c.rr1 = w; w += nb;
   c.scal = w;
-  h->st = (cudaStream_t)stream;
+  (void)stream;
   h->batch = (batch < 2 ? 2 : batch) & ~1;
   h->graph = nullptr; h->exec = nullptr; h->scal_host = nullptr;
+  h->mode = mode; h->pgrid = 0;
+  const int use_graph = (mode == 1);
+  if (mode == 2) {
+    int dev = 0, nsm = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel, CGP_T, 0);
+    if (!coop || per_sm < 1) { gnx_set_error("cooperative launch unsupported"); delete h; return GNX_ERR_CUDA; }
+    int want = (B + CGP_T - 1) / CGP_T;
+    if (want > nsm * per_sm) want = nsm * per_sm;
+    if (want > nb) want = nb;
+    h->pgrid = want < 1 ? 1 : want;
+  }
   cudaError_t err = cudaMallocHost(&h->scal_host, 8 * sizeof(double));
   if (err != cudaSuccess) { gnx_set_error("cudaMallocHost: %s", cudaGetErrorString(err)); delete h; return GNX_ERR_CUDA; }
   if (use_graph) {
@@ -340,10 +588,35 @@ extern "C" void gnx_cg_destroy(gnx_cg* h) {
 // x holds the initial guess on entry.  Synchronises the stream.
 // resid_host[0] = ||r||/||rhs|| (recurrence residual); info_host = {iterations, converged, graph launches}
 extern "C" int gnx_cg_solve(gnx_cg* h, double rtol, int32_t max_iter, double* resid_host,
-                            int32_t* info_host) {
+                            int32_t* info_host, void* stream) {
   GNX_CHECK_ARG(h && rtol > 0 && max_iter > 0);
   const CgPtrs& c = h->c;
-  cudaStream_t st = h->st;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->mode == 2) {
+    CgPtrs cc = c;
+    double rt = rtol;
+    int mi = max_iter;
+    if (c.B <= CGP_T) {
+      cg_small_kernel<1><<<1, CGP_T, sizeof(double) * c.B, st>>>(cc, rt, mi);
+      GNX_LAUNCH_CHECK();
+    } else if (c.B <= 2 * CGP_T) {
+      cg_small_kernel<2><<<1, CGP_T, sizeof(double) * c.B, st>>>(cc, rt, mi);
+      GNX_LAUNCH_CHECK();
+    } else {
+      void* args[] = {&cc, &rt, &mi};
+      GNX_CUDA(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel, dim3(h->pgrid), dim3(CGP_T), args, 0, st));
+    }
+    if (!resid_host && !info_host) return GNX_OK;            // fully asynchronous
+    GNX_CUDA(cudaMemcpyAsync(h->scal_host, c.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GNX_CUDA(cudaStreamSynchronize(st));
+    const double bb = h->scal_host[4];
+    if (resid_host) resid_host[0] = bb > 0 ? sqrt(h->scal_host[3] / bb) : 0.0;
+    const int done = h->scal_host[1] != 0.0;
+    if (info_host) { info_host[0] = (int32_t)h->scal_host[2]; info_host[1] = done; info_host[2] = 1; }
+    if (!done) { gnx_set_error("schur CG: no convergence in %d iterations (rel. resid %.3e)", (int)h->scal_host[2],
+                               bb > 0 ? sqrt(h->scal_host[3] / bb) : 0.0); return GNX_ERR_NOCONV; }
+    return GNX_OK;
+  }
   cg_init_kernel<<<c.nb, CG_T, 0, st>>>(c);
   cg_init_finalize_kernel<<<1, CG_T, 0, st>>>(c, rtol);
   GNX_LAUNCH_CHECK();

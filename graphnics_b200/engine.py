@@ -1,0 +1,220 @@
+"""Host driver of the mixed (q per edge | p | lambda) system on one GPU: pattern (once),
+assembly, right-hand side, Schur-complement solve, residual.  Thin orchestration over the
+C ABI (include/graphnics_b200.h); no arithmetic happens here.
+
+Replaces, for MixedHydraulicNetwork / NetworkStokes / TimeDepMixedHydraulicNetwork:
+ii_assemble + ii_convert + LUSolver("mumps") (graphnics/flowmodels/flow_models.py:343-348).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, check
+from .device import DeviceNetwork, current_stream
+
+__all__ = ["MixedSystem", "SolveInfo"]
+
+
+class SolveInfo:
+    def __init__(self):
+        self.cg_iterations = 0
+        self.cg_converged = True
+        self.cg_batches = 0
+        self.cg_rel_resid = 0.0
+        self.rel_resid = None      # ||b - A x|| / ||b|| of the monolithic system (if checked)
+        self.refinements = 0
+
+    def __repr__(self):
+        return (f"SolveInfo(cg_iterations={self.cg_iterations}, cg_rel_resid={self.cg_rel_resid:.2e}, "
+                f"rel_resid={self.rel_resid}, refinements={self.refinements})")
+
+
+class _Coeffs:
+    """gnx_mixed_coeffs_t + the tensors it points to."""
+
+    def __init__(self, a_edge, k_edge, sigma):
+        self.a_edge, self.k_edge, self.sigma = a_edge, k_edge, float(sigma)
+        self.c = _lib.gnx_mixed_coeffs_t()
+        self.c.a_edge = a_edge.data_ptr()
+        self.c.k_edge = k_edge.data_ptr() if k_edge is not None else None
+        self.c.sigma = float(sigma)
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+class MixedSystem:
+    def __init__(self, dn: DeviceNetwork, cg_batch=32, cg_mode=2):
+        self.dn = dn
+        self.lib = _lib.require_device()
+        self.N = dn.mixed_ndofs
+        self.nnz = dn.mixed_nnz
+        self.dev = dn.device
+        self.rowptr = None
+        self.colidx = None
+        self.cg_batch = cg_batch
+        self.cg_mode = int(cg_mode)
+        self._cg = None
+        self._solve_bufs = None
+        self._red_work = None
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _f64(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.dev)
+
+    def edge_array(self, value):
+        """scalar | [E] array-like | tensor -> float64 device tensor [E]"""
+        E = self.dn.E
+        if torch.is_tensor(value):
+            return value.to(device=self.dev, dtype=torch.float64).contiguous().reshape(E)
+        arr = np.broadcast_to(np.asarray(value, dtype=np.float64), (E,))
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+
+    def coeffs(self, a_edge, k_edge=None, sigma=1.0):
+        a = self.edge_array(a_edge)
+        k = None if k_edge is None else self.edge_array(k_edge)
+        return _Coeffs(a, k, sigma)
+
+    # ---- pattern (built once) ----------------------------------------------------------------
+    def build_pattern(self):
+        if self.rowptr is None:
+            self.rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=self.dev)
+            self.colidx = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
+            check(self.lib.gnx_build_pattern_mixed(self.dn.net_ref(), ptr(self.rowptr), ptr(self.colidx),
+                                                   current_stream()))
+        return self.rowptr, self.colidx
+
+    # ---- assembly ----------------------------------------------------------------------------
+    def assemble(self, co, out=None):
+        self.build_pattern()
+        vals = out if out is not None else self._f64(self.nnz)
+        check(self.lib.gnx_assemble_mixed(self.dn.net_ref(), co.ref(), ptr(self.rowptr), ptr(vals),
+                                          current_stream()))
+        return vals
+
+    def assemble_mass_q(self, coeff, out=None):
+        self.build_pattern()
+        vals = out if out is not None else self._f64(self.nnz)
+        check(self.lib.gnx_assemble_mass_q_mixed(self.dn.net_ref(), float(coeff), ptr(self.rowptr),
+                                                 ptr(vals), current_stream()))
+        return vals
+
+    def rhs(self, f_nodal=None, g_nodal=None, pbc_nodal=None, pbc_node=None, out=None):
+        b = out if out is not None else self._f64(self.N)
+        check(self.lib.gnx_assemble_rhs_mixed(self.dn.net_ref(), ptr(f_nodal), ptr(g_nodal), ptr(pbc_nodal),
+                                              ptr(pbc_node), ptr(b), current_stream()))
+        return b
+
+    def dof_coordinates(self, want_mid=True):
+        dn = self.dn
+        xq = self._f64(dn.E * (dn.m + 1), dn.gdim)
+        xm = self._f64(dn.E * dn.m, dn.gdim) if want_mid else None
+        check(self.lib.gnx_dof_coordinates_mixed(dn.net_ref(), ptr(dn.coords), ptr(dn.cells), ptr(xq), ptr(xm),
+                                                 current_stream()))
+        return xq, xm
+
+    # ---- Krylov building blocks ----------------------------------------------------------------
+    def spmv(self, vals, x, y=None):
+        y = y if y is not None else self._f64(self.N)
+        check(self.lib.gnx_spmv_csr_f64(self.N, ptr(self.rowptr), ptr(self.colidx), ptr(vals), ptr(x), ptr(y),
+                                        current_stream()))
+        return y
+
+    def residual(self, vals, x, b, r=None):
+        """(||b - A x||^2, ||b||^2) as a 2-element device tensor; r optional output."""
+        if self._red_work is None:
+            self._red_work = self._f64(int(self.lib.gnx_reduce_work_doubles(self.N)))
+        out2 = self._f64(2)
+        check(self.lib.gnx_residual_csr_f64(self.N, ptr(self.rowptr), ptr(self.colidx), ptr(vals), ptr(x), ptr(b),
+                                            ptr(r), ptr(out2), ptr(self._red_work), current_stream()))
+        return out2
+
+    # ---- solve ---------------------------------------------------------------------------------
+    def _bufs(self):
+        if self._solve_bufs is None:
+            dn = self.dn
+            E, B = dn.E, max(dn.B, 1)
+            d = {}
+            d["cond"], d["rsrc"], d["ftot"] = self._f64(E), self._f64(E), self._f64(E)
+            d["sdiag"], d["srhs"], d["P"] = self._f64(B), self._f64(B), torch.zeros(B, dtype=torch.float64, device=self.dev)
+            d["soff"] = self._f64(2 * E)
+            d["scol"] = torch.empty(2 * E, dtype=torch.int32, device=self.dev)
+            d["cgwork"] = self._f64(int(self.lib.gnx_cg_work_doubles(B)))
+            self._solve_bufs = d
+        return self._solve_bufs
+
+    def _cg_handle(self):
+        if self._cg is None and self.dn.B > 0:
+            d = self._bufs()
+            h = C.c_void_p()
+            check(self.lib.gnx_cg_create(self.dn.net_ref(), ptr(d["sdiag"]), ptr(d["soff"]), ptr(d["scol"]),
+                                         ptr(d["srhs"]), ptr(d["P"]), ptr(d["cgwork"]), self.cg_batch,
+                                         self.cg_mode, current_stream(), C.byref(h)))
+            self._cg = h
+        return self._cg
+
+    def eliminate(self, co, b):
+        """phase 1 + Schur assembly (device only, no sync)."""
+        d = self._bufs()
+        dn = self.dn
+        st = current_stream()
+        check(self.lib.gnx_edge_eliminate_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                                ptr(d["ftot"]), st))
+        if dn.B > 0:
+            b_lam = b[dn.lam_off:]
+            check(self.lib.gnx_schur_build(dn.net_ref(), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+                                           ptr(b_lam), ptr(d["sdiag"]), ptr(d["soff"]), ptr(d["scol"]),
+                                           ptr(d["srhs"]), st))
+
+    def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True):
+        """x = A^{-1} b for the operator described by `co` (never forms A).
+        sync=False (cg_mode 2 only): nothing returns to the host; `info` is not filled."""
+        dn = self.dn
+        d = self._bufs()
+        info = info if info is not None else SolveInfo()
+        x = x if x is not None else self._f64(self.N)
+        self.eliminate(co, b)
+        if dn.B > 0:
+            if not warm_start:
+                d["P"].zero_()
+            h = self._cg_handle()
+            if sync or self.cg_mode != 2:
+                resid = C.c_double(0.0)
+                inf = (C.c_int32 * 3)()
+                check(self.lib.gnx_cg_solve(h, float(rtol), int(max_iter), C.byref(resid), inf, current_stream()))
+                info.cg_iterations += int(inf[0])
+                info.cg_converged = bool(inf[1])
+                info.cg_batches += int(inf[2])
+                info.cg_rel_resid = float(resid.value)
+            else:
+                check(self.lib.gnx_cg_solve(h, float(rtol), int(max_iter), None, None, current_stream()))
+        check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                              ptr(d["P"]) if dn.B > 0 else None, ptr(x), current_stream()))
+        return x, info
+
+    def solve_checked(self, co, vals, b, rtol=1e-13, resid_tol=1e-10, max_refine=2):
+        """solve + monolithic residual check with (optional) iterative refinement."""
+        x, info = self.solve(co, b, rtol=rtol)
+        r = self._f64(self.N)
+        for it in range(max_refine + 1):
+            rr, bb = self.residual(vals, x, b, r).cpu().tolist()
+            info.rel_resid = float(np.sqrt(rr / bb)) if bb > 0 else float(np.sqrt(rr))
+            if info.rel_resid <= resid_tol or it == max_refine:
+                break
+            dx, _ = self.solve(co, r, rtol=rtol, info=info)
+            check(self.lib.gnx_axpby_dot(self.N, 1.0, ptr(dx), 1.0, ptr(x), None, None, current_stream()))
+            info.refinements += 1
+        return x, info
+
+    def close(self):
+        if self._cg is not None:
+            self.lib.gnx_cg_destroy(self._cg)
+            self._cg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

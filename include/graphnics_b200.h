@@ -157,18 +157,25 @@ int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, 
                     const double* ftot, const double* b_lam, double* sdiag, double* soff,
                     int32_t* scol, double* srhs, void* stream);
 
-/* Jacobi-PCG on the Schur system; 2 fused kernels per iteration (SpMV+<p,Sp> | update+<r,z>,<r,r>),
- * deterministic two-stage reductions, convergence tested on device, iterations replayed in
- * batches from a CUDA graph (captured once per handle on an internal stream).
+/* Jacobi-PCG on the Schur system; per iteration two fused phases (p-update+SpMV+<p,Sp> |
+ * x,r,z-update+<r,z>,<r,r>), deterministic two-stage reductions, convergence tested on device.
+ *   mode 2 (default): ONE persistent kernel per solve -- a single CTA with the search
+ *           direction in shared memory and all row state in registers when B <= 2048, else a
+ *           cooperative multi-CTA kernel with grid barriers; no host round trip, fully
+ *           asynchronous (and CUDA-graph capturable) when resid_host and info_host are NULL;
+ *   mode 1: two kernels per iteration replayed in batches from a CUDA graph (captured once
+ *           per handle on an internal stream), one stream sync per batch;
+ *   mode 0: as mode 1 without the graph.
  *   x [B] in/out (initial guess), work [>= gnx_cg_work_doubles(B)] doubles.
- * gnx_cg_solve SYNCHRONISES the stream once per batch; resid_host[0] = ||r||/||rhs||,
- * info_host[3] = {iterations, converged, batches}.  GNX_ERR_NOCONV if max_iter is hit. */
+ * resid_host[0] = ||r||/||rhs||, info_host[3] = {iterations, converged, batches};
+ * GNX_ERR_NOCONV if max_iter is hit (only detectable when info is requested in mode 2). */
 typedef struct gnx_cg gnx_cg_t;
 int64_t gnx_cg_work_doubles(int32_t B);
 int gnx_cg_create(const gnx_network_t* net, const double* sdiag, const double* soff,
                   const int32_t* scol, const double* srhs, double* x, double* work, int32_t batch,
-                  int32_t use_graph, void* stream, gnx_cg_t** out);
-int gnx_cg_solve(gnx_cg_t* h, double rtol, int32_t max_iter, double* resid_host, int32_t* info_host);
+                  int32_t mode, void* stream, gnx_cg_t** out);
+int gnx_cg_solve(gnx_cg_t* h, double rtol, int32_t max_iter, double* resid_host, int32_t* info_host,
+                 void* stream);
 void gnx_cg_destroy(gnx_cg_t* h);
 
 /* Phase 2: back-substitution, x [N] (dof order) from the multipliers P [B] (= sigma*lambda). */

@@ -1,0 +1,206 @@
+"""GPU parity tests (through the C ABI, via graphnics_b200.engine) against the CPU oracle.
+
+Bit-exact: mesh coordinates, cells, markers, tangents, tags, node tables, dof numbering, CSR
+pattern.  1e-12 relative: matrix entries, right-hand side.  1e-8 relative L2: solution fields.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from _util import y_graph, random_graph, golden_arrays, golden_graphs
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("Y", 0), ("Y", 1), ("Y", 3), ("Y", 6), ("Y", 10), ("Y3", 4), ("rand0", 0), ("rand0", 3),
+         ("rand1", 5), ("rand2", 7), ("honeycomb_2_2", 2), ("honeycomb_4_4", 5), ("YY_bifurcation", 5),
+         ("arterial_tree_N5", 3), ("arterial_tree_N7", 6), ("line_graph_3_dim3", 5), ("line_graph_2_dx2", 8)]
+
+
+def graph(name):
+    if name == "Y":
+        return y_graph()
+    if name == "Y3":
+        return y_graph(3)
+    if name.startswith("rand"):
+        return random_graph(int(name[4:]), V=14 + 3 * int(name[4:]), extra=5)
+    return golden_arrays(name)
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    from graphnics_b200.device import DeviceNetwork
+    from graphnics_b200.engine import MixedSystem
+    assert torch.cuda.is_available()
+    return DeviceNetwork, MixedSystem
+
+
+@pytest.mark.parametrize("name,n", CASES)
+def test_mesh_and_tables_bit_exact(eng, name, n):
+    DeviceNetwork, _ = eng
+    pos, edges = graph(name)
+    om = oracle.build_mesh(pos, edges, n)
+    dn = DeviceNetwork(pos, edges, n)
+    assert np.array_equal(dn.cells.cpu().numpy(), om.cells)
+    assert np.array_equal(dn.mf.cpu().numpy(), om.mf)
+    assert np.array_equal(dn.coords.cpu().numpy().view(np.int64), om.coords.view(np.int64))
+    assert np.array_equal(dn.tangents.cpu().numpy().view(np.int64), om.tangents.view(np.int64))
+    assert dn.bifurcation_ixs() == om.bif_ixs
+    assert dn.boundary_ixs() == om.bnd_ixs
+    assert np.array_equal(dn.vf_host(), om.vf)
+    assert np.array_equal(dn.parent_vertex_host(), om.parent_vertex)
+    # cell lengths (edge-local order) against the oracle geometry
+    h = dn.h.cpu().numpy().reshape(dn.E, dn.m)
+    assert np.allclose(h.sum(axis=1), oracle.edge_lengths(pos, edges), rtol=1e-13)
+    assert dn.B == om.B and dn.mixed_ndofs == oracle.mixed_layout(om)["N"]
+
+
+@pytest.mark.parametrize("name,n", CASES)
+def test_pattern_values_rhs(eng, name, n):
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = graph(name)
+    om = oracle.build_mesh(pos, edges, n)
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn)
+    rng = np.random.default_rng(3)
+    Res = rng.uniform(0.5, 2.0, size=len(edges))
+    A = oracle.assemble_mixed(om, Res)
+    rowptr, colidx = ms.build_pattern()
+    assert np.array_equal(rowptr.cpu().numpy(), A.indptr)
+    assert np.array_equal(colidx.cpu().numpy(), A.indices)
+    vals = ms.assemble(ms.coeffs(Res)).cpu().numpy()
+    np.testing.assert_allclose(vals, A.data, rtol=1e-12, atol=1e-300)
+    visc = rng.uniform(0.1, 1.0, size=len(edges))
+    A2 = oracle.assemble_mixed(om, Res, visc=visc)
+    np.testing.assert_allclose(ms.assemble(ms.coeffs(Res, visc)).cpu().numpy(), A2.data, rtol=1e-11, atol=1e-300)
+    D = oracle.assemble_mass_q_mixed(om, 2.5)
+    Dg = sp.csr_matrix((ms.assemble_mass_q(2.5).cpu().numpy(), A.indices, A.indptr), shape=A.shape)
+    assert abs(Dg - D).max() <= 1e-12 * abs(D).max()
+    # rhs with nodal (un-projected) data
+    import torch
+    lin = oracle.Coef(lambda x: 1.0 + 2.0 * x[..., 0] - 0.5 * x[..., 1], 1)
+    g = oracle.Coef(lambda x: np.sin(x[..., 0]) + x[..., 1] ** 2, 1)
+    f = oracle.Coef(lambda x: np.cos(x[..., 1]) - x[..., 0], 1)
+    b = oracle.assemble_mixed_rhs(om, f=f, g=g, p_bc=lin, project=False)
+    xq, xm = ms.dof_coordinates()
+    assert np.array_equal(xq.cpu().numpy().reshape(om.sub_coords.shape).view(np.int64), om.sub_coords.view(np.int64))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    nod = lambda c: dev(c(om.sub_coords).ravel())
+    bg = ms.rhs(nod(f), nod(g), nod(lin), dev(lin(pos))).cpu().numpy()
+    np.testing.assert_allclose(bg, b, rtol=1e-12, atol=1e-14)
+    # SpMV against scipy
+    x = rng.normal(size=A.shape[0])
+    y = ms.spmv(ms.assemble(ms.coeffs(Res)), dev(x)).cpu().numpy()
+    np.testing.assert_allclose(y, A @ x, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,n", CASES)
+@pytest.mark.parametrize("cg_mode", [2, 1, 0])
+def test_solve_matches_lu(eng, name, n, cg_mode):
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = graph(name)
+    om = oracle.build_mesh(pos, edges, n)
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn, cg_mode=cg_mode)
+    rng = np.random.default_rng(5)
+    Res = rng.uniform(0.5, 2.0, size=len(edges))
+    lin = oracle.Coef(lambda x: 1.0 + 2.0 * x[..., 0] - 0.5 * x[..., 1], 1)
+    g = oracle.Coef(lambda x: np.sin(3 * x[..., 0]) + x[..., 1], 1)
+    f = oracle.Coef(lambda x: np.cos(2 * x[..., 1]) - x[..., 0], 1)
+    A = oracle.assemble_mixed(om, Res)
+    b = oracle.assemble_mixed_rhs(om, f=f, g=g, p_bc=lin, project=False)
+    x_ref = oracle.lu_solve(A, b)
+    co = ms.coeffs(Res)
+    vals = ms.assemble(co)
+    bd = torch.from_numpy(b).cuda()
+    x, info = ms.solve_checked(co, vals, bd)
+    x = x.cpu().numpy()
+    lay = oracle.mixed_layout(om)
+    q, qr = x[:lay["p_off"]], x_ref[:lay["p_off"]]
+    p, pr = x[lay["p_off"]:lay["lam_off"]], x_ref[lay["p_off"]:lay["lam_off"]]
+    assert info.cg_converged
+    assert rel(q, qr) < 1e-8 and rel(p, pr) < 1e-8, (rel(q, qr), rel(p, pr), info)
+    if om.B:
+        assert rel(x[lay["lam_off"]:], x_ref[lay["lam_off"]:]) < 1e-8
+    assert info.rel_resid < 1e-10, info
+
+
+def test_stokes_and_sigma_scaled_solve(eng):
+    """NetworkStokes-type operator (a M + k K) and a theta-scheme operator (sigma != 1)."""
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = graph("rand1")
+    n = 4
+    om = oracle.build_mesh(pos, edges, n)
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn)
+    rng = np.random.default_rng(7)
+    Res = rng.uniform(0.5, 2.0, size=len(edges))
+    visc = rng.uniform(0.1, 1.0, size=len(edges))
+    b = rng.normal(size=ms.N)
+    b[oracle.mixed_layout(om)["lam_off"]:] = 0.0
+    A = oracle.assemble_mixed(om, Res, visc=visc)
+    x_ref = oracle.lu_solve(A, b)
+    co = ms.coeffs(Res, visc)
+    x, info = ms.solve_checked(co, ms.assemble(co), torch.from_numpy(b).cuda())
+    assert rel(x.cpu().numpy(), x_ref) < 1e-8, info
+    # D + theta*dt*A with D = Ainv*M:  a = Ainv + s*Res, sigma = s
+    s, Ainv = 0.05, 2.0
+    Aeff = (oracle.assemble_mass_q_mixed(om, Ainv) + s * oracle.assemble_mixed(om, Res)).tocsr()
+    x_ref = oracle.lu_solve(Aeff, b)
+    co = ms.coeffs(Ainv + s * Res, None, s)
+    vals = ms.assemble(co)
+    rp, ci = ms.build_pattern()
+    Ag = sp.csr_matrix((vals.cpu().numpy(), ci.cpu().numpy(), rp.cpu().numpy()), shape=Aeff.shape)
+    assert abs(Ag - Aeff).max() <= 1e-12 * abs(Aeff).max()
+    x, info = ms.solve_checked(co, vals, torch.from_numpy(b).cuda())
+    assert rel(x.cpu().numpy(), x_ref) < 1e-8, info
+
+
+def test_reference_known_answers(eng):
+    """SURVEY.md Appendix C (Ohm/Kirchhoff closed form) and tests/test_flow_models.py:17-71
+    (mass conservation at every bifurcation)."""
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = y_graph()
+    dn = DeviceNetwork(pos, edges, 6)
+    ms = MixedSystem(dn)
+    co = ms.coeffs([1.0, 2.0, 3.0])
+    pbc = torch.from_numpy(2.0 - pos[:, 1]).cuda()
+    xq, _ = ms.dof_coordinates(False)
+    b = ms.rhs(None, None, (2.0 - xq[:, 1]).contiguous(), pbc)
+    x, info = ms.solve(co, b)
+    x = x.cpu().numpy()
+    m = dn.m
+    q = x[:dn.p_off].reshape(3, m + 1)
+    assert np.allclose(q[0], 0.741549228561398, rtol=1e-12)
+    assert np.allclose(q[1], 0.444929537136839, rtol=1e-12)
+    assert np.allclose(q[2], 0.296619691424559, rtol=1e-12)
+    assert np.isclose(x[dn.lam_off], 1.629225385719301, rtol=1e-12)
+    # mass conservation on the reference's own graphs (n=5, Res=1, p_bc = x[0])
+    for name in ("line_graph_3_dim3", "Y_bifurcation", "YY_bifurcation", "honeycomb_4_4"):
+        pos, edges = golden_arrays(name)
+        dn = DeviceNetwork(pos, edges, 5)
+        ms = MixedSystem(dn)
+        co = ms.coeffs(1.0)
+        xq, _ = ms.dof_coordinates(False)
+        b = ms.rhs(None, None, xq[:, 0].contiguous(), torch.from_numpy(np.ascontiguousarray(pos[:, 0])).cuda())
+        x, info = ms.solve(co, b)
+        x = x.cpu().numpy()
+        q = x[:dn.p_off].reshape(dn.E, dn.m + 1)
+        loc = dn.loc_host
+        for bnode in dn.bifurcation_ixs():
+            tot = 0.0
+            for i, (u, v) in enumerate(edges):
+                flip = u > v
+                if v == bnode:
+                    tot += q[i, loc[0] if flip else loc[dn.m]]
+                if u == bnode:
+                    tot -= q[i, loc[dn.m] if flip else loc[0]]
+            assert abs(tot) < 1e-10, (name, bnode, tot)
