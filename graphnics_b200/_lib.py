@@ -55,7 +55,10 @@ PROTOTYPES = {
     "gnx_build_pattern_mixed": (_I, [_NET, _P, _P, _P]),
     "gnx_assemble_mixed": (_I, [_NET, _CO, _P, _P, _P]),
     "gnx_assemble_mass_q_mixed": (_I, [_NET, _D, _P, _P, _P]),
-    "gnx_assemble_rhs_mixed": (_I, [_NET, _P, _P, _P, _P, _P, _P]),
+    "gnx_assemble_rhs_mixed": (_I, [_NET, _P, _P, _D, _D, _P, _P, _P, _P]),
+    "gnx_eval_expr": (_I, [_P, _P, _I, _L, _I, _P, _P, _P, _P]),
+    "gnx_project_p1_edges": (_I, [_NET, _P, _P, _P, _P, _P]),
+    "gnx_project_end_values": (_I, [_NET, _P, _P, _I, _I, _P, _P]),
     "gnx_dof_coordinates_mixed": (_I, [_NET, _P, _P, _P, _P, _P]),
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

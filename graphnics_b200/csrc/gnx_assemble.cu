@@ -73,21 +73,23 @@ extern "C" int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff,
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mixed_rhs_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ f_nodal,
-                 const double* __restrict__ g_nodal, const double* __restrict__ pbc_nodal,
-                 const double* __restrict__ pbc_node, double* __restrict__ b) {
+                 const double* __restrict__ g_nodal, double fc, double gc,
+                 const double* __restrict__ pbc_out, const double* __restrict__ pbc_node,
+                 double* __restrict__ b) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= d.N) return;
-  b[r] = gnx_mixed_rhs_row(net, d, r, f_nodal, g_nodal, pbc_nodal, pbc_node);
+  b[r] = gnx_mixed_rhs_row(net, d, r, f_nodal, g_nodal, fc, gc, pbc_out, pbc_node);
 }
 
 extern "C" int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_nodal,
-                                      const double* g_nodal, const double* pbc_nodal,
-                                      const double* pbc_node, double* b, void* stream) {
+                                      const double* g_nodal, double f_const, double g_const,
+                                      const double* pbc_out, const double* pbc_node, double* b,
+                                      void* stream) {
   if (int rc = check_net(net)) return rc;
   GNX_CHECK_ARG(b && net->h);
   const GnxMixedDims d = gnx_mixed_dims(*net);
   mixed_rhs_kernel<<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
-      *net, d, f_nodal, g_nodal, pbc_nodal, pbc_node, b);
+      *net, d, f_nodal, g_nodal, f_const, g_const, pbc_out, pbc_node, b);
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }

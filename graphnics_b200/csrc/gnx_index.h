@@ -233,9 +233,10 @@ GNX_HD void gnx_mixed_row_emit(const gnx_network_t& net, const GnxMixedDims& d, 
 }
 
 // One entry of MixedHydraulicNetwork.L_form (flow_models.py:299-332), row r.
+// f/g: nodal arrays in q-dof layout, or NULL -> the constants fc / gc.
 GNX_HD double gnx_mixed_rhs_row(const gnx_network_t& net, const GnxMixedDims& d, int64_t r,
-                                const double* f_nodal, const double* g_nodal,
-                                const double* pbc_nodal, const double* pbc_node) {
+                                const double* f_nodal, const double* g_nodal, double fc, double gc,
+                                const double* pbc_out, const double* pbc_node) {
   const int32_t m = d.m;
   double out = 0.0;
   if (r < d.p_off) {
@@ -249,27 +250,30 @@ GNX_HD double gnx_mixed_rhs_row(const gnx_network_t& net, const GnxMixedDims& d,
     if (t == 0 || t == m) {
       const int32_t node = (t == 0) ? gnx_imin(u, v) : gnx_imax(u, v);
       if (net.bix[node] < 0) {                // degree-1 node == boundary
-        if (node == v) { if (pbc_nodal) out -= pbc_nodal[r]; }          // edge INTO node: BOUN_OUT
+        if (node == v) { if (pbc_out) out -= pbc_out[e]; }              // edge INTO node: BOUN_OUT
         else           { if (pbc_node) out += pbc_node[node]; }         // edge OUT of node: BOUN_IN
       }
     }
     // L[i] += gs[i] v dx_i  (:325)  P1 x P1 mass action on the projected nodal g
+    const double* he = net.h + (int64_t)e * m;
     if (g_nodal) {
-      const double* he = net.h + (int64_t)e * m;
       const double gt = g_nodal[r];
       if (t > 0) out += he[flip ? m - t : t - 1] * (g_nodal[qb + net.loc[t - 1]] + 2.0 * gt) * (1.0 / 6.0);
       if (t < m) out += he[flip ? m - 1 - t : t] * (2.0 * gt + g_nodal[qb + net.loc[t + 1]]) * (1.0 / 6.0);
+    } else if (gc != 0.0) {
+      if (t > 0) out += he[flip ? m - t : t - 1] * gc * 0.5;
+      if (t < m) out += he[flip ? m - 1 - t : t] * gc * 0.5;
     }
   } else if (r < d.lam_off) {
     // L[E] += fs[i] phi dx_i  (:327)
-    if (f_nodal) {
+    if (f_nodal || fc != 0.0) {
       const int32_t c = (int32_t)(r - d.p_off);
       const int32_t e = c >> net.n;
       const int32_t s = gnx_inv_gray(c & (m - 1));
       const bool flip = net.edges[2 * e] > net.edges[2 * e + 1];
       const int64_t qb = (int64_t)e * (m + 1);
       const double hc = net.h[(int64_t)e * m + (flip ? m - 1 - s : s)];
-      out = hc * (f_nodal[qb + net.loc[s]] + f_nodal[qb + net.loc[s + 1]]) * 0.5;
+      out = f_nodal ? hc * (f_nodal[qb + net.loc[s]] + f_nodal[qb + net.loc[s + 1]]) * 0.5 : hc * fc;
     }
   }
   return out;

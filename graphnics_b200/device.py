@@ -147,11 +147,46 @@ class DeviceNetwork:
     def boundary_ixs(self):
         return self.bnd_nodes.cpu().tolist()
 
+    def _host_mesh(self):
+        if getattr(self, "_mesh_view", None) is None:
+            from .mesh import Mesh1D
+            self._mesh_view = Mesh1D(self)
+        return self._mesh_view
+
+    def edges_host(self):
+        if getattr(self, "_edges_h", None) is None:
+            self._edges_h = self.edges.cpu().numpy().astype(np.int64)
+        return self._edges_h
+
+    def pos_host(self):
+        if getattr(self, "_pos_h", None) is None:
+            self._pos_h = self.pos.cpu().numpy()
+        return self._pos_h
+
+    def sub_cells_host(self):
+        """cells of a SubMesh in SubMesh-local vertex numbering [m,2] (same for every edge)."""
+        if getattr(self, "_subc", None) is None:
+            j = np.arange(self.m, dtype=np.int64)
+            s = j.copy()
+            sh = 1
+            while sh < 64:
+                s ^= s >> sh
+                sh <<= 1
+            loc = self.loc_host.astype(np.int64)
+            self._subc = np.sort(np.stack([loc[s], loc[s + 1]], axis=1), axis=1)
+        return self._subc
+
     def vf_host(self):
         """vf[E, m+1]: vertex tags of every SubMesh in SubMesh-local numbering
         (fenics_graph.py:141-156)."""
+        if getattr(self, "_vf_h", None) is not None:
+            return self._vf_h
+        self._vf_h = self._vf_host()
+        return self._vf_h
+
+    def _vf_host(self):
         E, m = self.E, self.m
-        edges = self.edges.cpu().numpy()
+        edges = self.edges_host()
         vf = np.zeros((E, m + 1), dtype=np.int64)
         flip = edges[:, 0] > edges[:, 1]
         lu = np.where(flip, self.loc_host[m], self.loc_host[0])
@@ -163,6 +198,11 @@ class DeviceNetwork:
 
     def parent_vertex_host(self):
         """parent_vertex[E, m+1]: global vertex id of every SubMesh-local vertex (A5)."""
+        if getattr(self, "_pv_h", None) is None:
+            self._pv_h = self._parent_vertex_host()
+        return self._pv_h
+
+    def _parent_vertex_host(self):
         E, m, n, V = self.E, self.m, self.n, self.V
         edges = self.edges.cpu().numpy().astype(np.int64)
         lo, hi = edges.min(axis=1), edges.max(axis=1)

@@ -101,19 +101,61 @@ class MixedSystem:
                                                  ptr(vals), current_stream()))
         return vals
 
-    def rhs(self, f_nodal=None, g_nodal=None, pbc_nodal=None, pbc_node=None, out=None):
+    def mass_vals(self, coeff):
+        """values of coeff * blockdiag(M_e) on the pattern, cached per coefficient"""
+        key = float(coeff)
+        if getattr(self, "_mass_cache", None) is None or self._mass_cache[0] != key:
+            self._mass_cache = (key, self.assemble_mass_q(key))
+        return self._mass_cache[1]
+
+    def rhs(self, f_nodal=None, g_nodal=None, pbc_out=None, pbc_node=None, f_const=0.0, g_const=0.0, out=None):
+        """MixedHydraulicNetwork.L_form; see gnx_assemble_rhs_mixed."""
         b = out if out is not None else self._f64(self.N)
-        check(self.lib.gnx_assemble_rhs_mixed(self.dn.net_ref(), ptr(f_nodal), ptr(g_nodal), ptr(pbc_nodal),
-                                              ptr(pbc_node), ptr(b), current_stream()))
+        check(self.lib.gnx_assemble_rhs_mixed(self.dn.net_ref(), ptr(f_nodal), ptr(g_nodal), float(f_const),
+                                              float(g_const), ptr(pbc_out), ptr(pbc_node), ptr(b),
+                                              current_stream()))
         return b
 
     def dof_coordinates(self, want_mid=True):
+        """(xq [E(m+1), gdim], xmid [E m, gdim]) -- cached."""
         dn = self.dn
-        xq = self._f64(dn.E * (dn.m + 1), dn.gdim)
-        xm = self._f64(dn.E * dn.m, dn.gdim) if want_mid else None
-        check(self.lib.gnx_dof_coordinates_mixed(dn.net_ref(), ptr(dn.coords), ptr(dn.cells), ptr(xq), ptr(xm),
-                                                 current_stream()))
-        return xq, xm
+        if getattr(self, "_xq", None) is None or (want_mid and getattr(self, "_xmid", None) is None):
+            xq = self._f64(dn.E * (dn.m + 1), dn.gdim)
+            xm = self._f64(dn.E * dn.m, dn.gdim) if want_mid else None
+            check(self.lib.gnx_dof_coordinates_mixed(dn.net_ref(), ptr(dn.coords), ptr(dn.cells), ptr(xq), ptr(xm),
+                                                     current_stream()))
+            self._xq = xq
+            if want_mid:
+                self._xmid = xm
+        return self._xq, (self._xmid if want_mid else None)
+
+    # ---- coefficients ---------------------------------------------------------------------------
+    def project_coefficient(self, coef):
+        """project(coef, CG1(submesh_i)) for all edges (flow_models.py:315-317) -> [E(m+1)] q-dof layout"""
+        dn = self.dn
+        xq, xm = self.dof_coordinates(want_mid=coef.degree >= 2)
+        cn = coef.eval_device(xq, pts_per_edge=dn.m + 1, tangents=dn.tangents,
+                              cell_index=None)
+        cm = coef.eval_device(xm, pts_per_edge=dn.m, tangents=dn.tangents) if coef.degree >= 2 else None
+        out = self._f64(dn.E * (dn.m + 1))
+        work = self._f64(8 * dn.E * (dn.m + 1))
+        check(self.lib.gnx_project_p1_edges(dn.net_ref(), ptr(cn), ptr(cm), ptr(out), ptr(work), current_stream()))
+        return out
+
+    def project_end_values(self, coef, window=64):
+        """projected coefficient at the v-end of every edge (the BOUN_OUT term, flow_models.py:324)"""
+        dn = self.dn
+        out = self._f64(dn.E)
+        if coef.user is not None:          # python callback: project everything, pick the ends
+            full = self.project_coefficient(coef).reshape(dn.E, dn.m + 1)
+            edges = dn.edges_host()
+            flip = edges[:, 0] > edges[:, 1]
+            lv = np.where(flip, dn.loc_host[0], dn.loc_host[dn.m]).astype(np.int64)
+            return full[torch.arange(dn.E, device=self.dev), torch.from_numpy(lv).to(self.dev)].contiguous()
+        prog = coef.program()
+        check(self.lib.gnx_project_end_values(dn.net_ref(), ptr(dn.coords), C.byref(prog), int(coef.degree),
+                                              int(window), ptr(out), current_stream()))
+        return out
 
     # ---- Krylov building blocks ----------------------------------------------------------------
     def spmv(self, vals, x, y=None):

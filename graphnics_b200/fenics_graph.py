@@ -1,0 +1,264 @@
+"""FenicsGraph: drop-in for graphnics/fenics_graph.py:28-311 -- a networkx.DiGraph whose
+`make_mesh` / `make_submeshes` / tangent computations run as CUDA kernels (graphnics_b200.device)
+instead of DOLFIN `MeshEditor`/`refine`/`adapt`, xii `EmbeddedMesh` and Python callbacks.
+
+Same attributes after `make_mesh(n)`: geom_dim, num_edges, mesh, mf, bifurcation_ixs,
+num_bifurcations, boundary_ixs, tangents, tangent, edges[e]['tangent']; after
+`make_submeshes()`: edges[e]['submesh'], edges[e]['vf'].
+"""
+import networkx as nx
+import numpy as np
+
+from .coefficients import (UserExpression, UFLExpr, Constant, dot, grad, tangent_components,
+                           as_coefficient)
+from .device import DeviceNetwork
+from .mesh import Mesh1D, SubMesh, CellMarker, VertexMarker
+
+__all__ = ["BIF_IN", "BIF_OUT", "BOUN_IN", "BOUN_OUT", "FenicsGraph", "GlobalFlux",
+           "GlobalCrossectionFlux", "TangentFunction", "copy_from_nx_graph", "nxgraph_attribute_to_dolfin"]
+
+# Marker tags (graphnics/fenics_graph.py:22-25)
+BIF_IN = 1
+BIF_OUT = 2
+BOUN_IN = 3
+BOUN_OUT = 4
+
+
+class _TangentField:
+    """`G.tangent`: DG0 vector field (tangent of the edge a cell belongs to) -- kept implicit."""
+
+    def __init__(self, G):
+        self.G = G
+
+    def vector(self):
+        from .function import Vector
+        dn = self.G._dn
+        t = dn.tangents.repeat_interleave(dn.m, dim=0)
+        return Vector(t.reshape(-1))
+
+    def __call__(self, *x):
+        from .function import Function, FunctionSpace
+        f = Function(FunctionSpace(self.G.mesh, "DG", 0), net=self.G._dn, role="cell")
+        out = []
+        for k in range(self.G.geom_dim):
+            f.vector().tensor.copy_(self.G._dn.tangents[:, k].repeat_interleave(self.G._dn.m))
+            f.vector().touch()
+            out.append(f(*x))
+        return np.asarray(out)
+
+
+class FenicsGraph(nx.DiGraph):
+    """Class for constructing meshes and associated functions from networkx directed graphs.
+    Node attribute "pos" (2 or 3 coordinates) is required; node labels must be 0..V-1 in
+    insertion order (true for every reference generator; the reference silently mis-indexes
+    otherwise, fenics_graph.py:71-72 -- we raise)."""
+
+    def __init__(self):
+        nx.DiGraph.__init__(self)
+        self._dn = None
+        self._systems = {}
+
+    # ---- arrays the kernels consume ---------------------------------------------------------
+    def _graph_arrays(self):
+        nodes = list(self.nodes())
+        if nodes != list(range(len(nodes))):
+            raise ValueError("FenicsGraph needs node labels 0..V-1 in insertion order "
+                             "(use nx.convert_node_labels_to_integers)")
+        pos = np.asarray([self.nodes[v]["pos"] for v in nodes], dtype=np.float64)
+        edges = np.asarray([[u, v] for u, v in self.edges()], dtype=np.int64).reshape(-1, 2)
+        if len(edges) and (edges[:, 0] == edges[:, 1]).any():
+            raise ValueError("self-loops are not supported")
+        return pos, edges
+
+    def get_mesh(self, n=1):
+        """(mesh, mf) with 2^n cells on each edge (fenics_graph.py:58-99)."""
+        pos, edges = self._graph_arrays()
+        dn = DeviceNetwork(pos, edges, n)
+        return Mesh1D(dn), CellMarker(dn)
+
+    def make_mesh(self, n=1):
+        """Generates and stores the mesh with 2^n cells per edge (fenics_graph.py:102-129)."""
+        pos, edges = self._graph_arrays()
+        self.geom_dim = pos.shape[1]
+        self.num_edges = len(edges)
+        self._dn = DeviceNetwork(pos, edges, n)
+        self._systems = {}
+        self.mesh = self._dn._host_mesh()
+        self.mf = CellMarker(self._dn)
+        self.record_bifurcation_and_boundary_nodes()
+        self.assign_tangents()
+
+    def make_submeshes(self):
+        """Per-edge submeshes and vertex tag functions (fenics_graph.py:132-156)."""
+        if self._dn is None:
+            raise RuntimeError("call make_mesh() first")
+        for i, (u, v) in enumerate(self.edges):
+            self.edges[u, v]["submesh"] = SubMesh(self._dn, i)
+            self.edges[u, v]["vf"] = VertexMarker(self._dn, i)
+
+    def record_bifurcation_and_boundary_nodes(self):
+        """fenics_graph.py:161-184 (from the device vertex tables when a mesh exists)."""
+        if self._dn is not None:
+            self.bifurcation_ixs = self._dn.bifurcation_ixs()
+            self.boundary_ixs = self._dn.boundary_ixs()
+            if self._dn.n_lonely:
+                deg = self._dn.deg.cpu().numpy()
+                for v in np.nonzero(deg == 0)[0]:
+                    print(f"Node {v} in G is lonely (i.e. unconnected)")
+        else:
+            bif, bnd = [], []
+            for v in self.nodes():
+                k = len(self.in_edges(v)) + len(self.out_edges(v))
+                if k == 1:
+                    bnd.append(v)
+                elif k > 1:
+                    bif.append(v)
+                else:
+                    print(f"Node {v} in G is lonely (i.e. unconnected)")
+            self.bifurcation_ixs, self.boundary_ixs = bif, bnd
+        self.num_bifurcations = len(self.bifurcation_ixs)
+
+    def compute_edge_lengths(self):
+        """fenics_graph.py:187-198"""
+        if self._dn is not None:
+            L = self._dn.elen.cpu().numpy()
+            for i, e in enumerate(self.edges()):
+                self.edges()[e]["length"] = float(L[i])
+        else:
+            for e in self.edges():
+                v1, v2 = e
+                self.edges()[e]["length"] = np.linalg.norm(
+                    np.asarray(self.nodes()[v2]["pos"]) - np.asarray(self.nodes()[v1]["pos"]))
+
+    def compute_vertex_degrees(self):
+        """Weighted vertex degrees l_v/2 (fenics_graph.py:200-226)."""
+        try:
+            e = list(self.edges())[0]
+            self.edges()[e]["length"]
+        except KeyError:
+            self.compute_edge_lengths()
+        for v in self.nodes():
+            l_v = 0
+            for e in self.in_edges(v):
+                l_v += self.edges()[e]["length"]
+            for e in self.out_edges(v):
+                l_v += self.edges()[e]["length"]
+            self.nodes()[v]["degree"] = l_v / 2
+        degrees = nx.get_node_attributes(self, "degree")
+        self.degree_min = min(degrees.values())
+        self.degree_max = max(degrees.values())
+
+    def assign_tangents(self):
+        """Unit tangent of every edge (fenics_graph.py:230-253): edges[e]['tangent'], G.tangents,
+        G.tangent."""
+        tang = self._dn.tangents.cpu().numpy()
+        for i, (u, v) in enumerate(self.edges()):
+            self.edges[u, v]["tangent"] = tang[i]
+        self.tangents = list(nx.get_edge_attributes(self, "tangent").items())
+        self.tangent = _TangentField(self)
+
+    def dds(self, f):
+        """derivative df/ds along the graph (fenics_graph.py:255-259)"""
+        return dot(grad(f), tangent_components(3))
+
+    def dds_i(self, f, i):
+        """derivative df/ds along branch i (fenics_graph.py:261-266)"""
+        return dot(grad(f), [float(t) for t in self.tangents[i][1]])
+
+    def get_num_inlets_outlets(self):
+        """fenics_graph.py:268-277"""
+        tu, tv = self._dn.tag_u.cpu().numpy(), self._dn.tag_v.cpu().numpy()
+        return int((tu == BOUN_IN).sum() + (tv == BOUN_IN).sum()), int((tu == BOUN_OUT).sum() + (tv == BOUN_OUT).sum())
+
+    def mark_edge_vfs(self, node_ixs, tag_in, tag_out):
+        """Kept for API parity (fenics_graph.py:280-311): tags are produced by gnx_vertex_tables."""
+        return None
+
+    # ---- helpers used by the models -------------------------------------------------------------
+    def edge_attribute_array(self, key, default=1.0):
+        """[E] float array of a (constant-per-edge) attribute; Constants/floats accepted."""
+        out = np.empty(self.number_of_edges())
+        for i, e in enumerate(self.edges()):
+            v = self.edges[e].get(key, default)
+            if isinstance(v, UFLExpr):
+                if v.expr.free_symbols - set(v.params):
+                    raise NotImplementedError(
+                        f"edge attribute '{key}' varies along the edge; only per-edge constants are supported")
+                v = float(v.expr.subs({s: float(c) for s, c in v.params.items()}))
+            out[i] = float(v)
+        return out
+
+
+class GlobalFlux(UserExpression):
+    """Vector flux = scalar flux * tangent (fenics_graph.py:314-351)."""
+
+    def __init__(self, G, qs, **kwargs):
+        if not isinstance(qs, list):
+            qs = [qs]
+        self.G, self.qs = G, qs
+        super().__init__(**kwargs)
+
+    def eval_cell(self, values, x, cell):
+        edge = self.G.mf[cell.index]
+        tangent = self.G.tangents[edge][1]
+        qval = self.qs[edge](x) if len(self.qs) > 1 else self.qs[0](x)
+        for k in range(self.G.geom_dim):
+            values[k] = qval * tangent[k]
+
+    def value_shape(self):
+        return (self.G.geom_dim,)
+
+
+class GlobalCrossectionFlux(UserExpression):
+    """Scalar flux on the global mesh from the per-edge fluxes (fenics_graph.py:354-375)."""
+
+    def __init__(self, G, qs, **kwargs):
+        self.G, self.qs = G, qs
+        super().__init__(**kwargs)
+
+    def eval_cell(self, values, x, cell):
+        values[0] = self.qs[self.G.mf[cell.index]](x)
+
+    def value_shape(self):
+        return ()
+
+
+class TangentFunction(UserExpression):
+    """Tangent expression (fenics_graph.py:378-401); the kernels never call it."""
+
+    def __init__(self, G, degree, **kwargs):
+        self.G, self.degree = G, degree
+        super().__init__(**kwargs)
+
+    def eval_cell(self, values, x, cell):
+        edge = self.G.mf[cell.index]
+        for k in range(self.G.geom_dim):
+            values[k] = self.G.tangents[edge][1][k]
+
+    def value_shape(self):
+        return (self.G.geom_dim,)
+
+
+def copy_from_nx_graph(G_nx):
+    """Deep copy of an nx.Graph as FenicsGraph (fenics_graph.py:404-434)."""
+    G = FenicsGraph()
+    G.graph.update(G_nx.graph)
+    G.add_nodes_from((n, d.copy()) for n, d in G_nx._node.items())
+    for u, v in G_nx.edges():
+        G.add_edge(u, v)
+    for e in G.edges():
+        for key, val in G_nx.edges()[e].items():
+            G.edges()[e][key] = val
+    return G
+
+
+def nxgraph_attribute_to_dolfin(G, attr):
+    """DG0 function of an edge attribute (fenics_graph.py:437-460; the reference interpolates into
+    DG1, whose cellwise-constant values are the same)."""
+    from .function import Function, FunctionSpace
+    import torch
+    vals = np.asarray(list(nx.get_edge_attributes(G, attr).values()), dtype=np.float64)
+    f = Function(FunctionSpace(G.mesh, "DG", 0), net=G._dn, role="cell")
+    f.vector().tensor.copy_(torch.from_numpy(np.repeat(vals, G._dn.m)).to(G._dn.device))
+    f.vector().touch()
+    return f

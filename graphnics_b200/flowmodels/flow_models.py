@@ -1,0 +1,305 @@
+"""Flow models, drop-in for graphnics/flowmodels/flow_models.py:53-430.
+
+Same classes, constructor signatures, attributes and methods (`a_form`, `L_form`, `get_bc`,
+`solve`, `init_a_form`, `init_L_form`); the forms are opaque handles that `ii_assemble` turns into
+device CSR / vectors (graphnics_b200.la), and `solve()` is assembly kernels + the Schur-complement
+solver instead of ii_assemble -> ii_convert -> MUMPS.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..coefficients import Constant, as_coefficient
+from ..device import current_stream
+from ..engine import MixedSystem
+from ..function import FunctionSpace, TrialFunction, TestFunction, ii_Function
+from ..la import AssembledMatrix, AssembledVector, ii_assemble, apply_bc
+from ..mesh import SubMesh
+
+__all__ = ["HydraulicNetwork", "MixedHydraulicNetwork", "NetworkStokes", "NetworkPoisson", "RT"]
+
+# Network Raviart-Thomas type space (flow_models.py:132-137)
+RT = {
+    "flux_space": "CG",
+    "flux_degree": 1,
+    "pressure_space": "DG",
+    "pressure_degree": 0,
+}
+
+
+def _system(G, kind):
+    """One engine object per (graph mesh, model family): pattern and solver state are built once."""
+    if G._dn is None:
+        raise RuntimeError("call G.make_mesh() before building a model")
+    if kind not in G._systems:
+        if kind == "mixed":
+            G._systems[kind] = MixedSystem(G._dn)
+        else:
+            from ..engine_primal import PrimalSystem
+            G._systems[kind] = PrimalSystem(G._dn)
+    return G._systems[kind]
+
+
+class _MixedSpaces:
+    """W = [CG1(submesh_0..E-1), DG0(mesh), R x B] (flow_models.py:175-187), created lazily."""
+
+    def __init__(self, G):
+        self.G, self.net = G, G._dn
+        self.E, self.B, self.m = G._dn.E, G._dn.B, G._dn.m
+        self._cache = {}
+
+    def __len__(self):
+        return self.E + 1 + self.B
+
+    def sizes(self):
+        return [self.m + 1] * self.E + [self.E * self.m] + [1] * self.B
+
+    def role(self, i):
+        if i < self.E:
+            return "q_edge", i
+        return ("cell", None) if i == self.E else ("real", None)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i not in self._cache:
+            if i < self.E:
+                V = FunctionSpace(SubMesh(self.net, i), RT["flux_space"], RT["flux_degree"])
+            elif i == self.E:
+                V = FunctionSpace(self.G.mesh, RT["pressure_space"], RT["pressure_degree"])
+            else:
+                V = FunctionSpace(self.G.mesh, "R", 0)
+            self._cache[i] = V
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _LazyArgs:
+    def __init__(self, W, fn):
+        self.W, self.fn = W, fn
+
+    def __len__(self):
+        return len(self.W)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self.fn(V) for V in self.W[i]]
+        return self.fn(self.W[i])
+
+    def __iter__(self):
+        return (self.fn(V) for V in self.W)
+
+
+# ------------------------------------------------------------------------------------------
+# form handles
+# ------------------------------------------------------------------------------------------
+class _MixedAForm:
+    def __init__(self, model, sigma=1.0, mass=0.0):
+        self.model, self.sigma, self.mass = model, sigma, mass
+
+    def assemble(self):
+        ms = self.model._system()
+        co = self.model._coeffs(self.sigma, self.mass)
+        return AssembledMatrix(ms, ms.assemble(co), co, "mixed")
+
+
+class _MixedMassForm:
+    """TimeDepMixedHydraulicNetwork.mass_matrix_q(coeff) (time_stepping.py:75-101)."""
+
+    def __init__(self, model, coeff):
+        self.model, self.coeff = model, coeff
+
+    def assemble(self):
+        ms = self.model._system()
+        return AssembledMatrix(ms, ms.assemble_mass_q(float(self.coeff)), None, "mass")
+
+
+class _MassVectorForm:
+    def __init__(self, model, u, coeff):
+        self.model, self.u, self.coeff = model, u, coeff
+
+    def assemble(self):
+        ms = self.model._system()
+        x = self.u.tensor() if isinstance(self.u, ii_Function) else self.u
+        return AssembledVector(ms, ms.spmv(ms.mass_vals(float(self.coeff)), x))
+
+
+class _MixedLForm:
+    """MixedHydraulicNetwork.L_form (flow_models.py:299-332).  Like the reference, f, g and the
+    outlet p_bc are L2-projected onto CG1 of every edge when the form is BUILT (:315-317); the inlet
+    p_bc term is evaluated when the form is ASSEMBLED (:324)."""
+
+    def __init__(self, model, zero=False):
+        self.model = model
+        ms = model._system()
+        dn = ms.dn
+        self.f_nodal = self.g_nodal = self.pbc_out = None
+        self.f_const = self.g_const = 0.0
+        self.zero = zero
+        if zero:
+            return
+        f, g, pbc = (as_coefficient(c) for c in (model.f, model.g, model.p_bc))
+        if f.is_constant:
+            self.f_const = f.const_value()
+        else:
+            self.f_nodal = ms.project_coefficient(f)
+        if g.is_constant:
+            self.g_const = g.const_value()
+        else:
+            self.g_nodal = ms.project_coefficient(g)
+        if pbc.is_constant:
+            c = pbc.const_value()
+            self.pbc_out = None if c == 0.0 else torch.full((dn.E,), c, dtype=torch.float64, device=dn.device)
+        else:
+            self.pbc_out = ms.project_end_values(pbc)
+        self._pbc = pbc
+
+    def assemble(self):
+        ms = self.model._system()
+        if self.zero:
+            return AssembledVector(ms, torch.zeros(ms.N, dtype=torch.float64, device=ms.dev))
+        pbc = as_coefficient(self.model.p_bc)
+        pbc_node = None
+        if not (pbc.is_constant and pbc.const_value() == 0.0):
+            pbc_node = pbc.eval_device(ms.dn.pos)
+        b = ms.rhs(self.f_nodal, self.g_nodal, self.pbc_out, pbc_node, self.f_const, self.g_const)
+        return AssembledVector(ms, b)
+
+
+# ------------------------------------------------------------------------------------------
+# models
+# ------------------------------------------------------------------------------------------
+class MixedHydraulicNetwork:
+    """Dual mixed form of the hydraulic equations  Res*q + d/ds p = g,  d/ds q = f  on graph G,
+    bifurcation conditions q_in = q_out and continuous normal stress (flow_models.py:140-350).
+
+    Edge attribute "Res" (default 1) is the resistance (:228-231)."""
+
+    def __init__(self, G, f=Constant(0), g=Constant(0), p_bc=Constant(0), space=RT):
+        self.G = G
+        self.f, self.g, self.p_bc = f, g, p_bc
+        if space is not RT and space != RT:
+            raise NotImplementedError("only the network Raviart-Thomas pair (CG1 flux, DG0 pressure) is implemented")
+        self.W = _MixedSpaces(G)
+        self.meshes = _LazyArgs(self.W, lambda V: V.mesh())
+        self.qp = _LazyArgs(self.W, TrialFunction)
+        self.vphi = _LazyArgs(self.W, TestFunction)
+
+    # -- engine hooks ----------------------------------------------------------------------------
+    def _system(self):
+        return _system(self.G, "mixed")
+
+    def _visc_edge(self):
+        return None
+
+    def _coeffs(self, sigma=1.0, mass=0.0):
+        """operator  mass*M + sigma*(Res M + visc K)  with couplings scaled by sigma"""
+        ms = self._system()
+        res = self.G.edge_attribute_array("Res", 1.0)
+        visc = self._visc_edge()
+        return ms.coeffs(mass + sigma * res, None if visc is None else sigma * visc, sigma)
+
+    # -- reference API ---------------------------------------------------------------------------
+    def a_form(self, a=None):
+        return _MixedAForm(self)
+
+    def init_a_form(self):
+        return _MixedAForm(self)
+
+    def init_L_form(self):
+        return _MixedLForm(self, zero=True)
+
+    def L_form(self):
+        return _MixedLForm(self)
+
+    def get_bc(self):
+        return [[], []]
+
+    def solve(self):
+        W = self.W
+        a = self.a_form()
+        L = self.L_form()
+        A, b = map(ii_assemble, (a, L))
+        qp = ii_Function(W)
+        ms = self._system()
+        _, self.solve_info = ms.solve(A.coeffs, b.tensor, x=qp.tensor())
+        qp.touch()
+        return qp
+
+
+class NetworkStokes(MixedHydraulicNetwork):
+    """MixedHydraulicNetwork + viscous term (mu/Ainv) dds(q) dds(v) (flow_models.py:353-430).
+    The reference stores `nu` but reads `self.mu` (AttributeError as shipped); here mu := nu."""
+
+    def __init__(self, G, f=Constant(0), g=Constant(0), p_bc=Constant(0), nu=Constant(1), space=RT):
+        self.nu = nu
+        self.mu = nu
+        super().__init__(G=G, f=f, g=g, p_bc=p_bc, space=space)
+
+    def _visc_edge(self):
+        return float(self.mu) / self.G.edge_attribute_array("Ainv", 1.0)
+
+
+class HydraulicNetwork:
+    """Primal mixed form: q in DG0(mesh), p in CG1(mesh), strong Dirichlet p = p_bc on boundary
+    nodes (flow_models.py:53-126)."""
+
+    def __init__(self, G, f=Constant(0), g=Constant(0), p_bc=Constant(0), Res=Constant(1), degree=1):
+        if degree != 1:
+            raise NotImplementedError("only degree=1 (DG0 flux, CG1 pressure) is implemented")
+        self.G = G
+        self.f, self.g, self.p_bc, self.Res = f, g, p_bc, Res
+        self.W = [FunctionSpace(G.mesh, "DG", degree - 1), FunctionSpace(G.mesh, "CG", degree)]
+        self.qp = list(map(TrialFunction, self.W))
+        self.vphi = list(map(TestFunction, self.W))
+
+    def _system(self):
+        return _system(self.G, "primal")
+
+    def _coeffs(self, sigma=1.0, mass=0.0):
+        return self._system().coeffs(mass + sigma * float(as_coefficient(self.Res).const_value()), sigma)
+
+    def a_form(self):
+        from ..engine_primal import PrimalAForm
+        return PrimalAForm(self)
+
+    def L_form(self):
+        from ..engine_primal import PrimalLForm
+        return PrimalLForm(self)
+
+    def get_bc(self):
+        from ..engine_primal import DirichletBC
+        return [[], [DirichletBC(self.W[1], self.p_bc, "on_boundary")]]
+
+    def solve(self):
+        a = self.a_form()
+        L = self.L_form()
+        W_bcs = self.get_bc()
+        A, b = map(ii_assemble, (a, L))
+        A, b = apply_bc(A, b, W_bcs)
+        qp = ii_Function(self.W)
+        ps = self._system()
+        _, self.solve_info = ps.solve(A.coeffs, b.tensor, x=qp.tensor())
+        qp.touch()
+        return qp
+
+
+class NetworkPoisson:
+    """(kappa d/ds u, d/ds v) = (f, v) on the network, CG1 (flow_models.py:15-50).  Not on the
+    north-star path; provided through the primal engine's Schur system (q eliminated)."""
+
+    def __init__(self, G, f=Constant(0), p_bc=Constant(0), kappa=Constant(1), degree=1):
+        self.G, self.f, self.p_bc, self.kappa = G, f, p_bc, kappa
+        self.V = FunctionSpace(G.mesh, "CG", degree)
+
+    def solve(self):
+        # -(kappa u')' = f  <=>  primal hydraulic system with Res = 1/kappa, g = 0
+        model = HydraulicNetwork(self.G, f=self.f, g=Constant(0), p_bc=self.p_bc,
+                                 Res=Constant(1.0 / float(self.kappa)))
+        return model.solve()[1]

@@ -123,19 +123,59 @@ int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
 int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff, const int32_t* rowptr,
                               double* vals, void* stream);
 
-/* MixedHydraulicNetwork.L_form :299-332.  Nodal data live in q-dof layout [E*(m+1)]:
- *   g_nodal, f_nodal, pbc_nodal = the per-edge CG1 projections (:315-317) (any may be NULL = 0),
+/* Coefficient expressions (f, g, p_bc: dolfin Constant / Expression("c-string") / UFL in the
+ * reference, tests/test_flow_models.py:94-119) are compiled on the host to a small RPN program
+ * and interpreted on the device, one point per thread. */
+#define GNX_PROG_MAX 96
+#define GNX_PROG_PARAMS 8
+typedef struct gnx_program {
+  int32_t len;
+  int32_t reserved;
+  int16_t op[GNX_PROG_MAX];     /* opcode, see GNX_OP_* */
+  int16_t arg[GNX_PROG_MAX];    /* integer operand (coordinate / parameter index, integer power) */
+  double val[GNX_PROG_MAX];     /* constant operand */
+  double params[GNX_PROG_PARAMS]; /* run-time scalars (params[0] = t by convention) */
+} gnx_program_t;
+enum {
+  GNX_OP_CONST = 0, GNX_OP_X = 1, GNX_OP_PARAM = 2, GNX_OP_TAU = 3, GNX_OP_EDGE = 4,
+  GNX_OP_ADD = 10, GNX_OP_SUB, GNX_OP_MUL, GNX_OP_DIV, GNX_OP_POW, GNX_OP_NEG, GNX_OP_MIN, GNX_OP_MAX,
+  GNX_OP_SIN = 20, GNX_OP_COS, GNX_OP_TAN, GNX_OP_EXP, GNX_OP_LOG, GNX_OP_SQRT, GNX_OP_ABS, GNX_OP_TANH,
+  GNX_OP_SINH, GNX_OP_COSH, GNX_OP_ATAN, GNX_OP_ASIN, GNX_OP_ACOS, GNX_OP_FLOOR, GNX_OP_FMOD,
+  GNX_OP_POWI, GNX_OP_ATAN2, GNX_OP_SIGN, GNX_OP_LT, GNX_OP_GT, GNX_OP_LE, GNX_OP_GE, GNX_OP_SELECT,
+  GNX_OP_CEIL
+};
+/* out[i] = prog(x[i,:]) for i < npts.  If pts_per_edge > 0, point i lies on edge i / pts_per_edge
+ * and GNX_OP_TAU reads tangents[edge*gdim + arg], GNX_OP_EDGE reads edge_attr[edge]. */
+int gnx_eval_expr(const gnx_program_t* prog_host, const double* x, int32_t gdim, int64_t npts,
+                  int32_t pts_per_edge, const double* tangents, const double* edge_attr, double* out,
+                  void* stream);
+
+/* MixedHydraulicNetwork.L_form :299-332.
+ *   f_nodal, g_nodal [E*(m+1)] = the per-edge CG1 projections (:315-317) in q-dof layout, or NULL
+ *                                 to use the constants f_const / g_const (dolfin Constant data);
+ *   pbc_out  [E] = projected p_bc at the v-end of every edge (used where v is a boundary node:
+ *                  the `p_bcs[i]*v*ds(BOUN_OUT)` term :324), NULL = 0;
  *   pbc_node [V] = p_bc evaluated at graph nodes (the un-projected BOUN_IN term :324), NULL = 0.
  *   b [N] */
 int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_nodal, const double* g_nodal,
-                           const double* pbc_nodal, const double* pbc_node, double* b, void* stream);
+                           double f_const, double g_const, const double* pbc_out,
+                           const double* pbc_node, double* b, void* stream);
 
-/* project(c, CG1(submesh_i)) for all edges (:315-317): consistent-mass L2 projection.
- *   c_nodal, c_mid: coefficient evaluated at q-dof vertices [E*(m+1)] and at cell midpoints
- *   [E*m, p-dof order] (c_mid NULL => degree<=1 data).  out [E*(m+1)] q-dof layout.
- *   work [>= 4*E*(m+1)] doubles */
+/* project(c, CG1(submesh_i)) for all edges (:315-317): consistent-mass L2 projection by parallel
+ * cyclic reduction (diagonally dominant tridiagonal systems: couplings fall below 1 ulp after 7
+ * reduction steps, so the step count is independent of m).
+ *   c_nodal [E*(m+1)] coefficient at the q-dof vertices, c_mid [E*m] at cell midpoints in p-dof
+ *   order (NULL => degree<=1 data: midpoint = average).  out [E*(m+1)] q-dof layout.
+ *   work [>= 8*E*(m+1)] doubles */
 int gnx_project_p1_edges(const gnx_network_t* net, const double* c_nodal, const double* c_mid,
                          double* out, double* work, void* stream);
+
+/* Value at the v-end of every edge of the same projection of `prog` (degree = FEniCS degree of
+ * the Expression), computed from a window of the last `window` cells only (the inverse mass
+ * matrix decays like 0.268^k).  out [E]. */
+int gnx_project_end_values(const gnx_network_t* net, const double* coords,
+                           const gnx_program_t* prog_host, int32_t degree, int32_t window,
+                           double* out, void* stream);
 
 /* coordinates of the q-dof vertices [E*(m+1)*gdim] and of cell midpoints [E*m*gdim] (p-dof order),
  * gathered from the mesh coordinates -- inputs of coefficient evaluation. */

@@ -93,12 +93,14 @@ def hostcheck_lib():
     if _HC is None:
         src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
         out = os.path.join(HERE, "hostcheck", "libhostcheck.so")
-        hdr = os.path.join(ROOT, "graphnics_b200", "csrc", "gnx_index.h")
-        if (not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        hdrs = [os.path.join(ROOT, "graphnics_b200", "csrc", h) for h in ("gnx_index.h", "gnx_rpn.h")]
+        hdrs.append(os.path.join(ROOT, "include", "graphnics_b200.h"))
+        if (not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs])):
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
         _HC = C.CDLL(out)
         _HC.hc_ndofs.restype = C.c_int64
         _HC.hc_nnz.restype = C.c_int64
+        _HC.hc_rpn.restype = C.c_double
     return _HC
 
 
@@ -156,10 +158,18 @@ class HostNet:
         hc.hc_values(C.byref(self.net), vp(a), vp(k), C.c_double(a_const), C.c_double(sigma), vp(vals))
         return vals
 
-    def rhs(self, f=None, g=None, pbc_nodal=None, pbc_node=None):
+    def rhs(self, f=None, g=None, pbc_out=None, pbc_node=None, f_const=0.0, g_const=0.0):
         hc = hostcheck_lib()
         b = np.full(self.N, np.nan)
-        arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (f, g, pbc_nodal, pbc_node)]
+        arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (f, g, pbc_out, pbc_node)]
         vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
-        hc.hc_rhs(C.byref(self.net), *[vp(x) for x in arrs], vp(b))
+        hc.hc_rhs(C.byref(self.net), vp(arrs[0]), vp(arrs[1]), C.c_double(f_const), C.c_double(g_const),
+                  vp(arrs[2]), vp(arrs[3]), vp(b))
         return b
+
+    def end_values(self, nodal):
+        """value of a q-dof-layout nodal field at the v end of every edge"""
+        nodal = np.asarray(nodal).reshape(self.E, self.m + 1)
+        flip = self.edges[:, 0] > self.edges[:, 1]
+        lv = np.where(flip, self.loc[0], self.loc[self.m])
+        return nodal[np.arange(self.E), lv]

@@ -4,6 +4,7 @@
 // GPU-less container (`pytest -m "not gpu"`).  The product never loads this file.
 #include <cmath>
 #include "../../graphnics_b200/csrc/gnx_index.h"
+#include "../../graphnics_b200/csrc/gnx_rpn.h"
 
 extern "C" {
 
@@ -43,10 +44,14 @@ void hc_values(const gnx_network_t* net, const double* a_edge, const double* k_e
     gnx_mixed_row_emit<GNX_MODE_VALUES>(*net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
 }
 
-void hc_rhs(const gnx_network_t* net, const double* f, const double* g, const double* pbc_nodal,
-            const double* pbc_node, double* b) {
+void hc_rhs(const gnx_network_t* net, const double* f, const double* g, double fc, double gc,
+            const double* pbc_out, const double* pbc_node, double* b) {
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  for (int64_t r = 0; r < d.N; ++r) b[r] = gnx_mixed_rhs_row(*net, d, r, f, g, pbc_nodal, pbc_node);
+  for (int64_t r = 0; r < d.N; ++r) b[r] = gnx_mixed_rhs_row(*net, d, r, f, g, fc, gc, pbc_out, pbc_node);
+}
+
+double hc_rpn(const gnx_program_t* prog, const double* x, int gd, const double* tau, double ea) {
+  return gnx_rpn_eval(*prog, x, gd, tau, ea);
 }
 
 int64_t hc_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }

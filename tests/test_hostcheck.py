@@ -93,8 +93,12 @@ def test_rhs(name, n):
     f = oracle.Coef(lambda x: np.cos(x[..., 1]) - x[..., 0], 1)
     b = oracle.assemble_mixed_rhs(om, f=f, g=g, p_bc=lin, project=False)
     nod = lambda c: c(om.sub_coords).ravel()
-    bh = hn.rhs(f=nod(f), g=nod(g), pbc_nodal=nod(lin), pbc_node=lin(pos))
+    bh = hn.rhs(f=nod(f), g=nod(g), pbc_out=hn.end_values(nod(lin)), pbc_node=lin(pos))
     np.testing.assert_allclose(bh, b, rtol=1e-12, atol=1e-14)
+    # Constant data path
+    b2 = oracle.assemble_mixed_rhs(om, f=0.75, g=-1.25, p_bc=2.0)
+    bh2 = hn.rhs(f_const=0.75, g_const=-1.25, pbc_out=np.full(len(edges), 2.0), pbc_node=np.full(len(pos), 2.0))
+    np.testing.assert_allclose(bh2, b2, rtol=1e-12, atol=1e-14)
 
 
 def test_vf_tags_match_oracle():
@@ -113,3 +117,39 @@ def test_vf_tags_match_oracle():
         vf[ar, np.where(flip, loc[0], loc[m])] = t["tag_v"]
         assert np.array_equal(vf, om.vf), name
         assert t["bif_nodes"].tolist() == om.bif_ixs and t["bnd_nodes"].tolist() == om.bnd_ixs
+
+
+def test_rpn_interpreter_matches_sympy():
+    """graphnics_b200/csrc/gnx_rpn.h (host build) against sympy on the expressions the reference's
+    tests use (tests/test_flow_models.py:110-117, tests/test_time_stepping.py:36-56)."""
+    import ctypes as C
+    import sympy as sp
+    from _util import hostcheck_lib
+    from graphnics_b200.coefficients import (Expression, Constant, SpatialCoordinate, sin, cos, diff, dot, grad,
+                                            as_coefficient, conditional, lt)
+    hc = hostcheck_lib()
+    t = Constant(0.3)
+    xx = SpatialCoordinate(3)
+    q = t * sin(2 * 3.14 * xx[0])
+    p = t * cos(2 * 3.14 * xx[0])
+    cases = [Expression("x[0]", degree=2), Expression("2-x[1]", degree=2), Expression("-x[1]", degree=2),
+             Expression("t*sin(2*3.14*x[0]) + pow(x[1], 3) / (1 + x[2]*x[2])", degree=2, t=0.7),
+             3.0 * diff(q, t) + 10 * q + dot(grad(p), None), dot(grad(q), None),
+             conditional(lt(xx[0], 0.5), xx[1] ** 2, sp.sqrt(2) * xx[0])]
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(20, 3))
+    tau = rng.normal(size=(20, 3))
+    for c in cases:
+        cc = as_coefficient(c)
+        prog = cc.program()
+        ref = cc.eval_host(pts, tangents=tau)
+        for i in range(len(pts)):
+            x = np.ascontiguousarray(pts[i]); ta = np.ascontiguousarray(tau[i])
+            v = hc.hc_rpn(C.byref(prog), x.ctypes.data_as(C.c_void_p), 3, ta.ctypes.data_as(C.c_void_p), C.c_double(0.0))
+            assert np.isclose(v, ref[i], rtol=1e-13, atol=1e-13), (c, v, ref[i])
+    # mutable parameters
+    e = Expression("t*x[0]", degree=1, t=0.0)
+    cc = as_coefficient(e)
+    e.t = 2.5
+    assert np.isclose(cc.eval_host(np.array([[2.0, 0, 0]]))[0], 5.0)
+    assert cc.program().params[0] == 2.5
