@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: MixedHydraulicNetwork assemble+solve on a synthetic arterial tree
+(BASELINE.json configs[1]: binary Murray tree, generations 0..10 = 2047 edges, 2^9 cells per
+edge = 1 048 064 cells, N = 2 099 198 mixed DOFs), reported as MDOF/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = what `MixedHydraulicNetwork.solve()` does after the mesh exists
+(graphnics/flowmodels/flow_models.py:337-350): assemble the monolithic CSR values, assemble the
+right-hand side, solve.  Mesh, CSR pattern and solver workspaces are built once, outside the timed
+region (SURVEY.md 8d "built once").
+
+  value        device-resident inputs, CUDA events around every step (L2 flushed between steps)
+  e2e          the user-facing call `MixedHydraulicNetwork(G, p_bc=...).solve()` +
+               `qp.vector().get_local()` : host (numpy) coefficient data in, host solution out
+  roofline     the step's dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline the numpy/scipy oracle (oracle/, the CPU restatement of the reference path) on the
+               same workload on this box's host cores
+`--impl reference` times that CPU restatement alone (the real reference needs FEniCS + fenics_ii +
+PETSc/MUMPS, none of which can be installed offline -- DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MDOF/s (assemble+solve) MixedHydraulicNetwork on synthetic tree"
+TREE_LEVELS, TREE_N = 11, 9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def tree_arrays(levels=TREE_LEVELS):
+    from graphnics_b200.synthetic import murray_tree
+    pos, edges, radius, level = murray_tree(levels, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
+    return pos, edges
+
+
+def config_dict(levels, n, E, N, extra=None):
+    d = {"workload": f"C2 synthetic binary arterial tree: {levels} generations, E={E} edges, 2^{n} cells/edge, "
+                     f"N={N} DOFs; Res=1, p_bc=x[1], f=g=0 (demo/Tree Profiling.ipynb model); steady "
+                     f"MixedHydraulicNetwork assemble+solve",
+         "levels": levels, "n": n, "edges": E, "ndofs": N, "l2": "flushed between timed steps (256 MiB write)"}
+    d.update(extra or {})
+    return d
+
+
+# --------------------------------------------------------------------------------------------
+# CPU restatement (oracle) -- cpu_baseline and --impl reference
+# --------------------------------------------------------------------------------------------
+def oracle_step_factory(pos, edges, n):
+    import oracle
+    om = oracle.build_mesh(pos, edges, n)                    # built once, like the GPU arm
+    pbc = oracle.Coef(lambda x: x[..., 1], 1)
+    N = oracle.mixed_layout(om)["N"]
+
+    def step():
+        A = oracle.assemble_mixed(om, 1.0)
+        b = oracle.assemble_mixed_rhs(om, p_bc=pbc, project=False)
+        return oracle.lu_solve(A, b)
+    return step, N
+
+
+def cpu_baseline(pos, edges, budget_s=20.0):
+    """oracle on the full workload if it fits the budget, else on a coarser refinement."""
+    n = TREE_N
+    while True:
+        step, N = oracle_step_factory(pos, edges, n)
+        t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
+        if t <= budget_s or n <= 4:
+            break
+        n -= 2
+    reps = max(1, min(3, int(budget_s / max(t, 1e-3)) - 1))
+    ts = [t]
+    for _ in range(reps):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    best = min(ts)
+    return {"value": N / best / 1e6, "unit": "MDOF/s", "cores": 1, "kind": "port",
+            "sample": f"numpy/scipy oracle (COO->CSR assembly + SuperLU), same tree, 2^{n} cells/edge, N={N}, "
+                      f"best of {len(ts)} runs, {best:.2f} s per assemble+solve",
+            "seconds_per_step": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pos, edges = tree_arrays()
+    n = TREE_N
+    step, N = oracle_step_factory(pos, edges, n)
+    t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
+    while t * (args.steps + args.warmup) > 240.0 and n > 4:       # bounded sample
+        n -= 1
+        step, N = oracle_step_factory(pos, edges, n)
+        t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = N / dt / 1e6
+    full_N = 2047 * (2 * (1 << TREE_N) + 1) + 1023
+    sample = (f"numpy/scipy oracle of the reference path (FEniCS/fenics_ii/MUMPS not installable offline), "
+              f"same tree, 2^{n} cells/edge, N={N}")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MDOF/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(TREE_LEVELS, TREE_N, len(edges), full_N, {"sample_n": n, "sample_ndofs": N}),
+           "cpu_baseline": {"value": val, "unit": "MDOF/s", "cores": 1, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from graphnics_b200.device import DeviceNetwork
+    from graphnics_b200.engine import MixedSystem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        from graphnics_b200.parallel import run_partitioned_bench
+        return run_partitioned_bench(args, METRIC, config_dict, peaks, ClockSampler)
+
+    pos, edges = tree_arrays()
+    n = TREE_N
+    dn = DeviceNetwork(pos, edges, n, device=dev)
+    ms = MixedSystem(dn)
+    ms.build_pattern()
+    N, nnz, NC = ms.N, ms.nnz, dn.num_cells
+    Res_host = np.ones(dn.E)
+    co = ms.coeffs(Res_host)
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    b = torch.empty(N, dtype=torch.float64, device=dev)
+    x = torch.empty(N, dtype=torch.float64, device=dev)
+    xq, _ = ms.dof_coordinates(False)
+    pbc_out = ms.end_values(xq[:, 1].contiguous())
+    pbc_node = dn.pos[:, 1].contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        ms.assemble(co, out=vals)
+        ms.rhs(None, None, pbc_out, pbc_node, out=b)
+        ms.solve(co, b, x=x, sync=False)
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return ts
+
+    # ---- headline: K timed steps
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local).start()
+    ts = timed(step, args.steps, 0)
+    torch.cuda.synchronize()
+    ms_per_step = float(np.sum(ts) / args.steps)
+    value = N / (ms_per_step * 1e-3) / 1e6
+
+    # ---- accuracy of what was timed (monolithic residual of the assembled system)
+    rr, bb = ms.residual(vals, x, b).cpu().tolist()
+    rel_resid = float(np.sqrt(rr / bb))
+
+    # ---- per-kernel breakdown (each kernel alone, L2 flushed) and roofline
+    bufs = ms._bufs()
+    kernels = {}
+
+    def k(name, fn, bytes_):
+        t = float(np.mean(timed(fn, 10, 3)))
+        kernels[name] = {"ms": t, "algorithmic_bytes": int(bytes_), "GBps": bytes_ / t / 1e6}
+
+    k("mixed_rows_kernel<VALUES> (assembly)", lambda: ms.assemble(co, out=vals), 8 * nnz + 8 * NC)
+    k("mixed_rhs_kernel", lambda: ms.rhs(None, None, pbc_out, pbc_node, out=b), 8 * N)
+    k("edge_eliminate_kernel", lambda: ms.lib.gnx_edge_eliminate_mixed(
+        dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
+        bufs["ftot"].data_ptr(), torch.cuda.current_stream().cuda_stream), 8 * N + 8 * NC)
+    k("edge_eliminate+schur_build+cg+backsub (solve)", lambda: ms.solve(co, b, x=x, sync=False), 3 * 8 * N + 2 * 8 * NC)
+    y = torch.empty_like(x)
+    spmv_bytes = 12 * nnz + 4 * (N + 1) + 16 * N
+    k("spmv_kernel (not in the step; Krylov building block)", lambda: ms.spmv(vals, x, y), spmv_bytes)
+    hbm, peak_src = peaks()
+    dom = max((kk for kk in kernels if "not in the step" not in kk and "(solve)" not in kk),
+              key=lambda kk: kernels[kk]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
+            "frac": kernels[dom]["GBps"] / hbm, "traffic": None, "peak_source": peak_src}
+
+    # ---- e2e through the drop-in Python API, host data in / host solution out
+    e2e = e2e_python_api(pos, edges, n, dn, args)
+    clk = clocks.stop()
+
+    out = {"metric": METRIC, "value": value, "unit": "MDOF/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(TREE_LEVELS, n, dn.E, N, {"nnz": nnz, "bifurcations": dn.B}),
+           "rel_residual": rel_resid, "gpu_launches": 7 * args.steps, "kernels": kernels, "roofline": roof,
+           "e2e": e2e, "clocks": clk}
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(pos, edges)
+    print(json.dumps(out))
+
+
+def e2e_python_api(pos, edges, n, dn, args):
+    """`MixedHydraulicNetwork(G, p_bc=Expression("x[1]")).solve()` on a FenicsGraph, then the solution
+    copied to the host -- wall clock around a synchronised region."""
+    import torch
+    import graphnics_b200 as gn
+    G = gn.FenicsGraph()
+    G.add_nodes_from((i, {"pos": p}) for i, p in enumerate(pos.tolist()))
+    G.add_edges_from(map(tuple, edges.tolist()))
+    G.make_mesh(n)                       # built once (not timed), like the reference benchmark
+    res = gn.Constant(1.0)
+    for e in G.edges():
+        G.edges[e]["Res"] = res
+    p_bc = gn.Expression("x[1]", degree=2)
+
+    def step():
+        model = gn.MixedHydraulicNetwork(G, p_bc=p_bc)
+        qp = model.solve()
+        return qp.vector().get_local()
+
+    for _ in range(max(args.warmup, 3)):
+        xh = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        xh = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    N = xh.size
+    return {"value": N / dt / 1e6, "unit": "MDOF/s", "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(8 * dn.E + 2 * 1024), "d2h_bytes_per_step": int(8 * N),
+            "timer": "wall clock (perf_counter) around synchronised region",
+            "call": "MixedHydraulicNetwork(G, p_bc=Expression('x[1]')).solve(); qp.vector().get_local()"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

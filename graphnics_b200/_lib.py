@@ -71,6 +71,8 @@ PROTOTYPES = {
     "gnx_reduce_work_doubles": (_L, [_L]),
     "gnx_residual_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_axpby_dot": (_I, [_L, _D, _P, _D, _P, _P, _P, _P]),
+    "gnx_lincomb": (_I, [_L, _I, c_f64p, C.POINTER(C.c_void_p), _P, _P]),
+    "gnx_mass_apply_q_mixed": (_I, [_NET, _D, _P, _P, _P]),
 }
 
 _lib = None

@@ -411,12 +411,14 @@ def as_coefficient(c):
         return CompiledCoefficient(constant=c, degree=0)
     if isinstance(c, (int, float, np.floating, np.integer)):
         return CompiledCoefficient(constant=Constant(float(c)), degree=0)
-    if isinstance(c, Expression):
-        return CompiledCoefficient(ufl=c.as_ufl(), degree=c.degree)
-    if isinstance(c, UFLExpr):
-        if not c.expr.free_symbols - set(c.params):
-            pass
-        return CompiledCoefficient(ufl=c, degree=c.degree)
+    if isinstance(c, (Expression, UFLExpr)):
+        # compiled once per object; parameter VALUES (Constants, Expression attributes such as .t)
+        # are read every time the program is instantiated, so the cache never goes stale
+        cc = c.__dict__.get("_compiled")
+        if cc is None or cc.degree != c.degree:
+            cc = CompiledCoefficient(ufl=c.as_ufl() if isinstance(c, Expression) else c, degree=c.degree)
+            c.__dict__["_compiled"] = cc
+        return cc
     if isinstance(c, UserExpression):
         return CompiledCoefficient(user=c, degree=getattr(c, "degree", 2))
     if hasattr(c, "as_coefficient"):

@@ -128,3 +128,40 @@ extern "C" int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double*
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// y = coeff * blockdiag(M_e) x  on the q rows, 0 on the p / lambda rows: the action of
+// TimeDepMixedHydraulicNetwork.mass_matrix_q / mass_vector_q (time_stepping.py:75-123) without
+// going through the CSR values (row gather over the <= 2 cells of a vertex).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mass_apply_q_kernel(gnx_network_t net, GnxMixedDims d, double coeff, const double* __restrict__ x,
+                    double* __restrict__ y) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.N) return;
+  double out = 0.0;
+  if (r < d.p_off) {
+    const int32_t m = d.m;
+    const int32_t e = (int32_t)(r / (m + 1));
+    const int32_t l = (int32_t)(r - (int64_t)e * (m + 1));
+    const bool flip = net.edges[2 * e] > net.edges[2 * e + 1];
+    const int32_t t = net.tloc[l];
+    const int64_t qb = (int64_t)e * (m + 1);
+    const double* he = net.h + (int64_t)e * m;
+    const double xt = x[r];
+    if (t > 0) out += he[flip ? m - t : t - 1] * (x[qb + net.loc[t - 1]] + 2.0 * xt) * (1.0 / 6.0);
+    if (t < m) out += he[flip ? m - 1 - t : t] * (2.0 * xt + x[qb + net.loc[t + 1]]) * (1.0 / 6.0);
+    out *= coeff;
+  }
+  y[r] = out;
+}
+
+extern "C" int gnx_mass_apply_q_mixed(const gnx_network_t* net, double coeff, const double* x, double* y,
+                                      void* stream) {
+  if (int rc = check_net(net)) return rc;
+  GNX_CHECK_ARG(x && y && x != y && net->h);
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  mass_apply_q_kernel<<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(*net, d, coeff, x, y);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}

@@ -134,3 +134,34 @@ extern "C" int gnx_axpby_dot(int64_t n, double alpha, const double* x, double be
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
+
+// out = sum_k c[k] * v[k]  (k < nterms <= 4; out may alias v[0]) -- the theta-scheme right-hand side
+//   b = DDn + cn1 dt Ln1 - dt cn An x0 + dt cn Ln      (time_stepping.py:185)
+struct Lincomb { double c[4]; const double* v[4]; int n; };
+
+__global__ void __launch_bounds__(256)
+lincomb_kernel(int64_t n, Lincomb L, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = L.c[0] * L.v[0][i];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (k < L.n) acc += L.c[k] * L.v[k][i];
+    out[i] = acc;
+  }
+}
+
+extern "C" int gnx_lincomb(int64_t n, int32_t nterms, const double* coefs_host, const double* const* vecs_host,
+                           double* out, void* stream) {
+  GNX_CHECK_ARG(n > 0 && nterms >= 1 && nterms <= 4 && coefs_host && vecs_host && out);
+  Lincomb L;
+  L.n = nterms;
+  for (int k = 0; k < 4; ++k) {
+    L.c[k] = k < nterms ? coefs_host[k] : 0.0;
+    L.v[k] = k < nterms ? vecs_host[k] : nullptr;
+    GNX_CHECK_ARG(k >= nterms || L.v[k]);
+  }
+  int nb = gnx_blocks(n, 256 * 2);
+  if (nb > 148 * 16) nb = 148 * 16;
+  lincomb_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(n, L, out);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}

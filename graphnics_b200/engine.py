@@ -45,6 +45,18 @@ class _Coeffs:
         return C.byref(self.c)
 
 
+def lincomb(lib, coefs, vecs, out=None):
+    terms = [(float(c), v) for c, v in zip(coefs, vecs) if v is not None and float(c) != 0.0]
+    if not terms:
+        terms = [(0.0, vecs[0])]
+    k = len(terms)
+    out = out if out is not None else torch.empty_like(terms[0][1])
+    cs = (C.c_double * k)(*[c for c, _ in terms])
+    ps = (C.c_void_p * k)(*[v.data_ptr() for _, v in terms])
+    check(lib.gnx_lincomb(int(out.numel()), k, cs, ps, ptr(out), current_stream()))
+    return out
+
+
 class MixedSystem:
     def __init__(self, dn: DeviceNetwork, cg_batch=32, cg_mode=2):
         self.dn = dn
@@ -142,16 +154,22 @@ class MixedSystem:
         check(self.lib.gnx_project_p1_edges(dn.net_ref(), ptr(cn), ptr(cm), ptr(out), ptr(work), current_stream()))
         return out
 
+    def end_values(self, nodal):
+        """value at the v-end of every edge of a q-dof-layout nodal field [E(m+1)] -> [E]"""
+        dn = self.dn
+        if getattr(self, "_lv", None) is None:
+            edges = dn.edges_host()
+            flip = edges[:, 0] > edges[:, 1]
+            lv = np.where(flip, dn.loc_host[0], dn.loc_host[dn.m]).astype(np.int64)
+            self._lv = torch.from_numpy(lv + np.arange(dn.E, dtype=np.int64) * (dn.m + 1)).to(self.dev)
+        return nodal.reshape(-1)[self._lv].contiguous()
+
     def project_end_values(self, coef, window=64):
         """projected coefficient at the v-end of every edge (the BOUN_OUT term, flow_models.py:324)"""
         dn = self.dn
         out = self._f64(dn.E)
         if coef.user is not None:          # python callback: project everything, pick the ends
-            full = self.project_coefficient(coef).reshape(dn.E, dn.m + 1)
-            edges = dn.edges_host()
-            flip = edges[:, 0] > edges[:, 1]
-            lv = np.where(flip, dn.loc_host[0], dn.loc_host[dn.m]).astype(np.int64)
-            return full[torch.arange(dn.E, device=self.dev), torch.from_numpy(lv).to(self.dev)].contiguous()
+            return self.end_values(self.project_coefficient(coef))
         prog = coef.program()
         check(self.lib.gnx_project_end_values(dn.net_ref(), ptr(dn.coords), C.byref(prog), int(coef.degree),
                                               int(window), ptr(out), current_stream()))
@@ -163,6 +181,16 @@ class MixedSystem:
         check(self.lib.gnx_spmv_csr_f64(self.N, ptr(self.rowptr), ptr(self.colidx), ptr(vals), ptr(x), ptr(y),
                                         current_stream()))
         return y
+
+    def mass_apply(self, coeff, x, out=None):
+        """y = coeff * blockdiag(M_e) x on the q rows, 0 elsewhere (mass_vector_q, time_stepping.py:103-123)"""
+        y = out if out is not None else self._f64(self.N)
+        check(self.lib.gnx_mass_apply_q_mixed(self.dn.net_ref(), float(coeff), ptr(x), ptr(y), current_stream()))
+        return y
+
+    def lincomb(self, coefs, vecs, out=None):
+        """out = sum_k coefs[k] * vecs[k]  (<= 4 terms, one pass)"""
+        return lincomb(self.lib, coefs, vecs, out)
 
     def residual(self, vals, x, b, r=None):
         """(||b - A x||^2, ||b||^2) as a 2-element device tensor; r optional output."""
@@ -235,6 +263,10 @@ class MixedSystem:
         check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
                                               ptr(d["P"]) if dn.B > 0 else None, ptr(x), current_stream()))
         return x, info
+
+    def solve_bc(self, co, b, x, bcs=None, **kw):
+        """solve with the model's Dirichlet data applied (the mixed model has none, flow_models.py:334)"""
+        return self.solve(co, b, x=x, **kw)
 
     def solve_checked(self, co, vals, b, rtol=1e-13, resid_tol=1e-10, max_refine=2):
         """solve + monolithic residual check with (optional) iterative refinement."""

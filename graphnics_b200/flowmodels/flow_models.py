@@ -198,12 +198,16 @@ class MixedHydraulicNetwork:
     def _visc_edge(self):
         return None
 
+    @staticmethod
+    def _mass_coeff(c):
+        return float(as_coefficient(c).const_value())
+
     def _coeffs(self, sigma=1.0, mass=0.0):
         """operator  mass*M + sigma*(Res M + visc K)  with couplings scaled by sigma"""
         ms = self._system()
         res = self.G.edge_attribute_array("Res", 1.0)
         visc = self._visc_edge()
-        return ms.coeffs(mass + sigma * res, None if visc is None else sigma * visc, sigma)
+        return ms.coeffs(self._mass_coeff(mass) + sigma * res, None if visc is None else sigma * visc, sigma)
 
     # -- reference API ---------------------------------------------------------------------------
     def a_form(self, a=None):

@@ -1,0 +1,124 @@
+"""Time-dependent models and the theta-scheme loop, drop-in for
+graphnics/flowmodels/time_stepping.py:17-221.
+
+    (D + theta dt A) x^{n+1} = D x^n + theta dt L^{n+1} - (1-theta) dt A x^n + (1-theta) dt L^n
+
+The reference re-assembles, re-converts and re-factorises (fresh MUMPS LU) every step
+(:179-192).  Here the operator D + theta*dt*A is never formed: the structured solver takes its edge
+coefficients (a_e = Ainv + theta*dt*Res_e, sigma = theta*dt), so a step is: right-hand-side
+kernels + one fused linear combination + eliminate / Schur-CG / back-substitute + one mass apply.
+With `reassemble_lhs=False` nothing but the right-hand side is touched.
+
+Reference quirks kept on purpose: the loop runs t_steps-1 times and returns
+t_steps states; the loop variable is np.linspace(dt, T, t_steps-1) while the scheme uses dt;
+`t.assign(dt)` before the loop does not move the `.t` attribute of Expression data; forms (and,
+for the mixed model, the L2 projections inside L_form) are rebuilt at the END of each iteration,
+so projected data lag the inlet term by one step.
+"""
+import numpy as np
+
+from ..coefficients import Constant
+from ..function import ii_Function
+from ..la import ii_assemble, apply_bc, AssembledVector
+from .flow_models import HydraulicNetwork, MixedHydraulicNetwork, _MixedMassForm, _MassVectorForm
+
+__all__ = ["time_stepping_schemes", "TimeDepHydraulicNetwork", "TimeDepMixedHydraulicNetwork",
+           "time_stepping_stokes"]
+
+# time_stepping.py:17
+time_stepping_schemes = {"IE": {"b1": 0, "b2": 1}, "CN": {"b1": 0.5, "b2": 0.5}}
+
+
+class TimeDepHydraulicNetwork(HydraulicNetwork):
+    """time_stepping.py:20-64"""
+
+    def __init__(self, G, f=Constant(0), g=Constant(0), p_bc=Constant(0), Res=Constant(1), Ainv=Constant(1)):
+        self.Ainv = Ainv
+        super().__init__(G, f=f, g=g, p_bc=p_bc, Res=Res)
+
+    def mass_matrix_q(self, coeff):
+        from ..engine_primal import PrimalMassForm
+        return PrimalMassForm(self, coeff)
+
+    def mass_vector_q(self, u, coeff):
+        return _MassVectorForm(self, u, coeff)
+
+
+class TimeDepMixedHydraulicNetwork(MixedHydraulicNetwork):
+    """time_stepping.py:68-123.  Like the reference, the `Res` argument is accepted and dropped
+    (:70-73): resistance comes from the edge attribute "Res"."""
+
+    def __init__(self, G, f=Constant(0), g=Constant(0), p_bc=Constant(0), Res=Constant(1), Ainv=Constant(1)):
+        self.Ainv = Ainv
+        super().__init__(G, f=f, g=g, p_bc=p_bc)
+
+    def mass_matrix_q(self, coeff):
+        return _MixedMassForm(self, coeff)
+
+    def mass_vector_q(self, u, coeff):
+        return _MassVectorForm(self, u, coeff)
+
+
+def _as_state(model, qp0):
+    """initial state as a monolithic device vector in W layout (:147-165)"""
+    W = model.W
+    if qp0 is None:
+        return ii_Function(W)
+    if isinstance(qp0, ii_Function):
+        return qp0.copy()
+    raise TypeError("qp0 must be None or an ii_Function on model.W")
+
+
+def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step_scheme="IE",
+                         reassemble_lhs=True, progress=False):
+    """Time stepping for  1/A d/dt q + a(U, V) = L(V; f, g)  (time_stepping.py:126-221).
+    Returns the list of `t_steps` solutions (ii_Function), initial state first."""
+    sys_ = model._system()
+    dt = T / t_steps                                                  # :150
+    cn, cn1 = time_stepping_schemes[t_step_scheme].values()           # :151
+    ainv = model.Ainv
+
+    L = model.L_form()                                                # :157
+    qp0 = _as_state(model, qp0)                                       # :147-165
+    qps = [qp0.copy()]                                                # :167
+    x0 = qp0.tensor()
+
+    a_n = model.a_form().assemble() if cn != 0 else None              # An (:170) -- only CN multiplies by it
+    Ln = L.assemble().tensor                                          # :170
+    DDn = sys_.mass_apply(model._mass_coeff(ainv), x0)                # Dn assembled from qp0 (:155,170)
+    t.assign(dt)                                                      # :172
+    co_eff = model._coeffs(sigma=cn1 * dt, mass=ainv)                 # DDn1 + cn1*dt*An1 (:174,184)
+    bcs = model.get_bc()
+    a_n1 = a_n
+    N = sys_.N
+    b = x0.new_empty(N)
+    ax0 = x0.new_empty(N) if cn != 0 else None
+
+    steps = np.linspace(dt, T, t_steps - 1)                           # :176
+    if progress:
+        from tqdm import tqdm
+        steps = tqdm(steps)
+    for t_val in steps:
+        Ln1 = L.assemble().tensor                                     # :179
+        if reassemble_lhs:                                            # :180-181
+            co_eff = model._coeffs(sigma=cn1 * dt, mass=ainv)
+            if cn != 0:
+                a_n1 = model.a_form().assemble()
+        if cn != 0:                                                   # :185
+            sys_.spmv(a_n.vals, x0, ax0)
+        sys_.lincomb([1.0, cn1 * dt, -dt * cn, dt * cn], [DDn, Ln1, ax0, Ln if cn != 0 else None], out=b)
+        sol = ii_Function(model.W)                                    # :194-198
+        sys_.solve_bc(co_eff, b, sol.tensor(), bcs)                   # :187-192
+        sol.touch()
+        qps.append(sol)
+        x0 = sol.tensor()                                             # :201
+        t.assign(t_val + dt)                                          # :204
+        for func in (model.p_bc, model.g, model.f):                   # :207-211
+            try:
+                func.t = t_val + dt
+            except AttributeError:
+                pass
+        a_n, Ln = a_n1, Ln1                                           # :214-215
+        sys_.mass_apply(model._mass_coeff(ainv), x0, out=DDn)         # :216
+        L = model.L_form()                                            # :218-219
+    return qps

@@ -123,6 +123,11 @@ int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
 int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff, const int32_t* rowptr,
                               double* vals, void* stream);
 
+/* y = coeff * blockdiag(M_e) x on the q rows, 0 elsewhere: the action of mass_matrix_q /
+ * mass_vector_q (time_stepping.py:103-123, `DDn = DDn1*qp0.block_vec()` :216) without CSR values. */
+int gnx_mass_apply_q_mixed(const gnx_network_t* net, double coeff, const double* x, double* y,
+                           void* stream);
+
 /* Coefficient expressions (f, g, p_bc: dolfin Constant / Expression("c-string") / UFL in the
  * reference, tests/test_flow_models.py:94-119) are compiled on the host to a small RPN program
  * and interpreted on the device, one point per thread. */
@@ -237,6 +242,12 @@ int gnx_residual_csr_f64(int32_t nrows, const int32_t* rowptr, const int32_t* co
 /* y = alpha*x + beta*y ; out[0] = <x,y> (if out != NULL, computed on the UPDATED y) */
 int gnx_axpby_dot(int64_t n, double alpha, const double* x, double beta, double* y, double* out,
                   double* work, void* stream);
+
+/* out = sum_{k<nterms} coefs_host[k] * vecs_host[k]  (nterms <= 4; out may alias vecs_host[0]).
+ * The theta-scheme right-hand side b = DDn + cn1 dt Ln1 - dt cn An x0 + dt cn Ln
+ * (graphnics/flowmodels/time_stepping.py:185) in one pass. */
+int gnx_lincomb(int64_t n, int32_t nterms, const double* coefs_host, const double* const* vecs_host,
+                double* out, void* stream);
 
 #ifdef __cplusplus
 }

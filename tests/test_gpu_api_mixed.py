@@ -1,0 +1,180 @@
+"""The reference's own tests for the mixed model, run UNCHANGED IN SHAPE through the drop-in API
+(`from graphnics_b200 import *` instead of `from graphnics import *`), plus comparison of what the
+API produces with the CPU oracle.
+
+Mirrors /root/reference/tests/test_flow_models.py:17-71 (mass conservation), :122-161
+(manufactured solution, mixed) and tests/test_time_stepping.py:47-60,98-136 (time stepping, mixed).
+"""
+import networkx as nx
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mass_conservation():
+    """tests/test_flow_models.py:17-71"""
+    from graphnics_b200 import (line_graph, Y_bifurcation, YY_bifurcation, honeycomb, Constant, Expression,
+                                MixedHydraulicNetwork, ii_assemble, ii_convert, ii_Function, LUSolver,
+                                BIF_IN, BIF_OUT, near)
+    tests = {
+        "Graph line": line_graph(3, dim=3),
+        "Y bifurcation": Y_bifurcation(),
+        "YY bifurcation": YY_bifurcation(),
+        "honeycomb": honeycomb(4, 4),
+    }
+    for test_name in tests:
+        G = tests[test_name]
+        G.make_mesh(5)
+        G.make_submeshes()
+        prop_dict = {key: {"Res": Constant(1), "Ainv": Constant(1)} for key in list(G.edges.keys())}
+        nx.set_edge_attributes(G, prop_dict)
+        model = MixedHydraulicNetwork(G, p_bc=Expression("x[0]", degree=2))
+        W = model.W
+        a = model.a_form()
+        L = model.L_form()
+        A, b = map(ii_assemble, (a, L))
+        A, b = map(ii_convert, (A, b))
+        qp = ii_Function(W)
+        solver = LUSolver(A, "mumps")
+        solver.solve(qp.vector(), b)
+        edge_list = list(G.edges.keys())
+        for bif in G.bifurcation_ixs:
+            total_flux = 0
+            conn_edges = {
+                **{e: (1, BIF_IN, edge_list.index(e)) for e in G.in_edges(bif)},
+                **{e: (-1, BIF_OUT, edge_list.index(e)) for e in G.out_edges(bif)},
+            }
+            for e in conn_edges:
+                sign, tag, e_ix = conn_edges[e]
+                total_flux += sign * qp[e_ix](G.nodes[bif]["pos"])
+            assert near(total_flux, 1e-3, 2e-3), f"Mass is not conserved at bifurcation {bif} for {test_name}"
+            assert abs(total_flux) < 1e-10
+
+        # the same system from the oracle (matrix 1e-12, rhs 1e-12, solution 1e-8)
+        pos = np.asarray([G.nodes[v]["pos"] for v in G.nodes()], dtype=np.float64)
+        edges = np.asarray(list(G.edges()), dtype=np.int64)
+        om = oracle.build_mesh(pos, edges, 5)
+        Ao = oracle.assemble_mixed(om, 1.0)
+        bo = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda x: x[..., 0], 2), project=True)
+        Ag = A.tocsr()
+        assert np.array_equal(Ag.indptr, Ao.indptr) and np.array_equal(Ag.indices, Ao.indices)
+        np.testing.assert_allclose(Ag.data, Ao.data, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(b.get_local(), bo, rtol=1e-11, atol=1e-13)
+        xo = oracle.lu_solve(Ao, bo)
+        xg = qp.vector().get_local()
+        assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
+def hydraulic_manufactured_solution(G, Ainv, Res):
+    """tests/test_flow_models.py:94-119"""
+    from graphnics_b200 import SpatialCoordinate, sin, cos
+    xx = SpatialCoordinate(G.mesh)
+    q = sin(2 * 3.14 * xx[0])
+    p = cos(2 * 3.14 * xx[0])
+    g = Res * q + G.dds(p)
+    f = G.dds(q)
+    return f, q, p, g
+
+
+def test_mixed_hydraulic():
+    """tests/test_flow_models.py:122-161"""
+    from graphnics_b200 import (line_graph, Constant, MixedHydraulicNetwork, FunctionSpace, project, errornorm)
+    Ainv = 0.0
+    Res = 1
+    G = line_graph(2, dx=2)
+    G.make_mesh(8)
+    G.make_submeshes()
+    f, q, p, g = hydraulic_manufactured_solution(G, Ainv, Res)
+    p = project(p, FunctionSpace(G.mesh, "CG", 2))
+    prop_dict = {key: {"Res": Constant(Res), "Ainv": Constant(Ainv)} for key in list(G.edges.keys())}
+    nx.set_edge_attributes(G, prop_dict)
+    model = MixedHydraulicNetwork(G, f=f, g=g, p_bc=p)
+    sol = model.solve()
+    qh, ph = sol
+    pa = project(p, FunctionSpace(G.mesh, "CG", 2))
+    p_error = errornorm(ph, pa)
+    qa = project(q, FunctionSpace(G.mesh, "CG", 3))
+    q_error = errornorm(qh, qa)
+    assert q_error < 1e-2, f"Mixed hydraulic model not giving correct flux, q_error = {q_error}"
+    assert p_error < 1e-1, f"Mixed hydraulic model not giving correct pressure, p_error = {p_error}"
+
+    # against the oracle with the same (projected, degree 2) data
+    pos = np.array([[0.0, 0.0], [2.0, 0.0]])
+    edges = np.array([[0, 1]])
+    om = oracle.build_mesh(pos, edges, 8)
+    w = 2 * 3.14
+    co = lambda fn: oracle.Coef(fn, 2)
+    _, _, xo = oracle.solve_mixed(om, Res=1.0, f=co(lambda x: w * np.cos(w * x[..., 0])),
+                            g=co(lambda x: np.sin(w * x[..., 0]) - w * np.sin(w * x[..., 0])),
+                            p_bc=co(lambda x: np.cos(w * x[..., 0])), project=True)
+    xg = sol.vector().get_local()
+    assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo), np.linalg.norm(xg - xo) / np.linalg.norm(xo)
+
+
+def sympy_hydraulic_manufactured_solution(G, Ainv, Res):
+    """tests/test_time_stepping.py:47-60"""
+    import sympy as sym
+    from graphnics_b200 import Expression
+    x, t_, x_ = sym.symbols("x[0] t x_")
+    q = sym.sin(2 * sym.pi * x) + sym.cos(2 * sym.pi * t_)
+    f = q.diff(x)
+    dsp = -Res * q - Ainv * q.diff(t_)
+    p_ = sym.integrate(dsp, (x, 0, x_))
+    p = p_.subs(x_, x)
+    g = 0
+    q, p, f, g = [sym.printing.ccode(func) for func in [q, p, f, g]]
+    q, p, f, g = [Expression(func, degree=2, t=0) for func in [q, p, f, g]]
+    return q, p, f, g
+
+
+@pytest.mark.parametrize("scheme", ["IE", "CN"])
+def test_time_stepping_mixed_hydraulic(scheme):
+    """tests/test_time_stepping.py:98-136 (the reference only runs IE: "TODO: Test with CN")"""
+    from graphnics_b200 import (line_graph, Constant, TimeDepMixedHydraulicNetwork, time_stepping_stokes,
+                                FunctionSpace, project, errornorm)
+    G = line_graph(2)
+    G.make_mesh(5)
+    G.make_submeshes()
+    Ainv = 2
+    Res = 10
+    for e in G.edges():
+        G.edges()[e]["Ainv"] = Ainv
+        G.edges()[e]["Res"] = Res
+    T = 1
+    t_steps = 10
+    q, p, f, g = sympy_hydraulic_manufactured_solution(G, Ainv, Res)
+    t = Constant(0)
+    t.assign(0)
+    model = TimeDepMixedHydraulicNetwork(G, f=f, g=g, p_bc=p, Ainv=Ainv)
+    qps = time_stepping_stokes(model, t, t_steps=t_steps, T=T, t_step_scheme=scheme)
+    assert len(qps) == t_steps
+    qh, ph = qps[-1]
+    q.t = T
+    p.t = T
+    qa = project(q, FunctionSpace(G.mesh, "CG", 3))
+    pa = project(p, FunctionSpace(G.mesh, "CG", 2))
+    error_q = errornorm(qh, qa)
+    error_p = errornorm(ph, pa)
+    if scheme == "IE":
+        assert error_q < 1e-1, f"Large error in time stepping mixed hydraulic model, error_q={error_q:1.1e}"
+        assert error_p < 1e-1, f"Large error in time stepping mixed hydraulic model, error_q={error_p:1.1e}"
+
+    # every stored state against the oracle's literal restatement of the loop (quirks included)
+    pi = np.pi
+    om = oracle.build_mesh(np.array([[0.0, 0.0], [1.0, 0.0]]), np.array([[0, 1]]), 5)
+    TC = lambda fn: oracle.TimeCoef(fn, degree=2, clock="attr")
+    fo = TC(lambda x, tt: 2 * pi * np.cos(2 * pi * x[..., 0]))
+    def p_fn(x, tt):
+        X = x[..., 0]
+        # p = int_0^x (-Res q - Ainv dq/dt) dx
+        return (-Res * ((1 - np.cos(2 * pi * X)) / (2 * pi) + X * np.cos(2 * pi * tt))
+                + Ainv * 2 * pi * np.sin(2 * pi * tt) * X)
+    xs = oracle.time_stepping("mixed", om, f=fo, g=0.0, p_bc=TC(p_fn), Res=float(Res), Ainv=float(Ainv),
+                              t_steps=t_steps, T=T, scheme=scheme, project=True)
+    assert len(xs) == len(qps)
+    for k, (xo, qpk) in enumerate(zip(xs, qps)):
+        xg = qpk.vector().get_local()
+        assert np.linalg.norm(xg - xo) <= 1e-8 * max(np.linalg.norm(xo), 1e-30), (scheme, k)

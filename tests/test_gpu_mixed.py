@@ -91,7 +91,7 @@ def test_pattern_values_rhs(eng, name, n):
     assert np.array_equal(xq.cpu().numpy().reshape(om.sub_coords.shape).view(np.int64), om.sub_coords.view(np.int64))
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
     nod = lambda c: dev(c(om.sub_coords).ravel())
-    bg = ms.rhs(nod(f), nod(g), nod(lin), dev(lin(pos))).cpu().numpy()
+    bg = ms.rhs(nod(f), nod(g), ms.end_values(nod(lin)), dev(lin(pos))).cpu().numpy()
     np.testing.assert_allclose(bg, b, rtol=1e-12, atol=1e-14)
     # SpMV against scipy
     x = rng.normal(size=A.shape[0])
@@ -174,7 +174,7 @@ def test_reference_known_answers(eng):
     co = ms.coeffs([1.0, 2.0, 3.0])
     pbc = torch.from_numpy(2.0 - pos[:, 1]).cuda()
     xq, _ = ms.dof_coordinates(False)
-    b = ms.rhs(None, None, (2.0 - xq[:, 1]).contiguous(), pbc)
+    b = ms.rhs(None, None, ms.end_values((2.0 - xq[:, 1]).contiguous()), pbc)
     x, info = ms.solve(co, b)
     x = x.cpu().numpy()
     m = dn.m
@@ -190,7 +190,7 @@ def test_reference_known_answers(eng):
         ms = MixedSystem(dn)
         co = ms.coeffs(1.0)
         xq, _ = ms.dof_coordinates(False)
-        b = ms.rhs(None, None, xq[:, 0].contiguous(), torch.from_numpy(np.ascontiguousarray(pos[:, 0])).cuda())
+        b = ms.rhs(None, None, ms.end_values(xq[:, 0].contiguous()), torch.from_numpy(np.ascontiguousarray(pos[:, 0])).cuda())
         x, info = ms.solve(co, b)
         x = x.cpu().numpy()
         q = x[:dn.p_off].reshape(dn.E, dn.m + 1)

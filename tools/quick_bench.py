@@ -28,7 +28,7 @@ co = ms.coeffs(1.0)
 vals = ms.assemble(co)
 pbc_node = torch.from_numpy(np.ascontiguousarray(pos[:, 1])).cuda()
 xq, _ = ms.dof_coordinates(False)
-pbc_nodal = xq[:, 1].contiguous()
+pbc_nodal = ms.end_values(xq[:, 1].contiguous())
 b = ms.rhs(None, None, pbc_nodal, pbc_node)
 x = torch.empty(ms.N, dtype=torch.float64, device="cuda")
 def pat():
