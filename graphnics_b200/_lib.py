@@ -34,12 +34,27 @@ class gnx_mixed_coeffs_t(C.Structure):
     _fields_ = [("a_edge", C.c_void_p), ("k_edge", C.c_void_p), ("sigma", C.c_double)]
 
 
+MAX_LEVELS = 64
+
+
+class gnx_schur_plan_t(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("nl", C.c_int32), ("l_split", C.c_int32), ("nc", C.c_int32),
+        ("nnzc", C.c_int32), ("reserved", C.c_int32),
+        ("lvl_ptr", C.c_int32 * (MAX_LEVELS + 1)),
+        ("lvl_nodes", C.c_void_p), ("parent", C.c_void_p), ("pedge", C.c_void_p), ("ch_ptr", C.c_void_p),
+        ("ch_idx", C.c_void_p), ("core_nodes", C.c_void_p), ("crp", C.c_void_p), ("ccol", C.c_void_p),
+        ("cedge", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
 _D = C.c_double
 _NET = C.POINTER(gnx_network_t)
 _CO = C.POINTER(gnx_mixed_coeffs_t)
+_PLAN = C.POINTER(gnx_schur_plan_t)
 
 # name -> (restype, argtypes); every symbol of include/graphnics_b200.h
 PROTOTYPES = {
@@ -62,10 +77,8 @@ PROTOTYPES = {
     "gnx_dof_coordinates_mixed": (_I, [_NET, _P, _P, _P, _P, _P]),
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "gnx_cg_work_doubles": (_L, [_I]),
-    "gnx_cg_create": (_I, [_NET, _P, _P, _P, _P, _P, _P, _I, _I, _P, C.POINTER(_P)]),
-    "gnx_cg_solve": (_I, [_P, _D, _I, c_f64p, c_i32p, _P]),
-    "gnx_cg_destroy": (None, [_P]),
+    "gnx_schur_work_doubles": (_L, [_PLAN]),
+    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
     "gnx_edge_backsub_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P, _P]),
     "gnx_spmv_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "gnx_reduce_work_doubles": (_L, [_L]),

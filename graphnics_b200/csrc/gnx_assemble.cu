@@ -22,6 +22,48 @@ mixed_rows_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ 
   gnx_mixed_row_emit<MODE>(net, d, r, a_edge, k_edge, a_const, sg, rowptr, colidx, vals);
 }
 
+// Values only, staged: the q/p rows of a block occupy one contiguous CSR range; every thread
+// drops its <= 6 values into shared memory and the block streams the range out with fully
+// coalesced stores.  Blocks past the q/p rows handle the lambda rows (variable length) directly.
+constexpr int ASM_T = 256;
+__global__ void __launch_bounds__(ASM_T)
+mixed_values_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
+                    const double* __restrict__ k_edge, double a_const, double sg, int32_t nb_qp,
+                    double* __restrict__ vals) {
+  __shared__ double stage[ASM_T * 6];
+  __shared__ int64_t range[2];
+  if ((int32_t)blockIdx.x >= nb_qp) {
+    const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_qp) * ASM_T + threadIdx.x;
+    if (r < d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
+    return;
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * ASM_T;
+  const int64_t r = r0 + threadIdx.x;
+  const int64_t rlast = (r0 + ASM_T <= d.lam_off ? r0 + ASM_T : d.lam_off) - 1;
+  GnxRow row;
+  row.nnz = 0; row.start = 0;
+  if (r <= rlast) gnx_mixed_row_qp<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, row);
+  if (threadIdx.x == 0) range[0] = row.start;
+  if (r == rlast) range[1] = row.start + row.nnz;
+  __syncthreads();
+  const int64_t base = range[0];
+  const int32_t off = (int32_t)(row.start - base);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) if (i < row.nnz) stage[off + i] = row.val[i];
+  __syncthreads();
+  const int32_t len = (int32_t)(range[1] - base);
+  for (int32_t i = threadIdx.x; i < len; i += ASM_T) vals[base + i] = stage[i];
+}
+
+static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
+                         const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+  const int nb_qp = gnx_blocks(d.lam_off, ASM_T);
+  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
+  mixed_values_kernel<<<nb_qp + nb_lam, ASM_T, 0, st>>>(*net, d, a_edge, k_edge, a_const, sg, nb_qp, vals);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
 static int check_net(const gnx_network_t* net) {
   GNX_CHECK_ARG(net != nullptr);
   GNX_CHECK_ARG(net->V > 0 && net->E > 0 && net->n >= 0 && net->n <= 24 && net->B >= 0);
@@ -50,10 +92,7 @@ extern "C" int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coef
   GNX_CHECK_ARG(co && co->a_edge && vals && net->h);
   (void)rowptr;  // row starts are closed-form; kept in the ABI for pattern-agnostic callers
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  mixed_rows_kernel<MODE_VALUES><<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
-      *net, d, co->a_edge, co->k_edge, 1.0, co->sigma, nullptr, nullptr, vals);
-  GNX_LAUNCH_CHECK();
-  return GNX_OK;
+  return launch_values(net, d, co->a_edge, co->k_edge, 1.0, co->sigma, vals, (cudaStream_t)stream);
 }
 
 extern "C" int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff,
@@ -62,10 +101,7 @@ extern "C" int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff,
   GNX_CHECK_ARG(vals && net->h);
   (void)rowptr;
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  mixed_rows_kernel<MODE_VALUES><<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
-      *net, d, nullptr, nullptr, coeff, 0.0, nullptr, nullptr, vals);
-  GNX_LAUNCH_CHECK();
-  return GNX_OK;
+  return launch_values(net, d, nullptr, nullptr, coeff, 0.0, vals, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------

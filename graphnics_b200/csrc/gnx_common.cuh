@@ -86,4 +86,73 @@ __device__ __forceinline__ double gnx_group_sum(double v, int w) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------
+// Block-segmented scan / reduce: the block is tiled by segments of `seg` consecutive threads
+// (seg a power of two, 1 <= seg <= blockDim.x <= 1024, blockDim.x a multiple of max(seg,32)).
+// Fixed combination order -> deterministic.  `sh` holds >= 32 doubles per value; every call
+// contains block barriers, so all threads of the block must call it.
+// ---------------------------------------------------------------------------------------
+// inclusive scan of v inside the segment; *total = segment sum
+__device__ __forceinline__ double gnx_seg_incl_scan(double v, int seg, double* sh, double* total) {
+  const int lane = threadIdx.x & 31;
+  const int w = seg < 32 ? seg : 32;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(GNX_FULL, v, o, w);
+    if (o < w && (lane & (w - 1)) >= o) v += t;
+  }
+  if (seg <= 32) {
+    *total = __shfl_sync(GNX_FULL, v, w - 1, w);
+    return v;
+  }
+  const int wid = threadIdx.x >> 5;
+  const int wps = seg >> 5;                         // warps per segment (2..32)
+  __syncthreads();                                  // sh reuse
+  if (lane == 31) sh[wid] = v;
+  __syncthreads();
+  const int w0 = wid & ~(wps - 1);                  // first warp of my segment
+  double t = (lane < wps) ? sh[w0 + lane] : 0.0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double u = __shfl_up_sync(GNX_FULL, t, o);
+    if (o < wps && lane >= o) t += u;
+  }
+  *total = __shfl_sync(GNX_FULL, t, wps - 1);
+  const int me = wid - w0;
+  const double before = __shfl_sync(GNX_FULL, t, me > 0 ? me - 1 : 0);
+  return me > 0 ? v + before : v;
+}
+
+// segment sums of K values, broadcast to every thread of the segment
+template <int K>
+__device__ __forceinline__ void gnx_seg_sum(double (&v)[K], int seg, double* sh) {
+  const int lane = threadIdx.x & 31;
+  const int w = seg < 32 ? seg : 32;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(GNX_FULL, v[k], o, w);
+      if (o < w) v[k] += t;
+    }
+  }
+  if (seg <= 32) return;
+  const int wid = threadIdx.x >> 5;
+  const int wps = seg >> 5;
+  const int w0 = wid & ~(wps - 1);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = (lane < wps) ? sh[k * 32 + w0 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(GNX_FULL, t, o);
+    v[k] = t;
+  }
+}
+
 #endif  // GNX_COMMON_CUH

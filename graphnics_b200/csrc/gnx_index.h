@@ -174,6 +174,36 @@ GNX_HD int32_t gnx_imax(int32_t a, int32_t b) { return a > b ? a : b; }
 
 enum { GNX_MODE_PATTERN = 0, GNX_MODE_VALUES = 1 };
 
+// q- or p-row r (< lam_off) of the mixed matrix: start slot, sorted columns, values.
+template <int MODE>
+GNX_HD void gnx_mixed_row_qp(const gnx_network_t& net, const GnxMixedDims& d, int64_t r,
+                             const double* a_edge, const double* k_edge, double a_const, double sg,
+                             GnxRow& row) {
+  const int32_t m = d.m;
+  if (r < d.p_off) {
+    const int32_t e = (int32_t)(r / (m + 1));
+    const int32_t l = (int32_t)(r - (int64_t)e * (m + 1));
+    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+    const int32_t lo = gnx_imin(u, v), hi = gnx_imax(u, v);
+    const int32_t t = net.tloc[l];
+    double hl = 1.0, hr = 1.0, a = 1.0, k = 0.0;
+    if (MODE == GNX_MODE_VALUES) {
+      const bool flip = u > v;
+      const double* he = net.h + (int64_t)e * m;
+      if (t > 0) hl = he[flip ? m - t : t - 1];        // lo-frame cell s=t-1
+      if (t < m) hr = he[flip ? m - 1 - t : t];        // lo-frame cell s=t
+      a = a_edge ? a_edge[e] : a_const;
+      k = k_edge ? k_edge[e] : 0.0;
+    }
+    gnx_mixed_q_row(net, d, e, l, net.loc, t, u, v, net.bix[lo], net.bix[hi],
+                    net.ebif_prefix[e], hl, hr, a, k, sg, row);
+  } else {
+    const int32_t c = (int32_t)(r - d.p_off);
+    const int32_t e = c >> net.n;
+    gnx_mixed_p_row(net, d, c, net.loc, net.edges[2 * e], net.edges[2 * e + 1], sg, row);
+  }
+}
+
 // Whole-row emitter used by the pattern / value kernels (one thread per matrix row r).
 template <int MODE>
 GNX_HD void gnx_mixed_row_emit(const gnx_network_t& net, const GnxMixedDims& d, int64_t r,
@@ -182,28 +212,7 @@ GNX_HD void gnx_mixed_row_emit(const gnx_network_t& net, const GnxMixedDims& d, 
   const int32_t m = d.m;
   if (r < d.lam_off) {
     GnxRow row;
-    if (r < d.p_off) {
-      const int32_t e = (int32_t)(r / (m + 1));
-      const int32_t l = (int32_t)(r - (int64_t)e * (m + 1));
-      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-      const int32_t lo = gnx_imin(u, v), hi = gnx_imax(u, v);
-      const int32_t t = net.tloc[l];
-      double hl = 1.0, hr = 1.0, a = 1.0, k = 0.0;
-      if (MODE == GNX_MODE_VALUES) {
-        const bool flip = u > v;
-        const double* he = net.h + (int64_t)e * m;
-        if (t > 0) hl = he[flip ? m - t : t - 1];        // lo-frame cell s=t-1
-        if (t < m) hr = he[flip ? m - 1 - t : t];        // lo-frame cell s=t
-        a = a_edge ? a_edge[e] : a_const;
-        k = k_edge ? k_edge[e] : 0.0;
-      }
-      gnx_mixed_q_row(net, d, e, l, net.loc, t, u, v, net.bix[lo], net.bix[hi],
-                      net.ebif_prefix[e], hl, hr, a, k, sg, row);
-    } else {
-      const int32_t c = (int32_t)(r - d.p_off);
-      const int32_t e = c >> net.n;
-      gnx_mixed_p_row(net, d, c, net.loc, net.edges[2 * e], net.edges[2 * e + 1], sg, row);
-    }
+    gnx_mixed_row_qp<MODE>(net, d, r, a_edge, k_edge, a_const, sg, row);
     if (MODE == GNX_MODE_PATTERN) {
       rowptr[r] = (int32_t)row.start;
       for (int i = 0; i < 6; ++i) if (i < row.nnz) colidx[row.start + i] = row.col[i];

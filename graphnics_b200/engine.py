@@ -58,7 +58,7 @@ def lincomb(lib, coefs, vecs, out=None):
 
 
 class MixedSystem:
-    def __init__(self, dn: DeviceNetwork, cg_batch=32, cg_mode=2):
+    def __init__(self, dn: DeviceNetwork):
         self.dn = dn
         self.lib = _lib.require_device()
         self.N = dn.mixed_ndofs
@@ -66,9 +66,7 @@ class MixedSystem:
         self.dev = dn.device
         self.rowptr = None
         self.colidx = None
-        self.cg_batch = cg_batch
-        self.cg_mode = int(cg_mode)
-        self._cg = None
+        self._plan = None
         self._solve_bufs = None
         self._red_work = None
 
@@ -208,60 +206,79 @@ class MixedSystem:
             E, B = dn.E, max(dn.B, 1)
             d = {}
             d["cond"], d["rsrc"], d["ftot"] = self._f64(E), self._f64(E), self._f64(E)
-            d["sdiag"], d["srhs"], d["P"] = self._f64(B), self._f64(B), torch.zeros(B, dtype=torch.float64, device=self.dev)
-            d["soff"] = self._f64(2 * E)
-            d["scol"] = torch.empty(2 * E, dtype=torch.int32, device=self.dev)
-            d["cgwork"] = self._f64(int(self.lib.gnx_cg_work_doubles(B)))
+            d["P"] = torch.zeros(B, dtype=torch.float64, device=self.dev)
             self._solve_bufs = d
         return self._solve_bufs
 
-    def _cg_handle(self):
-        if self._cg is None and self.dn.B > 0:
-            d = self._bufs()
-            h = C.c_void_p()
-            check(self.lib.gnx_cg_create(self.dn.net_ref(), ptr(d["sdiag"]), ptr(d["soff"]), ptr(d["scol"]),
-                                         ptr(d["srhs"]), ptr(d["P"]), ptr(d["cgwork"]), self.cg_batch,
-                                         self.cg_mode, current_stream(), C.byref(h)))
-            self._cg = h
-        return self._cg
+    def schur_plan(self):
+        """symbolic rake/core plan of the Schur system (host analysis once, arrays on the device)"""
+        if self._plan is None and self.dn.B > 0:
+            from .schur_plan import SchurPlan
+            dn = self.dn
+            hp = SchurPlan(dn.edges_host(), dn.bix.cpu().numpy(), dn.B, max_levels=_lib.MAX_LEVELS)
+            lvl_ptr, lvl_nodes = hp.level_arrays()
+            keep = {}
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
+            s = _lib.gnx_schur_plan_t()
+            s.B, s.nl, s.l_split, s.nc, s.nnzc = dn.B, len(hp.levels), hp.split_level(), hp.nc, hp.nnzc
+            for i, v in enumerate(lvl_ptr):
+                s.lvl_ptr[i] = int(v)
+            for name, arr in (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
+                              ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
+                              ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge)):
+                t = dev(arr if len(arr) else np.zeros(1, dtype=np.int32))
+                keep[name] = t
+                setattr(s, name, t.data_ptr())
+            work = self._f64(int(self.lib.gnx_schur_work_doubles(C.byref(s))))
+            self._plan = (s, keep, work, hp)
+        return self._plan
 
     def eliminate(self, co, b):
-        """phase 1 + Schur assembly (device only, no sync)."""
+        """phase 1: per-edge scans -> edge scalars (device only, no sync)."""
         d = self._bufs()
+        check(self.lib.gnx_edge_eliminate_mixed(self.dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                                ptr(d["ftot"]), current_stream()))
+
+    def schur_arrays(self, co, b):
+        """explicit Schur diagonal / off-diagonals / rhs (inspection and tests)"""
         dn = self.dn
-        st = current_stream()
-        check(self.lib.gnx_edge_eliminate_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
-                                                ptr(d["ftot"]), st))
-        if dn.B > 0:
-            b_lam = b[dn.lam_off:]
-            check(self.lib.gnx_schur_build(dn.net_ref(), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
-                                           ptr(b_lam), ptr(d["sdiag"]), ptr(d["soff"]), ptr(d["scol"]),
-                                           ptr(d["srhs"]), st))
+        d = self._bufs()
+        self.eliminate(co, b)
+        out = dict(sdiag=self._f64(dn.B), srhs=self._f64(dn.B), soff=self._f64(2 * dn.E),
+                   scol=torch.empty(2 * dn.E, dtype=torch.int32, device=self.dev))
+        check(self.lib.gnx_schur_build(dn.net_ref(), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+                                       ptr(b[dn.lam_off:]), ptr(out["sdiag"]), ptr(out["soff"]), ptr(out["scol"]),
+                                       ptr(out["srhs"]), current_stream()))
+        return out
 
     def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True):
-        """x = A^{-1} b for the operator described by `co` (never forms A).
-        sync=False (cg_mode 2 only): nothing returns to the host; `info` is not filled."""
+        """x = A^{-1} b for the operator described by `co` (never forms A): edge elimination ->
+        one persistent Schur kernel (rake + core PCG) -> back-substitution.
+        sync=False: nothing returns to the host; `info` is not filled."""
         dn = self.dn
         d = self._bufs()
         info = info if info is not None else SolveInfo()
         x = x if x is not None else self._f64(self.N)
+        st = current_stream()
         self.eliminate(co, b)
         if dn.B > 0:
-            if not warm_start:
-                d["P"].zero_()
-            h = self._cg_handle()
-            if sync or self.cg_mode != 2:
+            plan, _, work, _ = self.schur_plan()
+            lam = x[dn.lam_off:]
+            args = (dn.net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+                    ptr(b[dn.lam_off:]), ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
+                    1 if warm_start else 0)
+            if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()
-                check(self.lib.gnx_cg_solve(h, float(rtol), int(max_iter), C.byref(resid), inf, current_stream()))
+                check(self.lib.gnx_schur_solve(*args, C.byref(resid), inf, st))
                 info.cg_iterations += int(inf[0])
                 info.cg_converged = bool(inf[1])
                 info.cg_batches += int(inf[2])
                 info.cg_rel_resid = float(resid.value)
             else:
-                check(self.lib.gnx_cg_solve(h, float(rtol), int(max_iter), None, None, current_stream()))
+                check(self.lib.gnx_schur_solve(*args, None, None, st))
         check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
-                                              ptr(d["P"]) if dn.B > 0 else None, ptr(x), current_stream()))
+                                              ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
         return x, info
 
     def solve_bc(self, co, b, x, bcs=None, **kw):
@@ -283,12 +300,5 @@ class MixedSystem:
         return x, info
 
     def close(self):
-        if self._cg is not None:
-            self.lib.gnx_cg_destroy(self._cg)
-            self._cg = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        self._plan = None
+        self._solve_bufs = None

@@ -1,0 +1,165 @@
+"""Symbolic analysis of the graph-level Schur system (built once per network, host side).
+
+After the per-edge elimination (gnx_edge_eliminate_mixed) the unknowns are the bifurcation
+multipliers; their matrix is a weighted graph Laplacian  S = sum_e cond_e (e_i - e_j)(e_i - e_j)^T
+(+ Dirichlet contributions of edges that end in boundary nodes).  Vertices of the bifurcation graph
+that have exactly ONE remaining bifurcation neighbour can be eliminated exactly and without fill
+("rake"): the parent only receives a diagonal and a right-hand-side update.  Repeating this level by
+level removes every tree-like part of the network -- an arterial tree completely, so the Krylov
+iteration of the reference-replacing solver (CG on the Schur complement) only ever sees the cyclic
+CORE of the graph (the whole lattice for a honeycomb, nothing for a tree).
+
+The plan is pure index data (it does not depend on conductances), so the time loop and repeated
+solves reuse it.  All arrays are int32, bifurcation-index based.
+"""
+import numpy as np
+
+__all__ = ["SchurPlan", "MAX_LEVELS"]
+
+MAX_LEVELS = 64          # rake levels kept in the kernel's parameter block; deeper parts go to the core
+
+
+class SchurPlan:
+    """
+    levels      list of int32 arrays: bifurcation indices eliminated at level l (up-sweep order)
+    parent[B]   bifurcation index of the node a raked node is folded into (-1: none / not raked)
+    pedge[B]    graph edge that links a raked node to its parent (-1 if parent == -1)
+    ch_ptr[B+1], ch_idx   children (raked nodes) of every node, CSR
+    core_nodes[nc], core_of[B], crp[nc+1], ccol[nnzc] (core-local), cedge[nnzc] (graph edge)
+    """
+
+    def __init__(self, edges, bix, B, max_levels=MAX_LEVELS):
+        edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+        bix = np.asarray(bix, dtype=np.int64)
+        self.B = int(B)
+        bu, bv = bix[edges[:, 0]], bix[edges[:, 1]]
+        inner = np.nonzero((bu >= 0) & (bv >= 0))[0]          # edges joining two bifurcations
+        eu, ev = bu[inner], bv[inner]
+        # half-edge lists (node, other, edge)
+        hn = np.concatenate([eu, ev])
+        ho = np.concatenate([ev, eu])
+        he = np.concatenate([inner, inner])
+        order = np.argsort(hn, kind="stable")
+        hn, ho, he = hn[order], ho[order], he[order]
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(hn, minlength=B))])
+        deg = np.diff(ptr).astype(np.int64)                   # remaining bifurcation-neighbour count
+        alive = np.ones(B, dtype=bool)
+        half_alive = np.ones(len(hn), dtype=bool)
+        parent = -np.ones(B, dtype=np.int64)
+        pedge = -np.ones(B, dtype=np.int64)
+        levels = []
+        # position of the reverse half-edge, to retire both directions of an edge together
+        rev = np.empty(len(hn), dtype=np.int64)
+        srt = np.argsort(he, kind="stable")
+        # every inner edge id appears exactly twice in `he`
+        rev[srt[0::2]] = srt[1::2]
+        rev[srt[1::2]] = srt[0::2]
+        while len(levels) < max_levels:
+            cand = np.nonzero(alive & (deg <= 1))[0]
+            if cand.size == 0:
+                break
+            # the single live half-edge of every degree-1 candidate
+            par = -np.ones(cand.size, dtype=np.int64)
+            pe = -np.ones(cand.size, dtype=np.int64)
+            hidx = -np.ones(cand.size, dtype=np.int64)
+            one = deg[cand] == 1
+            if one.any():
+                c1 = cand[one]
+                # first live half-edge of each node: vectorised via segmented argmax
+                starts, ends = ptr[c1], ptr[c1 + 1]
+                maxlen = int((ends - starts).max())
+                found = -np.ones(c1.size, dtype=np.int64)
+                for off in range(maxlen):
+                    idx = starts + off
+                    ok = (idx < ends) & (found < 0)
+                    okidx = idx[ok]
+                    live = half_alive[okidx]
+                    tmp = found[ok]
+                    tmp[live] = okidx[live]
+                    found[ok] = tmp
+                hidx[one] = found
+                par[one] = ho[found]
+                pe[one] = he[found]
+            # two mutually-adjacent candidates: keep the higher index for a later level
+            cand_mask = np.zeros(B, dtype=bool)
+            cand_mask[cand] = True
+            clash = one & (par >= 0)
+            clash[clash] = cand_mask[par[clash]] & (cand[clash] > par[clash])
+            keep = ~clash
+            cand, par, pe, hidx = cand[keep], par[keep], pe[keep], hidx[keep]
+            if cand.size == 0:
+                break
+            levels.append(cand.astype(np.int32))
+            alive[cand] = False
+            parent[cand] = par
+            pedge[cand] = pe
+            hp = hidx[hidx >= 0]
+            half_alive[hp] = False
+            half_alive[rev[hp]] = False
+            np.subtract.at(deg, par[par >= 0], 1)
+            deg[cand] = 0
+        self.levels = levels
+        self.parent = parent.astype(np.int32)
+        self.pedge = pedge.astype(np.int32)
+        # children CSR
+        kids = np.nonzero(parent >= 0)[0]
+        o = np.argsort(parent[kids], kind="stable")
+        self.ch_idx = kids[o].astype(np.int32)
+        self.ch_ptr = np.concatenate([[0], np.cumsum(np.bincount(parent[kids], minlength=B))]).astype(np.int32)
+        # core
+        core = np.nonzero(alive)[0]
+        self.core_nodes = core.astype(np.int32)
+        self.nc = int(core.size)
+        core_of = -np.ones(B, dtype=np.int64)
+        core_of[core] = np.arange(core.size)
+        self.core_of = core_of.astype(np.int32)
+        keep = half_alive & alive[hn] & alive[ho]
+        cn, co_, ce = core_of[hn[keep]], core_of[ho[keep]], he[keep]
+        self.crp = np.concatenate([[0], np.cumsum(np.bincount(cn, minlength=core.size))]).astype(np.int32)
+        self.ccol = co_.astype(np.int32)
+        self.cedge = ce.astype(np.int32)
+        self.nnzc = int(len(ce))
+
+    # level pointer / flat node list as the kernel wants them
+    def level_arrays(self):
+        sizes = [len(l) for l in self.levels]
+        lvl_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        nodes = np.concatenate(self.levels).astype(np.int32) if self.levels else np.zeros(0, dtype=np.int32)
+        return lvl_ptr, nodes
+
+    def split_level(self, small=2048):
+        """first level from which every later level has <= `small` nodes (handled by one CTA)"""
+        sizes = [len(l) for l in self.levels]
+        l = len(sizes)
+        while l > 0 and sizes[l - 1] <= small:
+            l -= 1
+        return l
+
+    # numpy model of the device algorithm (used by the CPU tests to pin the algebra)
+    def solve_host(self, cond, diag, rhs, core_solver=None):
+        d = np.array(diag, dtype=np.float64)
+        r = np.array(rhs, dtype=np.float64)
+        x = np.zeros(self.B)
+        w = np.where(self.pedge >= 0, -np.asarray(cond)[np.maximum(self.pedge, 0)], 0.0)
+
+        def gather(nodes):
+            for i in nodes:
+                for c in self.ch_idx[self.ch_ptr[i]:self.ch_ptr[i + 1]]:
+                    d[i] -= w[c] * w[c] / d[c]
+                    r[i] -= w[c] * r[c] / d[c]
+        for lv in self.levels:
+            gather(lv)
+        if self.nc:
+            gather(self.core_nodes)
+            import scipy.sparse as sp
+            import scipy.sparse.linalg as spla
+            rows = np.repeat(np.arange(self.nc), np.diff(self.crp))
+            S = sp.csr_matrix((-np.asarray(cond)[self.cedge], (rows, self.ccol)), shape=(self.nc, self.nc))
+            S = S + sp.diags(d[self.core_nodes])
+            x[self.core_nodes] = spla.spsolve(S.tocsc(), r[self.core_nodes]) if core_solver is None \
+                else core_solver(S, r[self.core_nodes])
+        for lv in reversed(self.levels):
+            for i in lv:
+                p = self.parent[i]
+                x[i] = (r[i] - (w[i] * x[p] if p >= 0 else 0.0)) / d[i]
+        return x

@@ -195,35 +195,54 @@ int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords, co
 int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                              const double* b, double* cond, double* rsrc, double* ftot, void* stream);
 
-/* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics).
+/* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics),
+ * as explicit arrays -- inspection / tests; gnx_schur_solve builds the same quantities itself.
  *   b_lam [B] (lambda rows of b, may be NULL), sdiag [B], soff [2E] (aligned with inc_edge),
  *   scol [2E] (bifurcation index of the other end, -1 = boundary), srhs [B] */
 int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, const double* rsrc,
                     const double* ftot, const double* b_lam, double* sdiag, double* soff,
                     int32_t* scol, double* srhs, void* stream);
 
-/* Jacobi-PCG on the Schur system; per iteration two fused phases (p-update+SpMV+<p,Sp> |
- * x,r,z-update+<r,z>,<r,r>), deterministic two-stage reductions, convergence tested on device.
- *   mode 2 (default): ONE persistent kernel per solve -- a single CTA with the search
- *           direction in shared memory and all row state in registers when B <= 2048, else a
- *           cooperative multi-CTA kernel with grid barriers; no host round trip, fully
- *           asynchronous (and CUDA-graph capturable) when resid_host and info_host are NULL;
- *   mode 1: two kernels per iteration replayed in batches from a CUDA graph (captured once
- *           per handle on an internal stream), one stream sync per batch;
- *   mode 0: as mode 1 without the graph.
- *   x [B] in/out (initial guess), work [>= gnx_cg_work_doubles(B)] doubles.
- * resid_host[0] = ||r||/||rhs||, info_host[3] = {iterations, converged, batches};
- * GNX_ERR_NOCONV if max_iter is hit (only detectable when info is requested in mode 2). */
-typedef struct gnx_cg gnx_cg_t;
-int64_t gnx_cg_work_doubles(int32_t B);
-int gnx_cg_create(const gnx_network_t* net, const double* sdiag, const double* soff,
-                  const int32_t* scol, const double* srhs, double* x, double* work, int32_t batch,
-                  int32_t mode, void* stream, gnx_cg_t** out);
-int gnx_cg_solve(gnx_cg_t* h, double rtol, int32_t max_iter, double* resid_host, int32_t* info_host,
-                 void* stream);
-void gnx_cg_destroy(gnx_cg_t* h);
+/* Symbolic plan of the Schur solve (index data only, built once per network on the host --
+ * graphnics_b200/schur_plan.py): tree-like parts of the bifurcation graph are eliminated exactly
+ * level by level ("rake": a node with one remaining neighbour folds into it without fill), the
+ * cyclic core that is left is solved by Jacobi-PCG.  All pointers are device pointers, indices are
+ * bifurcation indices unless stated. */
+#define GNX_MAX_LEVELS 64
+typedef struct gnx_schur_plan {
+  int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level swept by one CTA, core size */
+  int32_t nnzc, reserved;              /* off-diagonal entries of the core matrix */
+  int32_t lvl_ptr[GNX_MAX_LEVELS + 1]; /* level l = lvl_nodes[lvl_ptr[l] .. lvl_ptr[l+1]) */
+  const int32_t* lvl_nodes;            /* [lvl_ptr[nl]] */
+  const int32_t* parent;               /* [B] node a raked node folds into, -1 = none */
+  const int32_t* pedge;                /* [B] graph edge linking a raked node to its parent, or -1 */
+  const int32_t* ch_ptr;               /* [B+1] raked children of every node (CSR) */
+  const int32_t* ch_idx;
+  const int32_t* core_nodes;           /* [nc] */
+  const int32_t* crp;                  /* [nc+1] core matrix rows (CSR, core-local columns) */
+  const int32_t* ccol;                 /* [nnzc] */
+  const int32_t* cedge;                /* [nnzc] graph edge whose -cond is the entry */
+} gnx_schur_plan_t;
 
-/* Phase 2: back-substitution, x [N] (dof order) from the multipliers P [B] (= sigma*lambda). */
+/* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative
+ * grid otherwise): Schur diagonal/rhs gather, rake up-sweep, Jacobi-PCG on the core (two fused
+ * phases per iteration, deterministic reductions, convergence decided on the device), rake
+ * down-sweep.  Replaces ii_convert + LUSolver("mumps") (flow_models.py:344-348) together with
+ * gnx_edge_eliminate_mixed / gnx_edge_backsub_mixed.
+ *   P [B] out: sigma*lambda (in: initial guess of the core unknowns when warm != 0);
+ *   lam_out [B] (may be NULL) = P / sigma, i.e. the lambda block of the solution vector;
+ *   work [>= gnx_schur_work_doubles(plan)] doubles.
+ * Fully asynchronous (and CUDA-graph capturable) when resid_host and info_host are NULL; otherwise
+ * synchronises and returns resid_host[0] = ||r||/||rhs|| of the core CG, info_host[3] =
+ * {CG iterations, converged, CTAs}; GNX_ERR_NOCONV if max_iter was hit. */
+int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan);
+int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
+                    const double* cond, const double* rsrc, const double* ftot, const double* b_lam,
+                    double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
+                    int32_t warm, double* resid_host, int32_t* info_host, void* stream);
+
+/* Phase 2: back-substitution, the q and p blocks of x [N] (dof order) from the multipliers P [B]
+ * (= sigma*lambda; the lambda block itself is written by gnx_schur_solve). */
 int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                            const double* cond, const double* rsrc, const double* P, double* x,
                            void* stream);

@@ -100,14 +100,13 @@ def test_pattern_values_rhs(eng, name, n):
 
 
 @pytest.mark.parametrize("name,n", CASES)
-@pytest.mark.parametrize("cg_mode", [2, 1, 0])
-def test_solve_matches_lu(eng, name, n, cg_mode):
+def test_solve_matches_lu(eng, name, n):
     import torch
     DeviceNetwork, MixedSystem = eng
     pos, edges = graph(name)
     om = oracle.build_mesh(pos, edges, n)
     dn = DeviceNetwork(pos, edges, n)
-    ms = MixedSystem(dn, cg_mode=cg_mode)
+    ms = MixedSystem(dn)
     rng = np.random.default_rng(5)
     Res = rng.uniform(0.5, 2.0, size=len(edges))
     lin = oracle.Coef(lambda x: 1.0 + 2.0 * x[..., 0] - 0.5 * x[..., 1], 1)
@@ -204,3 +203,75 @@ def test_reference_known_answers(eng):
                 if u == bnode:
                     tot -= q[i, loc[dn.m] if flip else loc[0]]
             assert abs(tot) < 1e-10, (name, bnode, tot)
+
+
+def _big_graph(name):
+    from graphnics_b200.synthetic import murray_tree
+    if name == "tree14":                      # B = 8191: multi-CTA rake with a single-CTA top
+        pos, edges, _, _ = murray_tree(14, gdim=2)
+        return pos, edges
+    if name == "honeycomb40":                 # B ~ 3.4k, no rakeable node: cooperative PCG on the core
+        from graphnics_b200.generators import honeycomb
+        G = honeycomb(40, 40, mesh=False)
+        return G._graph_arrays()
+    if name == "lollipop":                    # cycle (core) with trees hanging off it (raked)
+        rng = np.random.default_rng(11)
+        nc = 3000
+        th = 2 * np.pi * np.arange(nc) / nc
+        pos = [np.stack([np.cos(th), np.sin(th)], 1) * 50]
+        edges = [np.stack([np.arange(nc), (np.arange(nc) + 1) % nc], 1)]
+        nxt = nc
+        for k in range(0, nc, 3):             # a 3-level binary tree on every third cycle node
+            par = [k]
+            for lev in range(3):
+                new = []
+                for p in par:
+                    for _ in range(2):
+                        pos.append(pos[0][k][None] * (1.1 + 0.1 * lev) + rng.normal(size=(1, 2)))
+                        edges.append(np.array([[p, nxt]]))
+                        new.append(nxt); nxt += 1
+                par = new
+        pos, edges = np.vstack(pos), np.vstack(edges)
+        order = np.lexsort((edges[:, 1], edges[:, 0]))
+        return pos, edges[order]
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name,n", [("tree14", 2), ("honeycomb40", 1), ("lollipop", 1)])
+def test_solve_large_graphs(eng, name, n):
+    """systems whose Schur solve needs the cooperative multi-CTA kernel (B > 2048)"""
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = _big_graph(name)
+    om = oracle.build_mesh(pos, edges, n)
+    dn = DeviceNetwork(pos, edges, n)
+    assert dn.B > 2048
+    ms = MixedSystem(dn)
+    rng = np.random.default_rng(9)
+    Res = rng.uniform(0.5, 2.0, size=len(edges))
+    lin = oracle.Coef(lambda x: 1.0 + 0.2 * x[..., 0] - 0.05 * x[..., 1], 1)
+    f = oracle.Coef(lambda x: np.cos(0.2 * x[..., 1]), 1)
+    A = oracle.assemble_mixed(om, Res)
+    b = oracle.assemble_mixed_rhs(om, f=f, g=0.0, p_bc=lin, project=False)
+    x_ref = oracle.lu_solve(A, b)
+    co = ms.coeffs(Res)
+    vals = ms.assemble(co)
+    rp, ci = ms.build_pattern()
+    assert np.array_equal(rp.cpu().numpy(), A.indptr) and np.array_equal(ci.cpu().numpy(), A.indices)
+    np.testing.assert_allclose(vals.cpu().numpy(), A.data, rtol=1e-12, atol=1e-300)
+    x, info = ms.solve_checked(co, vals, torch.from_numpy(b).cuda())
+    plan = ms.schur_plan()[3]
+    if name == "tree14":
+        assert plan.nc == 0 and info.cg_iterations == 0
+    if name == "honeycomb40":
+        assert plan.nc == dn.B and info.cg_iterations > 10
+    if name == "lollipop":
+        assert 0 < plan.nc < dn.B
+    assert info.cg_converged and info.cg_batches > 1
+    lay = oracle.mixed_layout(om)
+    x = x.cpu().numpy()
+    for lo, hi in ((0, lay["p_off"]), (lay["p_off"], lay["lam_off"]), (lay["lam_off"], lay["N"])):
+        assert rel(x[lo:hi], x_ref[lo:hi]) < 1e-8, (name, lo, rel(x[lo:hi], x_ref[lo:hi]), info)
+    # warm start from the converged multipliers: no more than a couple of iterations
+    info2 = ms.solve(co, torch.from_numpy(b).cuda(), x=torch.empty_like(torch.from_numpy(b).cuda()), warm_start=True)[1]
+    assert info2.cg_iterations <= max(2, info.cg_iterations // 4)

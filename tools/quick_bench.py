@@ -53,9 +53,6 @@ t = timed(step)
 print("assemble+solve (async) ms", t, "MDOF/s", ms.N / t[0] / 1e3)
 print("solve async:", timed(lambda: ms.solve(co, b, x=x, sync=False)))
 print("solve async max_iter=1:", timed(lambda: ms.solve(co, b, x=x, sync=False, max_iter=1)))
-for mode in (1, 0):
-    ms2 = MixedSystem(dn, cg_mode=mode); ms2.build_pattern()
-    print("mode", mode, "solve ms", timed(lambda: ms2.solve(co, b, x=x)))
 try:
     g = torch.cuda.CUDAGraph()
     s_ = torch.cuda.Stream()
