@@ -35,16 +35,17 @@ class gnx_mixed_coeffs_t(C.Structure):
 
 
 MAX_LEVELS = 64
+TOP_MAX = 2048
 
 
 class gnx_schur_plan_t(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("nl", C.c_int32), ("l_split", C.c_int32), ("nc", C.c_int32),
-        ("nnzc", C.c_int32), ("reserved", C.c_int32),
+        ("nnzc", C.c_int32), ("nt", C.c_int32),
         ("lvl_ptr", C.c_int32 * (MAX_LEVELS + 1)),
         ("lvl_nodes", C.c_void_p), ("parent", C.c_void_p), ("pedge", C.c_void_p), ("ch_ptr", C.c_void_p),
         ("ch_idx", C.c_void_p), ("core_nodes", C.c_void_p), ("crp", C.c_void_p), ("ccol", C.c_void_p),
-        ("cedge", C.c_void_p),
+        ("cedge", C.c_void_p), ("top_nodes", C.c_void_p), ("top_of", C.c_void_p), ("level_of", C.c_void_p),
     ]
 
 

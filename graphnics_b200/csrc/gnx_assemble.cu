@@ -55,8 +55,114 @@ mixed_values_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict_
   for (int32_t i = threadIdx.x; i < len; i += ASM_T) vals[base + i] = stage[i];
 }
 
+// ------------------------------------------------------------------------------------
+// Edge-tile value kernel (m <= 1024): a block owns TILE = 256*CPT cells = TILE/m whole edges.
+// A thread computes the q-rows of CPT consecutive positions along the edge (neighbour cells,
+// orientation and coefficients are per-thread, not per-row, work), ranks the <= 6 entries of each
+// row without local arrays and drops them into the block's contiguous CSR range in shared memory;
+// the range and the p-rows (pure sign patterns) are then streamed out with coalesced stores.
+// ------------------------------------------------------------------------------------
+template <int CPT>
+__global__ void __launch_bounds__(ASM_T)
+mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
+                         const double* __restrict__ k_edge, double a_const, double sg, int32_t nb_tiles,
+                         double* __restrict__ vals) {
+  constexpr int TILE = ASM_T * CPT;
+  __shared__ double stage[5 * TILE + 3 * ASM_T];
+  if ((int32_t)blockIdx.x >= nb_tiles) {
+    const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ASM_T + threadIdx.x;
+    if (r < d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
+    return;
+  }
+  const int32_t m = d.m, n = net.n;
+  const int32_t G = TILE >> n;
+  const int32_t e0 = blockIdx.x * G;
+  const int32_t nE = min(G, net.E - e0);
+  const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + net.ebif_prefix[e0];
+  const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + net.ebif_prefix[e0 + nE];
+  const int32_t k0 = threadIdx.x * CPT;
+  const int32_t le = k0 >> n;
+  if (le < nE) {
+    const int32_t e = e0 + le;
+    const int32_t t0 = k0 & (m - 1);
+    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+    const bool flip = u > v;
+    const int32_t blo = net.bix[flip ? v : u], bhi = net.bix[flip ? u : v];
+    const double a = a_edge ? a_edge[e] : a_const;
+    const double kk = k_edge ? k_edge[e] : 0.0;
+    const double sgn = flip ? -sg : sg;
+    const double* he = net.h + (int64_t)e * m;
+    const int32_t lm = __ldg(net.loc + m);
+    const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base);
+    const int32_t tlast = (t0 + CPT == m) ? m : t0 + CPT - 1;      // the edge's last thread also owns node m
+    double hl = t0 > 0 ? he[flip ? m - t0 : t0 - 1] : 0.0;         // lo-frame cell t-1
+    int32_t ll = t0 > 0 ? __ldg(net.loc + t0 - 1) : 0, lc = __ldg(net.loc + t0);
+    for (int32_t t = t0; t <= tlast; ++t) {
+      const bool hasl = t > 0, hasr = t < m;
+      const double hr = hasr ? he[flip ? m - 1 - t : t] : 0.0;     // lo-frame cell t
+      const int32_t lr = hasr ? __ldg(net.loc + t + 1) : 0;
+      const int32_t off = ebase + 5 * lc - (lc > 0 ? 2 - (blo >= 0) : 0) - (lc > lm ? 2 - (bhi >= 0) : 0);
+      double diag = 0.0;
+      const int32_t nq = 1 + hasl + hasr;
+      if (hasl) {
+        diag += a * hl * (2.0 / 6.0) + kk / hl;
+        stage[off + (ll > lc) + (hasr && ll > lr)] = a * hl * (1.0 / 6.0) - kk / hl;
+      }
+      if (hasr) {
+        diag += a * hr * (2.0 / 6.0) + kk / hr;
+        stage[off + (lr > lc) + (hasl && lr > ll)] = a * hr * (1.0 / 6.0) - kk / hr;
+      }
+      stage[off + (hasl && lc > ll) + (hasr && lc > lr)] = diag;
+      // p columns: cell t-1 (coefficient -sgn) and cell t (+sgn), ordered by their Gray index
+      const bool swp = hasl && hasr && gnx_gray(t - 1) > gnx_gray(t);
+      if (hasl) stage[off + nq + (swp ? 1 : 0)] = -sgn;
+      if (hasr) stage[off + nq + ((hasl && !swp) ? 1 : 0)] = sgn;
+      // lambda column at a bifurcation end: +sigma if the edge points INTO the node
+      if (t == 0 && blo >= 0) stage[off + nq + 1] = flip ? sg : -sg;
+      if (t == m && bhi >= 0) stage[off + nq + 1] = flip ? -sg : sg;
+      hl = hr; ll = lc; lc = lr;
+    }
+  }
+  __syncthreads();
+  const int32_t len = (int32_t)(end - base);
+  for (int32_t i = threadIdx.x; i < len; i += ASM_T) vals[base + i] = stage[i];
+  // p-rows of the tile's cells: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal
+  const int64_t c0 = (int64_t)e0 * m;
+  const int32_t ncell = nE * m;
+  double* vp = vals + d.p_nnz_off + 3 * c0;
+  for (int32_t i = threadIdx.x; i < 3 * ncell; i += ASM_T) {
+    const int32_t c = i / 3, j = i - 3 * c;
+    double val = 0.0;
+    if (j < 2) {
+      const int32_t e = e0 + (c >> n);
+      const bool flip = net.edges[2 * e] > net.edges[2 * e + 1];
+      const int32_t s = gnx_inv_gray(c & (m - 1));
+      const bool up = __ldg(net.loc + s) < __ldg(net.loc + s + 1);   // lower position has the lower dof number
+      const double sgn = flip ? -sg : sg;
+      val = ((j == 0) == up) ? -sgn : sgn;
+    }
+    vp[i] = val;
+  }
+}
+
+template <int CPT>
+static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
+                               const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+  const int G = (ASM_T * CPT) >> net->n;
+  const int nb_tiles = gnx_blocks(net->E, G);
+  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
+  mixed_values_tile_kernel<CPT><<<nb_tiles + nb_lam, ASM_T, 0, st>>>(*net, d, a_edge, k_edge, a_const, sg, nb_tiles, vals);
+}
+
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                          const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+  if (net->n <= 10) {
+    if (net->n == 0) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else if (net->n == 1) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else launch_values_tile<4>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    GNX_LAUNCH_CHECK();
+    return GNX_OK;
+  }
   const int nb_qp = gnx_blocks(d.lam_off, ASM_T);
   const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
   mixed_values_kernel<<<nb_qp + nb_lam, ASM_T, 0, st>>>(*net, d, a_edge, k_edge, a_const, sg, nb_qp, vals);

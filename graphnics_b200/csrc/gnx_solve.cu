@@ -90,14 +90,123 @@ edge_eliminate_kernel(gnx_network_t net, GnxMixedDims d, const double* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Edge-tile kernels (m <= 1024): a block owns TILE = 256*CPT cells = TILE/m whole edges.  The
+// three contiguous global ranges of the tile (p-block of b, q-block of b, cell lengths) are
+// streamed into shared memory with coalesced loads -- that is where all the memory-level
+// parallelism comes from -- and every permuted access (Gray-code cell order, first-encounter
+// vertex order, edge orientation) happens in shared memory.  A thread owns CPT consecutive cells:
+// serial prefix in registers + block-segmented scan of the thread totals.
+// ------------------------------------------------------------------------------------
+constexpr int ET_T = 256;
+
+struct TileCtx {
+  int32_t e0, nE, le, e, kk0, m;
+  bool active, flip;
+  int64_t pbase, qbase, hbase;
+};
+
+template <int CPT>
+__device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxMixedDims& d) {
+  constexpr int TILE = ET_T * CPT;
+  TileCtx c;
+  c.m = d.m;
+  const int32_t G = TILE >> net.n;
+  c.e0 = blockIdx.x * G;
+  c.nE = min(G, net.E - c.e0);
+  const int32_t k0 = threadIdx.x * CPT;
+  int32_t le = k0 >> net.n;
+  c.active = le < c.nE;
+  c.le = c.active ? le : c.nE - 1;
+  c.e = c.e0 + c.le;
+  c.kk0 = k0 & (c.m - 1);
+  c.flip = net.edges[2 * c.e] > net.edges[2 * c.e + 1];
+  c.pbase = d.p_off + (int64_t)c.e0 * c.m;
+  c.hbase = (int64_t)c.e0 * c.m;
+  c.qbase = (int64_t)c.e0 * (c.m + 1);
+  return c;
+}
+
+template <int CPT>
+__device__ __forceinline__ void tile_load(const TileCtx& c, const double* __restrict__ b,
+                                          const double* __restrict__ h, double* sF, double* sH, double* sG) {
+  const int32_t ncell = c.nE * c.m, nq = c.nE * (c.m + 1);
+#pragma unroll
+  for (int r = 0; r < CPT; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < ncell) { sF[i] = b[c.pbase + i]; sH[i] = h[c.hbase + i]; }
+  }
+#pragma unroll
+  for (int r = 0; r < CPT + 1; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < nq) sG[i] = b[c.qbase + i];
+  }
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(ET_T)
+edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
+                           double inv_sigma, const double* __restrict__ b,
+                           double* __restrict__ cond, double* __restrict__ rsrc, double* __restrict__ ftot) {
+  constexpr int TILE = ET_T * CPT;
+  __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
+  __shared__ double sh[3 * 32];
+  const TileCtx c = tile_ctx<CPT>(net, d);
+  tile_load<CPT>(c, b, net.h, sF, sH, sG);
+  __syncthreads();
+  const int32_t m = c.m;
+  const int32_t cb = c.le * m, qb = c.le * (m + 1);
+  double F[CPT], H[CPT];
+  double sumF = 0.0, sumG = 0.0, sumH = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int32_t kk = c.kk0 + i;
+    F[i] = c.active ? sF[cb + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
+    H[i] = sH[cb + kk];
+    sumG += sG[qb + __ldg(net.loc + (c.flip ? m - kk : kk))];
+    sumF += F[i];
+    sumH += H[i];
+  }
+  if (c.kk0 + CPT == m) sumG += sG[qb + __ldg(net.loc + (c.flip ? 0 : m))];
+  const int segT = m / CPT;
+  double tot;
+  const double incl = gnx_seg_incl_scan(sumF, segT, sh, &tot);
+  double cum = incl - sumF;                       // cumF at the first cell of this thread
+  double s2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) { s2 += H[i] * (cum + cum + F[i]) * 0.5; cum += F[i]; }
+  double acc[3] = {s2, sumG, sumH};
+  gnx_seg_sum<3>(acc, segT, sh);
+  if (c.active && c.kk0 == 0) {
+    const double a = a_edge[c.e];
+    cond[c.e] = 1.0 / (a * acc[2]);
+    rsrc[c.e] = acc[1] - a * acc[0];
+    ftot[c.e] = tot;
+  }
+}
+
+template <int CPT>
+static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
+                                  const double* b, double* cond, double* rsrc, double* ftot, cudaStream_t st) {
+  const int G = (ET_T * CPT) >> net->n;
+  edge_eliminate_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
+      *net, d, co->a_edge, 1.0 / co->sigma, b, cond, rsrc, ftot);
+}
+
 extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                                         const double* b, double* cond, double* rsrc, double* ftot,
                                         void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && cond && rsrc && ftot && net->h && co->sigma != 0.0);
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  const EdgeTiling t = edge_tiling(net->n);
-  edge_eliminate_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, (cudaStream_t)stream>>>(
-      *net, d, co->a_edge, 1.0 / co->sigma, b, t.seg, cond, rsrc, ftot);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, cond, rsrc, ftot, st);
+  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, cond, rsrc, ftot, st);
+  else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, cond, rsrc, ftot, st);
+  else {
+    const EdgeTiling t = edge_tiling(net->n);
+    edge_eliminate_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
+        *net, d, co->a_edge, 1.0 / co->sigma, b, t.seg, cond, rsrc, ftot);
+  }
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
@@ -216,8 +325,82 @@ __device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const* pa
   block_allreduce<K>(v, sh);
 }
 
+// The TOP part of the rake (levels >= l_split, <= GNX_TOP_MAX nodes) swept by ONE CTA: a thread
+// owns up to TOP_ROWS nodes, all plan data are fetched up front (independent loads), the running
+// diagonal / rhs / link weight live in shared memory, and a level costs one block barrier instead
+// of a chain of dependent global loads.  Children below the top part are final in global memory.
+constexpr int TOP_ROWS = GNX_TOP_MAX / SCH_T;
+constexpr size_t SCH_SMEM = 3 * GNX_TOP_MAX * sizeof(double);
+
+__device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double* sr, double* sw) {
+  const gnx_schur_plan_t& pl = a.plan;
+  const int tid = threadIdx.x;
+  int32_t node[TOP_ROWS], lev[TOP_ROWS], ptop[TOP_ROWS], k0[TOP_ROWS], k1[TOP_ROWS];
+  double d[TOP_ROWS], r[TOP_ROWS], w[TOP_ROWS];
+#pragma unroll
+  for (int q = 0; q < TOP_ROWS; ++q) {
+    const int32_t ti = tid + q * SCH_T;
+    lev[q] = -1; node[q] = 0; ptop[q] = -1; k0[q] = k1[q] = 0; d[q] = 1.0; r[q] = 0.0; w[q] = 0.0;
+    if (ti < pl.nt) {
+      const int32_t i = pl.top_nodes[ti];
+      node[q] = i;
+      lev[q] = pl.level_of[i];
+      const int32_t par = pl.parent[i];
+      if (par >= 0) { ptop[q] = pl.top_of[par]; w[q] = -a.cond[pl.pedge[i]]; }
+      k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
+      double di = __ldcg(a.d + i), ri = __ldcg(a.r + i);
+      for (int32_t k = k0[q]; k < k1[q]; ++k) {             // children below the top part: final
+        const int32_t c = pl.ch_idx[k];
+        if (pl.top_of[c] < 0) {
+          const double wc = -a.cond[pl.pedge[c]];
+          const double t = wc / __ldcg(a.d + c);
+          di -= wc * t;
+          ri -= t * __ldcg(a.r + c);
+        }
+      }
+      d[q] = di; r[q] = ri;
+      sd[ti] = di; sr[ti] = ri; sw[ti] = w[q];
+    }
+  }
+  __syncthreads();
+  for (int l = pl.l_split + 1; l < pl.nl; ++l) {            // up: level l_split has no top children
+#pragma unroll
+    for (int q = 0; q < TOP_ROWS; ++q) {
+      if (lev[q] == l) {
+        for (int32_t k = k0[q]; k < k1[q]; ++k) {
+          const int32_t tc = pl.top_of[pl.ch_idx[k]];      // L1 hits: fetched in the prologue
+          if (tc >= 0) {
+            const double wc = sw[tc];
+            const double t = wc / sd[tc];
+            d[q] -= wc * t;
+            r[q] -= t * sr[tc];
+          }
+        }
+        const int32_t ti = tid + q * SCH_T;
+        sd[ti] = d[q]; sr[ti] = r[q];
+      }
+    }
+    __syncthreads();
+  }
+  for (int l = pl.nl - 1; l >= pl.l_split; --l) {           // down: sr[] turns into the solution
+#pragma unroll
+    for (int q = 0; q < TOP_ROWS; ++q) {
+      if (lev[q] == l) {
+        double ri = r[q];
+        if (ptop[q] >= 0) ri -= w[q] * sr[ptop[q]];
+        const double xi = ri / d[q];
+        sr[tid + q * SCH_T] = xi;
+        a.P[node[q]] = xi;
+        if (a.lam_out) a.lam_out[node[q]] = xi * a.inv_sigma;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <bool SINGLE>
 __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
+  extern __shared__ double top_sh[];             // 3 * GNX_TOP_MAX doubles (dynamic, opt-in > 48 KB)
   __shared__ double red[2][3 * 32];
   const gnx_network_t& net = a.net;
   const gnx_schur_plan_t& pl = a.plan;
@@ -272,18 +455,13 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
   gsync();
 
   // ---- phase 1: rake up (level 0 has no children by construction)
-  const int ls = pl.l_split < 1 ? 1 : pl.l_split;
   for (int l = 1; l < pl.l_split; ++l) { up(l, t0, stride); gsync(); }
   double rr_final = 0.0, bb_final = 0.0;
   int it = 0;
   if (pl.nc == 0) {
-    if (blockIdx.x == 0) {                       // small levels: one CTA, block barriers only
-      for (int l = ls; l < pl.nl; ++l) { up(l, threadIdx.x, blockDim.x); __syncthreads(); }
-      for (int l = pl.nl - 1; l >= pl.l_split; --l) { down(l, threadIdx.x, blockDim.x); __syncthreads(); }
-    }
+    if (blockIdx.x == 0 && pl.nt > 0) top_solve(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
     if (pl.l_split > 0) gsync();
-  } else {
-    for (int l = ls; l < pl.nl; ++l) { up(l, t0, stride); gsync(); }
+  } else {                                       // a core exists: l_split == nl, no top part
     // ---- phase 2: Jacobi-PCG on the core
     double acc[3] = {0.0, 0.0, 0.0};
     for (int32_t i = t0; i < pl.nc; i += stride) {
@@ -356,9 +534,8 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
       if (a.lam_out) a.lam_out[node] = xi * a.inv_sigma;
     }
     if (pl.nl > 0) gsync();
-    // ---- phase 3 (part): rake down through the small levels
-    for (int l = pl.nl - 1; l >= pl.l_split; --l) { down(l, t0, stride); if (l > 0) gsync(); }
   }
+  // ---- phase 3: rake down
   for (int l = pl.l_split - 1; l >= 0; --l) { down(l, t0, stride); if (l > 0) gsync(); }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double tol2 = a.rtol * a.rtol * bb_final;
@@ -380,6 +557,9 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
   GNX_CHECK_ARG(plan->B == net->B && plan->B > 0 && plan->nl >= 0 && plan->nl <= GNX_MAX_LEVELS);
   GNX_CHECK_ARG(plan->l_split >= 0 && plan->l_split <= plan->nl && plan->nc >= 0 && plan->nc <= plan->B);
+  GNX_CHECK_ARG(plan->nt >= 0 && plan->nt <= GNX_TOP_MAX && (plan->nc == 0 || plan->l_split == plan->nl));
+  GNX_CHECK_ARG(plan->nt == 0 || (plan->top_nodes && plan->top_of && plan->level_of));
+  GNX_CHECK_ARG(plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
   GNX_CHECK_ARG(plan->nl == 0 || (plan->lvl_nodes && plan->parent && plan->pedge && plan->ch_ptr && plan->ch_idx));
   GNX_CHECK_ARG(plan->nc == 0 || (plan->core_nodes && plan->crp && plan->ccol && plan->cedge && plan->ch_ptr));
   cudaStream_t st = (cudaStream_t)stream;
@@ -388,7 +568,9 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
     GNX_CUDA(cudaGetDevice(&dev));
     GNX_CUDA(cudaDeviceGetAttribute(&g_sch_sms, cudaDevAttrMultiProcessorCount, dev));
     GNX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    GNX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_solve_kernel<false>, SCH_T, 0));
+    GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
+    GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
+    GNX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_solve_kernel<false>, SCH_T, SCH_SMEM));
     if (!coop || per_sm < 1) { gnx_set_error("cooperative launch unsupported on this device"); return GNX_ERR_CUDA; }
     g_sch_blocks_per_sm = per_sm;
   }
@@ -406,18 +588,17 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   a.scal = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   // grid: enough threads for the widest phase, capped by co-residency
-  int64_t widest = B;
-  int want = (int)((widest + SCH_T - 1) / SCH_T);
+  int want = (int)((B + SCH_T - 1) / SCH_T);
   const int cap = g_sch_sms * g_sch_blocks_per_sm;
   if (want > cap) want = cap;
   if (want > 2048) want = 2048;
   if (want <= 2) {
-    schur_solve_kernel<true><<<1, SCH_T, 0, st>>>(a);
+    schur_solve_kernel<true><<<1, SCH_T, SCH_SMEM, st>>>(a);
     GNX_LAUNCH_CHECK();
     want = 1;
   } else {
     void* args[] = {&a};
-    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<false>, dim3(want), dim3(SCH_T), args, 0, st));
+    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<false>, dim3(want), dim3(SCH_T), args, SCH_SMEM, st));
   }
   if (!resid_host && !info_host) return GNX_OK;              // fully asynchronous
   double scal[8];
@@ -485,16 +666,117 @@ edge_backsub_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict_
   if (active && gl == 0) x[f.qdof(net.loc, m)] = q0 + carryF;
 }
 
+template <int CPT>
+__global__ void __launch_bounds__(ET_T, 4)
+edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
+                         const double* __restrict__ k_edge, double inv_sigma, const double* __restrict__ b,
+                         const double* __restrict__ cond, const double* __restrict__ rsrc,
+                         const double* __restrict__ P, double* __restrict__ x) {
+  constexpr int TILE = ET_T * CPT;
+  __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
+  __shared__ double sh[32];
+  const TileCtx c = tile_ctx<CPT>(net, d);
+  tile_load<CPT>(c, b, net.h, sF, sH, sG);
+  const int32_t m = c.m;
+  const int32_t eu = net.edges[2 * c.e], ev = net.edges[2 * c.e + 1];
+  const int32_t bu = net.bix[eu], bv = net.bix[ev];
+  const double Pu = bu >= 0 ? P[bu] : 0.0;
+  const double Pv = bv >= 0 ? P[bv] : 0.0;
+  const double a = a_edge[c.e];
+  const double kv = k_edge ? k_edge[c.e] : 0.0;
+  const double q0 = cond[c.e] * (Pu - Pv + rsrc[c.e]);
+  __syncthreads();
+  const int32_t cb = c.le * m, qb = c.le * (m + 1);
+  int32_t ps[CPT], qs[CPT];                        // shared-memory slots of my p / q dofs
+  double F[CPT], H[CPT], Gq[CPT];
+  double sumF = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int32_t kk = c.kk0 + i;
+    ps[i] = cb + gnx_gray(c.flip ? m - 1 - kk : kk);
+    qs[i] = qb + __ldg(net.loc + (c.flip ? m - kk : kk));
+    F[i] = c.active ? sF[ps[i]] * inv_sigma : 0.0;
+    H[i] = sH[cb + kk];
+    Gq[i] = c.active ? sG[qs[i]] : 0.0;
+    sumF += F[i];
+  }
+  double Fl = 0.0, Hl = 1.0;                       // cell left of my first node
+  if (c.kk0 > 0) {
+    const int32_t kl = c.kk0 - 1;
+    Fl = c.active ? sF[cb + gnx_gray(c.flip ? m - 1 - kl : kl)] * inv_sigma : 0.0;
+    Hl = sH[cb + kl];
+  }
+  const int segT = m / CPT;
+  double totF, totD;
+  const double inclF = gnx_seg_incl_scan(sumF, segT, sh, &totF);
+  double cum = inclF - sumF;
+  double q[CPT], D[CPT];
+  double sumD = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    q[i] = q0 + cum;
+    double mq = a * H[i] * (3.0 * q[i] + F[i]) * (1.0 / 6.0);                      // h_j (2 q_j + q_{j+1})/6
+    const bool has_left = (i > 0) || (c.kk0 > 0);
+    const double fl = i > 0 ? F[i - 1] : Fl, hl = i > 0 ? H[i - 1] : Hl;
+    if (has_left) mq += a * hl * (3.0 * q[i] - fl) * (1.0 / 6.0);                  // h_{j-1}(q_{j-1} + 2 q_j)/6
+    if (kv != 0.0) {                                                               // stiffness (NetworkStokes)
+      mq -= kv * F[i] / H[i];
+      if (has_left) mq += kv * fl / hl;
+    }
+    D[i] = Gq[i] - mq;
+    sumD += D[i];
+    cum += F[i];
+  }
+  const double inclD = gnx_seg_incl_scan(sumD, segT, sh, &totD);
+  double cd = Pu + (inclD - sumD);
+  __syncthreads();                                  // every read of sF / sG is done: reuse them for x
+  if (c.active) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      cd += D[i];
+      sG[qs[i]] = q[i];
+      sF[ps[i]] = cd * inv_sigma;
+    }
+    if (c.kk0 + CPT == m) sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = q0 + totF;
+  }
+  __syncthreads();
+  const int32_t ncell = c.nE * m, nq = c.nE * (m + 1);
+#pragma unroll
+  for (int r = 0; r < CPT; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < ncell) x[c.pbase + i] = sF[i];
+  }
+#pragma unroll
+  for (int r = 0; r < CPT + 1; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < nq) x[c.qbase + i] = sG[i];
+  }
+}
+
+template <int CPT>
+static void launch_backsub_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
+                                const double* b, const double* cond, const double* rsrc, const double* P,
+                                double* x, cudaStream_t st) {
+  const int G = (ET_T * CPT) >> net->n;
+  edge_backsub_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
+      *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+}
+
 extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                                       const double* b, const double* cond, const double* rsrc,
                                       const double* P, double* x, void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && cond && rsrc && x && net->h && co->sigma != 0.0);
   GNX_CHECK_ARG(net->B == 0 || P);
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  const EdgeTiling t = edge_tiling(net->n);
   cudaStream_t st = (cudaStream_t)stream;
-  edge_backsub_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
-      *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, t.seg, x);
+  if (net->n == 0) launch_backsub_tile<1>(net, d, co, b, cond, rsrc, P, x, st);
+  else if (net->n == 1) launch_backsub_tile<2>(net, d, co, b, cond, rsrc, P, x, st);
+  else if (net->n <= 10) launch_backsub_tile<4>(net, d, co, b, cond, rsrc, P, x, st);
+  else {
+    const EdgeTiling t = edge_tiling(net->n);
+    edge_backsub_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
+        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, t.seg, x);
+  }
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }

@@ -220,12 +220,15 @@ class MixedSystem:
             keep = {}
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
             s = _lib.gnx_schur_plan_t()
-            s.B, s.nl, s.l_split, s.nc, s.nnzc = dn.B, len(hp.levels), hp.split_level(), hp.nc, hp.nnzc
+            l_split = hp.split_level(_lib.TOP_MAX) if hp.nc == 0 else len(hp.levels)
+            top, top_of, level_of = hp.top_arrays(l_split)
+            s.B, s.nl, s.l_split, s.nc, s.nnzc, s.nt = dn.B, len(hp.levels), l_split, hp.nc, hp.nnzc, len(top)
             for i, v in enumerate(lvl_ptr):
                 s.lvl_ptr[i] = int(v)
             for name, arr in (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
-                              ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge)):
+                              ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),
+                              ("top_nodes", top), ("top_of", top_of), ("level_of", level_of)):
                 t = dev(arr if len(arr) else np.zeros(1, dtype=np.int32))
                 keep[name] = t
                 setattr(s, name, t.data_ptr())

@@ -127,13 +127,26 @@ class SchurPlan:
         nodes = np.concatenate(self.levels).astype(np.int32) if self.levels else np.zeros(0, dtype=np.int32)
         return lvl_ptr, nodes
 
-    def split_level(self, small=2048):
-        """first level from which every later level has <= `small` nodes (handled by one CTA)"""
+    def split_level(self, top_max=2048):
+        """first level of the TOP part: the last levels, holding <= top_max nodes in total, are
+        swept by one CTA out of shared memory (dependent global loads cost ~1 us per level)"""
         sizes = [len(l) for l in self.levels]
-        l = len(sizes)
-        while l > 0 and sizes[l - 1] <= small:
+        l, tot = len(sizes), 0
+        while l > 0 and tot + sizes[l - 1] <= top_max:
+            tot += sizes[l - 1]
             l -= 1
         return l
+
+    def top_arrays(self, l_split):
+        """(top_nodes [nt], top_of [B], level_of [B]) for the levels >= l_split"""
+        level_of = np.full(self.B, len(self.levels), dtype=np.int32)
+        for l, nodes in enumerate(self.levels):
+            level_of[nodes] = l
+        top = np.concatenate(self.levels[l_split:]).astype(np.int32) if self.levels[l_split:] \
+            else np.zeros(0, dtype=np.int32)
+        top_of = -np.ones(self.B, dtype=np.int32)
+        top_of[top] = np.arange(len(top), dtype=np.int32)
+        return top, top_of, level_of
 
     # numpy model of the device algorithm (used by the CPU tests to pin the algebra)
     def solve_host(self, cond, diag, rhs, core_solver=None):

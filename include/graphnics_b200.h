@@ -209,9 +209,11 @@ int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, 
  * cyclic core that is left is solved by Jacobi-PCG.  All pointers are device pointers, indices are
  * bifurcation indices unless stated. */
 #define GNX_MAX_LEVELS 64
+#define GNX_TOP_MAX 2048
 typedef struct gnx_schur_plan {
-  int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level swept by one CTA, core size */
-  int32_t nnzc, reserved;              /* off-diagonal entries of the core matrix */
+  int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level of the TOP part, core size */
+  int32_t nnzc, nt;                    /* off-diagonal entries of the core matrix; #nodes in levels >= l_split
+                                          (<= GNX_TOP_MAX: swept by one CTA out of shared memory) */
   int32_t lvl_ptr[GNX_MAX_LEVELS + 1]; /* level l = lvl_nodes[lvl_ptr[l] .. lvl_ptr[l+1]) */
   const int32_t* lvl_nodes;            /* [lvl_ptr[nl]] */
   const int32_t* parent;               /* [B] node a raked node folds into, -1 = none */
@@ -222,6 +224,9 @@ typedef struct gnx_schur_plan {
   const int32_t* crp;                  /* [nc+1] core matrix rows (CSR, core-local columns) */
   const int32_t* ccol;                 /* [nnzc] */
   const int32_t* cedge;                /* [nnzc] graph edge whose -cond is the entry */
+  const int32_t* top_nodes;            /* [nt] nodes of the top part */
+  const int32_t* top_of;               /* [B] position in top_nodes, or -1 */
+  const int32_t* level_of;             /* [B] rake level of a node (nl for core nodes) */
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative
