@@ -57,6 +57,13 @@ _NET = C.POINTER(gnx_network_t)
 _CO = C.POINTER(gnx_mixed_coeffs_t)
 _PLAN = C.POINTER(gnx_schur_plan_t)
 
+
+class gnx_primal_coeffs_t(C.Structure):
+    _fields_ = [("a_const", C.c_double), ("a_cell", C.c_void_p), ("sigma", C.c_double)]
+
+
+_PCO = C.POINTER(gnx_primal_coeffs_t)
+
 # name -> (restype, argtypes); every symbol of include/graphnics_b200.h
 PROTOTYPES = {
     "gnx_last_error": (C.c_char_p, []),
@@ -79,7 +86,16 @@ PROTOTYPES = {
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
-    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
+    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
+    "gnx_primal_ndofs": (_L, [_NET]),
+    "gnx_primal_nnz": (_L, [_NET]),
+    "gnx_build_pattern_primal": (_I, [_NET, _P, _P, _P]),
+    "gnx_assemble_primal": (_I, [_NET, _PCO, _P, _P]),
+    "gnx_assemble_rhs_primal": (_I, [_NET, _P, _P, _I, _D, _P, _I, _D, _P, _P]),
+    "gnx_mass_apply_q_primal": (_I, [_NET, _PCO, _P, _P, _P]),
+    "gnx_apply_bc_primal": (_I, [_NET, _D, _P, _P, _P, _P]),
+    "gnx_edge_eliminate_primal": (_I, [_NET, _PCO, _P, _P, _P, _P, _P]),
+    "gnx_edge_backsub_primal": (_I, [_NET, _PCO, _P, _P, _P, _P, _P, _P]),
     "gnx_edge_backsub_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P, _P]),
     "gnx_spmv_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "gnx_reduce_work_doubles": (_L, [_L]),

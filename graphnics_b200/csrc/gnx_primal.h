@@ -43,7 +43,8 @@ GNX_HD int64_t gnx_cell_of(int32_t m, int32_t e, int32_t s) { return (int64_t)e 
 
 template <int MODE>
 GNX_HD void gnx_primal_row_emit(const gnx_network_t& net, const GnxPrimalDims& d, int64_t r,
-                                double a_const, double sg, int32_t* rowptr, int32_t* colidx, double* vals) {
+                                double a_const, const double* a_cell, double sg, int32_t* rowptr,
+                                int32_t* colidx, double* vals) {
   const int32_t m = d.m, n = net.n;
   if (r < d.NC) {                                            // ---- q-row of cell c
     const int32_t e = (int32_t)(r >> n);
@@ -61,7 +62,8 @@ GNX_HD void gnx_primal_row_emit(const gnx_network_t& net, const GnxPrimalDims& d
       rowptr[r] = (int32_t)st;
       colidx[st] = (int32_t)r; colidx[st + 1] = (int32_t)(d.p_off + c0); colidx[st + 2] = (int32_t)(d.p_off + c1);
     } else {
-      vals[st] = a_const * net.h[(int64_t)e * m + (flip ? m - 1 - s : s)];
+      const int64_t kl = (int64_t)e * m + (flip ? m - 1 - s : s);      // edge-local (u -> v) cell slot
+      vals[st] = (a_cell ? a_cell[kl] : a_const) * net.h[kl];
       vals[st + 1] = v0; vals[st + 2] = v1;
     }
   } else {
@@ -103,11 +105,13 @@ GNX_HD void gnx_primal_row_emit(const gnx_network_t& net, const GnxPrimalDims& d
 }
 
 // HydraulicNetwork.L_form (flow_models.py:94-101): L0 = g v dx (per cell), L1 = f phi dx (per vertex).
-// g/f given at vertices [NV] and cell midpoints [NC] (NULL -> constants gc / fc; *_mid NULL ->
-// degree <= 1 data, midpoint = average).
+// g/f are given CELL-WISE as triples (value at the cell's first stored vertex, at the midpoint, at
+// the second stored vertex) -- this also covers data that jump between edges (UserExpression with
+// eval_cell); NULL -> the constants gc / fc.  *_lin != 0: degree <= 1 data, FEniCS integrates the
+// linear interpolant, i.e. midpoint value = average of the ends.
 GNX_HD double gnx_primal_rhs_row(const gnx_network_t& net, const GnxPrimalDims& d, const int32_t* cells,
-                                 int64_t r, const double* f_vert, const double* f_mid, double fc,
-                                 const double* g_vert, const double* g_mid, double gc) {
+                                 int64_t r, const double* f_cell, int f_lin, double fc,
+                                 const double* g_cell, int g_lin, double gc) {
   const int32_t m = d.m, n = net.n;
   auto hcell = [&](int64_t c) {
     const int32_t e = (int32_t)(c >> n);
@@ -117,20 +121,19 @@ GNX_HD double gnx_primal_rhs_row(const gnx_network_t& net, const GnxPrimalDims& 
   };
   if (r < d.NC) {
     const double h = hcell(r);
-    if (!g_vert) return gc * h;
-    const double ga = g_vert[cells[2 * r]], gb = g_vert[cells[2 * r + 1]];
-    const double gm = g_mid ? g_mid[r] : 0.5 * (ga + gb);
+    if (!g_cell) return gc * h;
+    const double ga = g_cell[3 * r], gb = g_cell[3 * r + 2];
+    const double gm = g_lin ? 0.5 * (ga + gb) : g_cell[3 * r + 1];
     return h * (ga + 4.0 * gm + gb) * (1.0 / 6.0);
   }
   const int32_t w = (int32_t)(r - d.NC);
-  if (!f_vert && fc == 0.0) return 0.0;
+  if (!f_cell && fc == 0.0) return 0.0;
   auto load = [&](int64_t c) {                     // int f_I phi_w over cell c (w one of its vertices)
     const double h = hcell(c);
-    if (!f_vert) return fc * h * 0.5;
-    const int32_t va = cells[2 * c], vb = cells[2 * c + 1];
-    const double fa = f_vert[va], fb = f_vert[vb];
-    const double fm = f_mid ? f_mid[c] : 0.5 * (fa + fb);
-    const double fw = (va == w) ? fa : fb;
+    if (!f_cell) return fc * h * 0.5;
+    const double fa = f_cell[3 * c], fb = f_cell[3 * c + 2];
+    const double fm = f_lin ? 0.5 * (fa + fb) : f_cell[3 * c + 1];
+    const double fw = (cells[2 * c] == w) ? fa : fb;
     return h * (fw + 2.0 * fm) * (1.0 / 6.0);
   };
   double out = 0.0;

@@ -268,7 +268,7 @@ struct SchurArgs {
   gnx_network_t net;
   gnx_schur_plan_t plan;
   double inv_sigma;
-  const double *cond, *rsrc, *ftot, *b_lam;
+  const double *cond, *rsrc, *ftot, *b_lam, *b_node;
   double *P, *lam_out;
   double *d, *r;                              // [B]
   double *xc, *rc, *zc, *wc, *p0, *p1, *dg;   // [nc]
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
   // ---- phase 0: Schur diagonal and right-hand side (one thread per bifurcation, gather)
   for (int32_t bi = t0; bi < pl.B; bi += stride) {
     const int32_t node = net.bif_nodes[bi];
-    double diag = 0.0, rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : 0.0;
+    double diag = 0.0, rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : (a.b_node ? a.b_node[node] * a.inv_sigma : 0.0);
     for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
       const int32_t code = net.inc_edge[k];
       const int32_t e = code >> 1, end = code & 1;
@@ -551,7 +551,7 @@ static int g_sch_blocks_per_sm = -1, g_sch_sms = 0;
 // info_host[3] = {CG iterations, converged, grid blocks}.  Asynchronous when both are NULL.
 extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                                const double* cond, const double* rsrc, const double* ftot,
-                               const double* b_lam, double* P, double* lam_out, double* work,
+                               const double* b_lam, const double* b_node, double* P, double* lam_out, double* work,
                                double rtol, int32_t max_iter, int32_t warm, double* resid_host,
                                int32_t* info_host, void* stream) {
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
@@ -577,7 +577,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   SchurArgs a;
   a.net = *net; a.plan = *plan;
   a.inv_sigma = 1.0 / sigma;
-  a.cond = cond; a.rsrc = rsrc; a.ftot = ftot; a.b_lam = b_lam; a.P = P; a.lam_out = lam_out;
+  a.cond = cond; a.rsrc = rsrc; a.ftot = ftot; a.b_lam = b_lam; a.b_node = b_node; a.P = P; a.lam_out = lam_out;
   const int64_t B = plan->B, nc = plan->nc;
   double* w = work;
   a.d = w; w += B; a.r = w; w += B;

@@ -268,7 +268,7 @@ class MixedSystem:
             plan, _, work, _ = self.schur_plan()
             lam = x[dn.lam_off:]
             args = (dn.net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
-                    ptr(b[dn.lam_off:]), ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
+                    ptr(b[dn.lam_off:]), None, ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
                     1 if warm_start else 0)
             if sync:
                 resid = C.c_double(0.0)

@@ -176,17 +176,31 @@ class FenicsGraph(nx.DiGraph):
 
     # ---- helpers used by the models -------------------------------------------------------------
     def edge_attribute_array(self, key, default=1.0):
-        """[E] float array of a (constant-per-edge) attribute; Constants/floats accepted."""
-        out = np.empty(self.number_of_edges())
-        for i, e in enumerate(self.edges()):
-            v = self.edges[e].get(key, default)
-            if isinstance(v, UFLExpr):
-                if v.expr.free_symbols - set(v.params):
-                    raise NotImplementedError(
-                        f"edge attribute '{key}' varies along the edge; only per-edge constants are supported")
-                v = float(v.expr.subs({s: float(c) for s, c in v.params.items()}))
-            out[i] = float(v)
-        return out
+        """[E] float array of a (constant-per-edge) attribute; Constants / floats / constant UFL.
+        Objects shared by many edges (one `Constant` for the whole graph is the common case) are
+        converted once."""
+        # same order as self.edges(): by source node, then successor insertion order
+        vals = [d.get(key, default) for nbrs in self._succ.values() for d in nbrs.values()]
+        if vals and all(v is vals[0] for v in vals):                      # one shared object
+            vals, rep = vals[:1], len(vals)
+        else:
+            rep = 1
+        conv = {}
+        out = np.empty(len(vals))
+        for i, v in enumerate(vals):
+            k = id(v)
+            f = conv.get(k)
+            if f is None:
+                if isinstance(v, UFLExpr):
+                    if v.expr.free_symbols - set(v.params):
+                        raise NotImplementedError(
+                            f"edge attribute '{key}' varies along the edge; only per-edge constants are supported")
+                    f = float(v.expr.subs({s: float(c) for s, c in v.params.items()}))
+                else:
+                    f = float(v)
+                conv[k] = f
+            out[i] = f
+        return np.repeat(out, rep) if rep > 1 else out
 
 
 class GlobalFlux(UserExpression):

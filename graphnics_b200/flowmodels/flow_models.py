@@ -127,7 +127,7 @@ class _MassVectorForm:
     def assemble(self):
         ms = self.model._system()
         x = self.u.tensor() if isinstance(self.u, ii_Function) else self.u
-        return AssembledVector(ms, ms.spmv(ms.mass_vals(float(self.coeff)), x))
+        return AssembledVector(ms, ms.mass_apply(self.model._mass_coeff(self.coeff), x))
 
 
 class _MixedLForm:
@@ -266,8 +266,20 @@ class HydraulicNetwork:
     def _system(self):
         return _system(self.G, "primal")
 
+    def _cell_coeff(self, c):
+        """float for constants, else the per-cell mean (edge-local order) of a varying coefficient"""
+        cc = as_coefficient(c)
+        if cc.is_constant:
+            return float(cc.const_value())
+        return self._system().cell_average(cc)
+
+    _mass_coeff = _cell_coeff
+
     def _coeffs(self, sigma=1.0, mass=0.0):
-        return self._system().coeffs(mass + sigma * float(as_coefficient(self.Res).const_value()), sigma)
+        """operator  diag((mass + sigma*Res) h)  with couplings scaled by sigma"""
+        a = self._cell_coeff(self.Res)
+        mc = self._cell_coeff(mass) if not isinstance(mass, (int, float)) else float(mass)
+        return self._system().coeffs(mc + sigma * a, sigma)
 
     def a_form(self):
         from ..engine_primal import PrimalAForm

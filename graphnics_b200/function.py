@@ -95,14 +95,25 @@ class Vector:
         """call after writing to the underlying device memory"""
         self._store["version"] += 1
 
+    def _to_host(self):
+        """device -> PINNED host buffer (torch's caching host allocator) -> numpy view that owns it"""
+        t = self._t.detach()
+        if not t.is_cuda:
+            return t.numpy().copy()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
+
     def host_cached(self):
         if self._host is None or self._host_version != self._store["version"]:
-            self._host = self._t.detach().cpu().numpy().copy()
+            self._host = self._to_host()
             self._host_version = self._store["version"]
         return self._host
 
     def get_local(self):
-        return self.host_cached().copy()
+        """a fresh host copy (dolfin semantics: the caller owns it)"""
+        return self._to_host()
 
     def set_local(self, arr):
         self._t.copy_(torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self._t.device))

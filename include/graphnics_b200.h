@@ -234,6 +234,8 @@ typedef struct gnx_schur_plan {
  * phases per iteration, deterministic reductions, convergence decided on the device), rake
  * down-sweep.  Replaces ii_convert + LUSolver("mumps") (flow_models.py:344-348) together with
  * gnx_edge_eliminate_mixed / gnx_edge_backsub_mixed.
+ *   b_lam [B] (mixed model: lambda rows of b, enters as -b_lam/sigma) or b_node [V] (primal model:
+ *   p rows of b at the graph nodes, enters as +b_node/sigma); at most one of them non-NULL;
  *   P [B] out: sigma*lambda (in: initial guess of the core unknowns when warm != 0);
  *   lam_out [B] (may be NULL) = P / sigma, i.e. the lambda block of the solution vector;
  *   work [>= gnx_schur_work_doubles(plan)] doubles.
@@ -243,7 +245,7 @@ typedef struct gnx_schur_plan {
 int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan);
 int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                     const double* cond, const double* rsrc, const double* ftot, const double* b_lam,
-                    double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
+                    const double* b_node, double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
                     int32_t warm, double* resid_host, int32_t* info_host, void* stream);
 
 /* Phase 2: back-substitution, the q and p blocks of x [N] (dof order) from the multipliers P [B]
@@ -251,6 +253,43 @@ int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, doub
 int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                            const double* cond, const double* rsrc, const double* P, double* x,
                            void* stream);
+
+/* ---------------- primal model: HydraulicNetwork (flow_models.py:53-126) ---------------- */
+
+/* Operator  [ diag(a_c h_c)  s G ; -s G^T  0 ]  on  W = [DG0(mesh) | CG1(mesh)]  (q dof = global
+ * cell, p dof = NC + global vertex).  steady: a = Res (:87), s = 1; theta-scheme step:
+ * a = Ainv + theta*dt*Res, s = theta*dt (time_stepping.py:184).  a_cell (may be NULL -> a_const)
+ * is per cell in EDGE-LOCAL order (cell k of edge e at e*m + k, u -> v), like gnx_network_t.h. */
+typedef struct gnx_primal_coeffs {
+  double a_const;
+  const double* a_cell;
+  double sigma;
+} gnx_primal_coeffs_t;
+
+int64_t gnx_primal_ndofs(const gnx_network_t* net);
+int64_t gnx_primal_nnz(const gnx_network_t* net);
+/* a_form :79-91 after ii_assemble/ii_convert: closed-form CSR rows, sorted columns, explicit p diagonal */
+int gnx_build_pattern_primal(const gnx_network_t* net, int32_t* rowptr, int32_t* colidx, void* stream);
+int gnx_assemble_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, double* vals, void* stream);
+/* L_form :94-101.  f_cell / g_cell [NC*3]: the coefficient at (first stored vertex, midpoint, second
+ * stored vertex) of every cell, or NULL -> the constants; *_lin != 0: degree <= 1 data (midpoint :=
+ * average of the ends, what FEniCS integrates for a degree-1 Expression). */
+int gnx_assemble_rhs_primal(const gnx_network_t* net, const int32_t* cells, const double* f_cell,
+                            int32_t f_lin, double f_const, const double* g_cell, int32_t g_lin,
+                            double g_const, double* b, void* stream);
+/* y = diag(a_c h_c) x on the q rows, 0 on the p rows: mass_matrix_q / mass_vector_q (time_stepping.py:28-64) */
+int gnx_mass_apply_q_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, const double* x, double* y,
+                            void* stream);
+/* xii.apply_bc with DirichletBC(W[1], p_bc, "on_boundary") (:103-105,117): symmetric elimination of the
+ * degree-1 graph nodes.  bc_node [V] = p_bc at the graph nodes; vals and/or b may be NULL. */
+int gnx_apply_bc_primal(const gnx_network_t* net, double sigma, const double* bc_node, double* vals, double* b,
+                        void* stream);
+/* per-edge elimination / back-substitution of the primal system; b is the right-hand side AFTER
+ * gnx_apply_bc_primal.  Between the two: gnx_schur_solve(..., b_lam = NULL, b_node = b + NC, ...). */
+int gnx_edge_eliminate_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, const double* b,
+                              double* cond, double* rsrc, double* ftot, void* stream);
+int gnx_edge_backsub_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, const double* b,
+                            const double* cond, const double* rsrc, const double* P, double* x, void* stream);
 
 /* ---------------- Krylov building blocks ---------------- */
 

@@ -372,6 +372,15 @@ def apply_bc(A, b, dofs, vals):
     A.data[kill] = 0.0
     diag = kill & (rows == A.indices) & is_bc[rows]
     A.data[diag] = 1.0
+    # a caller's sum of blocks (time loop: D + theta*dt*A) may have pruned the explicit-zero p
+    # diagonal: insert the missing unit entries without touching the other explicit zeros
+    has_diag = np.zeros(N, dtype=bool)
+    has_diag[rows[diag]] = True
+    miss = np.asarray(dofs)[~has_diag[dofs]]
+    if len(miss):
+        A = sp.coo_matrix((np.concatenate([A.data, np.ones(len(miss))]),
+                           (np.concatenate([rows, miss]), np.concatenate([A.indices, miss]))), shape=A.shape).tocsr()
+        A.sort_indices()
     b[dofs] = vals
     return A, b
 

@@ -93,7 +93,7 @@ def hostcheck_lib():
     if _HC is None:
         src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
         out = os.path.join(HERE, "hostcheck", "libhostcheck.so")
-        hdrs = [os.path.join(ROOT, "graphnics_b200", "csrc", h) for h in ("gnx_index.h", "gnx_rpn.h")]
+        hdrs = [os.path.join(ROOT, "graphnics_b200", "csrc", h) for h in ("gnx_index.h", "gnx_rpn.h", "gnx_primal.h")]
         hdrs.append(os.path.join(ROOT, "include", "graphnics_b200.h"))
         if (not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs])):
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
@@ -101,6 +101,8 @@ def hostcheck_lib():
         _HC.hc_ndofs.restype = C.c_int64
         _HC.hc_nnz.restype = C.c_int64
         _HC.hc_rpn.restype = C.c_double
+        _HC.hc_primal_ndofs.restype = C.c_int64
+        _HC.hc_primal_nnz.restype = C.c_int64
     return _HC
 
 
@@ -165,6 +167,45 @@ class HostNet:
         vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
         hc.hc_rhs(C.byref(self.net), vp(arrs[0]), vp(arrs[1]), C.c_double(f_const), C.c_double(g_const),
                   vp(arrs[2]), vp(arrs[3]), vp(b))
+        return b
+
+    # ---- primal model ------------------------------------------------------------------------
+    def primal_pattern(self):
+        hc = hostcheck_lib()
+        N, nnz = int(hc.hc_primal_ndofs(C.byref(self.net))), int(hc.hc_primal_nnz(C.byref(self.net)))
+        rowptr = np.full(N + 1, -1, dtype=np.int32)
+        colidx = np.full(nnz, -1, dtype=np.int32)
+        hc.hc_primal_pattern(C.byref(self.net), rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p))
+        return rowptr, colidx
+
+    def cell_slot(self):
+        """global cell -> edge-local slot (order of `h` and of per-cell coefficients)"""
+        c = np.arange(self.E * self.m)
+        e, j = c >> self.n, c & (self.m - 1)
+        s = j.copy()
+        sh = 1
+        while sh < 64:
+            s ^= s >> sh
+            sh <<= 1
+        flip = (self.edges[:, 0] > self.edges[:, 1])[e]
+        return e * self.m + np.where(flip, self.m - 1 - s, s)
+
+    def primal_values(self, a_const=1.0, a_cell=None, sigma=1.0):
+        hc = hostcheck_lib()
+        vals = np.full(int(hc.hc_primal_nnz(C.byref(self.net))), np.nan)
+        a = None if a_cell is None else np.ascontiguousarray(a_cell, dtype=np.float64)
+        hc.hc_primal_values(C.byref(self.net), C.c_double(a_const), None if a is None else a.ctypes.data_as(C.c_void_p),
+                            C.c_double(sigma), vals.ctypes.data_as(C.c_void_p))
+        return vals
+
+    def primal_rhs(self, f_cell=None, f_lin=0, fc=0.0, g_cell=None, g_lin=0, gc=0.0):
+        hc = hostcheck_lib()
+        b = np.full(int(hc.hc_primal_ndofs(C.byref(self.net))), np.nan)
+        fa = None if f_cell is None else np.ascontiguousarray(f_cell, dtype=np.float64)
+        ga = None if g_cell is None else np.ascontiguousarray(g_cell, dtype=np.float64)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        hc.hc_primal_rhs(C.byref(self.net), vp(self.cells), vp(fa), int(f_lin), C.c_double(fc), vp(ga), int(g_lin),
+                         C.c_double(gc), vp(b))
         return b
 
     def end_values(self, nodal):

@@ -5,6 +5,7 @@
 #include <cmath>
 #include "../../graphnics_b200/csrc/gnx_index.h"
 #include "../../graphnics_b200/csrc/gnx_rpn.h"
+#include "../../graphnics_b200/csrc/gnx_primal.h"
 
 extern "C" {
 
@@ -52,6 +53,28 @@ void hc_rhs(const gnx_network_t* net, const double* f, const double* g, double f
 
 double hc_rpn(const gnx_program_t* prog, const double* x, int gd, const double* tau, double ea) {
   return gnx_rpn_eval(*prog, x, gd, tau, ea);
+}
+
+// ---- primal model (gnx_primal.h)
+int64_t hc_primal_ndofs(const gnx_network_t* net) { return gnx_primal_dims(*net).N; }
+int64_t hc_primal_nnz(const gnx_network_t* net) { return gnx_primal_dims(*net).nnz; }
+
+void hc_primal_pattern(const gnx_network_t* net, int32_t* rowptr, int32_t* colidx) {
+  const GnxPrimalDims d = gnx_primal_dims(*net);
+  for (int64_t r = 0; r < d.N; ++r)
+    gnx_primal_row_emit<GNX_MODE_PATTERN>(*net, d, r, 1.0, nullptr, 1.0, rowptr, colidx, nullptr);
+}
+
+void hc_primal_values(const gnx_network_t* net, double a_const, const double* a_cell, double sg, double* vals) {
+  const GnxPrimalDims d = gnx_primal_dims(*net);
+  for (int64_t r = 0; r < d.N; ++r)
+    gnx_primal_row_emit<GNX_MODE_VALUES>(*net, d, r, a_const, a_cell, sg, nullptr, nullptr, vals);
+}
+
+void hc_primal_rhs(const gnx_network_t* net, const int32_t* cells, const double* f_cell, int f_lin, double fc,
+                   const double* g_cell, int g_lin, double gc, double* b) {
+  const GnxPrimalDims d = gnx_primal_dims(*net);
+  for (int64_t r = 0; r < d.N; ++r) b[r] = gnx_primal_rhs_row(*net, d, cells, r, f_cell, f_lin, fc, g_cell, g_lin, gc);
 }
 
 int64_t hc_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }

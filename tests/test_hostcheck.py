@@ -101,6 +101,41 @@ def test_rhs(name, n):
     np.testing.assert_allclose(bh2, b2, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("name,n", CASES)
+def test_primal_pattern_values_rhs(name, n):
+    """HydraulicNetwork closed-form rows (gnx_primal.h) against the oracle's element-by-element assembly"""
+    pos, edges = graph(name)
+    om = oracle.build_mesh(pos, edges, n)
+    hn = HostNet(pos, edges, n)
+    rng = np.random.default_rng(2)
+    A = oracle.assemble_primal(om, 1.7)
+    rowptr, colidx = hn.primal_pattern()
+    assert np.array_equal(rowptr, A.indptr)
+    assert np.array_equal(colidx, A.indices)
+    np.testing.assert_allclose(hn.primal_values(a_const=1.7), A.data, rtol=1e-12, atol=1e-300)
+    # per-cell resistance (global cell order in the oracle, edge-local order in the kernels)
+    Rc = rng.uniform(0.5, 2.0, size=len(om.cells))
+    A2 = oracle.assemble_primal(om, Rc)
+    a_cell = np.empty_like(Rc)
+    a_cell[hn.cell_slot()] = Rc
+    np.testing.assert_allclose(hn.primal_values(a_cell=a_cell), A2.data, rtol=1e-12, atol=1e-300)
+    # mass matrix and a theta-scheme operator
+    D = oracle.assemble_mass_q_primal(om, 2.5)
+    Dg = sp.csr_matrix((hn.primal_values(a_const=2.5, sigma=0.0), colidx, rowptr), shape=A.shape)
+    assert abs(Dg - D).max() <= 1e-12 * abs(D).max()
+    # right-hand side, degree-2 and degree-1 data and constants
+    xa, xb = om.coords[om.cells[:, 0]], om.coords[om.cells[:, 1]]
+    pts = np.stack([xa, 0.5 * (xa + xb), xb], axis=1)
+    for deg in (2, 1):
+        g = oracle.Coef(lambda x: np.sin(x[..., 0]) + x[..., 1] ** 2, deg)
+        f = oracle.Coef(lambda x: np.cos(x[..., 1]) - x[..., 0], deg)
+        b = oracle.assemble_primal_rhs(om, f=f, g=g)
+        bh = hn.primal_rhs(f_cell=f(pts).ravel(), f_lin=deg <= 1, g_cell=g(pts).ravel(), g_lin=deg <= 1)
+        np.testing.assert_allclose(bh, b, rtol=1e-12, atol=1e-14)
+    b2 = oracle.assemble_primal_rhs(om, f=0.75, g=-1.25)
+    np.testing.assert_allclose(hn.primal_rhs(fc=0.75, gc=-1.25), b2, rtol=1e-12, atol=1e-14)
+
+
 def test_vf_tags_match_oracle():
     from _util import host_tables
     from graphnics_b200.device import submesh_numbering
