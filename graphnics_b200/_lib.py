@@ -72,7 +72,7 @@ PROTOTYPES = {
     "gnx_refine_1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gnx_edge_tangents": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "gnx_tables_work_ints": (_L, [_I, _I]),
-    "gnx_vertex_tables": (_I, [_P, _I, _I] + [_P] * 13),
+    "gnx_vertex_tables": (_I, [_P, _I, _I] + [_P] * 14),
     "gnx_mixed_ndofs": (_L, [_NET]),
     "gnx_mixed_nnz": (_L, [_NET]),
     "gnx_build_pattern_mixed": (_I, [_NET, _P, _P, _P]),

@@ -193,15 +193,17 @@ __global__ void degree_kernel(const int32_t* __restrict__ edges, int32_t E, int3
   atomicAdd(&deg[edges[2 * e + 1]], 1);
 }
 
-__global__ void node_flags_kernel(const int32_t* __restrict__ deg, int32_t V, int32_t* __restrict__ fbif,
-                                  int32_t* __restrict__ fbnd, int32_t* __restrict__ fdegbif,
-                                  int32_t* __restrict__ flonely) {
+// `cls` (classification degree) = the degree in the WHOLE graph; `deg` = the degree in this edge
+// list.  They differ only for a partition of a larger network (cls_deg != NULL).
+__global__ void node_flags_kernel(const int32_t* __restrict__ deg, const int32_t* __restrict__ cls, int32_t V,
+                                  int32_t* __restrict__ fbif, int32_t* __restrict__ fbnd,
+                                  int32_t* __restrict__ fdegbif, int32_t* __restrict__ flonely) {
   const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
-  const int32_t d = deg[v];
+  const int32_t d = cls[v];
   fbif[v] = d > 1;
   fbnd[v] = d == 1;
-  fdegbif[v] = d > 1 ? d : 0;
+  fdegbif[v] = d > 1 ? deg[v] : 0;
   if (d == 0) atomicAdd(flonely, 1);
 }
 
@@ -212,7 +214,7 @@ __global__ void node_compact_kernel(const int32_t* __restrict__ deg, int32_t V,
                                     int32_t* __restrict__ lam_ptr) {
   const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
-  const int32_t d = deg[v];
+  const int32_t d = deg[v];          // classification degree
   if (d > 1) {
     const int32_t b = sbif[v];
     bix[v] = b;
@@ -272,7 +274,7 @@ extern "C" int gnx_vertex_tables(const int32_t* edges, int32_t V, int32_t E, int
                                  int32_t* bix, int32_t* bif_nodes, int32_t* bnd_nodes,
                                  int32_t* inc_ptr, int32_t* inc_edge, int32_t* lam_ptr,
                                  int32_t* ebif_prefix, int32_t* tag_u, int32_t* tag_v,
-                                 int32_t* counts, int32_t* work, void* stream) {
+                                 int32_t* counts, int32_t* work, const int32_t* cls_deg, void* stream) {
   GNX_CHECK_ARG(edges && deg && bix && bif_nodes && bnd_nodes && inc_ptr && inc_edge && lam_ptr &&
                 ebif_prefix && tag_u && tag_v && counts && work && V > 0 && E > 0);
   GNX_CHECK_ARG((int64_t)E < (1ll << 30));
@@ -287,12 +289,13 @@ extern "C" int gnx_vertex_tables(const int32_t* edges, int32_t V, int32_t E, int
   GNX_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * V, st));
   GNX_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, st));
   degree_kernel<<<gnx_blocks(E, th), th, 0, st>>>(edges, E, deg);
-  node_flags_kernel<<<gnx_blocks(V, th), th, 0, st>>>(deg, V, w0, w1, w2, counts + 3);
+  const int32_t* cls = cls_deg ? cls_deg : deg;
+  node_flags_kernel<<<gnx_blocks(V, th), th, 0, st>>>(deg, cls, V, w0, w1, w2, counts + 3);
   GNX_LAUNCH_CHECK();
   if (scan_i32(w0, w0, V, counts + 0, bsum, st)) return GNX_ERR_CUDA;   // B
   if (scan_i32(w1, w1, V, counts + 1, bsum, st)) return GNX_ERR_CUDA;   // n_bnd
   if (scan_i32(w2, w2, V, counts + 2, bsum, st)) return GNX_ERR_CUDA;   // I
-  node_compact_kernel<<<gnx_blocks(V, th), th, 0, st>>>(deg, V, w0, w1, w2, bix, bif_nodes, bnd_nodes, lam_ptr);
+  node_compact_kernel<<<gnx_blocks(V, th), th, 0, st>>>(cls, V, w0, w1, w2, bix, bif_nodes, bnd_nodes, lam_ptr);
   set_tail_kernel<<<1, 1, 0, st>>>(lam_ptr, counts + 0, counts + 2);
   // incidence CSR over all nodes
   if (scan_i32(deg, inc_ptr, V, inc_ptr + V, bsum, st)) return GNX_ERR_CUDA;
@@ -300,7 +303,7 @@ extern "C" int gnx_vertex_tables(const int32_t* edges, int32_t V, int32_t E, int
   inc_fill_kernel<<<gnx_blocks(E, th), th, 0, st>>>(edges, E, w3, inc_edge);
   inc_sort_kernel<<<gnx_blocks(V, th), th, 0, st>>>(inc_ptr, V, inc_edge);
   // per-edge tags and the prefix of bifurcation ends
-  edge_tags_kernel<<<gnx_blocks(E, th), th, 0, st>>>(edges, E, deg, tag_u, tag_v, w0);
+  edge_tags_kernel<<<gnx_blocks(E, th), th, 0, st>>>(edges, E, cls, tag_u, tag_v, w0);
   GNX_LAUNCH_CHECK();
   if (scan_i32(w0, ebif_prefix, E, ebif_prefix + E, bsum, st)) return GNX_ERR_CUDA;
   return GNX_OK;

@@ -45,26 +45,80 @@ def submesh_numbering(n):
     return loc.astype(np.int32), tloc.astype(np.int32)
 
 
-class DeviceNetwork:
-    """Graph -> mesh on the GPU.  `pos` [V,gdim] float64, `edges` [E,2] ints (host or device)."""
+class _Tables:
+    """output of gnx_vertex_tables for one edge list (fenics_graph.py:161-184, :132-156, :280-311)"""
 
-    def __init__(self, pos, edges, n, device=None, with_mf=True):
+    def __init__(self, lib, edges_t, V, dev, cls_deg=None):
+        E = int(edges_t.shape[0])
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.deg = torch.empty(V, **i32)
+        self.bix = torch.empty(V, **i32)
+        self._bif_nodes = torch.empty(V, **i32)
+        self._bnd_nodes = torch.empty(V, **i32)
+        self.inc_ptr = torch.empty(V + 1, **i32)
+        self.inc_edge = torch.empty(2 * E, **i32)
+        self.lam_ptr = torch.empty(V + 1, **i32)
+        self.ebif_prefix = torch.empty(E + 1, **i32)
+        self.tag_u = torch.empty(E, **i32)
+        self.tag_v = torch.empty(E, **i32)
+        counts = torch.empty(4, **i32)
+        self._work = torch.empty(int(lib.gnx_tables_work_ints(V, E)), **i32)
+        check(lib.gnx_vertex_tables(ptr(edges_t), V, E, ptr(self.deg), ptr(self.bix), ptr(self._bif_nodes),
+                                    ptr(self._bnd_nodes), ptr(self.inc_ptr), ptr(self.inc_edge), ptr(self.lam_ptr),
+                                    ptr(self.ebif_prefix), ptr(self.tag_u), ptr(self.tag_v), ptr(counts),
+                                    ptr(self._work), ptr(cls_deg), current_stream()))
+        self._counts = counts
+
+    def counts(self):
+        return [int(c) for c in self._counts.cpu().tolist()]      # one small D2H sync
+
+
+def partition_range(E, rank, world):
+    """contiguous, equal-chunk edge range of `rank` (chunk = ceil(E / world); the last ranks may be short)"""
+    chunk = -(-E // world)
+    e0 = min(E, rank * chunk)
+    return e0, min(E, e0 + chunk), chunk
+
+
+class DeviceNetwork:
+    """Graph -> mesh on the GPU.  `pos` [V,gdim] float64, `edges` [E,2] ints (host or device).
+
+    part=(rank, world): this object holds one rank's contiguous EDGE RANGE of a larger network
+    (SURVEY.md 8e): mesh, cell lengths, incidence lists and dof layout cover the local edges only
+    (the rank's subdomain), nodes are classified by their degree in the whole network, and
+    `self.glob` keeps the whole network's tables for the (replicated) Schur solve.
+    """
+
+    def __init__(self, pos, edges, n, device=None, with_mf=True, part=None):
         lib = _lib.require_device()
         self.device = torch.device(device if device is not None else "cuda")
         dev = self.device
         pos_t = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64) if not torch.is_tensor(pos) else pos)
         edg_t = torch.as_tensor(np.ascontiguousarray(edges, dtype=np.int32) if not torch.is_tensor(edges) else edges)
         self.pos = pos_t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
-        self.edges = edg_t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous().reshape(-1, 2)
+        edges_all = edg_t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous().reshape(-1, 2)
         self.V, self.gdim = int(self.pos.shape[0]), int(self.pos.shape[1])
-        self.E = int(self.edges.shape[0])
         self.n = int(n)
         self.m = 1 << self.n
-        V, E, m, gd = self.V, self.E, self.m, self.gdim
-        self.num_cells = E * m
-        self.num_vertices = V + E * (m - 1)
-        st = current_stream()
+        self.part = part
+        self.glob = None
         with torch.cuda.device(dev):
+            if part is not None:
+                rank, world = part
+                self.E_glob = int(edges_all.shape[0])
+                self.e0, self.e1, self.chunk = partition_range(self.E_glob, rank, world)
+                if self.e1 <= self.e0:
+                    raise ValueError("empty edge range: more ranks than edges")
+                self.edges_glob = edges_all
+                self.glob = _Tables(lib, edges_all, self.V, dev)
+                self.edges = edges_all[self.e0:self.e1].contiguous()
+            else:
+                self.edges = edges_all
+            self.E = int(self.edges.shape[0])
+            V, E, m, gd = self.V, self.E, self.m, self.gdim
+            self.num_cells = E * m
+            self.num_vertices = V + E * (m - 1)
+            st = current_stream()
             # --- mesh (fenics_graph.py:58-99)
             self.coords = torch.empty((self.num_vertices, gd), dtype=torch.float64, device=dev)
             self.cells = torch.empty((self.num_cells, 2), dtype=torch.int32, device=dev)
@@ -78,33 +132,24 @@ class DeviceNetwork:
             check(lib.gnx_edge_tangents(ptr(self.pos), ptr(self.edges), E, gd, ptr(self.tangents),
                                         ptr(self.elen), st))
             # --- vertex tables (:161-184, :132-156, :280-311)
-            i32 = dict(dtype=torch.int32, device=dev)
-            self.deg = torch.empty(V, **i32)
-            self.bix = torch.empty(V, **i32)
-            self._bif_nodes = torch.empty(V, **i32)
-            self._bnd_nodes = torch.empty(V, **i32)
-            self.inc_ptr = torch.empty(V + 1, **i32)
-            self.inc_edge = torch.empty(2 * E, **i32)
-            self.lam_ptr = torch.empty(V + 1, **i32)
-            self.ebif_prefix = torch.empty(E + 1, **i32)
-            self.tag_u = torch.empty(E, **i32)
-            self.tag_v = torch.empty(E, **i32)
-            counts = torch.empty(4, **i32)
-            work = torch.empty(int(lib.gnx_tables_work_ints(V, E)), **i32)
-            check(lib.gnx_vertex_tables(ptr(self.edges), V, E, ptr(self.deg), ptr(self.bix),
-                                        ptr(self._bif_nodes), ptr(self._bnd_nodes), ptr(self.inc_ptr),
-                                        ptr(self.inc_edge), ptr(self.lam_ptr), ptr(self.ebif_prefix),
-                                        ptr(self.tag_u), ptr(self.tag_v), ptr(counts), ptr(work), st))
+            t = _Tables(lib, self.edges, V, dev, cls_deg=self.glob.deg if self.glob is not None else None)
+            self._tables = t
+            for name in ("deg", "bix", "_bif_nodes", "_bnd_nodes", "inc_ptr", "inc_edge", "lam_ptr",
+                         "ebif_prefix", "tag_u", "tag_v"):
+                setattr(self, name, getattr(t, name))
             loc, tloc = submesh_numbering(self.n)
             self.loc_host, self.tloc_host = loc, tloc
             self.loc = torch.from_numpy(loc).to(dev, non_blocking=True)
             self.tloc = torch.from_numpy(tloc).to(dev, non_blocking=True)
-            cnt = counts.cpu().tolist()          # one small D2H sync: sizes are needed on the host
-        self.B, self.n_bnd, self.I, self.n_lonely = (int(c) for c in cnt)
+            cnt = t.counts()
+            if self.glob is not None:
+                gcnt = self.glob.counts()
+                self.B_glob, self.I_glob = gcnt[0], gcnt[2]
+        self.B, self.n_bnd, self.I, self.n_lonely = cnt
         self.bif_nodes = self._bif_nodes[: self.B]
         self.bnd_nodes = self._bnd_nodes[: self.n_bnd]
         self._net = None
-        self._keep = work  # keep scratch alive until the stream has consumed it
+        self._gnet = None
 
     # ---- C struct view ------------------------------------------------------------------
     @property
@@ -122,6 +167,36 @@ class DeviceNetwork:
 
     def net_ref(self):
         return C.byref(self.net)
+
+    @property
+    def schur_net(self):
+        """network descriptor the Schur solve runs on: the WHOLE network (== net when not partitioned)"""
+        if self.glob is None:
+            return self.net
+        if self._gnet is None:
+            s = _lib.gnx_network_t()
+            g = self.glob
+            s.V, s.E, s.gdim, s.n = self.V, self.E_glob, self.gdim, self.n
+            s.B, s.n_bnd, s.I = self.B_glob, self.n_bnd, self.I_glob
+            s.pos, s.edges = self.pos.data_ptr(), self.edges_glob.data_ptr()
+            s.h = None
+            s.bix, s.bif_nodes = g.bix.data_ptr(), g._bif_nodes.data_ptr()
+            s.inc_ptr, s.inc_edge = g.inc_ptr.data_ptr(), g.inc_edge.data_ptr()
+            s.lam_ptr, s.ebif_prefix = g.lam_ptr.data_ptr(), g.ebif_prefix.data_ptr()
+            s.loc, s.tloc = self.loc.data_ptr(), self.tloc.data_ptr()
+            self._gnet = s
+        return self._gnet
+
+    def schur_net_ref(self):
+        return C.byref(self.schur_net)
+
+    def schur_edges_host(self):
+        """edge list the Schur plan is built from (the whole network)"""
+        if self.glob is None:
+            return self.edges_host()
+        if getattr(self, "_edges_gh", None) is None:
+            self._edges_gh = self.edges_glob.cpu().numpy().astype(np.int64)
+        return self._edges_gh
 
     # ---- sizes of the mixed system ---------------------------------------------------------
     @property

@@ -58,8 +58,9 @@ def lincomb(lib, coefs, vecs, out=None):
 
 
 class MixedSystem:
-    def __init__(self, dn: DeviceNetwork):
+    def __init__(self, dn: DeviceNetwork, group=None):
         self.dn = dn
+        self.group = group           # torch.distributed process group of a partitioned network
         self.lib = _lib.require_device()
         self.N = dn.mixed_ndofs
         self.nnz = dn.mixed_nnz
@@ -207,6 +208,14 @@ class MixedSystem:
             d = {}
             d["cond"], d["rsrc"], d["ftot"] = self._f64(E), self._f64(E), self._f64(E)
             d["P"] = torch.zeros(B, dtype=torch.float64, device=self.dev)
+            if dn.part is not None:
+                # edge scalars of the WHOLE network, gathered from all ranks (equal chunks; the tail of
+                # the last chunk is padding).  The per-rank source buffers are chunk-sized too.
+                world = dn.part[1]
+                for k in ("cond", "rsrc", "ftot"):
+                    d[k + "_pad"] = torch.zeros(dn.chunk, dtype=torch.float64, device=self.dev)
+                    d[k] = d[k + "_pad"][:E]
+                    d[k + "_glob"] = self._f64(world * dn.chunk)
             self._solve_bufs = d
         return self._solve_bufs
 
@@ -215,7 +224,7 @@ class MixedSystem:
         if self._plan is None and self.dn.B > 0:
             from .schur_plan import SchurPlan
             dn = self.dn
-            hp = SchurPlan(dn.edges_host(), dn.bix.cpu().numpy(), dn.B, max_levels=_lib.MAX_LEVELS)
+            hp = SchurPlan(dn.schur_edges_host(), dn.bix.cpu().numpy(), dn.B, max_levels=_lib.MAX_LEVELS)
             lvl_ptr, lvl_nodes = hp.level_arrays()
             keep = {}
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
@@ -254,20 +263,35 @@ class MixedSystem:
                                        ptr(out["srhs"]), current_stream()))
         return out
 
-    def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True):
+    def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True,
+              exchange=None, eliminated=False):
         """x = A^{-1} b for the operator described by `co` (never forms A): edge elimination ->
         one persistent Schur kernel (rake + core PCG) -> back-substitution.
-        sync=False: nothing returns to the host; `info` is not filled."""
+        sync=False: nothing returns to the host; `info` is not filled.
+        Partitioned network: between elimination and the Schur kernel the edge scalars of all ranks
+        are all-gathered (`exchange` / `eliminated` let a test play all ranks in one process)."""
         dn = self.dn
         d = self._bufs()
         info = info if info is not None else SolveInfo()
         x = x if x is not None else self._f64(self.N)
         st = current_stream()
-        self.eliminate(co, b)
+        if not eliminated:
+            self.eliminate(co, b)
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
             lam = x[dn.lam_off:]
-            args = (dn.net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+            cond, rsrc, ftot = d["cond"], d["rsrc"], d["ftot"]
+            if dn.part is not None:
+                # the only exchange of the solve: every rank needs the edge scalars of all edges
+                # (3 doubles per edge); the Schur solve itself is replicated, so no further traffic
+                if exchange is not None:          # single-process emulation of the ranks (tests)
+                    exchange(d)
+                else:
+                    import torch.distributed as dist
+                    for k in ("cond", "rsrc", "ftot"):
+                        dist.all_gather_into_tensor(d[k + "_glob"], d[k + "_pad"], group=self.group)
+                cond, rsrc, ftot = d["cond_glob"], d["rsrc_glob"], d["ftot_glob"]
+            args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(cond), ptr(rsrc), ptr(ftot),
                     ptr(b[dn.lam_off:]), None, ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
                     1 if warm_start else 0)
             if sync:

@@ -94,12 +94,15 @@ int gnx_edge_tangents(const double* pos, const int32_t* edges, int32_t E, int32_
  *   deg[V], bix[V], bif_nodes[V] (first B valid), bnd_nodes[V] (first n_bnd valid),
  *   inc_ptr[V+1], inc_edge[2E], lam_ptr[V+1] (first B+1 valid), ebif_prefix[E+1],
  *   tag_u[E], tag_v[E] (vf tag at the u / v end of every edge),
- *   counts[4] = {B, n_bnd, I, n_lonely}, work[>= gnx_tables_work_ints(V,E)] int32 scratch */
+ *   counts[4] = {B, n_bnd, I, n_lonely}, work[>= gnx_tables_work_ints(V,E)] int32 scratch;
+ *   cls_deg [V] or NULL: when `edges` is one rank's PART of a larger network, the node degrees in the
+ *   whole network -- nodes are classified (bifurcation / boundary) by cls_deg while the incidence
+ *   lists, lam_ptr, ebif_prefix and I count this part's edges only (subdomain tables). */
 int64_t gnx_tables_work_ints(int32_t V, int32_t E);
 int gnx_vertex_tables(const int32_t* edges, int32_t V, int32_t E, int32_t* deg, int32_t* bix,
                       int32_t* bif_nodes, int32_t* bnd_nodes, int32_t* inc_ptr, int32_t* inc_edge,
                       int32_t* lam_ptr, int32_t* ebif_prefix, int32_t* tag_u, int32_t* tag_v,
-                      int32_t* counts, int32_t* work, void* stream);
+                      int32_t* counts, int32_t* work, const int32_t* cls_deg, void* stream);
 
 /* ---------------- sparse assembly (graphnics/flowmodels/flow_models.py) ---------------- */
 

@@ -1,0 +1,62 @@
+"""Run under torchrun (one rank per GPU, NCCL): the edge-partitioned mixed solve of a synthetic tree
+and of a honeycomb against the oracle's monolithic LU solution.  Prints one OK line per case on rank 0.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_partitioned.py
+"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import oracle
+from graphnics_b200.parallel import PartitionedMixed, global_residual
+from graphnics_b200.synthetic import murray_tree
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cases = []
+    pos, edges, _, _ = murray_tree(10, gdim=2)
+    cases.append(("tree10", pos, edges, 4))
+    from graphnics_b200.generators import honeycomb
+    G = honeycomb(12, 12, mesh=False)
+    pos, edges = G._graph_arrays()
+    cases.append(("honeycomb12", pos, edges, 3))
+    ok = True
+    for name, pos, edges, n in cases:
+        pm = PartitionedMixed(pos, edges, n)
+        dn, ms = pm.dn, pm.ms
+        rng = np.random.default_rng(1)
+        Res = rng.uniform(0.5, 2.0, size=len(edges))
+        co = ms.coeffs(Res[dn.e0:dn.e1])
+        xq, _ = ms.dof_coordinates(False)
+        pbc = lambda x: 1.0 + 0.3 * x[..., 0] - 0.2 * x[..., 1]
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        b = ms.rhs(None, None, ms.end_values(dev(pbc(xq.cpu().numpy()))), dev(pbc(pos)), f_const=0.3)
+        vals = ms.assemble(co)
+        x, info = ms.solve(co, b)
+        resid = global_residual(ms, vals, x, b)
+        om = oracle.build_mesh(pos, edges, n)
+        A = oracle.assemble_mixed(om, Res)
+        bo = oracle.assemble_mixed_rhs(om, f=0.3, p_bc=oracle.Coef(pbc, 1), project=False)
+        xo = oracle.lu_solve(A, bo)
+        idx = pm.local_dofs_of_global()
+        err = np.linalg.norm(x.cpu().numpy() - xo[idx]) / np.linalg.norm(xo[idx])
+        t = torch.tensor([err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        good = float(t[0]) < 1e-8 and resid < 1e-10
+        ok = ok and good
+        if rank == 0:
+            print(f"{'OK' if good else 'FAIL'} {name}: world={world} N={pm.N_glob} max rel err vs oracle LU "
+                  f"{float(t[0]):.2e}, global residual {resid:.2e}, cg iterations {info.cg_iterations}")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
