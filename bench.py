@@ -265,7 +265,7 @@ def run_gpu(args):
     k("schur_solve_kernel (rake + core PCG, latency-bound)", lambda: ms.lib.gnx_schur_solve(
         dn.net_ref(), ctypes.byref(plan), 1.0, bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["ftot"].data_ptr(), b[dn.lam_off:].data_ptr(), None, bufs["P"].data_ptr(), lam.data_ptr(), work.data_ptr(),
-        1e-13, 100000, 0, None, None, torch.cuda.current_stream().cuda_stream), 8 * 3 * dn.E + 8 * 6 * dn.B)
+        1e-13, 100000, 0, 0, 0, None, None, torch.cuda.current_stream().cuda_stream), 8 * 3 * dn.E + 8 * 6 * dn.B)
     k("edge_backsub_kernel", lambda: ms.lib.gnx_edge_backsub_mixed(
         dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["P"].data_ptr(), x.data_ptr(), torch.cuda.current_stream().cuda_stream), 2 * 8 * N + 8 * NC)

@@ -86,7 +86,7 @@ PROTOTYPES = {
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
-    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
+    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, c_f64p, c_i32p, _P]),
     "gnx_primal_ndofs": (_L, [_NET]),
     "gnx_primal_nnz": (_L, [_NET]),
     "gnx_build_pattern_primal": (_I, [_NET, _P, _P, _P]),

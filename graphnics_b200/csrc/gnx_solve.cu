@@ -277,6 +277,14 @@ struct SchurArgs {
   double *scal;                               // [8]: tol2, converged, iterations, rr, bb
   double rtol;
   int32_t max_iter, warm;
+  // edge scalar e lives at arr[(e / chunk) * rank_stride + e % chunk]: the layout an all-gather of
+  // per-rank [cond | rsrc | ftot] blocks produces (one collective instead of three).  A single
+  // GPU passes chunk = INT32_MAX, i.e. plain arr[e].
+  int32_t chunk, rank_stride;
+  __device__ __forceinline__ int64_t eidx(int32_t e) const {
+    const int32_t r = e / chunk;
+    return (int64_t)r * rank_stride + (e - r * chunk);
+  }
 };
 
 extern "C" int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan) {
@@ -346,13 +354,13 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
       node[q] = i;
       lev[q] = pl.level_of[i];
       const int32_t par = pl.parent[i];
-      if (par >= 0) { ptop[q] = pl.top_of[par]; w[q] = -a.cond[pl.pedge[i]]; }
+      if (par >= 0) { ptop[q] = pl.top_of[par]; w[q] = -a.cond[a.eidx(pl.pedge[i])]; }
       k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
       double di = __ldcg(a.d + i), ri = __ldcg(a.r + i);
       for (int32_t k = k0[q]; k < k1[q]; ++k) {             // children below the top part: final
         const int32_t c = pl.ch_idx[k];
         if (pl.top_of[c] < 0) {
-          const double wc = -a.cond[pl.pedge[c]];
+          const double wc = -a.cond[a.eidx(pl.pedge[c])];
           const double t = wc / __ldcg(a.d + c);
           di -= wc * t;
           ri -= t * __ldcg(a.r + c);
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
     double di = a.d[i], ri = a.r[i];
     for (int32_t k = c0; k < c1; ++k) {
       const int32_t c = pl.ch_idx[k];
-      const double w = -a.cond[pl.pedge[c]];
+      const double w = -a.cond[a.eidx(pl.pedge[c])];
       const double t = w / __ldcg(a.d + c);
       di -= w * t;
       ri -= t * __ldcg(a.r + c);
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
       const int32_t i = pl.lvl_nodes[idx];
       const int32_t p = pl.parent[i];
       double ri = a.r[i];
-      if (p >= 0) ri += a.cond[pl.pedge[i]] * __ldcg(a.P + p);
+      if (p >= 0) ri += a.cond[a.eidx(pl.pedge[i])] * __ldcg(a.P + p);
       const double xi = ri / a.d[i];
       a.P[i] = xi;
       if (a.lam_out) a.lam_out[i] = xi * a.inv_sigma;
@@ -445,9 +453,10 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
     for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
       const int32_t code = net.inc_edge[k];
       const int32_t e = code >> 1, end = code & 1;
-      const double c = a.cond[e];
+      const int64_t ei = a.eidx(e);
+      const double c = a.cond[ei];
       diag += c;
-      rhs += end ? (c * a.rsrc[e] + a.ftot[e]) : (-c * a.rsrc[e]);
+      rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
     }
     a.d[bi] = diag;
     a.r[bi] = rhs;
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
       const double xi = a.warm ? a.P[node] : 0.0;
       double ax = di * xi;
       for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k) {
-        const double v = -a.cond[pl.cedge[k]];
+        const double v = -a.cond[a.eidx(pl.cedge[k])];
         a.cval[k] = v;
         if (a.warm) ax += v * a.P[pl.core_nodes[pl.ccol[k]]];
       }
@@ -552,8 +561,8 @@ static int g_sch_blocks_per_sm = -1, g_sch_sms = 0;
 extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                                const double* cond, const double* rsrc, const double* ftot,
                                const double* b_lam, const double* b_node, double* P, double* lam_out, double* work,
-                               double rtol, int32_t max_iter, int32_t warm, double* resid_host,
-                               int32_t* info_host, void* stream) {
+                               double rtol, int32_t max_iter, int32_t warm, int32_t chunk, int32_t rank_stride,
+                               double* resid_host, int32_t* info_host, void* stream) {
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
   GNX_CHECK_ARG(plan->B == net->B && plan->B > 0 && plan->nl >= 0 && plan->nl <= GNX_MAX_LEVELS);
   GNX_CHECK_ARG(plan->l_split >= 0 && plan->l_split <= plan->nl && plan->nc >= 0 && plan->nc <= plan->B);
@@ -587,6 +596,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   for (int k = 0; k < 5; ++k) { a.part[k] = w; w += 2048; }
   a.scal = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
+  a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
   // grid: enough threads for the widest phase, capped by co-residency
   int want = (int)((B + SCH_T - 1) / SCH_T);
   const int cap = g_sch_sms * g_sch_blocks_per_sm;

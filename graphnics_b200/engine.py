@@ -211,11 +211,12 @@ class MixedSystem:
             if dn.part is not None:
                 # edge scalars of the WHOLE network, gathered from all ranks (equal chunks; the tail of
                 # the last chunk is padding).  The per-rank source buffers are chunk-sized too.
+                # Layout: per rank one block [cond | rsrc | ftot] of 3*chunk doubles -> ONE collective.
                 world = dn.part[1]
-                for k in ("cond", "rsrc", "ftot"):
-                    d[k + "_pad"] = torch.zeros(dn.chunk, dtype=torch.float64, device=self.dev)
-                    d[k] = d[k + "_pad"][:E]
-                    d[k + "_glob"] = self._f64(world * dn.chunk)
+                d["pack"] = torch.zeros(3 * dn.chunk, dtype=torch.float64, device=self.dev)
+                for i, k in enumerate(("cond", "rsrc", "ftot")):
+                    d[k] = d["pack"][i * dn.chunk: i * dn.chunk + E]
+                d["gathered"] = self._f64(world * 3 * dn.chunk)
             self._solve_bufs = d
         return self._solve_bufs
 
@@ -281,6 +282,7 @@ class MixedSystem:
             plan, _, work, _ = self.schur_plan()
             lam = x[dn.lam_off:]
             cond, rsrc, ftot = d["cond"], d["rsrc"], d["ftot"]
+            chunk = stride = 0
             if dn.part is not None:
                 # the only exchange of the solve: every rank needs the edge scalars of all edges
                 # (3 doubles per edge); the Schur solve itself is replicated, so no further traffic
@@ -288,12 +290,13 @@ class MixedSystem:
                     exchange(d)
                 else:
                     import torch.distributed as dist
-                    for k in ("cond", "rsrc", "ftot"):
-                        dist.all_gather_into_tensor(d[k + "_glob"], d[k + "_pad"], group=self.group)
-                cond, rsrc, ftot = d["cond_glob"], d["rsrc_glob"], d["ftot_glob"]
+                    dist.all_gather_into_tensor(d["gathered"], d["pack"], group=self.group)
+                g = d["gathered"]
+                chunk, stride = dn.chunk, 3 * dn.chunk
+                cond, rsrc, ftot = g, g[chunk:], g[2 * chunk:]
             args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(cond), ptr(rsrc), ptr(ftot),
                     ptr(b[dn.lam_off:]), None, ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
-                    1 if warm_start else 0)
+                    1 if warm_start else 0, chunk, stride)
             if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()

@@ -218,9 +218,9 @@ class PrimalSystem:
                                                  ptr(d["ftot"]), st))
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
-            args = (dn.net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+            args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
                     None, ptr(b[self.p_off:]), ptr(d["P"]), None, ptr(work), float(rtol), int(max_iter),
-                    1 if warm_start else 0)
+                    1 if warm_start else 0, 0, 0)
             if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()

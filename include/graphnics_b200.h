@@ -241,7 +241,10 @@ typedef struct gnx_schur_plan {
  *   p rows of b at the graph nodes, enters as +b_node/sigma); at most one of them non-NULL;
  *   P [B] out: sigma*lambda (in: initial guess of the core unknowns when warm != 0);
  *   lam_out [B] (may be NULL) = P / sigma, i.e. the lambda block of the solution vector;
- *   work [>= gnx_schur_work_doubles(plan)] doubles.
+ *   work [>= gnx_schur_work_doubles(plan)] doubles;
+ *   chunk > 0 (edge-partitioned network): cond / rsrc / ftot are read through the all-gather layout
+ *   arr[(e / chunk) * rank_stride + e % chunk], so one collective of the per-rank [cond|rsrc|ftot]
+ *   blocks feeds the kernel directly; chunk = 0: plain arr[e].
  * Fully asynchronous (and CUDA-graph capturable) when resid_host and info_host are NULL; otherwise
  * synchronises and returns resid_host[0] = ||r||/||rhs|| of the core CG, info_host[3] =
  * {CG iterations, converged, CTAs}; GNX_ERR_NOCONV if max_iter was hit. */
@@ -249,7 +252,8 @@ int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan);
 int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                     const double* cond, const double* rsrc, const double* ftot, const double* b_lam,
                     const double* b_node, double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
-                    int32_t warm, double* resid_host, int32_t* info_host, void* stream);
+                    int32_t warm, int32_t chunk, int32_t rank_stride, double* resid_host, int32_t* info_host,
+                    void* stream);
 
 /* Phase 2: back-substitution, the q and p blocks of x [N] (dof order) from the multipliers P [B]
  * (= sigma*lambda; the lambda block itself is written by gnx_schur_solve). */

@@ -36,3 +36,4 @@ from .graph import *        # noqa: F401,F403
 from .mesh import *         # noqa: F401,F403
 from .fem import *          # noqa: F401,F403
 from .timeloop import *     # noqa: F401,F403
+from .elimination import *  # noqa: F401,F403

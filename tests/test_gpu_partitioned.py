@@ -60,11 +60,10 @@ def test_partitioned_solve_matches_monolithic_lu(name, n, world):
         ms.eliminate(co, bl)
         ranks.append((dn, ms, co, bl, idx))
     # the all-gather, played by hand
-    glob = {k: torch.cat([ms._bufs()[k + "_pad"] for _, ms, _, _, _ in ranks]) for k in ("cond", "rsrc", "ftot")}
+    gathered = torch.cat([ms._bufs()["pack"] for _, ms, _, _, _ in ranks])
 
     def exchange(d):
-        for k in glob:
-            d[k + "_glob"].copy_(glob[k])
+        d["gathered"].copy_(gathered)
     P = []
     for dn, ms, co, bl, idx in ranks:
         x, info = ms.solve(co, bl, exchange=exchange, eliminated=True)
