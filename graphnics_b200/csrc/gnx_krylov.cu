@@ -1,65 +1,102 @@
 // Krylov building blocks: bandwidth-bound fp64 CSR SpMV (row-block streaming through shared
 // memory), fused residual + norms, fused axpby + dot.  Deterministic two-stage reductions.
+#include <stdlib.h>
 #include "gnx_common.cuh"
 
-constexpr int SPMV_T = 256;          // threads == rows per block
-constexpr int SPMV_TILE = 2048;      // products staged per pass (16 KB)
-constexpr int SPMV_U = SPMV_TILE / SPMV_T;
+constexpr int SPMV_T = 256;          // threads per block
 
-// acc = sum_j A[r,j] x[j] for the row owned by this thread (r may be >= nrows: acc = 0)
-__device__ __forceinline__ double spmv_row_block(int32_t nrows, const int32_t* __restrict__ rowptr,
-                                                 const int32_t* __restrict__ colidx,
-                                                 const double* __restrict__ vals,
-                                                 const double* __restrict__ x, double* prod) {
-  const int32_t r0 = blockIdx.x * SPMV_T;
-  const int32_t r1 = min(r0 + SPMV_T, nrows);
-  const int32_t r = r0 + threadIdx.x;
+// acc[j] = sum_k A[r,k] x[k] for row r = r0 + threadIdx.x + j*SPMV_T (0 beyond nrows); a block owns
+// SPMV_T*RPT consecutive rows.  The block's contiguous (col, val) range is streamed with coalesced
+// loads, U pairs per thread and pass (2U independent loads in flight), x is gathered, the products are
+// staged in shared memory and every thread sums the short segments of its rows.
+template <int RPT, int U>
+__device__ __forceinline__ void spmv_row_block(int32_t nrows, const int32_t* __restrict__ rowptr,
+                                               const int32_t* __restrict__ colidx,
+                                               const double* __restrict__ vals,
+                                               const double* __restrict__ x, double* prod,
+                                               double (&acc)[RPT]) {
+  constexpr int TILE = SPMV_T * U;
+  const int32_t r0 = blockIdx.x * (SPMV_T * RPT);
+  const int32_t r1 = min(r0 + SPMV_T * RPT, nrows);
   const int32_t nz0 = rowptr[r0], nz1 = rowptr[r1];
-  int32_t a = 0, b = 0;
-  if (r < nrows) { a = rowptr[r]; b = rowptr[r + 1]; }
-  double acc = 0.0;
-  for (int32_t ts = nz0; ts < nz1; ts += SPMV_TILE) {
-    // coalesced stream of (val, col), gather x, stage the products
-    int32_t c[SPMV_U];
-    double v[SPMV_U];
+  int32_t a[RPT], b[RPT];
 #pragma unroll
-    for (int k = 0; k < SPMV_U; ++k) {
+  for (int j = 0; j < RPT; ++j) {
+    const int32_t r = r0 + threadIdx.x + j * SPMV_T;
+    a[j] = b[j] = 0;
+    if (r < nrows) { a[j] = rowptr[r]; b[j] = rowptr[r + 1]; }
+    acc[j] = 0.0;
+  }
+  for (int32_t ts = nz0; ts < nz1; ts += TILE) {
+    int32_t c[U];
+    double v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
       const int32_t i = ts + k * SPMV_T + threadIdx.x;
       const bool ok = i < nz1;
       c[k] = ok ? __ldg(colidx + i) : -1;
       v[k] = ok ? __ldg(vals + i) : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < SPMV_U; ++k) {
+    for (int k = 0; k < U; ++k) {
       const double xv = (c[k] >= 0) ? __ldg(x + c[k]) : 0.0;
       prod[k * SPMV_T + threadIdx.x] = v[k] * xv;
     }
     __syncthreads();
-    const int32_t lo = max(a, ts), hi = min(b, ts + SPMV_TILE);
-    for (int32_t i = lo; i < hi; ++i) acc += prod[i - ts];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int32_t lo = max(a[j], ts), hi = min(b[j], ts + TILE);
+      for (int32_t i = lo; i < hi; ++i) acc[j] += prod[i - ts];
+    }
     __syncthreads();
   }
-  return acc;
 }
 
+template <int RPT, int U>
 __global__ void __launch_bounds__(SPMV_T)
 spmv_kernel(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
             const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
-  __shared__ double prod[SPMV_TILE];
-  const double acc = spmv_row_block(nrows, rowptr, colidx, vals, x, prod);
-  const int32_t r = blockIdx.x * SPMV_T + threadIdx.x;
-  if (r < nrows) y[r] = acc;
+  __shared__ double prod[SPMV_T * U];
+  double acc[RPT];
+  spmv_row_block<RPT, U>(nrows, rowptr, colidx, vals, x, prod, acc);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int32_t r = blockIdx.x * (SPMV_T * RPT) + threadIdx.x + j * SPMV_T;
+    if (r < nrows) y[r] = acc[j];
+  }
+}
+
+static int spmv_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GNX_SPMV_VARIANT"); v = e ? atoi(e) : 0; }   // tuning knob
+  return v;
 }
 
 extern "C" int gnx_spmv_csr_f64(int32_t nrows, const int32_t* rowptr, const int32_t* colidx,
                                 const double* vals, const double* x, double* y, void* stream) {
   GNX_CHECK_ARG(nrows > 0 && rowptr && colidx && vals && x && y);
-  spmv_kernel<<<gnx_blocks(nrows, SPMV_T), SPMV_T, 0, (cudaStream_t)stream>>>(nrows, rowptr, colidx, vals, x, y);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (spmv_variant()) {
+    case 1: spmv_kernel<1, 8><<<gnx_blocks(nrows, SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+    case 2: spmv_kernel<2, 8><<<gnx_blocks(nrows, 2 * SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+    case 3: spmv_kernel<4, 16><<<gnx_blocks(nrows, 4 * SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+    case 4: spmv_kernel<4, 8><<<gnx_blocks(nrows, 4 * SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+    case 5: spmv_kernel<2, 4><<<gnx_blocks(nrows, 2 * SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+    // default: 256 rows x ~4 nnz = one 1024-product pass, 32 registers, 8 KB -> 8 CTAs/SM.  Measured on
+    // B200 (tools/tune_spmv.py, 135 M rows): 5.14 TB/s = 79 % of the measured HBM peak; the deeper-unrolled
+    // variants lose more to occupancy than they gain in loads in flight (4.1-5.1 TB/s).
+    default: spmv_kernel<1, 4><<<gnx_blocks(nrows, SPMV_T), SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, y); break;
+  }
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
 
-extern "C" int64_t gnx_reduce_work_doubles(int64_t n) { return 2 * ((n + SPMV_T - 1) / SPMV_T) + 2; }
+constexpr int RES_RPT = 1, RES_U = 4;
+constexpr int SPMV_ROWS = SPMV_T * RES_RPT;
+constexpr int SPMV_RPT = RES_RPT;
+constexpr int SPMV_TILE = SPMV_T * RES_U;
+
+extern "C" int64_t gnx_reduce_work_doubles(int64_t n) { return 2 * ((n + SPMV_ROWS - 1) / SPMV_ROWS) + 2; }
 
 __global__ void __launch_bounds__(SPMV_T)
 residual_kernel(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
@@ -67,14 +104,18 @@ residual_kernel(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t
                 const double* __restrict__ b, double* __restrict__ res, double* __restrict__ part) {
   __shared__ double prod[SPMV_TILE];
   __shared__ double sh[32];
-  const double acc = spmv_row_block(nrows, rowptr, colidx, vals, x, prod);
-  const int32_t r = blockIdx.x * SPMV_T + threadIdx.x;
+  double acc[SPMV_RPT];
+  spmv_row_block<RES_RPT, RES_U>(nrows, rowptr, colidx, vals, x, prod, acc);
   double rr = 0.0, bb = 0.0;
-  if (r < nrows) {
-    const double bi = b[r];
-    const double ri = bi - acc;
-    if (res) res[r] = ri;
-    rr = ri * ri; bb = bi * bi;
+#pragma unroll
+  for (int j = 0; j < SPMV_RPT; ++j) {
+    const int32_t r = blockIdx.x * SPMV_ROWS + threadIdx.x + j * SPMV_T;
+    if (r < nrows) {
+      const double bi = b[r];
+      const double ri = bi - acc[j];
+      if (res) res[r] = ri;
+      rr += ri * ri; bb += bi * bi;
+    }
   }
   rr = gnx_block_sum<false>(rr, sh);
   bb = gnx_block_sum<false>(bb, sh);
@@ -99,7 +140,7 @@ extern "C" int gnx_residual_csr_f64(int32_t nrows, const int32_t* rowptr, const 
                                     double* out2, double* work, void* stream) {
   GNX_CHECK_ARG(nrows > 0 && rowptr && colidx && vals && x && b && out2 && work);
   cudaStream_t st = (cudaStream_t)stream;
-  const int nb = gnx_blocks(nrows, SPMV_T);
+  const int nb = gnx_blocks(nrows, SPMV_ROWS);
   residual_kernel<<<nb, SPMV_T, 0, st>>>(nrows, rowptr, colidx, vals, x, b, r, work);
   final_reduce_kernel<<<1, 256, 0, st>>>(work, nb, 2, out2);
   GNX_LAUNCH_CHECK();
