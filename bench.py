@@ -279,8 +279,17 @@ def run_gpu(args):
     hbm, peak_src = peaks()
     dom = max((kk for kk in kernels if "not in the step" not in kk and "(solve" not in kk and "latency" not in kk),
               key=lambda kk: kernels[kk]["ms"])
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            tj = json.load(fh)
+        for key, rec in tj.get("kernels", {}).items():
+            if key in dom:
+                traffic, tsrc = rec["dram_bytes_read"] + rec["dram_bytes_write"], tj.get("source")
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
-            "frac": kernels[dom]["GBps"] / hbm, "traffic": None, "peak_source": peak_src}
+            "frac": kernels[dom]["GBps"] / hbm, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src}
 
     # ---- e2e through the drop-in Python API, host data in / host solution out
     e2e = e2e_python_api(pos, edges, n, dn, args)

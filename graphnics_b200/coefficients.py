@@ -361,17 +361,23 @@ class CompiledCoefficient:
         return p
 
     # -- evaluation -------------------------------------------------------------------------
-    def eval_device(self, x, pts_per_edge=0, tangents=None, edge_attr=None, cell_index=None):
-        """x: [npts, gdim] float64 CUDA tensor -> [npts] CUDA tensor."""
+    def eval_device(self, x, pts_per_edge=0, tangents=None, edge_attr=None, cell_index=None, out=None):
+        """x: [npts, gdim] float64 CUDA tensor -> [npts] CUDA tensor (`out` is reused when given)."""
         import torch
         from .device import current_stream
         npts, gd = int(x.shape[0]), int(x.shape[1])
         if self.is_constant:
+            if out is not None:
+                return out.fill_(self.const_value())
             return torch.full((npts,), self.const_value(), dtype=torch.float64, device=x.device)
         if self.user is not None:
             vals = self.eval_host(x.cpu().numpy(), cell_index)
+            if out is not None:
+                out.copy_(torch.from_numpy(vals))
+                return out
             return torch.from_numpy(vals).to(x.device)
-        out = torch.empty(npts, dtype=torch.float64, device=x.device)
+        if out is None:
+            out = torch.empty(npts, dtype=torch.float64, device=x.device)
         prog = self.program()
         lib = _lib.require_device()
         _lib.check(lib.gnx_eval_expr(C.byref(prog), _lib.ptr(x), gd, npts, int(pts_per_edge), _lib.ptr(tangents),

@@ -9,6 +9,7 @@
 //   q-rows :  (a M + k K) q |_j + P_j - P_{j-1} = b_q[j]   (P = sigma p, P_{-1} = P(u), P_m = P(v))
 //   sum    :  q_0 = cond (P(u) - P(v) + rsrc),  cond = 1/(a L),  rsrc = sum b_q - a sum_k h_k (cumF_k+cumF_{k+1})/2
 //   lam-row:  sum_in q_e(m) - sum_out q_e(0) = b_lam / sigma   (Kirchhoff) -> graph Laplacian in P(b)
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include "gnx_common.cuh"
 namespace cg = cooperative_groups;
@@ -289,7 +290,8 @@ struct SchurArgs {
 
 extern "C" int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan) {
   if (!plan) return 0;
-  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + plan->nnzc + 5 * 2048 + 8;
+  const int64_t nval = plan->ell_w > 0 ? (int64_t)plan->ell_w * plan->nc : 0;
+  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 8;
 }
 
 // All-reduce of K values over the block with ONE barrier.  `sh` holds K*32 doubles; callers
@@ -313,16 +315,29 @@ __device__ __forceinline__ void block_allreduce(double (&v)[K], double* sh) {
   }
 }
 
+// How the CTAs of one solve synchronise:
+//   SCH_SINGLE   one CTA, __syncthreads
+//   SCH_CLUSTER  one thread-block cluster (<= 16 CTAs on one GPC), hardware cluster barrier (~0.2 us)
+//   SCH_GRID     cooperative grid, software grid barrier (~2-3 us) -- only for phases that need > 16 CTAs
+enum { SCH_SINGLE = 0, SCH_CLUSTER = 1, SCH_GRID = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void sch_sync() {
+  if (MODE == SCH_SINGLE) __syncthreads();
+  else if (MODE == SCH_CLUSTER) cg::this_cluster().sync();
+  else cg::this_grid().sync();
+}
+
 // partials of every block are re-reduced by every block in the same order -> identical bits
-template <bool SINGLE, int K>
+template <int MODE, int K>
 __device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const* part, int nblk, double* sh) {
   block_allreduce<K>(v, sh);
-  if (SINGLE) return;
+  if (MODE == SCH_SINGLE) return;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) part[k][blockIdx.x] = v[k];
   }
-  cg::this_grid().sync();
+  sch_sync<MODE>();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double t = 0.0;
@@ -406,8 +421,138 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
   }
 }
 
-template <bool SINGLE>
-__global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
+// ------------------------------------------------------------------------------------
+// Cluster-resident Jacobi-PCG on the core (SCH_CLUSTER with an ELL plan): the CG of a cyclic
+// network is a chain of hundreds of tiny dependent steps, so what matters is the latency of one
+// iteration, not bandwidth.  The solve runs as ONE thread-block cluster of 16 CTAs; the search
+// direction p and the preconditioned residual z -- the only vectors a row reads from its
+// neighbours -- live in distributed shared memory (a CTA owns ell_R consecutive rows; a neighbour
+// is addressed as (CTA rank, offset) and read over DSMEM), the matrix is in ELL layout (fixed
+// width, independent coalesced loads, no row-pointer chain), dot products are combined through
+// per-CTA shared-memory slots read by every CTA in the same order (bitwise identical results), and
+// the two barriers of an iteration are hardware cluster barriers.
+// Shared memory: z[R] | p0[R] | p1[R] | slots[8].
+// ------------------------------------------------------------------------------------
+constexpr int CL_CTAS = 16;
+constexpr int CL_T = 512;            // threads per CTA in cluster mode (128 registers per thread available)
+constexpr int CL_RMAX = 5120;
+constexpr size_t CL_SMEM = (3 * CL_RMAX + 8) * sizeof(double);
+
+template <int K>
+__device__ __forceinline__ void cluster_allreduce(double (&v)[K], double* slot, double* sh, cg::cluster_group& cluster) {
+  block_allreduce<K>(v, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) slot[k] = v[k];
+  }
+  cluster.sync();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = 0.0;
+  for (int c = 0; c < CL_CTAS; ++c) {
+    const double* rs = cluster.map_shared_rank(slot, c);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += rs[k];
+  }
+}
+
+template <class Gather>
+__device__ __forceinline__ void core_pcg_cluster(const SchurArgs& a, double* sm, double (*red)[3 * 32], Gather gather,
+                                                 int& it, double& rr_out, double& bb_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const gnx_schur_plan_t& pl = a.plan;
+  const int32_t R = pl.ell_R, W = pl.ell_w, nc = pl.nc;
+  const int rank = (int)cluster.block_rank();
+  double* zs = sm;
+  double* pbuf[2] = {sm + R, sm + 2 * R};
+  double* slotA = sm + 3 * R;          // 3 values
+  double* slotB = sm + 3 * R + 4;      // 1-2 values
+  const int32_t row0 = rank * R;
+  const int32_t nloc = max(0, min(R, nc - row0));
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int32_t li = threadIdx.x; li < nloc; li += blockDim.x) {
+    const int32_t i = row0 + li;
+    const int32_t node = pl.core_nodes[i];
+    gather(node);
+    const double di = a.d[node];
+    const double xi = a.warm ? a.P[node] : 0.0;
+    double ax = di * xi;
+    for (int k = 0; k < W; ++k) {
+      const int32_t e = pl.ell_edge[(int64_t)k * nc + i];
+      double v = 0.0;
+      if (e >= 0) {
+        v = -a.cond[a.eidx(e)];
+        if (a.warm) {
+          const int32_t pc = pl.ell_col[(int64_t)k * nc + i];
+          ax += v * a.P[pl.core_nodes[(pc >> 16) * R + (pc & 0xffff)]];
+        }
+      }
+      a.cval[(int64_t)k * nc + i] = v;
+    }
+    const double bi = a.r[node];
+    const double ri = bi - ax;
+    const double zi = ri / di;
+    a.dg[i] = di; a.xc[i] = xi; a.rc[i] = ri;
+    zs[li] = zi; pbuf[0][li] = 0.0; pbuf[1][li] = 0.0;
+    acc[0] += ri * zi; acc[1] += ri * ri; acc[2] += bi * bi;
+  }
+  cluster_allreduce<3>(acc, slotA, red[0], cluster);
+  double rzc = acc[0], rzp = acc[0], rr = acc[1];
+  const double bb = acc[2];
+  const double tol2 = a.rtol * a.rtol * bb;
+  for (; it < a.max_iter; ++it) {
+    if (rr <= tol2) break;
+    const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
+    const double* p_old = pbuf[it & 1];
+    double* p_new = pbuf[(it & 1) ^ 1];
+    double pw[1] = {0.0};
+    for (int32_t li = threadIdx.x; li < nloc; li += blockDim.x) {
+      const int32_t i = row0 + li;
+      const double pi = zs[li] + beta * p_old[li];
+      double wi = a.dg[i] * pi;
+      for (int k = 0; k < W; ++k) {
+        const int32_t pc = pl.ell_col[(int64_t)k * nc + i];
+        if (pc >= 0) {
+          const double v = a.cval[(int64_t)k * nc + i];
+          const int rk = pc >> 16, off = pc & 0xffff;
+          const double* zr = cluster.map_shared_rank(zs, rk);
+          const double* pr = cluster.map_shared_rank(p_old, rk);
+          wi += v * (zr[off] + beta * pr[off]);
+        }
+      }
+      p_new[li] = pi;
+      a.wc[i] = wi;
+      pw[0] += pi * wi;
+    }
+    cluster_allreduce<1>(pw, slotB, red[1], cluster);
+    const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
+    double a2[2] = {0.0, 0.0};
+    for (int32_t li = threadIdx.x; li < nloc; li += blockDim.x) {
+      const int32_t i = row0 + li;
+      a.xc[i] += alpha * p_new[li];
+      const double ri = a.rc[i] - alpha * a.wc[i];
+      const double zi = ri / a.dg[i];
+      a.rc[i] = ri; zs[li] = zi;
+      a2[0] += ri * zi; a2[1] += ri * ri;
+    }
+    cluster_allreduce<2>(a2, slotA, red[0], cluster);
+    rzp = rzc; rzc = a2[0]; rr = a2[1];
+  }
+  rr_out = rr; bb_out = bb;
+  for (int32_t li = threadIdx.x; li < nloc; li += blockDim.x) {
+    const int32_t i = row0 + li;
+    const int32_t node = pl.core_nodes[i];
+    const double xi = a.xc[i];
+    a.P[node] = xi;
+    if (a.lam_out) a.lam_out[node] = xi * a.inv_sigma;
+  }
+  cluster.sync();      // nobody leaves (or reuses shared memory) while a neighbour may still read it
+}
+
+template <int MODE> struct SchThreads { static constexpr int value = SCH_T; };
+template <> struct SchThreads<SCH_CLUSTER> { static constexpr int value = CL_T; };
+
+template <int MODE>
+__global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel(SchurArgs a) {
   extern __shared__ double top_sh[];             // 3 * GNX_TOP_MAX doubles (dynamic, opt-in > 48 KB)
   __shared__ double red[2][3 * 32];
   const gnx_network_t& net = a.net;
@@ -415,7 +560,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
   const int nblk = gridDim.x;
   const int32_t stride = nblk * blockDim.x;
   const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  auto gsync = [&]() { if (SINGLE) __syncthreads(); else cg::this_grid().sync(); };
+  auto gsync = [&]() { sch_sync<MODE>(); };
 
   // parent i absorbs its raked children: d_i -= w^2/d_c, r_i -= w r_c/d_c  (w = -cond of the link)
   auto gather = [&](int32_t i) {
@@ -472,6 +617,9 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
     if (pl.l_split > 0) gsync();
   } else {                                       // a core exists: l_split == nl, no top part
     // ---- phase 2: Jacobi-PCG on the core
+    if (MODE == SCH_CLUSTER) {                   // launched only with an ELL plan (gnx_schur_solve)
+      core_pcg_cluster(a, top_sh, red, gather, it, rr_final, bb_final);
+    } else {
     double acc[3] = {0.0, 0.0, 0.0};
     for (int32_t i = t0; i < pl.nc; i += stride) {
       const int32_t node = pl.core_nodes[i];
@@ -492,7 +640,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
     }
     {
       double* const part[3] = {a.part[0], a.part[1], a.part[2]};
-      grid_allreduce<SINGLE, 3>(acc, part, nblk, red[0]);
+      grid_allreduce<MODE, 3>(acc, part, nblk, red[0]);
     }
     double rzc = acc[0], rzp = acc[0], rr = acc[1];
     const double bb = acc[2];
@@ -516,7 +664,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
       }
       {
         double* const part[1] = {a.part[3]};
-        grid_allreduce<SINGLE, 1>(pw, part, nblk, red[1]);
+        grid_allreduce<MODE, 1>(pw, part, nblk, red[1]);
       }
       const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
       double a2[2] = {0.0, 0.0};
@@ -531,7 +679,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
         // one buffer per reduction point is enough: consecutive uses of a buffer are separated by
         // the grid barrier of the other reduction point
         double* const part[2] = {a.part[0], a.part[1]};
-        grid_allreduce<SINGLE, 2>(a2, part, nblk, red[0]);
+        grid_allreduce<MODE, 2>(a2, part, nblk, red[0]);
       }
       rzp = rzc; rzc = a2[0]; rr = a2[1];
     }
@@ -541,6 +689,7 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
       const double xi = a.xc[i];
       a.P[node] = xi;
       if (a.lam_out) a.lam_out[node] = xi * a.inv_sigma;
+    }
     }
     if (pl.nl > 0) gsync();
   }
@@ -553,7 +702,32 @@ __global__ void __launch_bounds__(SCH_T) schur_solve_kernel(SchurArgs a) {
   }
 }
 
-static int g_sch_blocks_per_sm = -1, g_sch_sms = 0;
+static int g_sch_blocks_per_sm = -1, g_sch_sms = 0, g_sch_cluster_max = 0;
+
+static int sch_init() {
+  if (g_sch_blocks_per_sm >= 0) return GNX_OK;
+  int dev = 0, coop = 0, per_sm = 0;
+  GNX_CUDA(cudaGetDevice(&dev));
+  GNX_CUDA(cudaDeviceGetAttribute(&g_sch_sms, cudaDevAttrMultiProcessorCount, dev));
+  GNX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
+  GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
+  GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+  GNX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_solve_kernel<SCH_GRID>, SCH_T, SCH_SMEM));
+  if (!coop || per_sm < 1) { gnx_set_error("cooperative launch unsupported on this device"); return GNX_ERR_CUDA; }
+  // largest cluster this kernel can run as (16 needs the non-portable opt-in)
+  g_sch_cluster_max = 0;
+  if (cudaFuncSetAttribute(schur_solve_kernel<SCH_CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(CL_T); cfg.dynamicSmemBytes = CL_SMEM;
+    int mc = 0;
+    if (cudaOccupancyMaxPotentialClusterSize(&mc, schur_solve_kernel<SCH_CLUSTER>, &cfg) == cudaSuccess) g_sch_cluster_max = mc;
+  }
+  cudaGetLastError();
+  if (const char* e = getenv("GNX_SCHUR_NO_CLUSTER")) { if (atoi(e)) g_sch_cluster_max = 0; }   // tuning / debugging knob
+  g_sch_blocks_per_sm = per_sm;
+  return GNX_OK;
+}
 
 // P holds the initial guess of the core unknowns on entry when warm != 0.
 // resid_host[0] = ||r||/||rhs|| of the core system (recurrence residual; 0 for a pure tree),
@@ -569,20 +743,12 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   GNX_CHECK_ARG(plan->nt >= 0 && plan->nt <= GNX_TOP_MAX && (plan->nc == 0 || plan->l_split == plan->nl));
   GNX_CHECK_ARG(plan->nt == 0 || (plan->top_nodes && plan->top_of && plan->level_of));
   GNX_CHECK_ARG(plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
+  GNX_CHECK_ARG(plan->ell_w == 0 || (plan->ell_w <= 8 && plan->ell_col && plan->ell_edge && plan->ell_R > 0 &&
+                                    plan->ell_R <= CL_RMAX && (int64_t)plan->ell_R * CL_CTAS >= plan->nc));
   GNX_CHECK_ARG(plan->nl == 0 || (plan->lvl_nodes && plan->parent && plan->pedge && plan->ch_ptr && plan->ch_idx));
   GNX_CHECK_ARG(plan->nc == 0 || (plan->core_nodes && plan->crp && plan->ccol && plan->cedge && plan->ch_ptr));
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_sch_blocks_per_sm < 0) {
-    int dev = 0, coop = 0, per_sm = 0;
-    GNX_CUDA(cudaGetDevice(&dev));
-    GNX_CUDA(cudaDeviceGetAttribute(&g_sch_sms, cudaDevAttrMultiProcessorCount, dev));
-    GNX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
-    GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
-    GNX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_solve_kernel<false>, SCH_T, SCH_SMEM));
-    if (!coop || per_sm < 1) { gnx_set_error("cooperative launch unsupported on this device"); return GNX_ERR_CUDA; }
-    g_sch_blocks_per_sm = per_sm;
-  }
+  if (int rc = sch_init()) return rc;
   SchurArgs a;
   a.net = *net; a.plan = *plan;
   a.inv_sigma = 1.0 / sigma;
@@ -597,18 +763,34 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   a.scal = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
-  // grid: enough threads for the widest phase, capped by co-residency
+  // CTAs: enough threads for the widest phase.  <= 2 CTAs' worth runs as one CTA; a system with a
+  // Krylov core (hundreds of barriers) runs as ONE CLUSTER when that gives every thread <= 32 rows;
+  // everything else (wide rake levels of a large tree: few barriers, lots of rows) as a cooperative grid.
   int want = (int)((B + SCH_T - 1) / SCH_T);
   const int cap = g_sch_sms * g_sch_blocks_per_sm;
   if (want > cap) want = cap;
   if (want > 2048) want = 2048;
   if (want <= 2) {
-    schur_solve_kernel<true><<<1, SCH_T, SCH_SMEM, st>>>(a);
+    schur_solve_kernel<SCH_SINGLE><<<1, SCH_T, SCH_SMEM, st>>>(a);
     GNX_LAUNCH_CHECK();
     want = 1;
+  } else if (g_sch_cluster_max >= CL_CTAS && nc > 0 && plan->ell_w > 0 && nc <= CL_CTAS * CL_T) {
+    // a Krylov core with at most one row per thread of ONE cluster: cluster-resident PCG.  Measured on
+    // B200 (tools/time_schur.py): 7.3 us/iteration against 7.8 for the cooperative grid at 7.4 k unknowns;
+    // with more rows per thread the 16 SMs of a cluster lose to the full grid (80 k unknowns: 25.6 vs 7.9 us),
+    // so larger cores stay on the grid path.  Either way an iteration is latency-, not bandwidth-bound.
+    want = CL_CTAS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(want); cfg.blockDim = dim3(CL_T); cfg.dynamicSmemBytes = CL_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = want; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GNX_CUDA(cudaLaunchKernelEx(&cfg, schur_solve_kernel<SCH_CLUSTER>, a));
+    want = -want;                                  // reported as negative: cluster
   } else {
     void* args[] = {&a};
-    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<false>, dim3(want), dim3(SCH_T), args, SCH_SMEM, st));
+    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<SCH_GRID>, dim3(want), dim3(SCH_T), args, SCH_SMEM, st));
   }
   if (!resid_host && !info_host) return GNX_OK;              // fully asynchronous
   double scal[8];
@@ -618,7 +800,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   const double rel = bb > 0 ? sqrt(scal[3] / bb) : 0.0;
   if (resid_host) resid_host[0] = rel;
   const int done = scal[1] != 0.0;
-  if (info_host) { info_host[0] = (int32_t)scal[2]; info_host[1] = done; info_host[2] = want; }
+  if (info_host) { info_host[0] = (int32_t)scal[2]; info_host[1] = done; info_host[2] = want; }   // CTAs (< 0: one cluster)
   if (!done) {
     gnx_set_error("schur CG: no convergence in %d iterations (rel. resid %.3e)", (int)scal[2], rel);
     return GNX_ERR_NOCONV;

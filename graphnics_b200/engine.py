@@ -235,10 +235,13 @@ class MixedSystem:
             s.B, s.nl, s.l_split, s.nc, s.nnzc, s.nt = dn.B, len(hp.levels), l_split, hp.nc, hp.nnzc, len(top)
             for i, v in enumerate(lvl_ptr):
                 s.lvl_ptr[i] = int(v)
+            ell_w, ell_R, ell_col, ell_edge = hp.ell_arrays()
+            s.ell_w, s.ell_R = ell_w, ell_R
             for name, arr in (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
                               ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),
-                              ("top_nodes", top), ("top_of", top_of), ("level_of", level_of)):
+                              ("top_nodes", top), ("top_of", top_of), ("level_of", level_of),
+                              ("ell_col", ell_col), ("ell_edge", ell_edge)):
                 t = dev(arr if len(arr) else np.zeros(1, dtype=np.int32))
                 keep[name] = t
                 setattr(s, name, t.data_ptr())

@@ -84,15 +84,23 @@ class PrimalSystem:
             self._slot = torch.from_numpy(e * m + np.where(flip, m - 1 - s, s)).to(self.dev)
         return self._slot
 
-    def eval_cellwise(self, coef):
-        """coefficient at the 3 points of every cell -> [NC*3] (cell-wise: may jump between edges)"""
+    def eval_cellwise(self, coef, slot=None):
+        """coefficient at the 3 points of every cell -> [NC*3] (cell-wise: may jump between edges).
+        `slot` names a persistent output buffer (the time loop re-evaluates f and g every step)."""
         dn = self.dn
+        out = None
+        if slot is not None:
+            if getattr(self, "_cw", None) is None:
+                self._cw = {}
+            if slot not in self._cw:
+                self._cw[slot] = self._f64(3 * self.NC)
+            out = self._cw[slot]
         pts = self.cell_points().reshape(-1, dn.gdim)
         cell_index = None
         if coef.user is not None:
             cell_index = np.repeat(np.arange(self.NC), 3)
         tang = dn.tangents
-        return coef.eval_device(pts, pts_per_edge=3 * dn.m, tangents=tang, cell_index=cell_index)
+        return coef.eval_device(pts, pts_per_edge=3 * dn.m, tangents=tang, cell_index=cell_index, out=out)
 
     def cell_average(self, coef):
         """per-cell mean of a coefficient in EDGE-LOCAL order (Simpson; midpoint rule for degree <= 1)"""
@@ -130,23 +138,25 @@ class PrimalSystem:
         """HydraulicNetwork.L_form; f, g CompiledCoefficients (or None = 0)"""
         b = out if out is not None else self._f64(self.N)
 
-        def prep(c):
+        def prep(c, slot):
             if c is None:
                 return None, 0, 0.0
             if c.is_constant:
                 return None, 0, c.const_value()
-            return self.eval_cellwise(c), int(c.degree <= 1), 0.0
-        fc, fl, f0 = prep(f)
-        gc, gl, g0 = prep(g)
+            return self.eval_cellwise(c, slot), int(c.degree <= 1), 0.0
+        fc, fl, f0 = prep(f, "f")
+        gc, gl, g0 = prep(g, "g")
         check(self.lib.gnx_assemble_rhs_primal(self.dn.net_ref(), ptr(self.dn.cells), ptr(fc), fl, f0, ptr(gc), gl, g0,
                                                ptr(b), current_stream()))
         self._keep = (fc, gc)
         return b
 
     def bc_node_values(self, p_bc):
-        """p_bc at the graph nodes [V]"""
+        """p_bc at the graph nodes [V] (persistent buffer)"""
         c = as_coefficient(p_bc)
-        return c.eval_device(self.dn.pos)
+        if getattr(self, "_bcv", None) is None:
+            self._bcv = self._f64(self.dn.V)
+        return c.eval_device(self.dn.pos, out=self._bcv)
 
     def apply_bc(self, A, b, bcs):
         """xii.apply_bc(A, b, bcs) (flow_models.py:117), in place on copies"""

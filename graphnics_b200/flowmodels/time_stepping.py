@@ -70,9 +70,15 @@ def _as_state(model, qp0):
 
 
 def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step_scheme="IE",
-                         reassemble_lhs=True, progress=False):
+                         reassemble_lhs=True, progress=False, warm_start=True, check_every=0):
     """Time stepping for  1/A d/dt q + a(U, V) = L(V; f, g)  (time_stepping.py:126-221).
-    Returns the list of `t_steps` solutions (ii_Function), initial state first."""
+    Returns the list of `t_steps` solutions (ii_Function), initial state first.
+
+    Beyond the reference: the whole history lives in ONE device allocation (the returned functions
+    are views into it), steps are enqueued without host synchronisation, and the Krylov part of the
+    solve (only present when the network has cycles) starts from the previous step's multipliers.
+    `check_every=k` reads the solver status back every k steps (0: once, after the last step)."""
+    import torch
     sys_ = model._system()
     dt = T / t_steps                                                  # :150
     cn, cn1 = time_stepping_schemes[t_step_scheme].values()           # :151
@@ -80,8 +86,10 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
 
     L = model.L_form()                                                # :157
     qp0 = _as_state(model, qp0)                                       # :147-165
-    qps = [qp0.copy()]                                                # :167
-    x0 = qp0.tensor()
+    hist = torch.empty((t_steps, sys_.N), dtype=torch.float64, device=qp0.tensor().device)
+    hist[0].copy_(qp0.tensor())
+    qps = [ii_Function(model.W, data=hist[0])]                        # :167
+    x0 = hist[0]
 
     a_n = model.a_form().assemble() if cn != 0 else None              # An (:170) -- only CN multiplies by it
     Ln = L.assemble().tensor                                          # :170
@@ -98,7 +106,7 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
     if progress:
         from tqdm import tqdm
         steps = tqdm(steps)
-    for t_val in steps:
+    for k, t_val in enumerate(steps):
         Ln1 = L.assemble().tensor                                     # :179
         if reassemble_lhs:                                            # :180-181
             co_eff = model._coeffs(sigma=cn1 * dt, mass=ainv)
@@ -107,9 +115,11 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
         if cn != 0:                                                   # :185
             sys_.spmv(a_n.vals, x0, ax0)
         sys_.lincomb([1.0, cn1 * dt, -dt * cn, dt * cn], [DDn, Ln1, ax0, Ln if cn != 0 else None], out=b)
-        sol = ii_Function(model.W)                                    # :194-198
-        sys_.solve_bc(co_eff, b, sol.tensor(), bcs)                   # :187-192
-        sol.touch()
+        sol = ii_Function(model.W, data=hist[k + 1])                  # :194-198
+        last = k == len(steps) - 1
+        check = last or (check_every > 0 and (k + 1) % check_every == 0)
+        _, info = sys_.solve_bc(co_eff, b, sol.tensor(), bcs, warm_start=warm_start and k > 0, sync=check)   # :187-192
+        model.solve_info = info
         qps.append(sol)
         x0 = sol.tensor()                                             # :201
         t.assign(t_val + dt)                                          # :204

@@ -148,6 +148,26 @@ class SchurPlan:
         top_of[top] = np.arange(len(top), dtype=np.int32)
         return top, top_of, level_of
 
+    def ell_arrays(self, ctas=16, rmax=5120, wmax=8):
+        """ELL copy of the core matrix for the cluster-resident PCG: (w, R, col [w*nc] packed
+        (CTA << 16 | offset), edge [w*nc]); w = 0 when the core does not qualify."""
+        nc = self.nc
+        if nc == 0:
+            return 0, 0, np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        deg = np.diff(self.crp)
+        w = int(deg.max()) if len(deg) else 0
+        R = -(-nc // ctas)
+        if w == 0 or w > wmax or R > rmax:
+            return 0, 0, np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        col = -np.ones((w, nc), dtype=np.int64)
+        edge = -np.ones((w, nc), dtype=np.int64)
+        rows = np.repeat(np.arange(nc), deg)
+        k = np.arange(len(rows)) - self.crp[rows]
+        j = self.ccol.astype(np.int64)
+        col[k, rows] = ((j // R) << 16) | (j % R)
+        edge[k, rows] = self.cedge
+        return w, R, col.ravel().astype(np.int32), edge.ravel().astype(np.int32)
+
     # numpy model of the device algorithm (used by the CPU tests to pin the algebra)
     def solve_host(self, cond, diag, rhs, core_solver=None):
         d = np.array(diag, dtype=np.float64)

@@ -230,6 +230,12 @@ typedef struct gnx_schur_plan {
   const int32_t* top_nodes;            /* [nt] nodes of the top part */
   const int32_t* top_of;               /* [B] position in top_nodes, or -1 */
   const int32_t* level_of;             /* [B] rake level of a node (nl for core nodes) */
+  /* ELL copy of the core matrix for the cluster-resident PCG (ell_w = 0: not available -- core wider
+   * than 8 entries per row or larger than 16 x 5120 rows): entry k of core row i at [k*nc + i];
+   * ell_col packs (owning CTA << 16 | offset) for ell_R rows per CTA, -1 = padding */
+  int32_t ell_w, ell_R;
+  const int32_t* ell_col;              /* [ell_w*nc] */
+  const int32_t* ell_edge;             /* [ell_w*nc] graph edge whose -cond is the entry, -1 = padding */
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

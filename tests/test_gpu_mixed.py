@@ -267,7 +267,7 @@ def test_solve_large_graphs(eng, name, n):
         assert plan.nc == dn.B and info.cg_iterations > 10
     if name == "lollipop":
         assert 0 < plan.nc < dn.B
-    assert info.cg_converged and info.cg_batches > 1
+    assert info.cg_converged and abs(info.cg_batches) > 1      # > 1 CTA (negative: one cluster)
     lay = oracle.mixed_layout(om)
     x = x.cpu().numpy()
     for lo, hi in ((0, lay["p_off"]), (lay["p_off"], lay["lam_off"]), (lay["lam_off"], lay["N"])):
