@@ -41,6 +41,27 @@ __device__ __forceinline__ EdgeFrame edge_frame(const gnx_network_t& net, const 
 // ------------------------------------------------------------------------------------
 // phase 1: edge scalars
 // ------------------------------------------------------------------------------------
+// Where the edge scalars of (local) edge e go.  Single GPU: three local arrays.  Edge-partitioned
+// network: straight into the all-gather buffer of EVERY rank -- peer stores over NVLink issued by
+// the thread that holds the value (graphnics_b200/parallel.py maps the peers' buffers with
+// torch symmetric memory), so the collective is fused into the elimination kernel and only a
+// cross-GPU barrier is left between it and the Schur kernel.
+constexpr int GNX_MAX_PEERS = 8;
+struct EdgeOut {
+  double* base[GNX_MAX_PEERS];        // destination buffers (n = 1: base[0] = cond)
+  int32_t n;
+  int64_t off_rsrc, off_ftot;         // offsets of the rsrc / ftot arrays relative to base (in doubles)
+  __device__ __forceinline__ void put(int32_t e, double c, double r, double f) const {
+#pragma unroll
+    for (int k = 0; k < GNX_MAX_PEERS; ++k) {
+      if (k < n) {
+        double* p = base[k];
+        p[e] = c; p[off_rsrc + e] = r; p[off_ftot + e] = f;
+      }
+    }
+  }
+};
+
 // One thread per cell; a segment of `seg` = min(m, blockDim) consecutive threads owns one edge
 // (several edges per block when m < 256, several chunks per edge when m > 1024).
 struct EdgeTiling { int threads, seg, edges_per_block; };
@@ -55,8 +76,7 @@ static inline EdgeTiling edge_tiling(int32_t n) {
 
 __global__ void __launch_bounds__(1024)
 edge_eliminate_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
-                      double inv_sigma, const double* __restrict__ b, int seg,
-                      double* __restrict__ cond, double* __restrict__ rsrc, double* __restrict__ ftot) {
+                      double inv_sigma, const double* __restrict__ b, int seg, EdgeOut out) {
   __shared__ double sh[3 * 32];
   const int epb = blockDim.x / seg;
   const int32_t e = blockIdx.x * epb + threadIdx.x / seg;
@@ -85,9 +105,7 @@ edge_eliminate_kernel(gnx_network_t net, GnxMixedDims d, const double* __restric
   gnx_seg_sum<3>(acc, seg, sh);
   if (active && gl == 0) {
     const double a = a_edge[e];
-    cond[e] = 1.0 / (a * acc[2]);
-    rsrc[e] = acc[1] - a * acc[0];
-    ftot[e] = carry;
+    out.put(e, 1.0 / (a * acc[2]), acc[1] - a * acc[0], carry);
   }
 }
 
@@ -147,8 +165,7 @@ __device__ __forceinline__ void tile_load(const TileCtx& c, const double* __rest
 template <int CPT>
 __global__ void __launch_bounds__(ET_T)
 edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
-                           double inv_sigma, const double* __restrict__ b,
-                           double* __restrict__ cond, double* __restrict__ rsrc, double* __restrict__ ftot) {
+                           double inv_sigma, const double* __restrict__ b, EdgeOut out) {
   constexpr int TILE = ET_T * CPT;
   __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
   __shared__ double sh[3 * 32];
@@ -180,36 +197,62 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
   gnx_seg_sum<3>(acc, segT, sh);
   if (c.active && c.kk0 == 0) {
     const double a = a_edge[c.e];
-    cond[c.e] = 1.0 / (a * acc[2]);
-    rsrc[c.e] = acc[1] - a * acc[0];
-    ftot[c.e] = tot;
+    out.put(c.e, 1.0 / (a * acc[2]), acc[1] - a * acc[0], tot);
   }
 }
 
 template <int CPT>
 static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
-                                  const double* b, double* cond, double* rsrc, double* ftot, cudaStream_t st) {
+                                  const double* b, const EdgeOut& out, cudaStream_t st) {
   const int G = (ET_T * CPT) >> net->n;
-  edge_eliminate_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
-      *net, d, co->a_edge, 1.0 / co->sigma, b, cond, rsrc, ftot);
+  edge_eliminate_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b, out);
+}
+
+static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
+                            const EdgeOut& out, cudaStream_t st) {
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, st);
+  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, out, st);
+  else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, st);
+  else {
+    const EdgeTiling t = edge_tiling(net->n);
+    edge_eliminate_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
+        *net, d, co->a_edge, 1.0 / co->sigma, b, t.seg, out);
+  }
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
 }
 
 extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                                         const double* b, double* cond, double* rsrc, double* ftot,
                                         void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && cond && rsrc && ftot && net->h && co->sigma != 0.0);
-  const GnxMixedDims d = gnx_mixed_dims(*net);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, cond, rsrc, ftot, st);
-  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, cond, rsrc, ftot, st);
-  else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, cond, rsrc, ftot, st);
-  else {
-    const EdgeTiling t = edge_tiling(net->n);
-    edge_eliminate_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
-        *net, d, co->a_edge, 1.0 / co->sigma, b, t.seg, cond, rsrc, ftot);
+  EdgeOut out;
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  out.base[0] = cond; out.n = 1;
+  out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+  return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
+}
+
+// Edge-partitioned network: the same elimination, but every edge scalar is stored straight into the
+// all-gather buffer of every rank (peers_host[r] = device address, valid on THIS GPU, of rank r's
+// buffer; layout per rank block: [cond | rsrc | ftot] of `chunk` doubles each, block of rank q at
+// q * 3 * chunk).  No collective call is left; the caller separates this kernel from the Schur kernel
+// with a cross-GPU barrier.
+extern "C" int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
+                                            const double* b, int32_t world, int32_t rank, int32_t chunk,
+                                            double* const* peers_host, void* stream) {
+  GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && peers_host);
+  GNX_CHECK_ARG(world >= 1 && world <= GNX_MAX_PEERS && rank >= 0 && rank < world && chunk >= net->E);
+  EdgeOut out;
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  for (int k = 0; k < world; ++k) {
+    GNX_CHECK_ARG(peers_host[k] != nullptr);
+    out.base[k] = peers_host[k] + (int64_t)rank * 3 * chunk;
   }
-  GNX_LAUNCH_CHECK();
-  return GNX_OK;
+  out.n = world;
+  out.off_rsrc = chunk; out.off_ftot = 2 * (int64_t)chunk;
+  return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------

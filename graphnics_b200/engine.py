@@ -58,9 +58,14 @@ def lincomb(lib, coefs, vecs, out=None):
 
 
 class MixedSystem:
-    def __init__(self, dn: DeviceNetwork, group=None):
+    def __init__(self, dn: DeviceNetwork, group=None, exchange="auto"):
         self.dn = dn
         self.group = group           # torch.distributed process group of a partitioned network
+        # how a partitioned solve gathers the edge scalars: "p2p" = peer stores fused into the elimination
+        # kernel (torch symmetric memory maps the peers' buffers) + one cross-GPU barrier; "nccl" = one
+        # all_gather_into_tensor; "auto" = p2p when symmetric memory can be set up, else nccl
+        self.exchange_mode = exchange
+        self._p2p = None
         self.lib = _lib.require_device()
         self.N = dn.mixed_ndofs
         self.nnz = dn.mixed_nnz
@@ -249,6 +254,36 @@ class MixedSystem:
             self._plan = (s, keep, work, hp)
         return self._plan
 
+    def _p2p_setup(self):
+        """two symmetric all-gather buffers (alternating per solve: a fast rank may already be writing
+        the next solve's scalars into a peer that is still reading this solve's)"""
+        if self._p2p is not None or self.exchange_mode == "nccl":
+            return self._p2p
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            dn = self.dn
+            world = dn.part[1]
+            if world > 8:
+                raise RuntimeError("more than 8 peers")
+            group = self.group if self.group is not None else dist.group.WORLD
+            bufs, hdls, ptrs = [], [], []
+            for _ in range(2):
+                t = symm.empty(world * 3 * dn.chunk, dtype=torch.float64, device=self.dev)
+                t.zero_()
+                h = symm.rendezvous(t, group)
+                bufs.append(t); hdls.append(h)
+                ptrs.append((C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]))
+            self._p2p = dict(bufs=bufs, hdls=hdls, ptrs=ptrs, step=0)
+            self.exchange_mode = "p2p"
+        except Exception as ex:          # no peer access / symmetric memory: the NCCL collective still works
+            if self.exchange_mode == "p2p":
+                raise
+            self._p2p_error = repr(ex)
+            self.exchange_mode = "nccl"
+            self._p2p = None
+        return self._p2p
+
     def eliminate(self, co, b):
         """phase 1: per-edge scans -> edge scalars (device only, no sync)."""
         d = self._bufs()
@@ -279,14 +314,32 @@ class MixedSystem:
         info = info if info is not None else SolveInfo()
         x = x if x is not None else self._f64(self.N)
         st = current_stream()
-        if not eliminated:
+        p2p = None
+        if dn.part is not None and exchange is None and not eliminated and dn.B > 0:
+            p2p = self._p2p_setup()
+        loc_cond, loc_rsrc = d["cond"], d["rsrc"]
+        if p2p is not None:
+            # elimination with the all-gather fused in: peer stores over NVLink, then one barrier
+            k = p2p["step"] & 1
+            p2p["step"] += 1
+            rank, world = dn.part
+            check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), world, rank, dn.chunk,
+                                                        p2p["ptrs"][k], st))
+            p2p["hdls"][k].barrier(channel=0)
+            g = p2p["bufs"][k]
+            loc_cond = g[rank * 3 * dn.chunk:]
+            loc_rsrc = g[rank * 3 * dn.chunk + dn.chunk:]
+        elif not eliminated:
             self.eliminate(co, b)
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
             lam = x[dn.lam_off:]
             cond, rsrc, ftot = d["cond"], d["rsrc"], d["ftot"]
             chunk = stride = 0
-            if dn.part is not None:
+            if p2p is not None:
+                chunk, stride = dn.chunk, 3 * dn.chunk
+                cond, rsrc, ftot = g, g[chunk:], g[2 * chunk:]
+            elif dn.part is not None:
                 # the only exchange of the solve: every rank needs the edge scalars of all edges
                 # (3 doubles per edge); the Schur solve itself is replicated, so no further traffic
                 if exchange is not None:          # single-process emulation of the ranks (tests)
@@ -310,7 +363,7 @@ class MixedSystem:
                 info.cg_rel_resid = float(resid.value)
             else:
                 check(self.lib.gnx_schur_solve(*args, None, None, st))
-        check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+        check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(loc_cond), ptr(loc_rsrc),
                                               ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
         return x, info
 

@@ -27,11 +27,11 @@ __all__ = ["PartitionedMixed", "run_partitioned_bench", "global_residual"]
 class PartitionedMixed:
     """the mixed system of the whole network, this rank's share"""
 
-    def __init__(self, pos, edges, n, rank=None, world=None, device=None, group=None):
+    def __init__(self, pos, edges, n, rank=None, world=None, device=None, group=None, exchange="auto"):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.dn = DeviceNetwork(pos, edges, n, device=device, part=(self.rank, self.world))
-        self.ms = MixedSystem(self.dn, group=group)
+        self.ms = MixedSystem(self.dn, group=group, exchange=exchange)
         self.E_glob, self.m = self.dn.E_glob, self.dn.m
         self.N_glob = self.E_glob * (2 * self.m + 1) + self.dn.B
 
@@ -72,7 +72,7 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
     dev = torch.device("cuda", local)
     levels = tree_levels + int(np.ceil(np.log2(world)))
     pos, edges, _, _ = murray_tree(levels, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
-    pm = PartitionedMixed(pos, edges, n, device=dev)
+    pm = PartitionedMixed(pos, edges, n, device=dev, exchange=os.environ.get("GNX_EXCHANGE", "auto"))
     dn, ms = pm.dn, pm.ms
     ms.build_pattern()
     ms.schur_plan()
@@ -140,7 +140,10 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": config_dict(levels, n, pm.E_glob, N, {
                    "parallelism": f"edge-partitioned x{world} (contiguous equal edge ranges), replicated Schur solve, "
-                                  f"one all-gather of 24 B/edge per solve",
+                                  f"one exchange of 24 B/edge per solve",
+                   "exchange": ("peer stores over NVLink fused into the elimination kernel + one cross-GPU barrier"
+                                if ms.exchange_mode == "p2p" else
+                                f"NCCL all_gather_into_tensor ({getattr(ms, '_p2p_error', '')})"),
                    "edges_per_rank": dn.E, "ndofs_per_rank": N_loc, "bifurcations": dn.B}),
                "rel_residual": rel_resid, "gpu_launches": 5 * args.steps,
                "schur": {"rake_levels": len(hp.levels), "core": hp.nc},

@@ -198,6 +198,16 @@ int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords, co
 int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                              const double* b, double* cond, double* rsrc, double* ftot, void* stream);
 
+/* Edge-partitioned network (one process per GPU): the same elimination with the collective fused in --
+ * every edge scalar is stored straight into the all-gather buffer of EVERY rank over NVLink peer
+ * mappings.  peers_host[r] = device address (valid on this GPU) of rank r's buffer of
+ * world*3*chunk doubles; rank q's block [cond | rsrc | ftot] (chunk doubles each) sits at q*3*chunk --
+ * the layout gnx_schur_solve reads with (chunk, rank_stride = 3*chunk).  The caller puts a cross-GPU
+ * barrier between this kernel and gnx_schur_solve.  world <= 8. */
+int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
+                                 int32_t world, int32_t rank, int32_t chunk, double* const* peers_host,
+                                 void* stream);
+
 /* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics),
  * as explicit arrays -- inspection / tests; gnx_schur_solve builds the same quantities itself.
  *   b_lam [B] (lambda rows of b, may be NULL), sdiag [B], soff [2E] (aligned with inc_edge),

@@ -28,7 +28,7 @@ def main():
     cases.append(("honeycomb12", pos, edges, 3))
     ok = True
     for name, pos, edges, n in cases:
-        pm = PartitionedMixed(pos, edges, n)
+        pm = PartitionedMixed(pos, edges, n, exchange=os.environ.get("GNX_EXCHANGE", "auto"))
         dn, ms = pm.dn, pm.ms
         rng = np.random.default_rng(1)
         Res = rng.uniform(0.5, 2.0, size=len(edges))
@@ -39,6 +39,8 @@ def main():
         b = ms.rhs(None, None, ms.end_values(dev(pbc(xq.cpu().numpy()))), dev(pbc(pos)), f_const=0.3)
         vals = ms.assemble(co)
         x, info = ms.solve(co, b)
+        for _ in range(3):                      # repeated solves alternate the two exchange buffers
+            x, info = ms.solve(co, b)
         resid = global_residual(ms, vals, x, b)
         om = oracle.build_mesh(pos, edges, n)
         A = oracle.assemble_mixed(om, Res)
@@ -52,7 +54,8 @@ def main():
         ok = ok and good
         if rank == 0:
             print(f"{'OK' if good else 'FAIL'} {name}: world={world} N={pm.N_glob} max rel err vs oracle LU "
-                  f"{float(t[0]):.2e}, global residual {resid:.2e}, cg iterations {info.cg_iterations}")
+                  f"{float(t[0]):.2e}, global residual {resid:.2e}, cg iterations {info.cg_iterations}, "
+                  f"exchange {ms.exchange_mode} {getattr(ms, '_p2p_error', '')}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
