@@ -85,8 +85,8 @@ class MixedSystem:
         E = self.dn.E
         if torch.is_tensor(value):
             return value.to(device=self.dev, dtype=torch.float64).contiguous().reshape(E)
-        arr = np.broadcast_to(np.asarray(value, dtype=np.float64), (E,))
-        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+        arr = np.broadcast_to(np.asarray(value, dtype=np.float64), (E,)).copy()
+        return torch.from_numpy(arr).to(self.dev)
 
     def coeffs(self, a_edge, k_edge=None, sigma=1.0):
         a = self.edge_array(a_edge)
