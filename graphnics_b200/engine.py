@@ -367,6 +367,34 @@ class MixedSystem:
                                               ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
         return x, info
 
+    def assemble_rhs_solve(self, co, vals, b, x, rhs_kwargs=None, overlap=True, **solve_kw):
+        """One whole `MixedHydraulicNetwork.solve()` step (flow_models.py:337-350): CSR values, right-hand
+        side, solve.  The solver never reads the assembled values, so with overlap=True the assembly
+        kernel runs on the caller's stream while right-hand side -> elimination -> Schur kernel ->
+        back-substitution run on a HIGH-PRIORITY side stream: the Schur phase is latency-bound and
+        occupies one CTA (or one cluster, or a cross-GPU barrier when partitioned) and the
+        bandwidth-bound assembly fills the SMs it leaves idle.  Both streams are joined before return
+        (stream-ordered; no host synchronisation unless solve_kw asks for solver info)."""
+        rhs_kwargs = rhs_kwargs or {}
+        if not overlap:
+            self.assemble(co, out=vals)
+            self.rhs(out=b, **rhs_kwargs)
+            return self.solve(co, b, x=x, **solve_kw)
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_hi_stream", None) is None:
+            self._hi_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._ev = (torch.cuda.Event(), torch.cuda.Event())
+        hi, (ev0, ev1) = self._hi_stream, self._ev
+        ev0.record(cur)
+        hi.wait_event(ev0)
+        with torch.cuda.stream(hi):
+            self.rhs(out=b, **rhs_kwargs)
+            out = self.solve(co, b, x=x, **solve_kw)
+            ev1.record(hi)
+        self.assemble(co, out=vals)
+        cur.wait_event(ev1)
+        return out
+
     def solve_bc(self, co, b, x, bcs=None, **kw):
         """solve with the model's Dirichlet data applied (the mixed model has none, flow_models.py:334)"""
         return self.solve(co, b, x=x, **kw)

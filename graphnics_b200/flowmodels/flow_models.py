@@ -160,16 +160,21 @@ class _MixedLForm:
             self.pbc_out = ms.project_end_values(pbc)
         self._pbc = pbc
 
-    def assemble(self):
+    def rhs_kwargs(self):
+        """keyword arguments of MixedSystem.rhs for this form (the inlet p_bc term is evaluated NOW)"""
         ms = self.model._system()
-        if self.zero:
-            return AssembledVector(ms, torch.zeros(ms.N, dtype=torch.float64, device=ms.dev))
         pbc = as_coefficient(self.model.p_bc)
         pbc_node = None
         if not (pbc.is_constant and pbc.const_value() == 0.0):
             pbc_node = pbc.eval_device(ms.dn.pos)
-        b = ms.rhs(self.f_nodal, self.g_nodal, self.pbc_out, pbc_node, self.f_const, self.g_const)
-        return AssembledVector(ms, b)
+        return dict(f_nodal=self.f_nodal, g_nodal=self.g_nodal, pbc_out=self.pbc_out, pbc_node=pbc_node,
+                    f_const=self.f_const, g_const=self.g_const)
+
+    def assemble(self):
+        ms = self.model._system()
+        if self.zero:
+            return AssembledVector(ms, torch.zeros(ms.N, dtype=torch.float64, device=ms.dev))
+        return AssembledVector(ms, ms.rhs(**self.rhs_kwargs()))
 
 
 # ------------------------------------------------------------------------------------------
@@ -226,13 +231,18 @@ class MixedHydraulicNetwork:
         return [[], []]
 
     def solve(self):
+        """a_form + L_form + ii_assemble + ii_convert + LUSolver("mumps") (flow_models.py:337-350) as one
+        step: the CSR values (kept on `self.A`) are assembled while the solve runs."""
         W = self.W
-        a = self.a_form()
-        L = self.L_form()
-        A, b = map(ii_assemble, (a, L))
-        qp = ii_Function(W)
         ms = self._system()
-        _, self.solve_info = ms.solve(A.coeffs, b.tensor, x=qp.tensor())
+        L = self.L_form()
+        co = self._coeffs(1.0, 0.0)
+        ms.build_pattern()
+        vals = torch.empty(ms.nnz, dtype=torch.float64, device=ms.dev)
+        b = torch.empty(ms.N, dtype=torch.float64, device=ms.dev)
+        qp = ii_Function(W, data=torch.empty(ms.N, dtype=torch.float64, device=ms.dev))
+        _, self.solve_info = ms.assemble_rhs_solve(co, vals, b, qp.tensor(), L.rhs_kwargs())
+        self.A, self.b = AssembledMatrix(ms, vals, co, "mixed"), AssembledVector(ms, b)
         qp.touch()
         return qp
 

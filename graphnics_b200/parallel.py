@@ -87,10 +87,11 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
     pbc_node = dn.pos[:, 1].contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    rhs_kw = dict(pbc_out=pbc_out, pbc_node=pbc_node)
+    overlap = not getattr(args, "no_overlap", False)
+
     def step():
-        ms.assemble(co, out=vals)
-        ms.rhs(None, None, pbc_out, pbc_node, out=b)
-        ms.solve(co, b, x=x, sync=False)
+        ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=overlap, sync=False)
 
     clocks = ClockSampler(local).start() if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
@@ -117,9 +118,7 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
 
     def e2e_step():
         co2 = ms.coeffs(res_host.to(dev, non_blocking=True))
-        ms.assemble(co2, out=vals)
-        ms.rhs(None, None, pbc_out, pbc_node, out=b)
-        ms.solve(co2, b, x=x, sync=False)
+        ms.assemble_rhs_solve(co2, vals, b, x, rhs_kw, overlap=overlap, sync=False)
         xh.copy_(x, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     for _ in range(3):

@@ -69,3 +69,22 @@ def test_generators_match_reference_golden_without_mesh():
         gpos, gedges = golden_arrays(name)
         assert np.array_equal(edges, gedges), name
         assert np.array_equal(pos.view(np.int64), gpos.view(np.int64)), name
+
+
+def test_make_arterial_tree_matches_reference_run():
+    """data/generate_arterial_tree.py:34-188 (segment-intersection rejection included): edge lists equal
+    the reference's own run (62 / 119 edges at N = 6 / 7, demo/Tree Profiling.ipynb:54-55), positions to
+    rounding (the reference rotates with scipy's Rotation, we with the 2x2 matrix)."""
+    from _util import golden_arrays
+    from graphnics_b200 import make_arterial_tree
+    counts = []
+    for N in range(1, 8):
+        signs = np.tile([-1, 1], 200).tolist()
+        G = make_arterial_tree(N, directions=signs, gam=0.9, radius0=0.1, mesh=False)
+        pos, edges = G._graph_arrays()
+        gpos, gedges = golden_arrays(f"arterial_tree_N{N}")
+        assert np.array_equal(edges, gedges)
+        np.testing.assert_allclose(pos, gpos, rtol=0, atol=1e-12)
+        counts.append(len(edges))
+        assert len(signs) < 400 or N == 1          # `directions` is consumed, like the reference (:127)
+    assert counts == [1, 3, 7, 15, 31, 62, 119]
