@@ -46,7 +46,8 @@ class gnx_schur_plan_t(C.Structure):
         ("lvl_nodes", C.c_void_p), ("parent", C.c_void_p), ("pedge", C.c_void_p), ("ch_ptr", C.c_void_p),
         ("ch_idx", C.c_void_p), ("core_nodes", C.c_void_p), ("crp", C.c_void_p), ("ccol", C.c_void_p),
         ("cedge", C.c_void_p), ("top_nodes", C.c_void_p), ("top_of", C.c_void_p), ("level_of", C.c_void_p),
-        ("ell_w", C.c_int32), ("ell_R", C.c_int32), ("ell_col", C.c_void_p), ("ell_edge", C.c_void_p),
+        ("ell_w", C.c_int32), ("ell_R", C.c_int32), ("top_S", C.c_int32), ("reserved", C.c_int32),
+        ("ell_col", C.c_void_p), ("ell_edge", C.c_void_p),
     ]
 
 

@@ -396,18 +396,37 @@ __device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const* pa
 // diagonal / rhs / link weight live in shared memory, and a level costs one block barrier instead
 // of a chain of dependent global loads.  Children below the top part are final in global memory.
 constexpr int TOP_ROWS = GNX_TOP_MAX / SCH_T;
+constexpr int CL_CTAS = 16;          // CTAs of the one cluster a cluster-mode solve runs as
+constexpr int CL_T = 512;            // threads per CTA in cluster mode (128 registers per thread available)
 constexpr size_t SCH_SMEM = 3 * GNX_TOP_MAX * sizeof(double);
 
+// CLUSTER = false: one CTA of SCH_T threads, top-local index ti = tid + q*SCH_T.
+// CLUSTER = true : the top part is spread over the CTAs of one cluster, CTA `rank` owns the slots
+//                  [rank*S, (rank+1)*S) (S = plan.top_S, a power of two); a child / parent in another
+//                  CTA is read over distributed shared memory and a level costs one hardware cluster
+//                  barrier -- a whole tree of up to 16*2048 bifurcations then needs no grid barrier.
+template <bool CLUSTER, int ROWS>
 __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double* sr, double* sw) {
   const gnx_schur_plan_t& pl = a.plan;
-  const int tid = threadIdx.x;
-  int32_t node[TOP_ROWS], lev[TOP_ROWS], ptop[TOP_ROWS], k0[TOP_ROWS], k1[TOP_ROWS];
-  double d[TOP_ROWS], r[TOP_ROWS], w[TOP_ROWS];
+  const int tid = threadIdx.x, T = blockDim.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int32_t S = CLUSTER ? pl.top_S : GNX_TOP_MAX;
+  const int sshift = 31 - __clz(S);
+  const int32_t base = CLUSTER ? (int32_t)cluster.block_rank() * S : 0;
+  auto rd = [&](double* arr, int32_t tc) -> double {
+    if (!CLUSTER) return arr[tc];
+    const double* p = cluster.map_shared_rank(arr, tc >> sshift);
+    return p[tc & (S - 1)];
+  };
+  auto lsync = [&]() { if (CLUSTER) cluster.sync(); else __syncthreads(); };
+  int32_t node[ROWS], lev[ROWS], ptop[ROWS], k0[ROWS], k1[ROWS];
+  double d[ROWS], r[ROWS], w[ROWS];
 #pragma unroll
-  for (int q = 0; q < TOP_ROWS; ++q) {
-    const int32_t ti = tid + q * SCH_T;
+  for (int q = 0; q < ROWS; ++q) {
+    const int32_t li = tid + q * T;
+    const int32_t ti = base + li;
     lev[q] = -1; node[q] = 0; ptop[q] = -1; k0[q] = k1[q] = 0; d[q] = 1.0; r[q] = 0.0; w[q] = 0.0;
-    if (ti < pl.nt) {
+    if (li < S && ti < pl.nt) {
       const int32_t i = pl.top_nodes[ti];
       node[q] = i;
       lev[q] = pl.level_of[i];
@@ -425,42 +444,42 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
         }
       }
       d[q] = di; r[q] = ri;
-      sd[ti] = di; sr[ti] = ri; sw[ti] = w[q];
+      sd[li] = di; sr[li] = ri; sw[li] = w[q];
     }
   }
-  __syncthreads();
+  lsync();
   for (int l = pl.l_split + 1; l < pl.nl; ++l) {            // up: level l_split has no top children
 #pragma unroll
-    for (int q = 0; q < TOP_ROWS; ++q) {
+    for (int q = 0; q < ROWS; ++q) {
       if (lev[q] == l) {
         for (int32_t k = k0[q]; k < k1[q]; ++k) {
           const int32_t tc = pl.top_of[pl.ch_idx[k]];      // L1 hits: fetched in the prologue
           if (tc >= 0) {
-            const double wc = sw[tc];
-            const double t = wc / sd[tc];
+            const double wc = rd(sw, tc);
+            const double t = wc / rd(sd, tc);
             d[q] -= wc * t;
-            r[q] -= t * sr[tc];
+            r[q] -= t * rd(sr, tc);
           }
         }
-        const int32_t ti = tid + q * SCH_T;
-        sd[ti] = d[q]; sr[ti] = r[q];
+        const int32_t li = tid + q * T;
+        sd[li] = d[q]; sr[li] = r[q];
       }
     }
-    __syncthreads();
+    lsync();
   }
   for (int l = pl.nl - 1; l >= pl.l_split; --l) {           // down: sr[] turns into the solution
 #pragma unroll
-    for (int q = 0; q < TOP_ROWS; ++q) {
+    for (int q = 0; q < ROWS; ++q) {
       if (lev[q] == l) {
         double ri = r[q];
-        if (ptop[q] >= 0) ri -= w[q] * sr[ptop[q]];
+        if (ptop[q] >= 0) ri -= w[q] * rd(sr, ptop[q]);
         const double xi = ri / d[q];
-        sr[tid + q * SCH_T] = xi;
+        sr[tid + q * T] = xi;
         a.P[node[q]] = xi;
         if (a.lam_out) a.lam_out[node[q]] = xi * a.inv_sigma;
       }
     }
-    __syncthreads();
+    lsync();
   }
 }
 
@@ -476,8 +495,6 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
 // the two barriers of an iteration are hardware cluster barriers.
 // Shared memory: z[R] | p0[R] | p1[R] | slots[8].
 // ------------------------------------------------------------------------------------
-constexpr int CL_CTAS = 16;
-constexpr int CL_T = 512;            // threads per CTA in cluster mode (128 registers per thread available)
 constexpr int CL_RMAX = 5120;
 constexpr size_t CL_SMEM = (3 * CL_RMAX + 8) * sizeof(double);
 
@@ -656,8 +673,12 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   double rr_final = 0.0, bb_final = 0.0;
   int it = 0;
   if (pl.nc == 0) {
-    if (blockIdx.x == 0 && pl.nt > 0) top_solve(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
-    if (pl.l_split > 0) gsync();
+    if (MODE == SCH_CLUSTER) {                  // whole tree in one cluster's distributed shared memory
+      if (pl.nt > 0) top_solve<true, GNX_TOP_MAX / CL_T>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
+    } else {
+      if (blockIdx.x == 0 && pl.nt > 0) top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
+      if (pl.l_split > 0) gsync();
+    }
   } else {                                       // a core exists: l_split == nl, no top part
     // ---- phase 2: Jacobi-PCG on the core
     if (MODE == SCH_CLUSTER) {                   // launched only with an ELL plan (gnx_schur_solve)
@@ -783,7 +804,11 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
   GNX_CHECK_ARG(plan->B == net->B && plan->B > 0 && plan->nl >= 0 && plan->nl <= GNX_MAX_LEVELS);
   GNX_CHECK_ARG(plan->l_split >= 0 && plan->l_split <= plan->nl && plan->nc >= 0 && plan->nc <= plan->B);
-  GNX_CHECK_ARG(plan->nt >= 0 && plan->nt <= GNX_TOP_MAX && (plan->nc == 0 || plan->l_split == plan->nl));
+  const bool cluster_top = plan->top_S > 0;       // whole tree swept by one cluster
+  GNX_CHECK_ARG(plan->nt >= 0 && plan->nt <= (cluster_top ? CL_CTAS * plan->top_S : GNX_TOP_MAX));
+  GNX_CHECK_ARG(!cluster_top || (plan->nc == 0 && plan->l_split == 0 && plan->top_S <= GNX_TOP_MAX &&
+                                 (plan->top_S & (plan->top_S - 1)) == 0 && plan->top_S >= CL_T));
+  GNX_CHECK_ARG(plan->nc == 0 || plan->l_split == plan->nl);
   GNX_CHECK_ARG(plan->nt == 0 || (plan->top_nodes && plan->top_of && plan->level_of));
   GNX_CHECK_ARG(plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
   GNX_CHECK_ARG(plan->ell_w == 0 || (plan->ell_w <= 8 && plan->ell_col && plan->ell_edge && plan->ell_R > 0 &&
@@ -813,10 +838,24 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   const int cap = g_sch_sms * g_sch_blocks_per_sm;
   if (want > cap) want = cap;
   if (want > 2048) want = 2048;
-  if (want <= 2) {
+  if (cluster_top && g_sch_cluster_max < CL_CTAS) {
+    gnx_set_error("plan asks for a cluster-resident tree sweep but 16-CTA clusters are unavailable");
+    return GNX_ERR_CUDA;
+  }
+  if (want <= 2 && !cluster_top) {
     schur_solve_kernel<SCH_SINGLE><<<1, SCH_T, SCH_SMEM, st>>>(a);
     GNX_LAUNCH_CHECK();
     want = 1;
+  } else if (cluster_top) {
+    want = CL_CTAS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(want); cfg.blockDim = dim3(CL_T); cfg.dynamicSmemBytes = CL_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = want; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GNX_CUDA(cudaLaunchKernelEx(&cfg, schur_solve_kernel<SCH_CLUSTER>, a));
+    want = -want;
   } else if (g_sch_cluster_max >= CL_CTAS && nc > 0 && plan->ell_w > 0 && nc <= CL_CTAS * CL_T) {
     // a Krylov core with at most one row per thread of ONE cluster: cluster-resident PCG.  Measured on
     // B200 (tools/time_schur.py): 7.3 us/iteration against 7.8 for the cooperative grid at 7.4 k unknowns;

@@ -6,6 +6,7 @@ Replaces, for MixedHydraulicNetwork / NetworkStokes / TimeDepMixedHydraulicNetwo
 ii_assemble + ii_convert + LUSolver("mumps") (graphnics/flowmodels/flow_models.py:343-348).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -236,12 +237,23 @@ class MixedSystem:
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
             s = _lib.gnx_schur_plan_t()
             l_split = hp.split_level(_lib.TOP_MAX) if hp.nc == 0 else len(hp.levels)
+            top_S = 0
+            if hp.nc == 0 and _lib.TOP_MAX < dn.B <= 16 * _lib.TOP_MAX and os.environ.get("GNX_SCHUR_CLUSTER_TOP", "0") == "1":
+                # EXPERIMENT (off by default): sweep every level of a pure tree in one cluster's distributed
+                # shared memory.  Measured on B200 (tools/time_schur_tree.py) it LOSES to the default -- wide
+                # levels on the cooperative grid, the last <= 2048 nodes in one CTA's shared memory -- 59.8 vs
+                # 46.0 us at 16 k bifurcations: a DSMEM read (~215 cycles) + cluster barrier per level costs more
+                # than the three grid barriers it saves, because the one-CTA top part is so cheap per level.
+                l_split = 0
+                top_S = 512
+                while 16 * top_S < dn.B:
+                    top_S *= 2
             top, top_of, level_of = hp.top_arrays(l_split)
             s.B, s.nl, s.l_split, s.nc, s.nnzc, s.nt = dn.B, len(hp.levels), l_split, hp.nc, hp.nnzc, len(top)
             for i, v in enumerate(lvl_ptr):
                 s.lvl_ptr[i] = int(v)
             ell_w, ell_R, ell_col, ell_edge = hp.ell_arrays()
-            s.ell_w, s.ell_R = ell_w, ell_R
+            s.ell_w, s.ell_R, s.top_S = ell_w, ell_R, top_S
             for name, arr in (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
                               ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),

@@ -244,6 +244,8 @@ typedef struct gnx_schur_plan {
    * than 8 entries per row or larger than 16 x 5120 rows): entry k of core row i at [k*nc + i];
    * ell_col packs (owning CTA << 16 | offset) for ell_R rows per CTA, -1 = padding */
   int32_t ell_w, ell_R;
+  int32_t top_S, reserved;             /* > 0: a pure tree (nc = 0, l_split = 0) of <= 16*top_S nodes is swept by ONE
+                                          16-CTA cluster, top_S slots per CTA (power of two, 512..2048) */
   const int32_t* ell_col;              /* [ell_w*nc] */
   const int32_t* ell_edge;             /* [ell_w*nc] graph edge whose -cond is the entry, -1 = padding */
 } gnx_schur_plan_t;
