@@ -116,7 +116,9 @@ primal_bc_kernel(gnx_network_t net, GnxPrimalDims d, double sg, const double* __
                  double* __restrict__ vals, double* __restrict__ b) {
   const int32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= net.V) return;
-  if (net.inc_ptr[w + 1] - net.inc_ptr[w] != 1) return;          // degree-1 nodes only ("on_boundary")
+  // degree-1 nodes of the WHOLE network only ("on_boundary"); on an edge-partitioned network a
+  // bifurcation may have a single LOCAL edge, and a boundary node's edge may live on another rank
+  if (net.bix[w] >= 0 || net.inc_ptr[w + 1] - net.inc_ptr[w] != 1) return;
   const int32_t m = d.m;
   const int32_t code = net.inc_edge[net.inc_ptr[w]];
   const int32_t e = code >> 1, end = code & 1;

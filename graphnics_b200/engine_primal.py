@@ -39,8 +39,14 @@ class DirichletBC:
 
 
 class PrimalSystem:
-    def __init__(self, dn: DeviceNetwork):
+    """Edge-partitioned networks (DeviceNetwork(part=...)): q and the edge-interior p unknowns are owned
+    by the rank that owns the edge, the p unknowns at the graph nodes are replicated (like lambda in the
+    mixed model).  b's graph-node block must hold the GLOBAL values on every rank (f = 0, or summed by
+    the caller); the solve gathers the edge scalars with one all-gather and replicates the Schur solve."""
+
+    def __init__(self, dn: DeviceNetwork, group=None):
         self.dn = dn
+        self.group = group
         self.lib = _lib.require_device()
         self.dev = dn.device
         self.NC, self.NV = dn.num_cells, dn.num_vertices
@@ -205,9 +211,17 @@ class PrimalSystem:
     # ---- solve ----------------------------------------------------------------------------------
     def _bufs(self):
         if self._bufs_ is None:
-            E, B = self.dn.E, max(self.dn.B, 1)
-            self._bufs_ = dict(cond=self._f64(E), rsrc=self._f64(E), ftot=self._f64(E),
-                               P=torch.zeros(B, dtype=torch.float64, device=self.dev))
+            dn = self.dn
+            E, B = dn.E, max(dn.B, 1)
+            d = dict(P=torch.zeros(B, dtype=torch.float64, device=self.dev))
+            if dn.part is None:
+                d.update(cond=self._f64(E), rsrc=self._f64(E), ftot=self._f64(E))
+            else:                       # same packed all-gather layout as the mixed engine
+                d["pack"] = torch.zeros(3 * dn.chunk, dtype=torch.float64, device=self.dev)
+                for i, k in enumerate(("cond", "rsrc", "ftot")):
+                    d[k] = d["pack"][i * dn.chunk: i * dn.chunk + E]
+                d["gathered"] = self._f64(dn.part[1] * 3 * dn.chunk)
+            self._bufs_ = d
         return self._bufs_
 
     def schur_plan(self):
@@ -217,20 +231,37 @@ class PrimalSystem:
             self._plan = MixedSystem.schur_plan(self)
         return self._plan
 
-    def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True, bcs=None):
+    def eliminate(self, co, b):
+        d = self._bufs()
+        check(self.lib.gnx_edge_eliminate_primal(self.dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                                 ptr(d["ftot"]), current_stream()))
+
+    def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True, bcs=None,
+              exchange=None, eliminated=False):
         """x = A^{-1} b; b is the right-hand side AFTER apply_bc (Dirichlet values sit in b)."""
         dn = self.dn
         d = self._bufs()
         info = info if info is not None else SolveInfo()
         x = x if x is not None else self._f64(self.N)
         st = current_stream()
-        check(self.lib.gnx_edge_eliminate_primal(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
-                                                 ptr(d["ftot"]), st))
+        if not eliminated:
+            self.eliminate(co, b)
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
-            args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+            cond, rsrc, ftot = d["cond"], d["rsrc"], d["ftot"]
+            chunk = stride = 0
+            if dn.part is not None:
+                if exchange is not None:          # single-process emulation of the ranks (tests)
+                    exchange(d)
+                else:
+                    import torch.distributed as dist
+                    dist.all_gather_into_tensor(d["gathered"], d["pack"], group=self.group)
+                g = d["gathered"]
+                chunk, stride = dn.chunk, 3 * dn.chunk
+                cond, rsrc, ftot = g, g[chunk:], g[2 * chunk:]
+            args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(cond), ptr(rsrc), ptr(ftot),
                     None, ptr(b[self.p_off:]), ptr(d["P"]), None, ptr(work), float(rtol), int(max_iter),
-                    1 if warm_start else 0, 0, 0)
+                    1 if warm_start else 0, chunk, stride)
             if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()

@@ -96,3 +96,63 @@ def test_partitioned_solve_matches_monolithic_lu(name, n, world):
         S = part if S is None else S + part
     # the explicit-zero lambda diagonal is present on every rank: it sums to zero as well
     assert abs(S - A[lay["lam_off"]:]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name,n,world", [("honeycomb_4_4", 2, 3), ("tree7", 3, 4), ("rand2", 3, 2)])
+def test_partitioned_primal_solve_matches_monolithic_lu(name, n, world):
+    """HydraulicNetwork edge-partitioned (BASELINE config 3): q and interior p per rank, node p replicated"""
+    import torch
+    from graphnics_b200.device import DeviceNetwork
+    from graphnics_b200.engine_primal import PrimalSystem
+    if name.startswith("tree"):
+        pos, edges = _tree(int(name[4:]))
+    elif name.startswith("rand"):
+        pos, edges = random_graph(int(name[4:]), V=20, extra=5)
+    else:
+        pos, edges = golden_arrays(name)
+    om = oracle.build_mesh(pos, edges, n)
+    lay = oracle.primal_layout(om)
+    E, m, V = len(edges), 1 << n, len(pos)
+    pf = lambda x: 1.0 + 2.0 * x[..., 0] - 0.5 * x[..., 1]
+    A = oracle.assemble_primal(om, 1.3)
+    b = oracle.assemble_primal_rhs(om, f=0.0, g=-0.4)
+    dofs, bvals = oracle.primal_bc(om, oracle.Coef(pf, 1))
+    Abc, bbc = oracle.apply_bc(A, b, dofs, bvals)
+    x_ref = oracle.lu_solve(Abc, bbc)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    from graphnics_b200.coefficients import as_coefficient
+    ranks = []
+    for r in range(world):
+        dn = DeviceNetwork(pos, edges, n, part=(r, world))
+        ps = PrimalSystem(dn)
+        co = ps.coeffs(1.3)
+        bl = ps.rhs(None, as_coefficient(-0.4))
+        ps.apply_bc_rhs(1.0, dev(pf(pos)), bl)
+        # Dirichlet values are replicated data: every rank holds them at every boundary node
+        bn = bl[ps.p_off: ps.p_off + V]
+        bnd = torch.from_numpy(np.asarray(om.bnd_ixs)).cuda()
+        bn[bnd] = dev(pf(pos))[bnd]
+        ps.eliminate(co, bl)
+        ranks.append((dn, ps, co, bl))
+    gathered = torch.cat([ps._bufs()["pack"] for _, ps, _, _ in ranks])
+
+    def exchange(d):
+        d["gathered"].copy_(gathered)
+    for dn, ps, co, bl in ranks:
+        x, info = ps.solve(co, bl, exchange=exchange, eliminated=True)
+        assert info.cg_converged
+        x = x.cpu().numpy()
+        # q of the local cells = global cells [e0*m, e1*m); p at the graph nodes; p at local interior vertices
+        q_ref = x_ref[dn.e0 * m: dn.e1 * m]
+        assert np.linalg.norm(x[:ps.NC] - q_ref) <= 1e-8 * max(np.linalg.norm(q_ref), 1e-30), (name, world)
+        touched = np.unique(edges[dn.e0:dn.e1])
+        p_nodes = x[ps.p_off: ps.p_off + V]
+        p_ref = x_ref[lay["p_off"]: lay["p_off"] + V]
+        assert np.linalg.norm(p_nodes[touched] - p_ref[touched]) <= 1e-8 * np.linalg.norm(p_ref[touched])
+        # interior vertices: local id V + (k-level block) maps to the global id of the same (edge, position)
+        pv_loc = dn.parent_vertex_host()                      # [E_loc, m+1] local vertex ids
+        pv_glob = om.parent_vertex[dn.e0:dn.e1]               # global vertex ids, same local numbering pattern
+        interior = pv_loc >= V
+        xi = x[ps.p_off + pv_loc[interior]]
+        ri = x_ref[lay["p_off"] + pv_glob[interior]]
+        assert np.linalg.norm(xi - ri) <= 1e-8 * max(np.linalg.norm(ri), 1e-30)
