@@ -222,13 +222,14 @@ def run_gpu(args):
     def step():
         ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=not args.no_overlap, sync=False)
 
-    def timed(fn, reps, warm):
+    def timed(fn, reps, warm, do_flush=True):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
-            flush.fill_(1)
+            if do_flush:
+                flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             e1.synchronize()
@@ -291,6 +292,10 @@ def run_gpu(args):
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
             "frac": kernels[dom]["GBps"] / hbm, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src}
 
+    # ---- the same kernels where HBM, not launch latency, is the limit: a 17-generation tree, 2^7 cells per
+    #      edge (33.7 M DOFs, 1.1 GB of CSR values; every array is many times the 126 MB L2)
+    at_scale = kernels_at_scale(hbm, timed)
+
     # ---- e2e through the drop-in Python API, host data in / host solution out
     e2e = e2e_python_api(pos, edges, n, dn, args)
     clk = clocks.stop()
@@ -303,10 +308,60 @@ def run_gpu(args):
            "streams": ("1 (kernels back to back)" if args.no_overlap else
                        "2: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute on a "
                        "high-priority stream; joined before the step's end event"), "kernels": kernels, "roofline": roof,
-           "e2e": e2e, "clocks": clk}
+           "at_scale": at_scale, "e2e": e2e, "clocks": clk}
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(pos, edges)
     print(json.dumps(out))
+
+
+def kernels_at_scale(hbm, timed, levels=17, n=7):
+    import torch
+    from graphnics_b200.device import DeviceNetwork
+    from graphnics_b200.engine import MixedSystem
+    from graphnics_b200.synthetic import murray_tree
+    pos, edges, _, _ = murray_tree(levels, gdim=2)
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn)
+    ms.build_pattern()
+    N, nnz, NC = ms.N, ms.nnz, dn.num_cells
+    co = ms.coeffs(np.ones(dn.E))
+    vals = torch.empty(nnz, dtype=torch.float64, device=dn.device)
+    b = torch.empty(N, dtype=torch.float64, device=dn.device)
+    x = torch.empty(N, dtype=torch.float64, device=dn.device)
+    y = torch.empty(N, dtype=torch.float64, device=dn.device)
+    xq, _ = ms.dof_coordinates(False)
+    pbc_out = ms.end_values(xq[:, 1].contiguous())
+    pbc_node = dn.pos[:, 1].contiguous()
+    del xq
+    ms._xq = None
+    bufs = ms._bufs()
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    out = {"workload": f"binary tree, {levels} generations, E={dn.E}, 2^{n} cells/edge, N={N}, nnz={nnz} (L2 not flushed: "
+                       f"every array is >> L2)", "kernels": {}}
+
+    def k(name, fn, bytes_):
+        t = float(np.mean(timed(fn, 5, 2)))
+        out["kernels"][name] = {"ms": t, "algorithmic_bytes": int(bytes_), "GBps": bytes_ / t / 1e6,
+                                "frac_of_measured_hbm_peak": bytes_ / t / 1e6 / hbm}
+    k("mixed_values_tile_kernel (assembly)", lambda: ms.assemble(co, out=vals), 8 * nnz + 8 * NC)
+    k("mixed_rhs_kernel", lambda: ms.rhs(None, None, pbc_out, pbc_node, out=b), 8 * N)
+    k("edge_eliminate_tile_kernel", lambda: ms.eliminate(co, b), 8 * N + 8 * NC)
+    ms.solve(co, b, x=x, sync=False)
+    k("edge_backsub_tile_kernel", lambda: ms.lib.gnx_edge_backsub_mixed(
+        dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
+        bufs["P"].data_ptr(), x.data_ptr(), st()), 2 * 8 * N + 8 * NC)
+    k("spmv_kernel (CSR, fp64 values, int32 indices)", lambda: ms.spmv(vals, x, y), 12 * nnz + 4 * (N + 1) + 16 * N)
+    # what plain library kernels reach on the same buffers: a pure write stream is bounded well below the
+    # copy figure MEASURED_PEAKS.json quotes, which is the ceiling for the write-dominated assembly / rhs kernels
+    k("reference point: torch fill_ of the CSR values (pure write)", lambda: vals.fill_(1.0), 8 * nnz)
+    k("reference point: torch copy_ of N doubles (read + write)", lambda: y.copy_(x), 16 * N)
+    ms.assemble(co, out=vals)
+    t = float(np.mean(timed(lambda: ms.assemble_rhs_solve(co, vals, b, x, dict(pbc_out=pbc_out, pbc_node=pbc_node), sync=False), 5, 2)))
+    rr, bb = ms.residual(vals, x, b).cpu().tolist()
+    out["assemble_plus_solve"] = {"ms": t, "MDOF_per_s": N / t / 1e3, "rel_residual": float(np.sqrt(rr / bb))}
+    del vals, b, x, y, ms, dn
+    torch.cuda.empty_cache()
+    return out
 
 
 def e2e_python_api(pos, edges, n, dn, args):

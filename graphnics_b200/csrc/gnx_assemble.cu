@@ -82,15 +82,21 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + net.ebif_prefix[e0 + nE];
   const int32_t k0 = threadIdx.x * CPT;
   const int32_t le = k0 >> n;
+  uint32_t upmask = 0;                 // bit i: the lower position of my cell i has the lower q-dof number
+  int32_t pslot = 0;                   // first of my cells in the tile's p-row range (lo-frame cell t0)
+  double psgn = 0.0;
+  int32_t t0 = 0;
   if (le < nE) {
     const int32_t e = e0 + le;
-    const int32_t t0 = k0 & (m - 1);
+    t0 = k0 & (m - 1);
     const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
     const bool flip = u > v;
     const int32_t blo = net.bix[flip ? v : u], bhi = net.bix[flip ? u : v];
     const double a = a_edge ? a_edge[e] : a_const;
     const double kk = k_edge ? k_edge[e] : 0.0;
     const double sgn = flip ? -sg : sg;
+    psgn = sgn;
+    pslot = le * m;
     const double* he = net.h + (int64_t)e * m;
     const int32_t lm = __ldg(net.loc + m);
     const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base);
@@ -101,6 +107,7 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
       const bool hasl = t > 0, hasr = t < m;
       const double hr = hasr ? he[flip ? m - 1 - t : t] : 0.0;     // lo-frame cell t
       const int32_t lr = hasr ? __ldg(net.loc + t + 1) : 0;
+      if (hasr && lc < lr) upmask |= 1u << (t - t0);
       const int32_t off = ebase + 5 * lc - (lc > 0 ? 2 - (blo >= 0) : 0) - (lc > lm ? 2 - (bhi >= 0) : 0);
       double diag = 0.0;
       const int32_t nq = 1 + hasl + hasr;
@@ -126,23 +133,24 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   __syncthreads();
   const int32_t len = (int32_t)(end - base);
   for (int32_t i = threadIdx.x; i < len; i += ASM_T) vals[base + i] = stage[i];
-  // p-rows of the tile's cells: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal
+  __syncthreads();
+  // p-rows of the tile's cells: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal.  The
+  // sign pattern of my cells is already known (upmask); staged so that the stores are coalesced.
+  if (le < nE) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int32_t slot = 3 * (pslot + gnx_gray(t0 + i));
+      const bool up = (upmask >> i) & 1u;
+      stage[slot] = up ? -psgn : psgn;
+      stage[slot + 1] = up ? psgn : -psgn;
+      stage[slot + 2] = 0.0;
+    }
+  }
+  __syncthreads();
   const int64_t c0 = (int64_t)e0 * m;
   const int32_t ncell = nE * m;
   double* vp = vals + d.p_nnz_off + 3 * c0;
-  for (int32_t i = threadIdx.x; i < 3 * ncell; i += ASM_T) {
-    const int32_t c = i / 3, j = i - 3 * c;
-    double val = 0.0;
-    if (j < 2) {
-      const int32_t e = e0 + (c >> n);
-      const bool flip = net.edges[2 * e] > net.edges[2 * e + 1];
-      const int32_t s = gnx_inv_gray(c & (m - 1));
-      const bool up = __ldg(net.loc + s) < __ldg(net.loc + s + 1);   // lower position has the lower dof number
-      const double sgn = flip ? -sg : sg;
-      val = ((j == 0) == up) ? -sgn : sgn;
-    }
-    vp[i] = val;
-  }
+  for (int32_t i = threadIdx.x; i < 3 * ncell; i += ASM_T) vp[i] = stage[i];
 }
 
 template <int CPT>
@@ -223,6 +231,69 @@ mixed_rhs_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ f
   b[r] = gnx_mixed_rhs_row(net, d, r, f_nodal, g_nodal, fc, gc, pbc_out, pbc_node);
 }
 
+// Constant f / g (the steady models with boundary data only, and every Constant source): an edge-tile
+// kernel -- thread per CPT positions, values staged at their dof slots in shared memory, coalesced
+// stream-out; with f = g = 0 it reads nothing but the edge ends.  lambda rows are zero.
+template <int CPT>
+__global__ void __launch_bounds__(ASM_T)
+mixed_rhs_const_tile_kernel(gnx_network_t net, GnxMixedDims d, double fc, double gc,
+                            const double* __restrict__ pbc_out, const double* __restrict__ pbc_node,
+                            int32_t nb_tiles, double* __restrict__ b) {
+  constexpr int TILE = ASM_T * CPT;
+  __shared__ double sq[TILE + ASM_T], sp[TILE];
+  if ((int32_t)blockIdx.x >= nb_tiles) {
+    const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ASM_T + threadIdx.x;
+    if (r < d.N) b[r] = 0.0;
+    return;
+  }
+  const int32_t m = d.m, n = net.n;
+  const int32_t G = TILE >> n;
+  const int32_t e0 = blockIdx.x * G;
+  const int32_t nE = min(G, net.E - e0);
+  const int32_t k0 = threadIdx.x * CPT;
+  const int32_t le = k0 >> n;
+  if (le < nE) {
+    const int32_t e = e0 + le;
+    const int32_t t0 = k0 & (m - 1);
+    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+    const bool flip = u > v;
+    const bool need_h = (fc != 0.0) || (gc != 0.0);
+    const double* he = net.h + (int64_t)e * m;
+    const int32_t qb = le * (m + 1), cb = le * m;
+    const int32_t tlast = (t0 + CPT == m) ? m : t0 + CPT - 1;
+    double hl = (need_h && t0 > 0) ? he[flip ? m - t0 : t0 - 1] : 0.0;
+    for (int32_t t = t0; t <= tlast; ++t) {
+      const double hr = (need_h && t < m) ? he[flip ? m - 1 - t : t] : 0.0;
+      double out = gc * (hl + hr) * 0.5;
+      if (t == 0 || t == m) {                       // L[i] -= p_bcs[i] v ds(BOUN_OUT) - p_bc v ds(BOUN_IN)  (:324)
+        const int32_t node = (t == 0) ? gnx_imin(u, v) : gnx_imax(u, v);
+        if (net.bix[node] < 0) {
+          if (node == v) { if (pbc_out) out -= pbc_out[e]; }
+          else           { if (pbc_node) out += pbc_node[node]; }
+        }
+      }
+      sq[qb + __ldg(net.loc + t)] = out;
+      if (t < m) sp[cb + gnx_gray(t)] = fc * hr;   // L[E] += f phi dx_i  (:327)
+      hl = hr;
+    }
+  }
+  __syncthreads();
+  const int32_t ncell = nE * m, nq = nE * (m + 1);
+  double* bq = b + (int64_t)e0 * (m + 1);
+  double* bp = b + d.p_off + (int64_t)e0 * m;
+  for (int32_t i = threadIdx.x; i < nq; i += ASM_T) bq[i] = sq[i];
+  for (int32_t i = threadIdx.x; i < ncell; i += ASM_T) bp[i] = sp[i];
+}
+
+template <int CPT>
+static void launch_rhs_const_tile(const gnx_network_t* net, const GnxMixedDims& d, double fc, double gc,
+                                  const double* pbc_out, const double* pbc_node, double* b, cudaStream_t st) {
+  const int G = (ASM_T * CPT) >> net->n;
+  const int nb_tiles = gnx_blocks(net->E, G);
+  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
+  mixed_rhs_const_tile_kernel<CPT><<<nb_tiles + nb_lam, ASM_T, 0, st>>>(*net, d, fc, gc, pbc_out, pbc_node, nb_tiles, b);
+}
+
 extern "C" int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_nodal,
                                       const double* g_nodal, double f_const, double g_const,
                                       const double* pbc_out, const double* pbc_node, double* b,
@@ -230,6 +301,14 @@ extern "C" int gnx_assemble_rhs_mixed(const gnx_network_t* net, const double* f_
   if (int rc = check_net(net)) return rc;
   GNX_CHECK_ARG(b && net->h);
   const GnxMixedDims d = gnx_mixed_dims(*net);
+  if (!f_nodal && !g_nodal && net->n <= 10) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net->n == 0) launch_rhs_const_tile<1>(net, d, f_const, g_const, pbc_out, pbc_node, b, st);
+    else if (net->n == 1) launch_rhs_const_tile<2>(net, d, f_const, g_const, pbc_out, pbc_node, b, st);
+    else launch_rhs_const_tile<4>(net, d, f_const, g_const, pbc_out, pbc_node, b, st);
+    GNX_LAUNCH_CHECK();
+    return GNX_OK;
+  }
   mixed_rhs_kernel<<<gnx_blocks(d.N, 256), 256, 0, (cudaStream_t)stream>>>(
       *net, d, f_nodal, g_nodal, f_const, g_const, pbc_out, pbc_node, b);
   GNX_LAUNCH_CHECK();

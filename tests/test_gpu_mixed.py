@@ -93,6 +93,13 @@ def test_pattern_values_rhs(eng, name, n):
     nod = lambda c: dev(c(om.sub_coords).ravel())
     bg = ms.rhs(nod(f), nod(g), ms.end_values(nod(lin)), dev(lin(pos))).cpu().numpy()
     np.testing.assert_allclose(bg, b, rtol=1e-12, atol=1e-14)
+    # Constant data (edge-tile kernel), incl. a constant p_bc on both kinds of boundary ends
+    b2 = oracle.assemble_mixed_rhs(om, f=0.75, g=-1.25, p_bc=2.0)
+    bg2 = ms.rhs(None, None, dev(np.full(len(edges), 2.0)), dev(np.full(len(pos), 2.0)), f_const=0.75, g_const=-1.25)
+    np.testing.assert_allclose(bg2.cpu().numpy(), b2, rtol=1e-12, atol=1e-14)
+    b3 = oracle.assemble_mixed_rhs(om, p_bc=lin, project=False)
+    bg3 = ms.rhs(None, None, ms.end_values(nod(lin)), dev(lin(pos)))
+    np.testing.assert_allclose(bg3.cpu().numpy(), b3, rtol=1e-12, atol=1e-14)
     # SpMV against scipy
     x = rng.normal(size=A.shape[0])
     y = ms.spmv(ms.assemble(ms.coeffs(Res)), dev(x)).cpu().numpy()
