@@ -93,3 +93,59 @@ def test_golden_tables_from_the_reference_code():
         assert dn.boundary_ixs() == c["boundary_ixs"], name
         if "tangents" in c:
             assert np.array_equal(dn.tangents.cpu().numpy().view(np.int64), fromhex(c["tangents"]).view(np.int64)), name
+
+
+def test_postprocessing_helpers():
+    """GlobalFlux / GlobalCrossectionFlux (fenics_graph.py:314-375), nxgraph_attribute_to_dolfin (:437-460),
+    point evaluation of the solution components, tabulate_dof_coordinates (demo/Graphnics demo.ipynb:282)"""
+    import networkx as nx
+    import graphnics_b200 as gn
+    G = gn.Y_bifurcation()
+    G.make_mesh(5)
+    G.make_submeshes()
+    for i, e in enumerate(G.edges()):
+        G.edges[e]["Res"] = gn.Constant(1.0 + i)
+        G.edges[e]["radius"] = 0.1 * (i + 1)
+    model = gn.MixedHydraulicNetwork(G, p_bc=gn.Expression("2-x[1]", degree=2))
+    qp = model.solve()
+    E = G.num_edges
+    # SURVEY.md Appendix C closed form: q constant per edge
+    qs = [0.741549228561398, 0.444929537136839, 0.296619691424559]
+    for i in range(E):
+        assert abs(qp[i](G.nodes[1]["pos"]) - qs[i]) < 1e-11
+        assert np.allclose(qp[i].vector().get_local(), qs[i], rtol=1e-11)
+        assert qp[i].function_space().tabulate_dof_coordinates().shape == (G._dn.m + 1, 2)
+    assert abs(qp[E + 1](0.0, 0.0) - 1.629225385719301) < 1e-11          # the multiplier = pressure at the bifurcation
+    assert abs(qp[E]((0.0, 0.25)) - (2.0 - qs[0] * 1.0 * 0.25)) < 1e-2     # p drops linearly along edge 0 (DG0: cell mean, h/2 off)
+    flux = gn.GlobalFlux(G, [qp[i] for i in range(E)])
+    val = np.zeros(2)
+
+    class _Cell:
+        index = 0
+    flux.eval_cell(val, np.array([0.0, 0.1]), _Cell())
+    assert np.allclose(val, [0.0, qs[0]], atol=1e-11)                     # scalar flux times the tangent (0, 1)
+    cs = gn.GlobalCrossectionFlux(G, [qp[i] for i in range(E)])
+    v1 = np.zeros(1)
+    cs.eval_cell(v1, np.array([0.0, 0.1]), _Cell())
+    assert abs(v1[0] - qs[0]) < 1e-11
+    r = gn.nxgraph_attribute_to_dolfin(G, "radius")
+    assert abs(r(0.0, 0.2) - 0.1) < 1e-15 and abs(r(0.25, 0.75) - 0.3) < 1e-15
+
+
+def test_network_poisson_and_stokes_api():
+    """NetworkPoisson (flow_models.py:15-50) on a line: -u'' = 1, u(0)=u(1)=0 -> u = x(1-x)/2;
+    NetworkStokes (:353-430; broken as shipped, here mu := nu) reduces to the mixed model for nu = 0"""
+    import graphnics_b200 as gn
+    G = gn.line_graph(2)
+    G.make_mesh(7)
+    u = gn.NetworkPoisson(G, f=gn.Constant(1.0), p_bc=gn.Constant(0.0)).solve()
+    for x in (0.25, 0.5, 0.75):
+        assert abs(u(x, 0.0) - 0.5 * x * (1 - x)) < 1e-4
+    G = gn.Y_bifurcation()
+    G.make_mesh(4)
+    G.make_submeshes()
+    a = gn.MixedHydraulicNetwork(G, p_bc=gn.Expression("x[1]", degree=2)).solve().vector().get_local()
+    s0 = gn.NetworkStokes(G, p_bc=gn.Expression("x[1]", degree=2), nu=gn.Constant(0.0)).solve().vector().get_local()
+    assert np.allclose(a, s0, rtol=1e-12, atol=1e-14)
+    s1 = gn.NetworkStokes(G, p_bc=gn.Expression("x[1]", degree=2), nu=gn.Constant(0.5)).solve().vector().get_local()
+    assert np.allclose(a[: 3 * 17], s1[: 3 * 17], rtol=1e-9)      # q is constant per edge: the viscous term vanishes
