@@ -304,7 +304,7 @@ def run_gpu(args):
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(TREE_LEVELS, n, dn.E, N, {"nnz": nnz, "bifurcations": dn.B}),
-           "rel_residual": rel_resid, "gpu_launches": 5 * args.steps, "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
+           "rel_residual": rel_resid, "gpu_launches": 4 * args.steps, "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
            "streams": ("1 (kernels back to back)" if args.no_overlap else
                        "2: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute on a "
                        "high-priority stream; joined before the step's end event"), "kernels": kernels, "roofline": roof,

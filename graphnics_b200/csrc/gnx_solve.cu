@@ -162,18 +162,73 @@ __device__ __forceinline__ void tile_load(const TileCtx& c, const double* __rest
   }
 }
 
-template <int CPT>
+// Right-hand side with Constant f, g and boundary data only (MixedHydraulicNetwork.L_form :299-332 for
+// the steady models): cheap enough to be PRODUCED by the elimination kernel instead of being read by it.
+struct ConstRhs {
+  double fc, gc;
+  const double* pbc_out;     // [E] projected p_bc at the v end (BOUN_OUT term), or NULL
+  const double* pbc_node;    // [V] p_bc at the graph nodes (BOUN_IN term), or NULL
+  double* b;                 // [N] the right-hand side, WRITTEN by the kernel
+};
+
+// FUSED_RHS = false: b is an input, streamed into shared memory.
+// FUSED_RHS = true : the tile's part of b is computed in shared memory from `rhs` (same arithmetic as
+//                    mixed_rhs_const_tile_kernel), stored to rhs.b with coalesced stores and eliminated
+//                    right away -- one launch and one 8 B/dof read less per solve; blocks past the tiles
+//                    zero the lambda rows of b.
+template <int CPT, bool FUSED_RHS>
 __global__ void __launch_bounds__(ET_T)
 edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
-                           double inv_sigma, const double* __restrict__ b, EdgeOut out) {
+                           double inv_sigma, const double* __restrict__ b, EdgeOut out, ConstRhs rhs,
+                           int32_t nb_tiles) {
   constexpr int TILE = ET_T * CPT;
   __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
   __shared__ double sh[3 * 32];
+  if (FUSED_RHS && (int32_t)blockIdx.x >= nb_tiles) {
+    const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ET_T + threadIdx.x;
+    if (r < d.N) rhs.b[r] = 0.0;
+    return;
+  }
   const TileCtx c = tile_ctx<CPT>(net, d);
-  tile_load<CPT>(c, b, net.h, sF, sH, sG);
-  __syncthreads();
   const int32_t m = c.m;
   const int32_t cb = c.le * m, qb = c.le * (m + 1);
+  if (!FUSED_RHS) {
+    tile_load<CPT>(c, b, net.h, sF, sH, sG);
+    __syncthreads();
+  } else {
+    const int32_t ncell = c.nE * m, nq = c.nE * (m + 1);
+#pragma unroll
+    for (int r = 0; r < CPT; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < ncell) sH[i] = net.h[c.hbase + i];
+    }
+    __syncthreads();
+    if (c.active) {
+      const int32_t u = net.edges[2 * c.e], v = net.edges[2 * c.e + 1];
+      const int32_t tlast = (c.kk0 + CPT == m) ? m : c.kk0 + CPT - 1;
+      for (int32_t j = c.kk0; j <= tlast; ++j) {               // edge-local node j (u -> v), cells j-1 | j
+        const double hl = j > 0 ? sH[cb + j - 1] : 0.0, hr = j < m ? sH[cb + j] : 0.0;
+        double val = rhs.gc * (hl + hr) * 0.5;
+        if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val += rhs.pbc_node[u];     // edge OUT of a boundary node: BOUN_IN
+        if (j == m && net.bix[v] < 0 && rhs.pbc_out) val -= rhs.pbc_out[c.e];     // edge INTO a boundary node: BOUN_OUT
+        sG[qb + __ldg(net.loc + (c.flip ? m - j : j))] = val;
+        if (j < m) sF[cb + gnx_gray(c.flip ? m - 1 - j : j)] = rhs.fc * hr;
+      }
+    }
+    __syncthreads();
+    double* bq = rhs.b + c.qbase;
+    double* bp = rhs.b + c.pbase;
+#pragma unroll
+    for (int r = 0; r < CPT + 1; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < nq) bq[i] = sG[i];
+    }
+#pragma unroll
+    for (int r = 0; r < CPT; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < ncell) bp[i] = sF[i];
+    }
+  }
   double F[CPT], H[CPT];
   double sumF = 0.0, sumG = 0.0, sumH = 0.0;
 #pragma unroll
@@ -203,17 +258,27 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
 
 template <int CPT>
 static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
-                                  const double* b, const EdgeOut& out, cudaStream_t st) {
+                                  const double* b, const EdgeOut& out, const ConstRhs* rhs, cudaStream_t st) {
   const int G = (ET_T * CPT) >> net->n;
-  edge_eliminate_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b, out);
+  const int nb_tiles = gnx_blocks(net->E, G);
+  if (rhs) {
+    const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ET_T) : 0;
+    edge_eliminate_tile_kernel<CPT, true><<<nb_tiles + nb_lam, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma,
+                                                                            nullptr, out, *rhs, nb_tiles);
+  } else {
+    ConstRhs none = {0.0, 0.0, nullptr, nullptr, nullptr};
+    edge_eliminate_tile_kernel<CPT, false><<<nb_tiles, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b, out,
+                                                                      none, nb_tiles);
+  }
 }
 
 static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
-                            const EdgeOut& out, cudaStream_t st) {
+                            const EdgeOut& out, cudaStream_t st, const ConstRhs* rhs = nullptr) {
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, st);
-  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, out, st);
-  else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, st);
+  if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, rhs, st);
+  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, out, rhs, st);
+  else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, rhs, st);
+  else if (rhs) { gnx_set_error("fused rhs + elimination needs n <= 10"); return GNX_ERR_ARG; }
   else {
     const EdgeTiling t = edge_tiling(net->n);
     edge_eliminate_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
@@ -232,6 +297,33 @@ extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixe
   out.base[0] = cond; out.n = 1;
   out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
   return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
+}
+
+// MixedHydraulicNetwork.L_form with Constant f / g (flow_models.py:299-332) + elimination in ONE kernel:
+// b [N] is an OUTPUT (identical to gnx_assemble_rhs_mixed with f_nodal = g_nodal = NULL).  n <= 10.
+// peers_host != NULL: edge-partitioned variant, scalars stored to every rank (see the _p2p entry point).
+extern "C" int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
+                                       double g_const, const double* pbc_out, const double* pbc_node, double* b,
+                                       double* cond, double* rsrc, double* ftot, int32_t world, int32_t rank,
+                                       int32_t chunk, double* const* peers_host, void* stream) {
+  GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && net->n <= 10);
+  EdgeOut out;
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  if (peers_host) {
+    GNX_CHECK_ARG(world >= 1 && world <= GNX_MAX_PEERS && rank >= 0 && rank < world && chunk >= net->E);
+    for (int k = 0; k < world; ++k) {
+      GNX_CHECK_ARG(peers_host[k] != nullptr);
+      out.base[k] = peers_host[k] + (int64_t)rank * 3 * chunk;
+    }
+    out.n = world;
+    out.off_rsrc = chunk; out.off_ftot = 2 * (int64_t)chunk;
+  } else {
+    GNX_CHECK_ARG(cond && rsrc && ftot);
+    out.base[0] = cond; out.n = 1;
+    out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+  }
+  ConstRhs rhs = {f_const, g_const, pbc_out, pbc_node, b};
+  return launch_eliminate(net, co, nullptr, out, (cudaStream_t)stream, &rhs);
 }
 
 // Edge-partitioned network: the same elimination, but every edge scalar is stored straight into the

@@ -315,12 +315,14 @@ class MixedSystem:
         return out
 
     def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True,
-              exchange=None, eliminated=False):
+              exchange=None, eliminated=False, const_rhs=None):
         """x = A^{-1} b for the operator described by `co` (never forms A): edge elimination ->
         one persistent Schur kernel (rake + core PCG) -> back-substitution.
         sync=False: nothing returns to the host; `info` is not filled.
         Partitioned network: between elimination and the Schur kernel the edge scalars of all ranks
-        are all-gathered (`exchange` / `eliminated` let a test play all ranks in one process)."""
+        are all-gathered (`exchange` / `eliminated` let a test play all ranks in one process).
+        const_rhs = dict(f_const, g_const, pbc_out, pbc_node): b is PRODUCED (L_form with Constant f, g)
+        by the elimination kernel instead of being read by it (gnx_rhs_eliminate_mixed)."""
         dn = self.dn
         d = self._bufs()
         info = info if info is not None else SolveInfo()
@@ -330,17 +332,31 @@ class MixedSystem:
         if dn.part is not None and exchange is None and not eliminated and dn.B > 0:
             p2p = self._p2p_setup()
         loc_cond, loc_rsrc = d["cond"], d["rsrc"]
+        if const_rhs is not None and (dn.n > 10 or eliminated):
+            self.rhs(out=b, **const_rhs)           # no fused kernel for this case: plain right-hand side first
+            const_rhs = None
+        cr = None
+        if const_rhs is not None:
+            cr = (float(const_rhs.get("f_const", 0.0)), float(const_rhs.get("g_const", 0.0)),
+                  ptr(const_rhs.get("pbc_out")), ptr(const_rhs.get("pbc_node")), ptr(b))
         if p2p is not None:
             # elimination with the all-gather fused in: peer stores over NVLink, then one barrier
             k = p2p["step"] & 1
             p2p["step"] += 1
             rank, world = dn.part
-            check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), world, rank, dn.chunk,
-                                                        p2p["ptrs"][k], st))
+            if cr is not None:
+                check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, None, None, None, world, rank,
+                                                       dn.chunk, p2p["ptrs"][k], st))
+            else:
+                check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), world, rank, dn.chunk,
+                                                            p2p["ptrs"][k], st))
             p2p["hdls"][k].barrier(channel=0)
             g = p2p["bufs"][k]
             loc_cond = g[rank * 3 * dn.chunk:]
             loc_rsrc = g[rank * 3 * dn.chunk + dn.chunk:]
+        elif cr is not None:
+            check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, ptr(d["cond"]), ptr(d["rsrc"]),
+                                                   ptr(d["ftot"]), 0, 0, 0, None, st))
         elif not eliminated:
             self.eliminate(co, b)
         if dn.B > 0:
@@ -388,9 +404,13 @@ class MixedSystem:
         bandwidth-bound assembly fills the SMs it leaves idle.  Both streams are joined before return
         (stream-ordered; no host synchronisation unless solve_kw asks for solver info)."""
         rhs_kwargs = rhs_kwargs or {}
+        fused = rhs_kwargs.get("f_nodal") is None and rhs_kwargs.get("g_nodal") is None and self.dn.n <= 10
+        if fused:                                  # Constant f, g: the elimination kernel produces b itself
+            solve_kw = dict(solve_kw, const_rhs={k: v for k, v in rhs_kwargs.items() if k not in ("f_nodal", "g_nodal")})
         if not overlap:
             self.assemble(co, out=vals)
-            self.rhs(out=b, **rhs_kwargs)
+            if not fused:
+                self.rhs(out=b, **rhs_kwargs)
             return self.solve(co, b, x=x, **solve_kw)
         cur = torch.cuda.current_stream(self.dev)
         if getattr(self, "_hi_stream", None) is None:
@@ -400,7 +420,8 @@ class MixedSystem:
         ev0.record(cur)
         hi.wait_event(ev0)
         with torch.cuda.stream(hi):
-            self.rhs(out=b, **rhs_kwargs)
+            if not fused:
+                self.rhs(out=b, **rhs_kwargs)
             out = self.solve(co, b, x=x, **solve_kw)
             ev1.record(hi)
         self.assemble(co, out=vals)

@@ -144,7 +144,7 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
                                 if ms.exchange_mode == "p2p" else
                                 f"NCCL all_gather_into_tensor ({getattr(ms, '_p2p_error', '')})"),
                    "edges_per_rank": dn.E, "ndofs_per_rank": N_loc, "bifurcations": dn.B}),
-               "rel_residual": rel_resid, "gpu_launches": 5 * args.steps,
+               "rel_residual": rel_resid, "gpu_launches": 4 * args.steps,
                "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
                "roofline": {"bound": "hbm", "kernel": "per-rank step (assemble + rhs + eliminate + back-substitute)",
                             "achieved": (8 * (nnz_loc + dn.num_cells) + 8 * N_loc + 2 * 8 * (N_loc + dn.num_cells)

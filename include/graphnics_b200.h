@@ -198,6 +198,16 @@ int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords, co
 int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                              const double* b, double* cond, double* rsrc, double* ftot, void* stream);
 
+/* L_form with Constant f / g (what the steady models use: boundary data + constants) and the elimination
+ * in ONE kernel: b [N] is an OUTPUT, bit-identical to gnx_assemble_rhs_mixed(net, NULL, NULL, f_const,
+ * g_const, pbc_out, pbc_node, b).  Saves a launch and the 8 B/dof read of b.  n <= 10.
+ * peers_host != NULL selects the edge-partitioned output (see gnx_edge_eliminate_mixed_p2p; cond / rsrc /
+ * ftot are then ignored), else world / rank / chunk are ignored. */
+int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
+                            double g_const, const double* pbc_out, const double* pbc_node, double* b,
+                            double* cond, double* rsrc, double* ftot, int32_t world, int32_t rank,
+                            int32_t chunk, double* const* peers_host, void* stream);
+
 /* Edge-partitioned network (one process per GPU): the same elimination with the collective fused in --
  * every edge scalar is stored straight into the all-gather buffer of EVERY rank over NVLink peer
  * mappings.  peers_host[r] = device address (valid on this GPU) of rank r's buffer of

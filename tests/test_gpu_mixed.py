@@ -282,3 +282,32 @@ def test_solve_large_graphs(eng, name, n):
     # warm start from the converged multipliers: no more than a couple of iterations
     info2 = ms.solve(co, torch.from_numpy(b).cuda(), x=torch.empty_like(torch.from_numpy(b).cuda()), warm_start=True)[1]
     assert info2.cg_iterations <= max(2, info.cg_iterations // 4)
+
+
+@pytest.mark.parametrize("name,n", [("Y", 0), ("Y", 1), ("Y", 6), ("rand1", 5), ("honeycomb_4_4", 5), ("arterial_tree_N7", 6),
+                                    ("line_graph_2_dx2", 8)])
+def test_fused_rhs_elimination_and_overlapped_step(eng, name, n):
+    """gnx_rhs_eliminate_mixed (Constant f, g: b is produced by the elimination kernel) gives the same b
+    bit for bit as gnx_assemble_rhs_mixed, and the fused / overlapped step the same solution as the
+    plain sequence assemble -> rhs -> solve"""
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = graph(name)
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn)
+    rng = np.random.default_rng(8)
+    co = ms.coeffs(rng.uniform(0.5, 2.0, size=len(edges)))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    kw = dict(pbc_out=dev(rng.normal(size=len(edges))), pbc_node=dev(rng.normal(size=len(pos))), f_const=0.75, g_const=-1.25)
+    b_ref = ms.rhs(**kw)
+    vals_ref = ms.assemble(co)
+    x_ref, _ = ms.solve(co, b_ref)
+    for overlap in (False, True):
+        vals = torch.full((ms.nnz,), np.nan, dtype=torch.float64, device="cuda")
+        b = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+        x = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+        ms.assemble_rhs_solve(co, vals, b, x, kw, overlap=overlap)
+        torch.cuda.synchronize()
+        assert np.array_equal(b.cpu().numpy().view(np.int64), b_ref.cpu().numpy().view(np.int64))
+        assert np.array_equal(vals.cpu().numpy().view(np.int64), vals_ref.cpu().numpy().view(np.int64))
+        assert np.array_equal(x.cpu().numpy().view(np.int64), x_ref.cpu().numpy().view(np.int64))
