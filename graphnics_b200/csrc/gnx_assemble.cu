@@ -3,6 +3,7 @@
 // element contributions; deterministic, no atomics).
 // Reference behaviour replaced: graphnics/flowmodels/flow_models.py:200-332 (a_form, L_form,
 // init_a_form) + ii_assemble/ii_convert (:343-344); time_stepping.py:75-101 (mass_matrix_q).
+#include <stdlib.h>
 #include "gnx_common.cuh"
 
 extern "C" int64_t gnx_mixed_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }
@@ -111,13 +112,15 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
       const int32_t off = ebase + 5 * lc - (lc > 0 ? 2 - (blo >= 0) : 0) - (lc > lm ? 2 - (bhi >= 0) : 0);
       double diag = 0.0;
       const int32_t nq = 1 + hasl + hasr;
+      // the stiffness term k/h (NetworkStokes) costs two fp64 divisions per row: skipped when k == 0
+      const double kl = (kk != 0.0 && hasl) ? kk / hl : 0.0, kr = (kk != 0.0 && hasr) ? kk / hr : 0.0;
       if (hasl) {
-        diag += a * hl * (2.0 / 6.0) + kk / hl;
-        stage[off + (ll > lc) + (hasr && ll > lr)] = a * hl * (1.0 / 6.0) - kk / hl;
+        diag += a * hl * (2.0 / 6.0) + kl;
+        stage[off + (ll > lc) + (hasr && ll > lr)] = a * hl * (1.0 / 6.0) - kl;
       }
       if (hasr) {
-        diag += a * hr * (2.0 / 6.0) + kk / hr;
-        stage[off + (lr > lc) + (hasl && lr > ll)] = a * hr * (1.0 / 6.0) - kk / hr;
+        diag += a * hr * (2.0 / 6.0) + kr;
+        stage[off + (lr > lc) + (hasl && lr > ll)] = a * hr * (1.0 / 6.0) - kr;
       }
       stage[off + (hasl && lc > ll) + (hasr && lc > lr)] = diag;
       // p columns: cell t-1 (coefficient -sgn) and cell t (+sgn), ordered by their Gray index
@@ -165,8 +168,10 @@ static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, 
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                          const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
   if (net->n <= 10) {
-    if (net->n == 0) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else if (net->n == 1) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    static int cpt = -1;
+    if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 4; }     // tuning knob
+    if (net->n == 0 || cpt == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else if (net->n == 1 || cpt == 2) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
     else launch_values_tile<4>(net, d, a_edge, k_edge, a_const, sg, vals, st);
     GNX_LAUNCH_CHECK();
     return GNX_OK;

@@ -272,11 +272,17 @@ static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& 
   }
 }
 
+static int edge_cpt() {           // tuning knob: cells per thread of the edge-tile kernels (default 4)
+  static int cpt = -1;
+  if (cpt < 0) { const char* e = getenv("GNX_EDGE_CPT"); cpt = e ? atoi(e) : 4; }
+  return cpt;
+}
+
 static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                             const EdgeOut& out, cudaStream_t st, const ConstRhs* rhs = nullptr) {
   const GnxMixedDims d = gnx_mixed_dims(*net);
   if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, rhs, st);
-  else if (net->n == 1) launch_eliminate_tile<2>(net, d, co, b, out, rhs, st);
+  else if (net->n == 1 || (edge_cpt() == 2 && net->n <= 9)) launch_eliminate_tile<2>(net, d, co, b, out, rhs, st);
   else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, rhs, st);
   else if (rhs) { gnx_set_error("fused rhs + elimination needs n <= 10"); return GNX_ERR_ARG; }
   else {
@@ -1136,7 +1142,7 @@ extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_
   const GnxMixedDims d = gnx_mixed_dims(*net);
   cudaStream_t st = (cudaStream_t)stream;
   if (net->n == 0) launch_backsub_tile<1>(net, d, co, b, cond, rsrc, P, x, st);
-  else if (net->n == 1) launch_backsub_tile<2>(net, d, co, b, cond, rsrc, P, x, st);
+  else if (net->n == 1 || (edge_cpt() == 2 && net->n <= 9)) launch_backsub_tile<2>(net, d, co, b, cond, rsrc, P, x, st);
   else if (net->n <= 10) launch_backsub_tile<4>(net, d, co, b, cond, rsrc, P, x, st);
   else {
     const EdgeTiling t = edge_tiling(net->n);
