@@ -181,7 +181,7 @@ class FenicsGraph(nx.DiGraph):
         converted once."""
         # same order as self.edges(): by source node, then successor insertion order
         vals = [d.get(key, default) for nbrs in self._succ.values() for d in nbrs.values()]
-        if vals and all(v is vals[0] for v in vals):                      # one shared object
+        if vals and vals.count(vals[0]) == len(vals):                     # one shared object / one value
             vals, rep = vals[:1], len(vals)
         else:
             rep = 1
