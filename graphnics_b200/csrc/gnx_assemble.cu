@@ -99,38 +99,36 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     psgn = sgn;
     pslot = le * m;
     const double* he = net.h + (int64_t)e * m;
-    const int32_t lm = __ldg(net.loc + m);
     const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base);
     const int32_t tlast = (t0 + CPT == m) ? m : t0 + CPT - 1;      // the edge's last thread also owns node m
+    const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
+    const int32_t blo1 = blo >= 0, bhi1 = bhi >= 0;
     double hl = t0 > 0 ? he[flip ? m - t0 : t0 - 1] : 0.0;         // lo-frame cell t-1
-    int32_t ll = t0 > 0 ? __ldg(net.loc + t0 - 1) : 0, lc = __ldg(net.loc + t0);
     for (int32_t t = t0; t <= tlast; ++t) {
       const bool hasl = t > 0, hasr = t < m;
       const double hr = hasr ? he[flip ? m - 1 - t : t] : 0.0;     // lo-frame cell t
-      const int32_t lr = hasr ? __ldg(net.loc + t + 1) : 0;
-      if (hasr && lc < lr) upmask |= 1u << (t - t0);
-      const int32_t off = ebase + 5 * lc - (lc > 0 ? 2 - (blo >= 0) : 0) - (lc > lm ? 2 - (bhi >= 0) : 0);
-      double diag = 0.0;
-      const int32_t nq = 1 + hasl + hasr;
+      const int2 tb = __ldg(tab + t);                              // row offset + packed slot order (device.row_table)
+      const int32_t f = tb.y;
+      const int32_t off = ebase + tb.x + ((f & 1) ? blo1 : 0) + ((f & 2) ? bhi1 : 0);
+      if (hasr && (f & (1 << 17))) upmask |= 1u << (t - t0);
       // the stiffness term k/h (NetworkStokes) costs two fp64 divisions per row: skipped when k == 0
       const double kl = (kk != 0.0 && hasl) ? kk / hl : 0.0, kr = (kk != 0.0 && hasr) ? kk / hr : 0.0;
+      double diag = 0.0;
       if (hasl) {
         diag += a * hl * (2.0 / 6.0) + kl;
-        stage[off + (ll > lc) + (hasr && ll > lr)] = a * hl * (1.0 / 6.0) - kl;
+        stage[off + ((f >> 2) & 7)] = a * hl * (1.0 / 6.0) - kl;
+        stage[off + ((f >> 11) & 7)] = -sgn;                       // p column of cell t-1
       }
       if (hasr) {
         diag += a * hr * (2.0 / 6.0) + kr;
-        stage[off + (lr > lc) + (hasl && lr > ll)] = a * hr * (1.0 / 6.0) - kr;
+        stage[off + ((f >> 8) & 7)] = a * hr * (1.0 / 6.0) - kr;
+        stage[off + ((f >> 14) & 7)] = sgn;                        // p column of cell t
       }
-      stage[off + (hasl && lc > ll) + (hasr && lc > lr)] = diag;
-      // p columns: cell t-1 (coefficient -sgn) and cell t (+sgn), ordered by their Gray index
-      const bool swp = hasl && hasr && gnx_gray(t - 1) > gnx_gray(t);
-      if (hasl) stage[off + nq + (swp ? 1 : 0)] = -sgn;
-      if (hasr) stage[off + nq + ((hasl && !swp) ? 1 : 0)] = sgn;
-      // lambda column at a bifurcation end: +sigma if the edge points INTO the node
-      if (t == 0 && blo >= 0) stage[off + nq + 1] = flip ? sg : -sg;
-      if (t == m && bhi >= 0) stage[off + nq + 1] = flip ? -sg : sg;
-      hl = hr; ll = lc; lc = lr;
+      stage[off + ((f >> 5) & 7)] = diag;
+      // lambda column at a bifurcation end (last slot of the row): +sigma if the edge points INTO the node
+      if (t == 0 && blo1) stage[off + 3] = flip ? sg : -sg;
+      if (t == m && bhi1) stage[off + 3] = flip ? -sg : sg;
+      hl = hr;
     }
   }
   __syncthreads();
@@ -167,7 +165,7 @@ static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, 
 
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                          const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
-  if (net->n <= 10) {
+  if (net->n <= 10 && net->rowtab) {
     static int cpt = -1;
     if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 4; }     // tuning knob
     if (net->n == 0 || cpt == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);

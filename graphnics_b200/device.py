@@ -45,6 +45,40 @@ def submesh_numbering(n):
     return loc.astype(np.int32), tloc.astype(np.int32)
 
 
+def row_table(n):
+    """Per-position table of the mixed q-rows (the same for every edge), [m+1, 2] int32:
+      [t, 0] = CSR offset of the row of position t inside its edge's range, assuming neither end is a
+               bifurcation: 5*loc[t] - 2*(loc[t] > 0) - 2*(loc[t] > loc[m]);
+      [t, 1] = bit 0: loc[t] > 0, bit 1: loc[t] > loc[m] (add one slot each if the lo / hi end carries a
+               multiplier), bits 2-4 / 5-7 / 8-10: slot of the left-neighbour / diagonal / right-neighbour
+               q entry, bits 11-13 / 14-16: slot of the p entry of cell t-1 / cell t, bit 17: loc[t] < loc[t+1]
+               (order of the two q columns in the p-row of cell t).
+    Columns inside a row are sorted (q columns by SubMesh-local number, then p columns by global cell)."""
+    m = 1 << n
+    loc, _ = submesh_numbering(n)
+    loc = loc.astype(np.int64)
+    t = np.arange(m + 1)
+    lm = loc[m]
+    hasl, hasr = t > 0, t < m
+    ll = np.where(hasl, loc[np.maximum(t - 1, 0)], -1)
+    lr = np.where(hasr, loc[np.minimum(t + 1, m)], -1)
+    l = loc
+    gray = lambda x: x ^ (x >> 1)
+    nq = 1 + hasl.astype(np.int64) + hasr
+    pl = (hasl & (ll > l)).astype(np.int64) + (hasl & hasr & (ll > lr))
+    pc = (hasl & (l > ll)).astype(np.int64) + (hasr & (l > lr))
+    pr = (hasr & (lr > l)).astype(np.int64) + (hasl & hasr & (lr > ll))
+    swp = hasl & hasr & (gray(np.maximum(t - 1, 0)) > gray(t))
+    ppl = nq + swp
+    ppr = nq + (hasl & ~swp)
+    up = hasr & (l < lr)
+    f0, f1 = l > 0, l > lm
+    A = 5 * l - 2 * f0 - 2 * f1
+    Bf = (f0.astype(np.int64) | (f1.astype(np.int64) << 1) | (pl << 2) | (pc << 5) | (pr << 8) | (ppl << 11)
+          | (ppr << 14) | (up.astype(np.int64) << 17))
+    return np.ascontiguousarray(np.stack([A, Bf], axis=1).astype(np.int32))
+
+
 class _Tables:
     """output of gnx_vertex_tables for one edge list (fenics_graph.py:161-184, :132-156, :280-311)"""
 
@@ -141,6 +175,7 @@ class DeviceNetwork:
             self.loc_host, self.tloc_host = loc, tloc
             self.loc = torch.from_numpy(loc).to(dev, non_blocking=True)
             self.tloc = torch.from_numpy(tloc).to(dev, non_blocking=True)
+            self.rowtab = torch.from_numpy(row_table(self.n)).to(dev, non_blocking=True) if self.n <= 10 else None
             cnt = t.counts()
             if self.glob is not None:
                 gcnt = self.glob.counts()
@@ -162,6 +197,7 @@ class DeviceNetwork:
                          "ebif_prefix", "loc", "tloc"):
                 setattr(s, name, getattr(self, name).data_ptr())
             s.bif_nodes = self._bif_nodes.data_ptr()
+            s.rowtab = self.rowtab.data_ptr() if self.rowtab is not None else None
             self._net = s
         return self._net
 

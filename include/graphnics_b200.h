@@ -55,6 +55,10 @@ typedef struct gnx_network {
   const int32_t* ebif_prefix; /* [E+1]     exclusive scan over edges of #ends that are bifurcations */
   const int32_t* loc;         /* [m+1]     SubMesh-local vertex id of position t counted from min(u,v) */
   const int32_t* tloc;        /* [m+1]     inverse of loc */
+  const int32_t* rowtab;      /* [2*(m+1)] per position t: CSR row offset inside an edge and the packed slot order of
+                                 its q-row (same for every edge; built once by the host, device.row_table); the
+                                 edge-tile assembly kernel needs it, every other entry point ignores it (may be NULL
+                                 for n > 10) */
 } gnx_network_t;
 
 /* Edge-wise operator coefficients of the (generalised) mixed system
