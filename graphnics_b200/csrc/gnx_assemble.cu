@@ -63,13 +63,33 @@ mixed_values_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict_
 // row without local arrays and drops them into the block's contiguous CSR range in shared memory;
 // the range and the p-rows (pure sign patterns) are then streamed out with coalesced stores.
 // ------------------------------------------------------------------------------------
+// vals[base .. base+len) = stage[sh .. sh+len), sh = base & 1: 128-bit copies on the 16-byte aligned
+// interior, scalar head / tail.  `stage` is 16-byte aligned and `vals` at least 16-byte aligned.
+__device__ __forceinline__ void stream_out(const double* stage, double* __restrict__ vals, int64_t base, int32_t len) {
+  const int32_t sh = (int32_t)(base & 1);
+  double* gp = vals + (base - sh);                     // 16-byte aligned
+  const int32_t total = len + sh;
+  const int32_t npairs = total >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(stage);
+  double2* g2 = reinterpret_cast<double2*>(gp);
+#pragma unroll 4
+  for (int32_t p = threadIdx.x; p < npairs; p += ASM_T) {
+    const double2 v = s2[p];
+    if (p == 0 && sh) gp[1] = v.y; else g2[p] = v;
+  }
+  if (threadIdx.x == 0 && (total & 1) && total - 1 >= sh) gp[total - 1] = stage[total - 1];
+}
+
 template <int CPT>
 __global__ void __launch_bounds__(ASM_T)
 mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                          const double* __restrict__ k_edge, double a_const, double sg, int32_t nb_tiles,
                          double* __restrict__ vals) {
   constexpr int TILE = ASM_T * CPT;
-  __shared__ double stage[5 * TILE + 3 * ASM_T];
+  // staging buffer, 16-byte aligned; the block's CSR range is staged SHIFTED by the parity of its first
+  // slot so that shared and global addresses are 16-byte congruent and the stream-out uses 128-bit
+  // loads/stores (the stream-out loops are where this kernel spends its instructions)
+  __shared__ __align__(16) double stage[5 * TILE + 3 * ASM_T + 2];
   if ((int32_t)blockIdx.x >= nb_tiles) {
     const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ASM_T + threadIdx.x;
     if (r < d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
@@ -99,7 +119,7 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     psgn = sgn;
     pslot = le * m;
     const double* he = net.h + (int64_t)e * m;
-    const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base);
+    const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
     const int32_t tlast = (t0 + CPT == m) ? m : t0 + CPT - 1;      // the edge's last thread also owns node m
     const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
     const int32_t blo1 = blo >= 0, bhi1 = bhi >= 0;
@@ -132,15 +152,16 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     }
   }
   __syncthreads();
-  const int32_t len = (int32_t)(end - base);
-  for (int32_t i = threadIdx.x; i < len; i += ASM_T) vals[base + i] = stage[i];
+  stream_out(stage, vals, base, (int32_t)(end - base));
   __syncthreads();
   // p-rows of the tile's cells: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal.  The
   // sign pattern of my cells is already known (upmask); staged so that the stores are coalesced.
+  const int64_t pbase = d.p_nnz_off + 3 * (int64_t)e0 * m;
+  const int32_t psh = (int32_t)(pbase & 1);
   if (le < nE) {
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const int32_t slot = 3 * (pslot + gnx_gray(t0 + i));
+      const int32_t slot = psh + 3 * (pslot + gnx_gray(t0 + i));
       const bool up = (upmask >> i) & 1u;
       stage[slot] = up ? -psgn : psgn;
       stage[slot + 1] = up ? psgn : -psgn;
@@ -148,10 +169,7 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     }
   }
   __syncthreads();
-  const int64_t c0 = (int64_t)e0 * m;
-  const int32_t ncell = nE * m;
-  double* vp = vals + d.p_nnz_off + 3 * c0;
-  for (int32_t i = threadIdx.x; i < 3 * ncell; i += ASM_T) vp[i] = stage[i];
+  stream_out(stage, vals, pbase, 3 * nE * m);
 }
 
 template <int CPT>
@@ -165,7 +183,7 @@ static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, 
 
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                          const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
-  if (net->n <= 10 && net->rowtab) {
+  if (net->n <= 10 && net->rowtab && ((uintptr_t)vals & 15) == 0) {
     static int cpt = -1;
     if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 4; }     // tuning knob
     if (net->n == 0 || cpt == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
