@@ -15,6 +15,8 @@ from .la import *               # noqa: F401,F403
 from .fenics_graph import *     # noqa: F401,F403
 from .generators import *       # noqa: F401,F403
 from .flowmodels import *       # noqa: F401,F403
+from .graph_utils import *      # noqa: F401,F403
+from .plot import *             # noqa: F401,F403
 
 DOLFIN_EPS = 3.0e-16
 

@@ -392,11 +392,11 @@ class CompiledCoefficient:
         if self.user is not None:
             out = np.empty(len(x))
             buf = np.zeros(1)
-            has_cell = type(self.user).eval_cell is not UserExpression.__dict__.get("eval_cell", None) \
-                and hasattr(self.user, "eval_cell")
+            has_cell = callable(getattr(self.user, "eval_cell", None))
+            has_eval = callable(getattr(self.user, "eval", None))
             for i, xi in enumerate(x):
-                if has_cell and cell_index is not None:
-                    self.user.eval_cell(buf, xi, _Cell(cell_index[i]))
+                if has_cell and (cell_index is not None or not has_eval):
+                    self.user.eval_cell(buf, xi, _Cell(cell_index[i] if cell_index is not None else 0))
                 else:
                     self.user.eval(buf, xi)
                 out[i] = buf[0]

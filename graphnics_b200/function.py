@@ -318,6 +318,27 @@ def project(v, V, **kw):
 
 
 def interpolate(v, V):
+    """dolfin.interpolate.  Into CG1 / DG0 on the global network mesh: a real Function (nodal / midpoint
+    values, evaluated on the device for expressions, on the host for UserExpression callbacks); into the
+    higher-order spaces the reference's tests use for exact solutions: the expression itself."""
+    mesh = V.mesh()
+    dn = getattr(mesh, "_dn", None)
+    lowest = (V.family == "CG" and V.degree == 1) or (V.family == "DG" and V.degree == 0)
+    if dn is not None and isinstance(mesh, Mesh1D) and lowest and not isinstance(v, (Function, ExactFunction)):
+        coef = as_coefficient(v)
+        if V.family == "CG":
+            cells_h = mesh.cells()
+            adj = np.zeros(dn.num_vertices, dtype=np.int64)          # one adjacent cell per vertex (eval_cell data)
+            adj[cells_h[:, 1]] = np.arange(len(cells_h))
+            adj[cells_h[:, 0]] = np.arange(len(cells_h))
+            vals = coef.eval_device(dn.coords, cell_index=adj if coef.user is not None else None)
+            role = "vertex"
+        else:
+            c = dn.cells.long()
+            mid = (0.5 * (dn.coords[c[:, 0]] + dn.coords[c[:, 1]])).contiguous()
+            vals = coef.eval_device(mid, pts_per_edge=dn.m, tangents=dn.tangents, cell_index=np.arange(dn.num_cells))
+            role = "cell"
+        return Function(V, vals.to(torch.float64).contiguous(), net=dn, role=role)
     return ExactFunction(v, V)
 
 
