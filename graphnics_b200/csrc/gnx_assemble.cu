@@ -5,6 +5,7 @@
 // init_a_form) + ii_assemble/ii_convert (:343-344); time_stepping.py:75-101 (mass_matrix_q).
 #include <stdlib.h>
 #include "gnx_common.cuh"
+#include "gnx_tma.cuh"
 
 extern "C" int64_t gnx_mixed_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }
 extern "C" int64_t gnx_mixed_nnz(const gnx_network_t* net) { return gnx_mixed_dims(*net).nnz; }
@@ -80,16 +81,61 @@ __device__ __forceinline__ void stream_out(const double* stage, double* __restri
   if (threadIdx.x == 0 && (total & 1) && total - 1 >= sh) gp[total - 1] = stage[total - 1];
 }
 
-template <int CPT>
+// The q-row range and the p-row range of a tile are staged side by side; BULK: each leaves the SM as ONE
+// bulk copy issued by thread 0 (gnx_tma.cuh); otherwise the block streams them out itself.
+template <int CPT> constexpr int asm_stage_doubles() { return (5 * ASM_T * CPT + 3 * ASM_T + 4) + (3 * ASM_T * CPT + 4); }
+
+// q-row of lo-frame position t of one edge -> its slots in the staged CSR range; returns the row's table flags.
+// STIFF = false compiles the stiffness term k/h (NetworkStokes; two fp64 divisions per row) out.
+struct AsmEdge {
+  const double* he;          // cell lengths of the edge (u -> v order)
+  double a, kk, sgn;         // mass coefficient, stiffness coefficient, +-sigma (orientation of the lo frame)
+  int32_t ebase, blo1, bhi1; // staged offset of the edge's range, 1 if the lo / hi end carries a multiplier
+  bool flip;                 // u > v: the lo frame runs against the edge
+};
+template <bool STIFF>
+__device__ __forceinline__ int32_t asm_qrow(double* stage, const int2* __restrict__ tab, const AsmEdge& E, int32_t t,
+                                            int32_t m, double sg) {
+  const bool hasl = t > 0, hasr = t < m;
+  const double hl = hasl ? E.he[E.flip ? m - t : t - 1] : 0.0;       // lo-frame cell t-1
+  const double hr = hasr ? E.he[E.flip ? m - 1 - t : t] : 0.0;       // lo-frame cell t
+  const int2 tb = __ldg(tab + t);                                    // row offset + packed slot order (device.row_table)
+  const int32_t f = tb.y;
+  const int32_t off = E.ebase + tb.x + ((f & 1) ? E.blo1 : 0) + ((f & 2) ? E.bhi1 : 0);
+  double kl = 0.0, kr = 0.0;
+  if (STIFF) { if (hasl) kl = E.kk / hl; if (hasr) kr = E.kk / hr; }
+  double diag = 0.0;
+  if (hasl) {
+    diag += E.a * hl * (2.0 / 6.0) + kl;
+    stage[off + ((f >> 2) & 7)] = E.a * hl * (1.0 / 6.0) - kl;
+    stage[off + ((f >> 11) & 7)] = -E.sgn;                           // p column of cell t-1
+  }
+  if (hasr) {
+    diag += E.a * hr * (2.0 / 6.0) + kr;
+    stage[off + ((f >> 8) & 7)] = E.a * hr * (1.0 / 6.0) - kr;
+    stage[off + ((f >> 14) & 7)] = E.sgn;                            // p column of cell t
+  }
+  stage[off + ((f >> 5) & 7)] = diag;
+  // lambda column at a bifurcation end (last slot of the row): +sigma if the edge points INTO the node
+  if (t == 0 && E.blo1) stage[off + 3] = E.flip ? sg : -sg;
+  if (t == m && E.bhi1) stage[off + 3] = E.flip ? -sg : sg;
+  return f;
+}
+
+// Cells are dealt to the lanes of a warp round-robin (cell = 32 * CPT * warp + 32 * round + lane): in every
+// round a warp touches 32 neighbouring rows, i.e. shared-memory addresses 5 (q) / 3 (p) doubles apart --
+// conflict-free, where a thread owning CPT consecutive cells hit every bank 4 times.
+template <int CPT, bool BULK, bool STIFF>
 __global__ void __launch_bounds__(ASM_T)
 mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                          const double* __restrict__ k_edge, double a_const, double sg, int32_t nb_tiles,
                          double* __restrict__ vals) {
   constexpr int TILE = ASM_T * CPT;
   // staging buffer, 16-byte aligned; the block's CSR range is staged SHIFTED by the parity of its first
-  // slot so that shared and global addresses are 16-byte congruent and the stream-out uses 128-bit
-  // loads/stores (the stream-out loops are where this kernel spends its instructions)
-  __shared__ __align__(16) double stage[5 * TILE + 3 * ASM_T + 2];
+  // slot so that shared and global addresses are 16-byte congruent and the stream-out uses bulk copies
+  // or 128-bit loads/stores
+  extern __shared__ __align__(16) double stage[];
+  double* const stage_p = stage + 5 * TILE + 3 * ASM_T + 4;          // q range: <= 5 TILE + 3 (TILE/m) + 1
   if ((int32_t)blockIdx.x >= nb_tiles) {
     const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ASM_T + threadIdx.x;
     if (r < d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
@@ -101,93 +147,92 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   const int32_t nE = min(G, net.E - e0);
   const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + net.ebif_prefix[e0];
   const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + net.ebif_prefix[e0 + nE];
-  const int32_t k0 = threadIdx.x * CPT;
-  const int32_t le = k0 >> n;
-  uint32_t upmask = 0;                 // bit i: the lower position of my cell i has the lower q-dof number
-  int32_t pslot = 0;                   // first of my cells in the tile's p-row range (lo-frame cell t0)
-  double psgn = 0.0;
-  int32_t t0 = 0;
-  if (le < nE) {
-    const int32_t e = e0 + le;
-    t0 = k0 & (m - 1);
-    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-    const bool flip = u > v;
-    const int32_t blo = net.bix[flip ? v : u], bhi = net.bix[flip ? u : v];
-    const double a = a_edge ? a_edge[e] : a_const;
-    const double kk = k_edge ? k_edge[e] : 0.0;
-    const double sgn = flip ? -sg : sg;
-    psgn = sgn;
-    pslot = le * m;
-    const double* he = net.h + (int64_t)e * m;
-    const int32_t ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
-    const int32_t tlast = (t0 + CPT == m) ? m : t0 + CPT - 1;      // the edge's last thread also owns node m
-    const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
-    const int32_t blo1 = blo >= 0, bhi1 = bhi >= 0;
-    double hl = t0 > 0 ? he[flip ? m - t0 : t0 - 1] : 0.0;         // lo-frame cell t-1
-    for (int32_t t = t0; t <= tlast; ++t) {
-      const bool hasl = t > 0, hasr = t < m;
-      const double hr = hasr ? he[flip ? m - 1 - t : t] : 0.0;     // lo-frame cell t
-      const int2 tb = __ldg(tab + t);                              // row offset + packed slot order (device.row_table)
-      const int32_t f = tb.y;
-      const int32_t off = ebase + tb.x + ((f & 1) ? blo1 : 0) + ((f & 2) ? bhi1 : 0);
-      if (hasr && (f & (1 << 17))) upmask |= 1u << (t - t0);
-      // the stiffness term k/h (NetworkStokes) costs two fp64 divisions per row: skipped when k == 0
-      const double kl = (kk != 0.0 && hasl) ? kk / hl : 0.0, kr = (kk != 0.0 && hasr) ? kk / hr : 0.0;
-      double diag = 0.0;
-      if (hasl) {
-        diag += a * hl * (2.0 / 6.0) + kl;
-        stage[off + ((f >> 2) & 7)] = a * hl * (1.0 / 6.0) - kl;
-        stage[off + ((f >> 11) & 7)] = -sgn;                       // p column of cell t-1
-      }
-      if (hasr) {
-        diag += a * hr * (2.0 / 6.0) + kr;
-        stage[off + ((f >> 8) & 7)] = a * hr * (1.0 / 6.0) - kr;
-        stage[off + ((f >> 14) & 7)] = sgn;                        // p column of cell t
-      }
-      stage[off + ((f >> 5) & 7)] = diag;
-      // lambda column at a bifurcation end (last slot of the row): +sigma if the edge points INTO the node
-      if (t == 0 && blo1) stage[off + 3] = flip ? sg : -sg;
-      if (t == m && bhi1) stage[off + 3] = flip ? -sg : sg;
-      hl = hr;
-    }
-  }
-  __syncthreads();
-  stream_out(stage, vals, base, (int32_t)(end - base));
-  __syncthreads();
-  // p-rows of the tile's cells: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal.  The
-  // sign pattern of my cells is already known (upmask); staged so that the stores are coalesced.
   const int64_t pbase = d.p_nnz_off + 3 * (int64_t)e0 * m;
   const int32_t psh = (int32_t)(pbase & 1);
-  if (le < nE) {
+  const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
+  const int32_t k0 = (threadIdx.x >> 5) * (32 * CPT) + (threadIdx.x & 31);
+  AsmEdge E;
+  int32_t cur = -1;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-      const int32_t slot = psh + 3 * (pslot + gnx_gray(t0 + i));
-      const bool up = (upmask >> i) & 1u;
-      stage[slot] = up ? -psgn : psgn;
-      stage[slot + 1] = up ? psgn : -psgn;
-      stage[slot + 2] = 0.0;
+  for (int i = 0; i < CPT; ++i) {
+    const int32_t k = k0 + 32 * i;                   // cell of the tile
+    const int32_t le = k >> n;
+    if (le >= nE) break;
+    const int32_t t = k & (m - 1);                   // lo-frame position along the edge
+    if (le != cur) {                                 // (warp-uniform for m >= 32)
+      cur = le;
+      const int32_t e = e0 + le;
+      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+      E.flip = u > v;
+      E.blo1 = net.bix[E.flip ? v : u] >= 0;
+      E.bhi1 = net.bix[E.flip ? u : v] >= 0;
+      E.a = a_edge ? a_edge[e] : a_const;
+      E.kk = (STIFF && k_edge) ? k_edge[e] : 0.0;
+      E.sgn = E.flip ? -sg : sg;
+      E.he = net.h + (int64_t)e * m;
+      E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
     }
+    const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
+    if (t == m - 1) asm_qrow<STIFF>(stage, tab, E, m, m, sg);       // the edge's last cell also owns node m
+    // p-row of lo-frame cell t: (-sgn, +sgn) ordered by the q-dof number, explicit zero diagonal
+    const int32_t slot = psh + 3 * (le * m + gnx_gray(t));
+    const bool up = (f >> 17) & 1;
+    stage_p[slot] = up ? -E.sgn : E.sgn;
+    stage_p[slot + 1] = up ? E.sgn : -E.sgn;
+    stage_p[slot + 2] = 0.0;
   }
-  __syncthreads();
-  stream_out(stage, vals, pbase, 3 * nE * m);
+  if (BULK) {
+    gnx_fence_async_smem();
+    __syncthreads();
+    gnx_bulk_stream_out(stage, vals, base, (int32_t)(end - base));
+    gnx_bulk_stream_out(stage_p, vals, pbase, 3 * nE * m);
+    if (threadIdx.x == 0) { gnx_bulk_commit(); gnx_bulk_wait_read(); }
+  } else {
+    __syncthreads();
+    stream_out(stage, vals, base, (int32_t)(end - base));
+    stream_out(stage_p, vals, pbase, 3 * nE * m);
+  }
+}
+
+template <int CPT, bool BULK, bool STIFF>
+static void launch_values_tile3(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
+                                const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+  const int G = (ASM_T * CPT) >> net->n;
+  const int nb_tiles = gnx_blocks(net->E, G);
+  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
+  constexpr int smem = asm_stage_doubles<CPT>() * (int)sizeof(double);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(mixed_values_tile_kernel<CPT, BULK, STIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  mixed_values_tile_kernel<CPT, BULK, STIFF><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_const,
+                                                                                    sg, nb_tiles, vals);
 }
 
 template <int CPT>
 static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                                const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
-  const int G = (ASM_T * CPT) >> net->n;
-  const int nb_tiles = gnx_blocks(net->E, G);
-  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
-  mixed_values_tile_kernel<CPT><<<nb_tiles + nb_lam, ASM_T, 0, st>>>(*net, d, a_edge, k_edge, a_const, sg, nb_tiles, vals);
+  static int bulk = -1;
+  if (bulk < 0) { const char* e = getenv("GNX_ASM_BULK"); bulk = e ? atoi(e) : 1; }    // tuning knob
+  if (bulk) {
+    if (k_edge) launch_values_tile3<CPT, true, true>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else launch_values_tile3<CPT, true, false>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+  } else {
+    if (k_edge) launch_values_tile3<CPT, false, true>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else launch_values_tile3<CPT, false, false>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+  }
 }
 
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
                          const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
   if (net->n <= 10 && net->rowtab && ((uintptr_t)vals & 15) == 0) {
     static int cpt = -1;
-    if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 4; }     // tuning knob
-    if (net->n == 0 || cpt == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else if (net->n == 1 || cpt == 2) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 2; }     // tuning knob
+    // a tile (256 * CPT cells) holds whole edges: CPT >= m / 256
+    const int c = net->n >= 10 ? 4 : (net->n == 9 && cpt < 2) ? 2 : cpt;
+    if (net->n == 0 || c == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    else if (net->n == 1 || c == 2) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
     else launch_values_tile<4>(net, d, a_edge, k_edge, a_const, sg, vals, st);
     GNX_LAUNCH_CHECK();
     return GNX_OK;

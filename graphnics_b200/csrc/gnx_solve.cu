@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <cooperative_groups.h>
 #include "gnx_common.cuh"
+#include "gnx_tma.cuh"
 namespace cg = cooperative_groups;
 
 struct EdgeFrame {
@@ -123,6 +124,16 @@ struct TileCtx {
   int32_t e0, nE, le, e, kk0, m;
   bool active, flip;
   int64_t pbase, qbase, hbase;
+  int32_t shp, shq, shh;     // staging shifts (parity of the range starts, gnx_tma.cuh); 0 without bulk copies
+};
+
+// shared-memory tile of the edge kernels: p-range of b (or x), cell lengths, q-range of b (or x)
+template <int CPT> struct TileSmem {
+  static constexpr int TILE = 256 * CPT;
+  __align__(16) double F[TILE + 2];
+  __align__(16) double H[TILE + 2];
+  __align__(16) double G[TILE + 256 + 2];
+  __align__(8) uint64_t bar;
 };
 
 template <int CPT>
@@ -143,23 +154,82 @@ __device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxM
   c.pbase = d.p_off + (int64_t)c.e0 * c.m;
   c.hbase = (int64_t)c.e0 * c.m;
   c.qbase = (int64_t)c.e0 * (c.m + 1);
+  c.shp = c.shq = c.shh = 0;
+  return c;
+}
+template <int CPT, bool BULK>
+__device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxMixedDims& d) {
+  TileCtx c = tile_ctx<CPT>(net, d);
+  if (BULK) { c.shp = (int32_t)(c.pbase & 1); c.shq = (int32_t)(c.qbase & 1); c.shh = (int32_t)(c.hbase & 1); }
   return c;
 }
 
-template <int CPT>
+// Tile inputs -> shared memory.  BULK: thread 0 hands the (up to three) contiguous ranges to the copy
+// engine, completion on ts.bar; callers run tile_wait() after their next __syncthreads().  Otherwise the
+// block loads them itself.  WITH_B = false loads only the cell lengths.
+template <int CPT, bool BULK, bool WITH_B>
 __device__ __forceinline__ void tile_load(const TileCtx& c, const double* __restrict__ b,
-                                          const double* __restrict__ h, double* sF, double* sH, double* sG) {
+                                          const double* __restrict__ h, TileSmem<CPT>& ts) {
   const int32_t ncell = c.nE * c.m, nq = c.nE * (c.m + 1);
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      gnx_mbar_init(&ts.bar, 1);
+      uint32_t bytes = gnx_bulk_body_bytes(c.hbase, ncell);
+      if (WITH_B) bytes += gnx_bulk_body_bytes(c.pbase, ncell) + gnx_bulk_body_bytes(c.qbase, nq);
+      gnx_mbar_expect_tx(&ts.bar, bytes);
+      gnx_bulk_stream_in(ts.H, h, c.hbase, ncell, &ts.bar);
+      if (WITH_B) {
+        gnx_bulk_stream_in(ts.F, b, c.pbase, ncell, &ts.bar);
+        gnx_bulk_stream_in(ts.G, b, c.qbase, nq, &ts.bar);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < CPT; ++r) {
     const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) { sF[i] = b[c.pbase + i]; sH[i] = h[c.hbase + i]; }
+    if (i < ncell) { if (WITH_B) ts.F[i] = b[c.pbase + i]; ts.H[i] = h[c.hbase + i]; }
   }
+  if (WITH_B) {
+#pragma unroll
+    for (int r = 0; r < CPT + 1; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < nq) ts.G[i] = b[c.qbase + i];
+    }
+  }
+}
+// after the __syncthreads() that follows tile_load (it publishes the barrier's initialisation and the
+// odd ends thread 0 loaded by hand)
+template <int CPT, bool BULK>
+__device__ __forceinline__ void tile_wait(TileSmem<CPT>& ts) { if (BULK) gnx_mbar_wait(&ts.bar, 0); }
+
+// Tile outputs (staged in ts.F / ts.G at the dof slots) -> out[p range], out[q range].  BULK: callers
+// run tile_store_done() before the block exits.
+template <int CPT, bool BULK>
+__device__ __forceinline__ void tile_store(const TileCtx& c, TileSmem<CPT>& ts, double* __restrict__ out) {
+  const int32_t ncell = c.nE * c.m, nq = c.nE * (c.m + 1);
+  if (BULK) {
+    gnx_fence_async_smem();
+    __syncthreads();
+    gnx_bulk_stream_out(ts.G, out, c.qbase, nq);
+    gnx_bulk_stream_out(ts.F, out, c.pbase, ncell);
+    if (threadIdx.x == 0) gnx_bulk_commit();
+    return;
+  }
+  __syncthreads();
 #pragma unroll
   for (int r = 0; r < CPT + 1; ++r) {
     const int32_t i = threadIdx.x + r * ET_T;
-    if (i < nq) sG[i] = b[c.qbase + i];
+    if (i < nq) out[c.qbase + i] = ts.G[i];
   }
+#pragma unroll
+  for (int r = 0; r < CPT; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < ncell) out[c.pbase + i] = ts.F[i];
+  }
+}
+template <bool BULK> __device__ __forceinline__ void tile_store_done() {
+  if (BULK && threadIdx.x == 0) gnx_bulk_wait_read();
 }
 
 // Right-hand side with Constant f, g and boundary data only (MixedHydraulicNetwork.L_form :299-332 for
@@ -176,66 +246,47 @@ struct ConstRhs {
 //                    mixed_rhs_const_tile_kernel), stored to rhs.b with coalesced stores and eliminated
 //                    right away -- one launch and one 8 B/dof read less per solve; blocks past the tiles
 //                    zero the lambda rows of b.
-template <int CPT, bool FUSED_RHS>
+template <int CPT, bool FUSED_RHS, bool BULK>
 __global__ void __launch_bounds__(ET_T)
 edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                            double inv_sigma, const double* __restrict__ b, EdgeOut out, ConstRhs rhs,
                            int32_t nb_tiles) {
-  constexpr int TILE = ET_T * CPT;
-  __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
+  __shared__ TileSmem<CPT> ts;
   __shared__ double sh[3 * 32];
   if (FUSED_RHS && (int32_t)blockIdx.x >= nb_tiles) {
     const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ET_T + threadIdx.x;
     if (r < d.N) rhs.b[r] = 0.0;
     return;
   }
-  const TileCtx c = tile_ctx<CPT>(net, d);
+  const TileCtx c = tile_ctx<CPT, BULK>(net, d);
   const int32_t m = c.m;
-  const int32_t cb = c.le * m, qb = c.le * (m + 1);
-  if (!FUSED_RHS) {
-    tile_load<CPT>(c, b, net.h, sF, sH, sG);
-    __syncthreads();
-  } else {
-    const int32_t ncell = c.nE * m, nq = c.nE * (m + 1);
-#pragma unroll
-    for (int r = 0; r < CPT; ++r) {
-      const int32_t i = threadIdx.x + r * ET_T;
-      if (i < ncell) sH[i] = net.h[c.hbase + i];
-    }
-    __syncthreads();
+  const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
+  double* const sF = ts.F; double* const sH = ts.H; double* const sG = ts.G;
+  tile_load<CPT, BULK, !FUSED_RHS>(c, b, net.h, ts);
+  __syncthreads();
+  tile_wait<CPT, BULK>(ts);
+  if (FUSED_RHS) {
     if (c.active) {
       const int32_t u = net.edges[2 * c.e], v = net.edges[2 * c.e + 1];
       const int32_t tlast = (c.kk0 + CPT == m) ? m : c.kk0 + CPT - 1;
       for (int32_t j = c.kk0; j <= tlast; ++j) {               // edge-local node j (u -> v), cells j-1 | j
-        const double hl = j > 0 ? sH[cb + j - 1] : 0.0, hr = j < m ? sH[cb + j] : 0.0;
+        const double hl = j > 0 ? sH[cbH + j - 1] : 0.0, hr = j < m ? sH[cbH + j] : 0.0;
         double val = rhs.gc * (hl + hr) * 0.5;
         if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val += rhs.pbc_node[u];     // edge OUT of a boundary node: BOUN_IN
         if (j == m && net.bix[v] < 0 && rhs.pbc_out) val -= rhs.pbc_out[c.e];     // edge INTO a boundary node: BOUN_OUT
         sG[qb + __ldg(net.loc + (c.flip ? m - j : j))] = val;
-        if (j < m) sF[cb + gnx_gray(c.flip ? m - 1 - j : j)] = rhs.fc * hr;
+        if (j < m) sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = rhs.fc * hr;
       }
     }
-    __syncthreads();
-    double* bq = rhs.b + c.qbase;
-    double* bp = rhs.b + c.pbase;
-#pragma unroll
-    for (int r = 0; r < CPT + 1; ++r) {
-      const int32_t i = threadIdx.x + r * ET_T;
-      if (i < nq) bq[i] = sG[i];
-    }
-#pragma unroll
-    for (int r = 0; r < CPT; ++r) {
-      const int32_t i = threadIdx.x + r * ET_T;
-      if (i < ncell) bp[i] = sF[i];
-    }
+    tile_store<CPT, BULK>(c, ts, rhs.b);
   }
   double F[CPT], H[CPT];
   double sumF = 0.0, sumG = 0.0, sumH = 0.0;
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     const int32_t kk = c.kk0 + i;
-    F[i] = c.active ? sF[cb + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
-    H[i] = sH[cb + kk];
+    F[i] = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
+    H[i] = sH[cbH + kk];
     sumG += sG[qb + __ldg(net.loc + (c.flip ? m - kk : kk))];
     sumF += F[i];
     sumH += H[i];
@@ -254,22 +305,37 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
     const double a = a_edge[c.e];
     out.put(c.e, 1.0 / (a * acc[2]), acc[1] - a * acc[0], tot);
   }
+  if (FUSED_RHS) tile_store_done<BULK>();
 }
 
-template <int CPT>
-static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
-                                  const double* b, const EdgeOut& out, const ConstRhs* rhs, cudaStream_t st) {
+// tuning knob: tile inputs / outputs through the copy engine (default) or by the block's own loads / stores.
+// Bulk copies need 16-byte aligned arrays (torch allocations are 512-byte aligned; checked per call).
+static bool edge_bulk(const void* p0, const void* p1 = nullptr, const void* p2 = nullptr) {
+  static int bulk = -1;
+  if (bulk < 0) { const char* e = getenv("GNX_EDGE_BULK"); bulk = e ? atoi(e) : 1; }
+  return bulk && (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) == 0;
+}
+
+template <int CPT, bool BULK>
+static void launch_eliminate_tile2(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
+                                   const double* b, const EdgeOut& out, const ConstRhs* rhs, cudaStream_t st) {
   const int G = (ET_T * CPT) >> net->n;
   const int nb_tiles = gnx_blocks(net->E, G);
   if (rhs) {
     const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ET_T) : 0;
-    edge_eliminate_tile_kernel<CPT, true><<<nb_tiles + nb_lam, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma,
-                                                                            nullptr, out, *rhs, nb_tiles);
+    edge_eliminate_tile_kernel<CPT, true, BULK><<<nb_tiles + nb_lam, ET_T, 0, st>>>(
+        *net, d, co->a_edge, 1.0 / co->sigma, nullptr, out, *rhs, nb_tiles);
   } else {
     ConstRhs none = {0.0, 0.0, nullptr, nullptr, nullptr};
-    edge_eliminate_tile_kernel<CPT, false><<<nb_tiles, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b, out,
-                                                                      none, nb_tiles);
+    edge_eliminate_tile_kernel<CPT, false, BULK><<<nb_tiles, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b,
+                                                                             out, none, nb_tiles);
   }
+}
+template <int CPT>
+static void launch_eliminate_tile(const gnx_network_t* net, const GnxMixedDims& d, const gnx_mixed_coeffs_t* co,
+                                  const double* b, const EdgeOut& out, const ConstRhs* rhs, cudaStream_t st) {
+  if (edge_bulk(net->h, rhs ? rhs->b : b)) launch_eliminate_tile2<CPT, true>(net, d, co, b, out, rhs, st);
+  else launch_eliminate_tile2<CPT, false>(net, d, co, b, out, rhs, st);
 }
 
 static int edge_cpt() {           // tuning knob: cells per thread of the edge-tile kernels (default 4)
@@ -1038,17 +1104,17 @@ edge_backsub_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict_
   if (active && gl == 0) x[f.qdof(net.loc, m)] = q0 + carryF;
 }
 
-template <int CPT>
+template <int CPT, bool BULK>
 __global__ void __launch_bounds__(ET_T, 4)
 edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                          const double* __restrict__ k_edge, double inv_sigma, const double* __restrict__ b,
                          const double* __restrict__ cond, const double* __restrict__ rsrc,
                          const double* __restrict__ P, double* __restrict__ x) {
-  constexpr int TILE = ET_T * CPT;
-  __shared__ double sF[TILE], sH[TILE], sG[TILE + ET_T];
+  __shared__ TileSmem<CPT> ts;
   __shared__ double sh[32];
-  const TileCtx c = tile_ctx<CPT>(net, d);
-  tile_load<CPT>(c, b, net.h, sF, sH, sG);
+  const TileCtx c = tile_ctx<CPT, BULK>(net, d);
+  tile_load<CPT, BULK, true>(c, b, net.h, ts);
+  double* const sF = ts.F; double* const sH = ts.H; double* const sG = ts.G;
   const int32_t m = c.m;
   const int32_t eu = net.edges[2 * c.e], ev = net.edges[2 * c.e + 1];
   const int32_t bu = net.bix[eu], bv = net.bix[ev];
@@ -1058,25 +1124,26 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   const double kv = k_edge ? k_edge[c.e] : 0.0;
   const double q0 = cond[c.e] * (Pu - Pv + rsrc[c.e]);
   __syncthreads();
-  const int32_t cb = c.le * m, qb = c.le * (m + 1);
+  tile_wait<CPT, BULK>(ts);
+  const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
   int32_t ps[CPT], qs[CPT];                        // shared-memory slots of my p / q dofs
   double F[CPT], H[CPT], Gq[CPT];
   double sumF = 0.0;
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     const int32_t kk = c.kk0 + i;
-    ps[i] = cb + gnx_gray(c.flip ? m - 1 - kk : kk);
+    ps[i] = cbF + gnx_gray(c.flip ? m - 1 - kk : kk);
     qs[i] = qb + __ldg(net.loc + (c.flip ? m - kk : kk));
     F[i] = c.active ? sF[ps[i]] * inv_sigma : 0.0;
-    H[i] = sH[cb + kk];
+    H[i] = sH[cbH + kk];
     Gq[i] = c.active ? sG[qs[i]] : 0.0;
     sumF += F[i];
   }
   double Fl = 0.0, Hl = 1.0;                       // cell left of my first node
   if (c.kk0 > 0) {
     const int32_t kl = c.kk0 - 1;
-    Fl = c.active ? sF[cb + gnx_gray(c.flip ? m - 1 - kl : kl)] * inv_sigma : 0.0;
-    Hl = sH[cb + kl];
+    Fl = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kl : kl)] * inv_sigma : 0.0;
+    Hl = sH[cbH + kl];
   }
   const int segT = m / CPT;
   double totF, totD;
@@ -1111,18 +1178,8 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     }
     if (c.kk0 + CPT == m) sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = q0 + totF;
   }
-  __syncthreads();
-  const int32_t ncell = c.nE * m, nq = c.nE * (m + 1);
-#pragma unroll
-  for (int r = 0; r < CPT; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) x[c.pbase + i] = sF[i];
-  }
-#pragma unroll
-  for (int r = 0; r < CPT + 1; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < nq) x[c.qbase + i] = sG[i];
-  }
+  tile_store<CPT, BULK>(c, ts, x);
+  tile_store_done<BULK>();
 }
 
 template <int CPT>
@@ -1130,8 +1187,12 @@ static void launch_backsub_tile(const gnx_network_t* net, const GnxMixedDims& d,
                                 const double* b, const double* cond, const double* rsrc, const double* P,
                                 double* x, cudaStream_t st) {
   const int G = (ET_T * CPT) >> net->n;
-  edge_backsub_tile_kernel<CPT><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
-      *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+  if (edge_bulk(net->h, b, x))
+    edge_backsub_tile_kernel<CPT, true><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
+        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+  else
+    edge_backsub_tile_kernel<CPT, false><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
+        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
 }
 
 extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
