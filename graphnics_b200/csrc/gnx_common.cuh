@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "gnx_index.h"
 
 void gnx_set_error(const char* fmt, ...);
@@ -30,6 +31,32 @@ void gnx_set_error(const char* fmt, ...);
 #define GNX_LAUNCH_CHECK() GNX_CUDA(cudaGetLastError())
 
 static inline int gnx_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched with gnx_launch_dependent may be
+// scheduled while its predecessor on the stream is still draining; it must run gnx_pdl_wait() before it
+// touches anything an earlier kernel wrote (a no-op under an ordinary launch).  A predecessor that calls
+// gnx_pdl_trigger() lets the dependent grid become resident as soon as all of ITS blocks have started.
+__device__ __forceinline__ void gnx_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gnx_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// GNX_PDL=0 (tuning knob): ordinary launches.  Measured on the C2 step: 59.4 -> 53.3 us with dependent
+// launches; letting the back-substitution grid become resident DURING the Schur kernel (an early trigger
+// there) takes SM slots from the overlapped assembly and loses (61.5 us).
+static inline bool gnx_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GNX_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t gnx_launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                               cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = gnx_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 constexpr unsigned GNX_FULL = 0xffffffffu;
 

@@ -133,7 +133,7 @@ template <int CPT> struct TileSmem {
   __align__(16) double F[TILE + 2];
   __align__(16) double H[TILE + 2];
   __align__(16) double G[TILE + 256 + 2];
-  __align__(8) uint64_t bar;
+  __align__(8) uint64_t bar, bar_h;
 };
 
 template <int CPT>
@@ -164,44 +164,55 @@ __device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxM
   return c;
 }
 
-// Tile inputs -> shared memory.  BULK: thread 0 hands the (up to three) contiguous ranges to the copy
-// engine, completion on ts.bar; callers run tile_wait() after their next __syncthreads().  Otherwise the
-// block loads them itself.  WITH_B = false loads only the cell lengths.
-template <int CPT, bool BULK, bool WITH_B>
-__device__ __forceinline__ void tile_load(const TileCtx& c, const double* __restrict__ b,
-                                          const double* __restrict__ h, TileSmem<CPT>& ts) {
-  const int32_t ncell = c.nE * c.m, nq = c.nE * (c.m + 1);
+// Tile inputs -> shared memory.  BULK: thread 0 hands the contiguous ranges to the copy engine, completion
+// on ts.bar_h (cell lengths) and ts.bar (the two ranges of b); callers run tile_wait() after their next
+// __syncthreads().  Otherwise the block loads them itself.
+template <int CPT, bool BULK>
+__device__ __forceinline__ void tile_load_h(const TileCtx& c, const double* __restrict__ h, TileSmem<CPT>& ts) {
+  const int32_t ncell = c.nE * c.m;
   if (BULK) {
     if (threadIdx.x == 0) {
+      gnx_mbar_init(&ts.bar_h, 1);
       gnx_mbar_init(&ts.bar, 1);
-      uint32_t bytes = gnx_bulk_body_bytes(c.hbase, ncell);
-      if (WITH_B) bytes += gnx_bulk_body_bytes(c.pbase, ncell) + gnx_bulk_body_bytes(c.qbase, nq);
-      gnx_mbar_expect_tx(&ts.bar, bytes);
-      gnx_bulk_stream_in(ts.H, h, c.hbase, ncell, &ts.bar);
-      if (WITH_B) {
-        gnx_bulk_stream_in(ts.F, b, c.pbase, ncell, &ts.bar);
-        gnx_bulk_stream_in(ts.G, b, c.qbase, nq, &ts.bar);
-      }
+      gnx_mbar_expect_tx(&ts.bar_h, gnx_bulk_body_bytes(c.hbase, ncell));
+      gnx_bulk_stream_in(ts.H, h, c.hbase, ncell, &ts.bar_h);
     }
     return;
   }
 #pragma unroll
   for (int r = 0; r < CPT; ++r) {
     const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) { if (WITH_B) ts.F[i] = b[c.pbase + i]; ts.H[i] = h[c.hbase + i]; }
+    if (i < ncell) ts.H[i] = h[c.hbase + i];
   }
-  if (WITH_B) {
-#pragma unroll
-    for (int r = 0; r < CPT + 1; ++r) {
-      const int32_t i = threadIdx.x + r * ET_T;
-      if (i < nq) ts.G[i] = b[c.qbase + i];
+}
+template <int CPT, bool BULK>
+__device__ __forceinline__ void tile_load_b(const TileCtx& c, const double* __restrict__ b, TileSmem<CPT>& ts) {
+  const int32_t ncell = c.nE * c.m, nq = c.nE * (c.m + 1);
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      gnx_mbar_expect_tx(&ts.bar, gnx_bulk_body_bytes(c.pbase, ncell) + gnx_bulk_body_bytes(c.qbase, nq));
+      gnx_bulk_stream_in(ts.F, b, c.pbase, ncell, &ts.bar);
+      gnx_bulk_stream_in(ts.G, b, c.qbase, nq, &ts.bar);
     }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < CPT; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < ncell) ts.F[i] = b[c.pbase + i];
+  }
+#pragma unroll
+  for (int r = 0; r < CPT + 1; ++r) {
+    const int32_t i = threadIdx.x + r * ET_T;
+    if (i < nq) ts.G[i] = b[c.qbase + i];
   }
 }
 // after the __syncthreads() that follows tile_load (it publishes the barrier's initialisation and the
 // odd ends thread 0 loaded by hand)
-template <int CPT, bool BULK>
-__device__ __forceinline__ void tile_wait(TileSmem<CPT>& ts) { if (BULK) gnx_mbar_wait(&ts.bar, 0); }
+template <int CPT, bool BULK, bool WITH_B>
+__device__ __forceinline__ void tile_wait(TileSmem<CPT>& ts) {
+  if (BULK) { gnx_mbar_wait(&ts.bar_h, 0); if (WITH_B) gnx_mbar_wait(&ts.bar, 0); }
+}
 
 // Tile outputs (staged in ts.F / ts.G at the dof slots) -> out[p range], out[q range].  BULK: callers
 // run tile_store_done() before the block exits.
@@ -258,13 +269,15 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
     if (r < d.N) rhs.b[r] = 0.0;
     return;
   }
+  gnx_pdl_trigger();                              // the Schur kernel may become resident (it waits for this grid)
   const TileCtx c = tile_ctx<CPT, BULK>(net, d);
   const int32_t m = c.m;
   const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
   double* const sF = ts.F; double* const sH = ts.H; double* const sG = ts.G;
-  tile_load<CPT, BULK, !FUSED_RHS>(c, b, net.h, ts);
+  tile_load_h<CPT, BULK>(c, net.h, ts);
+  if (!FUSED_RHS) tile_load_b<CPT, BULK>(c, b, ts);
   __syncthreads();
-  tile_wait<CPT, BULK>(ts);
+  tile_wait<CPT, BULK, !FUSED_RHS>(ts);
   if (FUSED_RHS) {
     if (c.active) {
       const int32_t u = net.edges[2 * c.e], v = net.edges[2 * c.e + 1];
@@ -785,6 +798,7 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   const int32_t stride = nblk * blockDim.x;
   const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
   auto gsync = [&]() { sch_sync<MODE>(); };
+  gnx_pdl_wait();                                 // the edge scalars come from the elimination kernel
 
   // parent i absorbs its raked children: d_i -= w^2/d_c, r_i -= w r_c/d_c  (w = -cond of the link)
   auto gather = [&](int32_t i) {
@@ -1007,7 +1021,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
     return GNX_ERR_CUDA;
   }
   if (want <= 2 && !cluster_top) {
-    schur_solve_kernel<SCH_SINGLE><<<1, SCH_T, SCH_SMEM, st>>>(a);
+    GNX_CUDA(gnx_launch_dependent(schur_solve_kernel<SCH_SINGLE>, dim3(1), dim3(SCH_T), SCH_SMEM, st, a));
     GNX_LAUNCH_CHECK();
     want = 1;
   } else if (cluster_top) {
@@ -1113,7 +1127,9 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   __shared__ TileSmem<CPT> ts;
   __shared__ double sh[32];
   const TileCtx c = tile_ctx<CPT, BULK>(net, d);
-  tile_load<CPT, BULK, true>(c, b, net.h, ts);
+  tile_load_h<CPT, BULK>(c, net.h, ts);           // static data: in flight while the kernels before finish
+  gnx_pdl_wait();                                 // P (and, transitively, b) come from the kernels before
+  tile_load_b<CPT, BULK>(c, b, ts);
   double* const sF = ts.F; double* const sH = ts.H; double* const sG = ts.G;
   const int32_t m = c.m;
   const int32_t eu = net.edges[2 * c.e], ev = net.edges[2 * c.e + 1];
@@ -1124,7 +1140,7 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   const double kv = k_edge ? k_edge[c.e] : 0.0;
   const double q0 = cond[c.e] * (Pu - Pv + rsrc[c.e]);
   __syncthreads();
-  tile_wait<CPT, BULK>(ts);
+  tile_wait<CPT, BULK, true>(ts);
   const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
   int32_t ps[CPT], qs[CPT];                        // shared-memory slots of my p / q dofs
   double F[CPT], H[CPT], Gq[CPT];
@@ -1188,8 +1204,8 @@ static void launch_backsub_tile(const gnx_network_t* net, const GnxMixedDims& d,
                                 double* x, cudaStream_t st) {
   const int G = (ET_T * CPT) >> net->n;
   if (edge_bulk(net->h, b, x))
-    edge_backsub_tile_kernel<CPT, true><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
-        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+    gnx_launch_dependent(edge_backsub_tile_kernel<CPT, true>, dim3(gnx_blocks(net->E, G)), dim3(ET_T), 0, st,
+                         *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
   else
     edge_backsub_tile_kernel<CPT, false><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
         *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);

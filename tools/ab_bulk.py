@@ -2,6 +2,7 @@
 GNX_ASM_BULK / GNX_EDGE_BULK = 0 | 1, C2 size and at scale; per-kernel and whole-step times (CUDA events,
 L2 flushed), plus a digest of the outputs (must be identical across variants)."""
 import os, sys, subprocess, json, hashlib
+KEYS = ("GNX_ASM_BULK", "GNX_EDGE_BULK", "GNX_PDL")
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import numpy as np, torch
@@ -27,7 +28,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             e0.record(); fn(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
         return float(np.median(ts)) * 1e3
 
-    out = {"asm_bulk,edge_bulk,asm_cpt,edge_cpt": ",".join(os.environ.get(k, "-") for k in ("GNX_ASM_BULK", "GNX_EDGE_BULK", "GNX_ASM_CPT", "GNX_EDGE_CPT")), "N": ms.N}
+    out = {",".join(KEYS): ",".join(os.environ.get(k, "-") for k in KEYS), "N": ms.N}
     out["asm_us"] = timed(lambda: ms.assemble(co, out=vals))
     out["step_us"] = timed(lambda: ms.assemble_rhs_solve(co, vals, b, x, kw, overlap=True, sync=False))
     out["step_serial_us"] = timed(lambda: ms.assemble_rhs_solve(co, vals, b, x, kw, overlap=False, sync=False))
@@ -41,8 +42,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps(out))
 else:
     for lv, n in ((11, 9), (17, 7), (12, 4)):
-        for a, e, c, ec in (("1", "1", "2", "4"), ("1", "1", "1", "4"), ("1", "1", "2", "2"), ("1", "0", "2", "2")):
+        for vals in (("1", "1", "0"), ("1", "1", "1"), ("1", "1", "2")):
             r = subprocess.run([sys.executable, __file__, "child", str(lv), str(n)],
-                               env=dict(os.environ, GNX_ASM_BULK=a, GNX_EDGE_BULK=e, GNX_ASM_CPT=c, GNX_EDGE_CPT=ec),
-                               capture_output=True, text=True)
+                               env=dict(os.environ, **dict(zip(KEYS, vals))), capture_output=True, text=True)
             print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-800:], flush=True)
