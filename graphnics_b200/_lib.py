@@ -36,6 +36,8 @@ class gnx_mixed_coeffs_t(C.Structure):
 
 MAX_LEVELS = 64
 TOP_MAX = 2048
+AGG_MAX = 128                 # GNX_AGG_MAX: aggregates (= CTAs) of the two-level PCG
+TWO_LEVEL_MIN_CORE = int(os.environ.get("GNX_TWO_LEVEL_MIN_CORE", "2048"))   # smaller cores: one CTA or one cluster, plain Jacobi
 
 
 class gnx_schur_plan_t(C.Structure):
@@ -46,8 +48,9 @@ class gnx_schur_plan_t(C.Structure):
         ("lvl_nodes", C.c_void_p), ("parent", C.c_void_p), ("pedge", C.c_void_p), ("ch_ptr", C.c_void_p),
         ("ch_idx", C.c_void_p), ("core_nodes", C.c_void_p), ("crp", C.c_void_p), ("ccol", C.c_void_p),
         ("cedge", C.c_void_p), ("top_nodes", C.c_void_p), ("top_of", C.c_void_p), ("level_of", C.c_void_p),
-        ("ell_w", C.c_int32), ("ell_R", C.c_int32), ("top_S", C.c_int32), ("reserved", C.c_int32),
+        ("ell_w", C.c_int32), ("ell_R", C.c_int32), ("top_S", C.c_int32), ("na", C.c_int32),
         ("ell_col", C.c_void_p), ("ell_edge", C.c_void_p),
+        ("agg_ptr", C.c_void_p), ("col_agg", C.c_void_p), ("cut_ptr", C.c_void_p), ("cut_k", C.c_void_p),
     ]
 
 

@@ -494,6 +494,7 @@ struct SchurArgs {
   double *d, *r;                              // [B]
   double *xc, *rc, *zc, *wc, *p0, *p1, *dg;   // [nc]
   double *cval;                               // [nnzc]
+  double *Eg, *sE;                            // two-level PCG: coarse matrix [na*na], aggregate sums of r [na]
   double *part[5];                            // [nblk] each
   double *scal;                               // [8]: tol2, converged, iterations, rr, bb
   double rtol;
@@ -511,7 +512,8 @@ struct SchurArgs {
 extern "C" int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan) {
   if (!plan) return 0;
   const int64_t nval = plan->ell_w > 0 ? (int64_t)plan->ell_w * plan->nc : 0;
-  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 8;
+  const int64_t coarse = plan->na > 0 ? (int64_t)plan->na * plan->na + plan->na : 0;
+  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 8 + coarse;
 }
 
 // All-reduce of K values over the block with ONE barrier.  `sh` holds K*32 doubles; callers
@@ -539,13 +541,13 @@ __device__ __forceinline__ void block_allreduce(double (&v)[K], double* sh) {
 //   SCH_SINGLE   one CTA, __syncthreads
 //   SCH_CLUSTER  one thread-block cluster (<= 16 CTAs on one GPC), hardware cluster barrier (~0.2 us)
 //   SCH_GRID     cooperative grid, software grid barrier (~2-3 us) -- only for phases that need > 16 CTAs
-enum { SCH_SINGLE = 0, SCH_CLUSTER = 1, SCH_GRID = 2 };
+enum { SCH_SINGLE = 0, SCH_CLUSTER = 1, SCH_GRID = 2, SCH_GRID_TL = 3 };   // 3: grid + two-level PCG on the core
 
 template <int MODE>
 __device__ __forceinline__ void sch_sync() {
   if (MODE == SCH_SINGLE) __syncthreads();
   else if (MODE == SCH_CLUSTER) cg::this_cluster().sync();
-  else cg::this_grid().sync();
+  else cg::this_grid().sync();                  // SCH_GRID, SCH_GRID_TL
 }
 
 // partials of every block are re-reduced by every block in the same order -> identical bits
@@ -785,6 +787,180 @@ __device__ __forceinline__ void core_pcg_cluster(const SchurArgs& a, double* sm,
   cluster.sync();      // nobody leaves (or reuses shared memory) while a neighbour may still read it
 }
 
+// ------------------------------------------------------------------------------------
+// Two-level PCG on a large core (cooperative grid, plan.na CTAs, CTA J owns the rows of aggregate J).
+// Jacobi alone needs O(diameter) iterations on a lattice-like core (2499 on the 200 x 200 honeycomb);
+// the additive coarse correction  M^-1 = D^-1 + W (W^T S W)^-1 W^T  over na <= 128 compact aggregates
+// (W = their indicator vectors) removes the smooth error Jacobi cannot reach (608 iterations there).
+// It costs no extra grid barrier:
+//  * the coarse matrix E = W^T S W (na x na) is summed once per solve over fixed lists (row J by CTA J),
+//    and EVERY CTA inverts it by Gauss-Jordan in its own shared memory -- the same arithmetic in the same
+//    order, so all CTAs hold the same bits and the inverse never travels;
+//  * per iteration CTA J publishes s_J = sum of r over its rows together with its dot-product partials
+//    (the barrier of the existing all-reduce), every CTA then forms y = E^-1 s and s.y redundantly, and
+//    the preconditioned residual is never stored whole: z_j = r_j/d_j + y[aggregate(j)] is rebuilt by
+//    whoever reads it.
+// Shared memory: E^-1 [na][na+1] | s | y | pivot row | pivot column | 8 x na partials.
+// ------------------------------------------------------------------------------------
+constexpr int AGG_LD = GNX_AGG_MAX + 1;          // odd leading dimension: column walks are conflict-free
+constexpr size_t TL_SMEM = ((size_t)GNX_AGG_MAX * AGG_LD + 12 * GNX_AGG_MAX) * sizeof(double);
+
+template <class Gather>
+__device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm, double (*red)[3 * 32], Gather gather,
+                                                  int& it, double& rr_final, double& bb_final) {
+  const gnx_schur_plan_t& pl = a.plan;
+  const int na = pl.na, T = blockDim.x, tid = threadIdx.x, J = blockIdx.x;     // gridDim.x == na
+  double* const Ei = sm;
+  double* const s_sh = Ei + GNX_AGG_MAX * AGG_LD;
+  double* const y_sh = s_sh + GNX_AGG_MAX;
+  double* const rk = y_sh + GNX_AGG_MAX;
+  double* const ck = rk + GNX_AGG_MAX;
+  double* const part8 = ck + GNX_AGG_MAX;
+  const int32_t r0 = pl.agg_ptr[J], r1 = pl.agg_ptr[J + 1];
+  cg::grid_group grid = cg::this_grid();
+
+  // ---- raked children, matrix values, residual of the initial guess; row sums for the coarse diagonal
+  double acc[3] = {0.0, 0.0, 0.0};
+  double v2[2] = {0.0, 0.0};                     // sum of r, sum of row sums over my aggregate
+  for (int32_t i = r0 + tid; i < r1; i += T) {
+    const int32_t node = pl.core_nodes[i];
+    gather(node);
+    const double di = a.d[node];
+    const double xi = a.warm ? a.P[node] : 0.0;
+    double ax = di * xi, rs = di;
+    for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k) {
+      const double v = -a.cond[a.eidx(pl.cedge[k])];
+      a.cval[k] = v;
+      rs += v;
+      if (a.warm) ax += v * a.P[pl.core_nodes[pl.ccol[k]]];
+    }
+    const double bi = a.r[node];
+    const double ri = bi - ax;
+    const double zi = ri / di;
+    a.dg[i] = di; a.xc[i] = xi; a.rc[i] = ri; a.zc[i] = zi; a.p0[i] = 0.0; a.p1[i] = 0.0;
+    acc[0] += ri * zi; acc[1] += ri * ri; acc[2] += bi * bi;
+    v2[0] += ri; v2[1] += rs;
+  }
+  block_allreduce<2>(v2, red[1]);                // (its barrier also publishes cval inside the CTA)
+  // row J of E: off-diagonal = sum of the entries that couple J to K, diagonal = sum of my row sums - those
+  for (int32_t K = tid; K < na; K += T) {
+    double e = 0.0;
+    if (K != J)
+      for (int32_t c = pl.cut_ptr[J * na + K]; c < pl.cut_ptr[J * na + K + 1]; ++c) e += a.cval[pl.cut_k[c]];
+    rk[K] = e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double off = 0.0;
+    for (int32_t K = 0; K < na; ++K) if (K != J) off += rk[K];
+    rk[J] = v2[1] - off;
+    a.sE[J] = v2[0];
+  }
+  __syncthreads();
+  for (int32_t K = tid; K < na; K += T) a.Eg[J * na + K] = rk[K];
+  {
+    double* const part[3] = {a.part[0], a.part[1], a.part[2]};
+    grid_allreduce<SCH_GRID, 3>(acc, part, na, red[0]);          // its grid barrier publishes Eg and sE
+  }
+  // ---- every CTA: E -> E^-1 in shared memory (in-place Gauss-Jordan; E is SPD, no pivoting).
+  // Thread t owns column t & 127 of rows (t >> 7) + 8 u.
+  const int cj = tid & (GNX_AGG_MAX - 1), ci0 = tid >> 7;
+  constexpr int RSTEP = SCH_T / GNX_AGG_MAX;
+  if (cj < na)
+    for (int i = ci0; i < na; i += RSTEP) Ei[i * AGG_LD + cj] = __ldcg(a.Eg + i * na + cj);
+  __syncthreads();
+  for (int k = 0; k < na; ++k) {
+    if (tid < na) { rk[tid] = Ei[k * AGG_LD + tid]; ck[tid] = Ei[tid * AGG_LD + k]; }
+    __syncthreads();
+    const double ip = 1.0 / rk[k];
+    if (cj < na) {
+      const double rkj = rk[cj] * ip;
+      for (int i = ci0; i < na; i += RSTEP) {
+        double v;
+        if (i == k) v = (cj == k) ? ip : rkj;
+        else if (cj == k) v = -ck[i] * ip;
+        else v = Ei[i * AGG_LD + cj] - ck[i] * rkj;
+        Ei[i * AGG_LD + cj] = v;
+      }
+    }
+    __syncthreads();
+  }
+  // y = E^-1 s (all of it, every CTA), returns s.y
+  auto coarse = [&]() -> double {
+    for (int32_t K = tid; K < na; K += T) s_sh[K] = __ldcg(a.sE + K);
+    __syncthreads();
+    double pv = 0.0;
+    if (cj < na) {
+      const int c1 = min(na, ci0 * 16 + 16);
+      for (int c = ci0 * 16; c < c1; ++c) pv += Ei[cj * AGG_LD + c] * s_sh[c];
+    }
+    part8[ci0 * GNX_AGG_MAX + cj] = pv;
+    __syncthreads();
+    double sg[1] = {0.0};
+    if (tid < na) {
+      double y = 0.0;
+#pragma unroll
+      for (int q = 0; q < RSTEP; ++q) y += part8[q * GNX_AGG_MAX + tid];
+      y_sh[tid] = y;
+      sg[0] = y * s_sh[tid];
+    }
+    block_allreduce<1>(sg, red[1]);
+    __syncthreads();                              // red[1] is the next reduction's buffer, too
+    return sg[0];
+  };
+  double rr = acc[1];
+  const double bb = acc[2];
+  const double tol2 = a.rtol * a.rtol * bb;
+  double rzc = acc[0] + coarse(), rzp = rzc;
+  for (; it < a.max_iter; ++it) {
+    if (rr <= tol2) break;
+    const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
+    const double* p_old = (it & 1) ? a.p1 : a.p0;
+    double* p_new = (it & 1) ? a.p0 : a.p1;
+    const double yJ = y_sh[J];
+    double pw[1] = {0.0};
+    for (int32_t i = r0 + tid; i < r1; i += T) {
+      const double pi = (a.zc[i] + yJ) + beta * p_old[i];
+      double wi = a.dg[i] * pi;
+      for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k) {
+        const int32_t j = pl.ccol[k];
+        wi += a.cval[k] * ((__ldcg(a.zc + j) + y_sh[pl.col_agg[k]]) + beta * __ldcg(p_old + j));
+      }
+      p_new[i] = pi;
+      a.wc[i] = wi;
+      pw[0] += pi * wi;
+    }
+    {
+      double* const part[1] = {a.part[3]};
+      grid_allreduce<SCH_GRID, 1>(pw, part, na, red[1]);
+    }
+    const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
+    double v3[3] = {0.0, 0.0, 0.0};               // r.D^-1 r, r.r, sum of r over my aggregate
+    for (int32_t i = r0 + tid; i < r1; i += T) {
+      a.xc[i] += alpha * p_new[i];
+      const double ri = a.rc[i] - alpha * a.wc[i];
+      const double zi = ri / a.dg[i];
+      a.rc[i] = ri; a.zc[i] = zi;
+      v3[0] += ri * zi; v3[1] += ri * ri; v3[2] += ri;
+    }
+    block_allreduce<3>(v3, red[0]);
+    if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; a.sE[J] = v3[2]; }
+    grid.sync();
+    double t2[2] = {0.0, 0.0};
+    for (int i = tid; i < na; i += T) { t2[0] += __ldcg(a.part[0] + i); t2[1] += __ldcg(a.part[1] + i); }
+    __syncthreads();                              // red[0] reuse
+    block_allreduce<2>(t2, red[0]);
+    rzp = rzc; rzc = t2[0] + coarse(); rr = t2[1];
+  }
+  rr_final = rr; bb_final = bb;
+  for (int32_t i = r0 + tid; i < r1; i += T) {
+    const int32_t node = pl.core_nodes[i];
+    const double xi = a.xc[i];
+    a.P[node] = xi;
+    if (a.lam_out) a.lam_out[node] = xi * a.inv_sigma;
+  }
+}
+
 template <int MODE> struct SchThreads { static constexpr int value = SCH_T; };
 template <> struct SchThreads<SCH_CLUSTER> { static constexpr int value = CL_T; };
 
@@ -861,6 +1037,8 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
     // ---- phase 2: Jacobi-PCG on the core
     if (MODE == SCH_CLUSTER) {                   // launched only with an ELL plan (gnx_schur_solve)
       core_pcg_cluster(a, top_sh, red, gather, it, rr_final, bb_final);
+    } else if (MODE == SCH_GRID_TL) {            // launched with na CTAs and TL_SMEM (gnx_schur_solve)
+      core_pcg_twolevel(a, top_sh, red, gather, it, rr_final, bb_final);
     } else {
     double acc[3] = {0.0, 0.0, 0.0};
     for (int32_t i = t0; i < pl.nc; i += stride) {
@@ -953,8 +1131,10 @@ static int sch_init() {
   GNX_CUDA(cudaDeviceGetAttribute(&g_sch_sms, cudaDevAttrMultiProcessorCount, dev));
   GNX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
+  GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_GRID_TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
   GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCH_SMEM));
   GNX_CUDA(cudaFuncSetAttribute(schur_solve_kernel<SCH_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+  static_assert(TL_SMEM >= SCH_SMEM, "the two-level kernel also holds the top part");
   GNX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_solve_kernel<SCH_GRID>, SCH_T, SCH_SMEM));
   if (!coop || per_sm < 1) { gnx_set_error("cooperative launch unsupported on this device"); return GNX_ERR_CUDA; }
   // largest cluster this kernel can run as (16 needs the non-portable opt-in)
@@ -993,6 +1173,8 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
                                     plan->ell_R <= CL_RMAX && (int64_t)plan->ell_R * CL_CTAS >= plan->nc));
   GNX_CHECK_ARG(plan->nl == 0 || (plan->lvl_nodes && plan->parent && plan->pedge && plan->ch_ptr && plan->ch_idx));
   GNX_CHECK_ARG(plan->nc == 0 || (plan->core_nodes && plan->crp && plan->ccol && plan->cedge && plan->ch_ptr));
+  GNX_CHECK_ARG(plan->na == 0 || (plan->na >= 2 && plan->na <= GNX_AGG_MAX && plan->na <= plan->nc && plan->agg_ptr &&
+                                  plan->col_agg && plan->cut_ptr && plan->cut_k));
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = sch_init()) return rc;
   SchurArgs a;
@@ -1006,7 +1188,8 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   a.p0 = w; w += nc; a.p1 = w; w += nc; a.dg = w; w += nc;
   a.cval = w; w += plan->nnzc;
   for (int k = 0; k < 5; ++k) { a.part[k] = w; w += 2048; }
-  a.scal = w;
+  a.scal = w; w += 8;
+  a.Eg = w; w += (int64_t)plan->na * plan->na; a.sE = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
   // CTAs: enough threads for the widest phase.  <= 2 CTAs' worth runs as one CTA; a system with a
@@ -1020,7 +1203,16 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
     gnx_set_error("plan asks for a cluster-resident tree sweep but 16-CTA clusters are unavailable");
     return GNX_ERR_CUDA;
   }
-  if (want <= 2 && !cluster_top) {
+  if (plan->na > 0) {
+    // two-level PCG: one CTA per aggregate on the cooperative grid (every phase before it is grid-stride)
+    if (plan->na > g_sch_sms) {
+      gnx_set_error("two-level PCG needs %d co-resident CTAs, the device runs %d", plan->na, g_sch_sms);
+      return GNX_ERR_CUDA;
+    }
+    want = plan->na;
+    void* args[] = {&a};
+    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<SCH_GRID_TL>, dim3(want), dim3(SCH_T), args, TL_SMEM, st));
+  } else if (want <= 2 && !cluster_top) {
     GNX_CUDA(gnx_launch_dependent(schur_solve_kernel<SCH_SINGLE>, dim3(1), dim3(SCH_T), SCH_SMEM, st, a));
     GNX_LAUNCH_CHECK();
     want = 1;

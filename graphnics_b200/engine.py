@@ -231,7 +231,14 @@ class MixedSystem:
         if self._plan is None and self.dn.B > 0:
             from .schur_plan import SchurPlan
             dn = self.dn
-            hp = SchurPlan(dn.schur_edges_host(), dn.bix.cpu().numpy(), dn.B, max_levels=_lib.MAX_LEVELS)
+            bix_h = dn.bix.cpu().numpy()
+            hp = SchurPlan(dn.schur_edges_host(), bix_h, dn.B, max_levels=_lib.MAX_LEVELS)
+            agg = None
+            if hp.nc > _lib.TWO_LEVEL_MIN_CORE and os.environ.get("GNX_SCHUR_TWO_LEVEL", "1") != "0":
+                # large cyclic core: two-level PCG, aggregates cut by coordinate bisection of the node positions
+                node_of = np.empty(dn.B, dtype=np.int64)
+                node_of[bix_h[bix_h >= 0]] = np.nonzero(bix_h >= 0)[0]
+                agg = hp.aggregate_core(dn.pos.cpu().numpy()[node_of], na=_lib.AGG_MAX)
             lvl_ptr, lvl_nodes = hp.level_arrays()
             keep = {}
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
@@ -254,7 +261,10 @@ class MixedSystem:
                 s.lvl_ptr[i] = int(v)
             ell_w, ell_R, ell_col, ell_edge = hp.ell_arrays()
             s.ell_w, s.ell_R, s.top_S = ell_w, ell_R, top_S
-            for name, arr in (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
+            s.na = agg["na"] if agg is not None else 0
+            extra = () if agg is None else (("agg_ptr", agg["agg_ptr"]), ("col_agg", agg["col_agg"]),
+                                            ("cut_ptr", agg["cut_ptr"]), ("cut_k", agg["cut_k"]))
+            for name, arr in extra + (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
                               ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),
                               ("top_nodes", top), ("top_of", top_of), ("level_of", level_of),

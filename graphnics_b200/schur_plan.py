@@ -32,6 +32,7 @@ class SchurPlan:
         edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
         bix = np.asarray(bix, dtype=np.int64)
         self.B = int(B)
+        self.agg = None                                       # set by aggregate_core (two-level PCG)
         bu, bv = bix[edges[:, 0]], bix[edges[:, 1]]
         inner = np.nonzero((bu >= 0) & (bv >= 0))[0]          # edges joining two bifurcations
         eu, ev = bu[inner], bv[inner]
@@ -148,40 +149,40 @@ class SchurPlan:
         top_of[top] = np.arange(len(top), dtype=np.int32)
         return top, top_of, level_of
 
-    def aggregate_core(self, na_max=128, min_core=2049, per_agg=64):
-        """Coarse space of the two-level preconditioner: the core is split into `na` compact aggregates
-        (graph Voronoi cells of farthest-point seeds) and RENUMBERED so that every aggregate is a
-        contiguous range of core rows.  Returns None for small cores (plain Jacobi is used), else a dict
-        with na, agg_ptr [na+1], agg_of [nc], cut_ptr [na*na+1], cut_k (indices into the core CSR of the
-        entries that couple aggregate I to aggregate J != I, grouped by (I, J) in a fixed order)."""
+    def aggregate_core(self, pos, na=128):
+        """Coarse space of the two-level preconditioner (additive: Jacobi + piecewise-constant coarse
+        correction): the core is cut into `na` compact, equally sized aggregates by recursive coordinate
+        bisection of the node positions `pos` [B, gdim] (positions only steer the QUALITY of the
+        aggregates; any partition gives a symmetric positive definite preconditioner), and the core is
+        RENUMBERED so that every aggregate is a contiguous range of core rows (one CTA per aggregate in
+        the kernel).  Sets self.agg = dict(na, agg_ptr [na+1], col_agg [nnzc] aggregate of every CSR
+        column, cut_ptr [na*na+1], cut_k: the CSR entries that couple aggregate I to J != I, grouped by
+        (I, J) in a fixed order -- the coarse matrix is summed over these lists, deterministically)."""
         nc = self.nc
-        if nc < min_core:
-            return None
-        import scipy.sparse as sp
-        from scipy.sparse.csgraph import shortest_path
-        na = int(min(na_max, max(8, nc // per_agg)))
-        rows = np.repeat(np.arange(nc), np.diff(self.crp))
-        adj = sp.csr_matrix((np.ones(len(rows)), (rows, self.ccol)), shape=(nc, nc))
-        dist = np.full(nc, np.inf)
+        na = int(min(na, nc))
+        p = np.asarray(pos, dtype=np.float64)[self.core_nodes]
         owner = np.zeros(nc, dtype=np.int64)
-        seed = 0
-        for k in range(na):
-            d = shortest_path(adj, method="D", unweighted=True, indices=seed)
-            closer = d < dist
-            owner[closer] = k
-            dist[closer] = d[closer]
-            seed = int(np.argmax(dist))
-            if dist[seed] == 0:
-                na = k + 1
-                break
+        todo = [(np.arange(nc), na, 0)]
+        while todo:
+            idx, k, base = todo.pop()
+            if k == 1:
+                owner[idx] = base
+                continue
+            ext = p[idx].max(axis=0) - p[idx].min(axis=0)
+            ax = int(np.argmax(ext))
+            k0 = k // 2
+            cut = len(idx) * k0 // k
+            o = np.argsort(p[idx, ax], kind="stable")
+            todo.append((idx[o[:cut]], k0, base))
+            todo.append((idx[o[cut:]], k - k0, base + k0))
         # renumber the core: aggregates become contiguous ranges (stable inside an aggregate)
         order = np.argsort(owner, kind="stable")
         newpos = np.empty(nc, dtype=np.int64)
         newpos[order] = np.arange(nc)
-        deg = np.diff(self.crp)
-        new_deg = deg[order]
-        new_crp = np.concatenate([[0], np.cumsum(new_deg)]).astype(np.int64)
-        src = np.concatenate([np.arange(self.crp[i], self.crp[i + 1]) for i in order]) if nc else np.zeros(0, np.int64)
+        deg = np.diff(self.crp).astype(np.int64)
+        new_crp = np.concatenate([[0], np.cumsum(deg[order])]).astype(np.int64)
+        src = np.repeat(self.crp[order].astype(np.int64), deg[order]) + \
+            (np.arange(int(deg.sum())) - np.repeat(new_crp[:-1], deg[order]))
         self.core_nodes = self.core_nodes[order].astype(np.int32)
         self.core_of = -np.ones(self.B, dtype=np.int32)
         self.core_of[self.core_nodes] = np.arange(nc, dtype=np.int32)
@@ -190,7 +191,6 @@ class SchurPlan:
         self.crp = new_crp.astype(np.int32)
         agg_of = owner[order]
         agg_ptr = np.concatenate([[0], np.cumsum(np.bincount(agg_of, minlength=na))]).astype(np.int32)
-        # coupling lists
         rows = np.repeat(np.arange(nc), np.diff(self.crp))
         I, J = agg_of[rows], agg_of[self.ccol]
         cut = np.nonzero(I != J)[0]
@@ -198,8 +198,8 @@ class SchurPlan:
         o = np.argsort(key, kind="stable")
         cut_k = cut[o].astype(np.int32)
         cut_ptr = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=na * na))]).astype(np.int32)
-        self.agg = dict(na=na, agg_ptr=agg_ptr, agg_of=agg_of.astype(np.int32), cut_ptr=cut_ptr,
-                        cut_k=cut_k if len(cut_k) else np.zeros(1, dtype=np.int32))
+        self.agg = dict(na=na, agg_ptr=agg_ptr, agg_of=agg_of.astype(np.int32), col_agg=J.astype(np.int32),
+                        cut_ptr=cut_ptr, cut_k=cut_k if len(cut_k) else np.zeros(1, dtype=np.int32))
         return self.agg
 
     def ell_arrays(self, ctas=16, rmax=5120, wmax=8):

@@ -237,6 +237,7 @@ int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, 
  * bifurcation indices unless stated. */
 #define GNX_MAX_LEVELS 64
 #define GNX_TOP_MAX 2048
+#define GNX_AGG_MAX 128
 typedef struct gnx_schur_plan {
   int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level of the TOP part, core size */
   int32_t nnzc, nt;                    /* off-diagonal entries of the core matrix; #nodes in levels >= l_split
@@ -258,10 +259,18 @@ typedef struct gnx_schur_plan {
    * than 8 entries per row or larger than 16 x 5120 rows): entry k of core row i at [k*nc + i];
    * ell_col packs (owning CTA << 16 | offset) for ell_R rows per CTA, -1 = padding */
   int32_t ell_w, ell_R;
-  int32_t top_S, reserved;             /* > 0: a pure tree (nc = 0, l_split = 0) of <= 16*top_S nodes is swept by ONE
+  int32_t top_S;                       /* > 0: a pure tree (nc = 0, l_split = 0) of <= 16*top_S nodes is swept by ONE
                                           16-CTA cluster, top_S slots per CTA (power of two, 512..2048) */
+  int32_t na;                          /* > 0: two-level preconditioner, the core rows are grouped into na aggregates */
   const int32_t* ell_col;              /* [ell_w*nc] */
   const int32_t* ell_edge;             /* [ell_w*nc] graph edge whose -cond is the entry, -1 = padding */
+  /* Two-level PCG on a large core (na > 0, 2 <= na <= GNX_AGG_MAX; cooperative grid of na CTAs, one per
+   * aggregate): preconditioner  M^-1 = D^-1 + W (W^T S W)^-1 W^T  with W the piecewise-constant
+   * indicator vectors of the aggregates.  Core rows are numbered aggregate by aggregate. */
+  const int32_t* agg_ptr;              /* [na+1] core rows of aggregate J = agg_ptr[J] .. agg_ptr[J+1]) */
+  const int32_t* col_agg;              /* [nnzc] aggregate of the column of every core entry */
+  const int32_t* cut_ptr;              /* [na*na+1] cut_k[cut_ptr[I*na+J] ..): core entries coupling aggregate I to J != I */
+  const int32_t* cut_k;
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

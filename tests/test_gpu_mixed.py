@@ -221,9 +221,13 @@ def _big_graph(name):
         from graphnics_b200.generators import honeycomb
         G = honeycomb(40, 40, mesh=False)
         return G._graph_arrays()
-    if name == "lollipop":                    # cycle (core) with trees hanging off it (raked)
+    if name == "honeycomb70":                 # B ~ 10k > 8192: two-level PCG, one CTA per aggregate
+        from graphnics_b200.generators import honeycomb
+        G = honeycomb(70, 70, mesh=False)
+        return G._graph_arrays()
+    if name in ("lollipop", "lollipop9k"):    # cycle (core) with trees hanging off it (raked)
         rng = np.random.default_rng(11)
-        nc = 3000
+        nc = 3000 if name == "lollipop" else 9000
         th = 2 * np.pi * np.arange(nc) / nc
         pos = [np.stack([np.cos(th), np.sin(th)], 1) * 50]
         edges = [np.stack([np.arange(nc), (np.arange(nc) + 1) % nc], 1)]
@@ -244,7 +248,8 @@ def _big_graph(name):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name,n", [("tree14", 2), ("honeycomb40", 1), ("lollipop", 1)])
+@pytest.mark.parametrize("name,n", [("tree14", 2), ("honeycomb40", 1), ("lollipop", 1), ("honeycomb70", 1),
+                                    ("lollipop9k", 1)])
 def test_solve_large_graphs(eng, name, n):
     """systems whose Schur solve needs the cooperative multi-CTA kernel (B > 2048)"""
     import torch
@@ -274,6 +279,10 @@ def test_solve_large_graphs(eng, name, n):
         assert plan.nc == dn.B and info.cg_iterations > 10
     if name == "lollipop":
         assert 0 < plan.nc < dn.B
+    if name in ("honeycomb70", "lollipop9k"):  # core > 8192 rows: two-level PCG on 128 CTAs
+        assert plan.nc > 8192 and plan.agg["na"] == 128 and info.cg_batches == 128
+        if name == "lollipop9k":
+            assert plan.nc < dn.B
     assert info.cg_converged and abs(info.cg_batches) > 1      # > 1 CTA (negative: one cluster)
     lay = oracle.mixed_layout(om)
     x = x.cpu().numpy()
