@@ -195,7 +195,13 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: whatever native libraries write to file descriptor 1 (the NCCL
+        # version banner) goes to stderr, Python's own stdout keeps the original descriptor
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(keep, "w", buffering=1)
         dist.init_process_group("nccl", device_id=dev)
     if world > 1:
         from graphnics_b200.parallel import run_partitioned_bench
