@@ -228,6 +228,8 @@ def run_gpu(args):
     def step():
         ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=not args.no_overlap, sync=False)
 
+    host_us = []          # host time to enqueue one call (no synchronisation inside)
+
     def timed(fn, reps, warm, do_flush=True):
         for _ in range(warm):
             fn()
@@ -237,7 +239,7 @@ def run_gpu(args):
             if do_flush:
                 flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
+            e0.record(); t0 = time.perf_counter(); fn(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
             e1.synchronize()
             ts.append(e0.elapsed_time(e1))
         return ts
@@ -249,6 +251,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ts = timed(step, args.steps, 0)
     torch.cuda.synchronize()
+    host_enqueue_us = float(np.median(host_us))
     ms_per_step = float(np.sum(ts) / args.steps)
     value = N / (ms_per_step * 1e-3) / 1e6
 
@@ -274,7 +277,7 @@ def run_gpu(args):
     k("schur_solve_kernel (rake + core PCG, latency-bound)", lambda: ms.lib.gnx_schur_solve(
         dn.net_ref(), ctypes.byref(plan), 1.0, bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["ftot"].data_ptr(), b[dn.lam_off:].data_ptr(), None, bufs["P"].data_ptr(), lam.data_ptr(), work.data_ptr(),
-        1e-13, 100000, 0, 0, 0, None, None, torch.cuda.current_stream().cuda_stream), 8 * 3 * dn.E + 8 * 6 * dn.B)
+        1e-13, 100000, 0, 0, 0, None, None, None, torch.cuda.current_stream().cuda_stream), 8 * 3 * dn.E + 8 * 6 * dn.B)
     k("edge_backsub_kernel", lambda: ms.lib.gnx_edge_backsub_mixed(
         dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["P"].data_ptr(), x.data_ptr(), torch.cuda.current_stream().cuda_stream), 2 * 8 * N + 8 * NC)
@@ -310,7 +313,8 @@ def run_gpu(args):
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(TREE_LEVELS, n, dn.E, N, {"nnz": nnz, "bifurcations": dn.B}),
-           "rel_residual": rel_resid, "gpu_launches": 4 * args.steps, "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
+           "rel_residual": rel_resid, "gpu_launches": 4 * args.steps, "host_enqueue_us_per_step": host_enqueue_us,
+           "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
            "streams": ("1 (kernels back to back)" if args.no_overlap else
                        "2: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute on a "
                        "high-priority stream; joined before the step's end event"), "kernels": kernels, "roofline": roof,

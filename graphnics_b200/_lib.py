@@ -54,6 +54,11 @@ class gnx_schur_plan_t(C.Structure):
     ]
 
 
+class gnx_exchange_t(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("chunk", C.c_int32), ("reserved", C.c_int32),
+                ("peers_host", C.POINTER(C.c_void_p)), ("epoch", C.c_int64), ("reserved2", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
@@ -61,6 +66,7 @@ _D = C.c_double
 _NET = C.POINTER(gnx_network_t)
 _CO = C.POINTER(gnx_mixed_coeffs_t)
 _PLAN = C.POINTER(gnx_schur_plan_t)
+_EX = C.POINTER(gnx_exchange_t)
 
 
 class gnx_primal_coeffs_t(C.Structure):
@@ -89,11 +95,13 @@ PROTOTYPES = {
     "gnx_project_end_values": (_I, [_NET, _P, _P, _I, _I, _P, _P]),
     "gnx_dof_coordinates_mixed": (_I, [_NET, _P, _P, _P, _P, _P]),
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
-    "gnx_edge_eliminate_mixed_p2p": (_I, [_NET, _CO, _P, _I, _I, _I, C.POINTER(C.c_void_p), _P]),
-    "gnx_rhs_eliminate_mixed": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(C.c_void_p), _P]),
+    "gnx_edge_eliminate_mixed_p2p": (_I, [_NET, _CO, _P, _EX, _P]),
+    "gnx_rhs_eliminate_mixed": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P, _EX, _P]),
+    "gnx_step_mixed": (_I, [_NET, _CO, _P, _P, _D, _D, _P, _P, _P, _P, _NET, _PLAN, _P, _P, _P, _P, _P, _D, _I, _I,
+                            _EX, c_f64p, c_i32p, _P, _P, _P, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
-    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, c_f64p, c_i32p, _P]),
+    "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _EX, c_f64p, c_i32p, _P]),
     "gnx_primal_ndofs": (_L, [_NET]),
     "gnx_primal_nnz": (_L, [_NET]),
     "gnx_build_pattern_primal": (_I, [_NET, _P, _P, _P]),

@@ -373,62 +373,61 @@ static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* 
   return GNX_OK;
 }
 
+static void edge_out_local(EdgeOut& out, double* cond, double* rsrc, double* ftot) {
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  out.base[0] = cond; out.n = 1;
+  out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+}
+
 extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                                         const double* b, double* cond, double* rsrc, double* ftot,
                                         void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && cond && rsrc && ftot && net->h && co->sigma != 0.0);
   EdgeOut out;
-  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
-  out.base[0] = cond; out.n = 1;
-  out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+  edge_out_local(out, cond, rsrc, ftot);
   return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
 }
 
 // MixedHydraulicNetwork.L_form with Constant f / g (flow_models.py:299-332) + elimination in ONE kernel:
 // b [N] is an OUTPUT (identical to gnx_assemble_rhs_mixed with f_nodal = g_nodal = NULL).  n <= 10.
-// peers_host != NULL: edge-partitioned variant, scalars stored to every rank (see the _p2p entry point).
+// ex != NULL: edge-partitioned variant, scalars stored to every rank.
+
+// Edge-partitioned network (gnx_exchange): every edge scalar is stored straight into the gather buffer of
+// every rank; block of rank q at q*3*chunk, the world flag words behind the world blocks.
+static int edge_out_exchange(EdgeOut& out, const gnx_exchange_t* ex, int32_t E) {
+  GNX_CHECK_ARG(ex->peers_host && ex->world >= 1 && ex->world <= GNX_MAX_PEERS && ex->rank >= 0 &&
+                ex->rank < ex->world && ex->chunk >= E && ex->epoch >= 0);
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  for (int k = 0; k < ex->world; ++k) {
+    GNX_CHECK_ARG(ex->peers_host[k] != nullptr);
+    out.base[k] = ex->peers_host[k] + (int64_t)ex->rank * 3 * ex->chunk;
+  }
+  out.n = ex->world;
+  out.off_rsrc = ex->chunk; out.off_ftot = 2 * (int64_t)ex->chunk;
+  return GNX_OK;
+}
+
 extern "C" int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
                                        double g_const, const double* pbc_out, const double* pbc_node, double* b,
-                                       double* cond, double* rsrc, double* ftot, int32_t world, int32_t rank,
-                                       int32_t chunk, double* const* peers_host, void* stream) {
+                                       double* cond, double* rsrc, double* ftot, const gnx_exchange_t* ex,
+                                       void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && net->n <= 10);
   EdgeOut out;
-  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
-  if (peers_host) {
-    GNX_CHECK_ARG(world >= 1 && world <= GNX_MAX_PEERS && rank >= 0 && rank < world && chunk >= net->E);
-    for (int k = 0; k < world; ++k) {
-      GNX_CHECK_ARG(peers_host[k] != nullptr);
-      out.base[k] = peers_host[k] + (int64_t)rank * 3 * chunk;
-    }
-    out.n = world;
-    out.off_rsrc = chunk; out.off_ftot = 2 * (int64_t)chunk;
+  if (ex) {
+    if (int rc = edge_out_exchange(out, ex, net->E)) return rc;
   } else {
     GNX_CHECK_ARG(cond && rsrc && ftot);
-    out.base[0] = cond; out.n = 1;
-    out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+    edge_out_local(out, cond, rsrc, ftot);
   }
   ConstRhs rhs = {f_const, g_const, pbc_out, pbc_node, b};
   return launch_eliminate(net, co, nullptr, out, (cudaStream_t)stream, &rhs);
 }
 
-// Edge-partitioned network: the same elimination, but every edge scalar is stored straight into the
-// all-gather buffer of every rank (peers_host[r] = device address, valid on THIS GPU, of rank r's
-// buffer; layout per rank block: [cond | rsrc | ftot] of `chunk` doubles each, block of rank q at
-// q * 3 * chunk).  No collective call is left; the caller separates this kernel from the Schur kernel
-// with a cross-GPU barrier.
 extern "C" int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
-                                            const double* b, int32_t world, int32_t rank, int32_t chunk,
-                                            double* const* peers_host, void* stream) {
-  GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && peers_host);
-  GNX_CHECK_ARG(world >= 1 && world <= GNX_MAX_PEERS && rank >= 0 && rank < world && chunk >= net->E);
+                                            const double* b, const gnx_exchange_t* ex, void* stream) {
+  GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && ex);
   EdgeOut out;
-  for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
-  for (int k = 0; k < world; ++k) {
-    GNX_CHECK_ARG(peers_host[k] != nullptr);
-    out.base[k] = peers_host[k] + (int64_t)rank * 3 * chunk;
-  }
-  out.n = world;
-  out.off_rsrc = chunk; out.off_ftot = 2 * (int64_t)chunk;
+  if (int rc = edge_out_exchange(out, ex, net->E)) return rc;
   return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
 }
 
@@ -503,6 +502,12 @@ struct SchurArgs {
   // per-rank [cond | rsrc | ftot] blocks produces (one collective instead of three).  A single
   // GPU passes chunk = INT32_MAX, i.e. plain arr[e].
   int32_t chunk, rank_stride;
+  // edge-partitioned solve with the flag protocol (gnx_exchange): tell every rank that my scalars have landed
+  // (my elimination kernel is complete when this kernel runs), then wait until every rank has told me
+  const long long* wait_flags;                // [wait_world] flag words of my gather buffer, or NULL
+  long long* sig_flags[GNX_MAX_PEERS];        // my flag word in every rank's gather buffer
+  long long wait_epoch;
+  int32_t wait_world;
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
     const int32_t r = e / chunk;
     return (int64_t)r * rank_stride + (e - r * chunk);
@@ -975,6 +980,22 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
   auto gsync = [&]() { sch_sync<MODE>(); };
   gnx_pdl_wait();                                 // the edge scalars come from the elimination kernel
+  if (a.wait_flags) {                             // ... and, edge-partitioned, from the other ranks' over NVLink
+    if ((int)threadIdx.x < a.wait_world) {
+      if (blockIdx.x == 0)
+        asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[threadIdx.x]), "l"(a.wait_epoch) : "memory");
+      const long long* f = a.wait_flags + threadIdx.x;
+      long long v;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= a.wait_epoch) break;
+        __nanosleep(64);
+        if (++spins > (1u << 25)) __trap();       // seconds: a rank is missing -- fail instead of hanging the GPU
+      }
+    }
+    __syncthreads();
+  }
 
   // parent i absorbs its raked children: d_i -= w^2/d_c, r_i -= w r_c/d_c  (w = -cond of the link)
   auto gather = [&](int32_t i) {
@@ -1158,7 +1179,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
                                const double* cond, const double* rsrc, const double* ftot,
                                const double* b_lam, const double* b_node, double* P, double* lam_out, double* work,
                                double rtol, int32_t max_iter, int32_t warm, int32_t chunk, int32_t rank_stride,
-                               double* resid_host, int32_t* info_host, void* stream) {
+                               const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* stream) {
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
   GNX_CHECK_ARG(plan->B == net->B && plan->B > 0 && plan->nl >= 0 && plan->nl <= GNX_MAX_LEVELS);
   GNX_CHECK_ARG(plan->l_split >= 0 && plan->l_split <= plan->nl && plan->nc >= 0 && plan->nc <= plan->B);
@@ -1192,6 +1213,17 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   a.Eg = w; w += (int64_t)plan->na * plan->na; a.sE = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
+  a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_world = 0;
+  if (ex && ex->epoch > 0) {
+    GNX_CHECK_ARG(ex->peers_host && ex->world >= 1 && ex->world <= GNX_MAX_PEERS && ex->rank >= 0 &&
+                  ex->rank < ex->world && ex->peers_host[ex->rank] && ex->chunk == chunk);
+    a.wait_flags = reinterpret_cast<const long long*>(ex->peers_host[ex->rank] + (int64_t)ex->world * 3 * ex->chunk);
+    a.wait_epoch = ex->epoch; a.wait_world = ex->world;
+    for (int k = 0; k < ex->world; ++k) {
+      GNX_CHECK_ARG(ex->peers_host[k] != nullptr);
+      a.sig_flags[k] = reinterpret_cast<long long*>(ex->peers_host[k] + (int64_t)ex->world * 3 * ex->chunk) + ex->rank;
+    }
+  }
   // CTAs: enough threads for the widest phase.  <= 2 CTAs' worth runs as one CTA; a system with a
   // Krylov core (hundreds of barriers) runs as ONE CLUSTER when that gives every thread <= 32 rows;
   // everything else (wide rake levels of a large tree: few barriers, lots of rows) as a cooperative grid.

@@ -1,0 +1,54 @@
+// One MixedHydraulicNetwork.solve() step (flow_models.py:337-350) behind ONE call: CSR values on the
+// caller's stream, right-hand side + elimination -> Schur kernel -> back-substitution on a side stream,
+// forked and joined with the two events the caller provides.  The kernels are the ones of the separate
+// entry points (bit-identical results); what this saves is host time -- four Python/ctypes round trips,
+// stream-context switches and event calls cost more than the 55 us the GPU needs for the C2 step.
+#include "gnx_common.cuh"
+
+extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const int32_t* rowptr,
+                              double* vals, double f_const, double g_const, const double* pbc_out,
+                              const double* pbc_node, double* b, double* x, const gnx_network_t* schur_net,
+                              const gnx_schur_plan_t* plan, double* cond, double* rsrc, double* ftot, double* P,
+                              double* work, double rtol, int32_t max_iter, int32_t warm, const gnx_exchange_t* ex,
+                              double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join, void* side_stream, void* stream) {
+  GNX_CHECK_ARG(net && co && b && x && (ex || (cond && rsrc && ftot)));
+  GNX_CHECK_ARG(!ex || (ex->epoch > 0 && ex->peers_host && ex->rank >= 0 && ex->rank < ex->world));
+  GNX_CHECK_ARG(net->B == 0 || (schur_net && plan && P && work));
+  cudaStream_t main_st = (cudaStream_t)stream;
+  cudaStream_t solve_st = side_stream ? (cudaStream_t)side_stream : main_st;
+  const bool fork = side_stream != nullptr && vals != nullptr;
+  if (fork) {
+    GNX_CHECK_ARG(ev_fork && ev_join);
+    GNX_CUDA(cudaEventRecord((cudaEvent_t)ev_fork, main_st));
+    GNX_CUDA(cudaStreamWaitEvent(solve_st, (cudaEvent_t)ev_fork, 0));
+  } else {
+    solve_st = main_st;
+    if (vals) if (int rc = gnx_assemble_mixed(net, co, rowptr, vals, main_st)) return rc;
+  }
+  if (int rc = gnx_rhs_eliminate_mixed(net, co, f_const, g_const, pbc_out, pbc_node, b, cond, rsrc, ftot, ex,
+                                       solve_st)) return rc;
+  int32_t chunk = 0, stride = 0;
+  if (ex) {                                     // the scalars of ALL edges, as the ranks stored them into my buffer
+    double* g = ex->peers_host[ex->rank];
+    chunk = ex->chunk; stride = 3 * ex->chunk;
+    cond = g + (int64_t)ex->rank * stride;      // my own block: what the back-substitution reads
+    rsrc = cond + chunk;
+    if (net->B > 0) {
+      double* lam = x + gnx_mixed_dims(*net).lam_off;
+      if (int rc = gnx_schur_solve(schur_net, plan, co->sigma, g, g + chunk, g + 2 * (int64_t)chunk,
+                                   b + gnx_mixed_dims(*net).lam_off, nullptr, P, lam, work, rtol, max_iter, warm, chunk,
+                                   stride, ex, resid_host, info_host, solve_st)) return rc;
+    }
+  } else if (net->B > 0) {
+    double* lam = x + gnx_mixed_dims(*net).lam_off;
+    if (int rc = gnx_schur_solve(schur_net, plan, co->sigma, cond, rsrc, ftot, b + gnx_mixed_dims(*net).lam_off, nullptr,
+                                 P, lam, work, rtol, max_iter, warm, 0, 0, nullptr, resid_host, info_host, solve_st)) return rc;
+  }
+  if (int rc = gnx_edge_backsub_mixed(net, co, b, cond, rsrc, net->B > 0 ? P : nullptr, x, solve_st)) return rc;
+  if (fork) {
+    GNX_CUDA(cudaEventRecord((cudaEvent_t)ev_join, solve_st));
+    if (int rc = gnx_assemble_mixed(net, co, rowptr, vals, main_st)) return rc;
+    GNX_CUDA(cudaStreamWaitEvent(main_st, (cudaEvent_t)ev_join, 0));
+  }
+  return GNX_OK;
+}

@@ -291,12 +291,18 @@ class MixedSystem:
             group = self.group if self.group is not None else dist.group.WORLD
             bufs, hdls, ptrs = [], [], []
             for _ in range(2):
-                t = symm.empty(world * 3 * dn.chunk, dtype=torch.float64, device=self.dev)
+                # world blocks [cond | rsrc | ftot] + world 64-bit flag words (include/graphnics_b200.h: gnx_exchange)
+                t = symm.empty(world * 3 * dn.chunk + world, dtype=torch.float64, device=self.dev)
                 t.zero_()
+                torch.cuda.synchronize(self.dev)           # flags are zero before any peer can reach them
                 h = symm.rendezvous(t, group)
                 bufs.append(t); hdls.append(h)
                 ptrs.append((C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]))
-            self._p2p = dict(bufs=bufs, hdls=hdls, ptrs=ptrs, step=0)
+            for h in hdls:
+                h.barrier(channel=0)
+            torch.cuda.synchronize(self.dev)
+            self._p2p = dict(bufs=bufs, hdls=hdls, ptrs=ptrs, step=0,
+                             flags=os.environ.get("GNX_P2P_BARRIER", "0") != "1")
             self.exchange_mode = "p2p"
         except Exception as ex:          # no peer access / symmetric memory: the NCCL collective still works
             if self.exchange_mode == "p2p":
@@ -305,6 +311,17 @@ class MixedSystem:
             self.exchange_mode = "nccl"
             self._p2p = None
         return self._p2p
+
+    def _exchange(self, p2p):
+        """descriptor of this solve's exchange (gnx_exchange_t): alternating gather buffer, next epoch"""
+        k = p2p["step"] & 1
+        p2p["step"] += 1
+        rank, world = self.dn.part
+        ex = _lib.gnx_exchange_t()
+        ex.world, ex.rank, ex.chunk = world, rank, self.dn.chunk
+        ex.peers_host = p2p["ptrs"][k]
+        ex.epoch = p2p["step"] if p2p["flags"] else 0      # 0: separate barrier kernel (GNX_P2P_BARRIER=1)
+        return k, ex
 
     def eliminate(self, co, b):
         """phase 1: per-edge scans -> edge scalars (device only, no sync)."""
@@ -349,24 +366,24 @@ class MixedSystem:
         if const_rhs is not None:
             cr = (float(const_rhs.get("f_const", 0.0)), float(const_rhs.get("g_const", 0.0)),
                   ptr(const_rhs.get("pbc_out")), ptr(const_rhs.get("pbc_node")), ptr(b))
+        ex = None
         if p2p is not None:
-            # elimination with the all-gather fused in: peer stores over NVLink, then one barrier
-            k = p2p["step"] & 1
-            p2p["step"] += 1
+            # elimination with the all-gather fused in: peer stores over NVLink + one flag word per rank that
+            # the Schur kernel waits for (or, GNX_P2P_BARRIER=1, a separate cross-GPU barrier kernel)
+            k, ex = self._exchange(p2p)
             rank, world = dn.part
             if cr is not None:
-                check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, None, None, None, world, rank,
-                                                       dn.chunk, p2p["ptrs"][k], st))
+                check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, None, None, None, C.byref(ex), st))
             else:
-                check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), world, rank, dn.chunk,
-                                                            p2p["ptrs"][k], st))
-            p2p["hdls"][k].barrier(channel=0)
+                check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), C.byref(ex), st))
+            if ex.epoch == 0:
+                p2p["hdls"][k].barrier(channel=0)
             g = p2p["bufs"][k]
             loc_cond = g[rank * 3 * dn.chunk:]
             loc_rsrc = g[rank * 3 * dn.chunk + dn.chunk:]
         elif cr is not None:
             check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, ptr(d["cond"]), ptr(d["rsrc"]),
-                                                   ptr(d["ftot"]), 0, 0, 0, None, st))
+                                                   ptr(d["ftot"]), None, st))
         elif not eliminated:
             self.eliminate(co, b)
         if dn.B > 0:
@@ -390,7 +407,7 @@ class MixedSystem:
                 cond, rsrc, ftot = g, g[chunk:], g[2 * chunk:]
             args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(cond), ptr(rsrc), ptr(ftot),
                     ptr(b[dn.lam_off:]), None, ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
-                    1 if warm_start else 0, chunk, stride)
+                    1 if warm_start else 0, chunk, stride, C.byref(ex) if ex is not None and ex.epoch > 0 else None)
             if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()
@@ -417,6 +434,12 @@ class MixedSystem:
         fused = rhs_kwargs.get("f_nodal") is None and rhs_kwargs.get("g_nodal") is None and self.dn.n <= 10
         if fused:                                  # Constant f, g: the elimination kernel produces b itself
             solve_kw = dict(solve_kw, const_rhs={k: v for k, v in rhs_kwargs.items() if k not in ("f_nodal", "g_nodal")})
+        if fused and x is not None and not solve_kw.get("eliminated") and solve_kw.get("exchange") is None:
+            p2p = None
+            if self.dn.part is not None and self.dn.B > 0:
+                p2p = self._p2p_setup()
+            if self.dn.part is None or (p2p is not None and p2p["flags"]):
+                return self._step_native(co, vals, b, x, solve_kw.pop("const_rhs"), overlap, p2p=p2p, **solve_kw)
         if not overlap:
             self.assemble(co, out=vals)
             if not fused:
@@ -437,6 +460,46 @@ class MixedSystem:
         self.assemble(co, out=vals)
         cur.wait_event(ev1)
         return out
+
+    def _step_native(self, co, vals, b, x, const_rhs, overlap, rtol=1e-13, max_iter=100000, warm_start=False,
+                     info=None, sync=True, p2p=None, **_):
+        """the whole step behind ONE library call (gnx_step_mixed): same kernels, streams and events as the
+        Python-sequenced path above, a fraction of its host time"""
+        dn = self.dn
+        d = self._bufs()
+        info = info if info is not None else SolveInfo()
+        if getattr(self, "_hi_stream", None) is None:
+            self._hi_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._ev = (torch.cuda.Event(), torch.cuda.Event())
+        if getattr(self, "_ev_ptr", None) is None:
+            for ev in self._ev:
+                ev.record()                                # a torch event owns a CUDA event from its first record on
+            self._ev_ptr = tuple(C.c_void_p(ev.cuda_event) for ev in self._ev)
+            self._hi_ptr = C.c_void_p(self._hi_stream.cuda_stream)
+        plan = work = None
+        if dn.B > 0:
+            plan, _, work, _ = self.schur_plan()
+        resid = inf = None
+        if sync and dn.B > 0:
+            resid = C.c_double(0.0)
+            inf = (C.c_int32 * 3)()
+        ex = None
+        if p2p is not None:
+            _, ex = self._exchange(p2p)
+        check(self.lib.gnx_step_mixed(
+            dn.net_ref(), co.ref(), ptr(self.rowptr), ptr(vals), float(const_rhs.get("f_const", 0.0)),
+            float(const_rhs.get("g_const", 0.0)), ptr(const_rhs.get("pbc_out")), ptr(const_rhs.get("pbc_node")), ptr(b),
+            ptr(x), dn.schur_net_ref() if dn.B > 0 else None, C.byref(plan) if plan is not None else None,
+            ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]), ptr(d["P"]) if dn.B > 0 else None, ptr(work), float(rtol),
+            int(max_iter), 1 if warm_start else 0, C.byref(ex) if ex is not None else None,
+            C.byref(resid) if resid is not None else None, inf,
+            self._ev_ptr[0], self._ev_ptr[1], self._hi_ptr if overlap else None, current_stream()))
+        if resid is not None:
+            info.cg_iterations += int(inf[0])
+            info.cg_converged = bool(inf[1])
+            info.cg_batches += int(inf[2])
+            info.cg_rel_resid = float(resid.value)
+        return x, info
 
     def solve_bc(self, co, b, x, bcs=None, **kw):
         """solve with the model's Dirichlet data applied (the mixed model has none, flow_models.py:334)"""

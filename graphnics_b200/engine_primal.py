@@ -261,7 +261,7 @@ class PrimalSystem:
                 cond, rsrc, ftot = g, g[chunk:], g[2 * chunk:]
             args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(cond), ptr(rsrc), ptr(ftot),
                     None, ptr(b[self.p_off:]), ptr(d["P"]), None, ptr(work), float(rtol), int(max_iter),
-                    1 if warm_start else 0, chunk, stride)
+                    1 if warm_start else 0, chunk, stride, None)
             if sync:
                 resid = C.c_double(0.0)
                 inf = (C.c_int32 * 3)()

@@ -100,10 +100,11 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
     dist.barrier()
     torch.cuda.synchronize()
     tot = 0.0
+    host_us = []
     for _ in range(args.steps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); step(); e1.record()
+        e0.record(); t0 = time.perf_counter(); step(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
         e1.synchronize()
         tot += e0.elapsed_time(e1)
     torch.cuda.synchronize()
@@ -145,6 +146,7 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
                                 f"NCCL all_gather_into_tensor ({getattr(ms, '_p2p_error', '')})"),
                    "edges_per_rank": dn.E, "ndofs_per_rank": N_loc, "bifurcations": dn.B}),
                "rel_residual": rel_resid, "gpu_launches": 4 * args.steps,
+               "host_enqueue_us_per_step": float(np.median(host_us)),
                "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
                "roofline": {"bound": "hbm", "kernel": "per-rank step (assemble + rhs + eliminate + back-substitute)",
                             "achieved": (8 * (nnz_loc + dn.num_cells) + 8 * N_loc + 2 * 8 * (N_loc + dn.num_cells)

@@ -202,25 +202,36 @@ int gnx_dof_coordinates_mixed(const gnx_network_t* net, const double* coords, co
 int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
                              const double* b, double* cond, double* rsrc, double* ftot, void* stream);
 
+/* Edge-partitioned network (one process per GPU): where the edge scalars of a solve go and how the ranks
+ * tell each other that they have arrived.  Every rank owns one GATHER BUFFER per solve in flight (callers
+ * alternate two): world blocks [cond | rsrc | ftot] of `chunk` doubles each (block of rank q at
+ * q*3*chunk -- the layout gnx_schur_solve reads with chunk, rank_stride = 3*chunk), followed by `world`
+ * 64-bit flag words.  peers_host[r] is the device address, valid on THIS GPU, of rank r's buffer (NVLink
+ * peer mapping, e.g. torch symmetric memory).  The elimination kernel stores its scalars straight into all
+ * buffers.  With epoch > 0 the Schur kernel (gnx_schur_solve given the same descriptor) starts by writing
+ * `epoch` into flag word `rank` of every buffer (st.release.sys; its predecessor on the stream, the
+ * elimination kernel, is complete, so this rank's scalars have landed everywhere) and then waits until all
+ * `world` flag words of its own buffer are >= epoch (ld.acquire.sys) -- no collective call and no barrier
+ * kernel is left.  epoch must grow from solve to solve on a buffer; epoch = 0: no flags, the caller
+ * separates the two kernels with its own cross-GPU barrier.  world <= 8. */
+typedef struct gnx_exchange {
+  int32_t world, rank, chunk, reserved;
+  double* const* peers_host;   /* [world], host array of device addresses */
+  int64_t epoch;
+  void* reserved2;
+} gnx_exchange_t;
+
 /* L_form with Constant f / g (what the steady models use: boundary data + constants) and the elimination
  * in ONE kernel: b [N] is an OUTPUT, bit-identical to gnx_assemble_rhs_mixed(net, NULL, NULL, f_const,
  * g_const, pbc_out, pbc_node, b).  Saves a launch and the 8 B/dof read of b.  n <= 10.
- * peers_host != NULL selects the edge-partitioned output (see gnx_edge_eliminate_mixed_p2p; cond / rsrc /
- * ftot are then ignored), else world / rank / chunk are ignored. */
+ * ex != NULL selects the edge-partitioned output (cond / rsrc / ftot are then ignored). */
 int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
                             double g_const, const double* pbc_out, const double* pbc_node, double* b,
-                            double* cond, double* rsrc, double* ftot, int32_t world, int32_t rank,
-                            int32_t chunk, double* const* peers_host, void* stream);
+                            double* cond, double* rsrc, double* ftot, const gnx_exchange_t* ex, void* stream);
 
-/* Edge-partitioned network (one process per GPU): the same elimination with the collective fused in --
- * every edge scalar is stored straight into the all-gather buffer of EVERY rank over NVLink peer
- * mappings.  peers_host[r] = device address (valid on this GPU) of rank r's buffer of
- * world*3*chunk doubles; rank q's block [cond | rsrc | ftot] (chunk doubles each) sits at q*3*chunk --
- * the layout gnx_schur_solve reads with (chunk, rank_stride = 3*chunk).  The caller puts a cross-GPU
- * barrier between this kernel and gnx_schur_solve.  world <= 8. */
+/* Edge-partitioned network: gnx_edge_eliminate_mixed with the collective fused in (see gnx_exchange). */
 int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
-                                 int32_t world, int32_t rank, int32_t chunk, double* const* peers_host,
-                                 void* stream);
+                                 const gnx_exchange_t* ex, void* stream);
 
 /* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics),
  * as explicit arrays -- inspection / tests; gnx_schur_solve builds the same quantities itself.
@@ -286,6 +297,8 @@ typedef struct gnx_schur_plan {
  *   chunk > 0 (edge-partitioned network): cond / rsrc / ftot are read through the all-gather layout
  *   arr[(e / chunk) * rank_stride + e % chunk], so one collective of the per-rank [cond|rsrc|ftot]
  *   blocks feeds the kernel directly; chunk = 0: plain arr[e].
+ *   ex != NULL with ex->epoch > 0: wait for the flag words of all ranks before reading the edge scalars
+ *   (see gnx_exchange); NULL otherwise.
  * Fully asynchronous (and CUDA-graph capturable) when resid_host and info_host are NULL; otherwise
  * synchronises and returns resid_host[0] = ||r||/||rhs|| of the core CG, info_host[3] =
  * {CG iterations, converged, CTAs}; GNX_ERR_NOCONV if max_iter was hit. */
@@ -293,7 +306,7 @@ int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan);
 int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                     const double* cond, const double* rsrc, const double* ftot, const double* b_lam,
                     const double* b_node, double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
-                    int32_t warm, int32_t chunk, int32_t rank_stride, double* resid_host, int32_t* info_host,
+                    int32_t warm, int32_t chunk, int32_t rank_stride, const gnx_exchange_t* ex, double* resid_host, int32_t* info_host,
                     void* stream);
 
 /* Phase 2: back-substitution, the q and p blocks of x [N] (dof order) from the multipliers P [B]
@@ -301,6 +314,24 @@ int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, doub
 int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                            const double* cond, const double* rsrc, const double* P, double* x,
                            void* stream);
+
+/* One MixedHydraulicNetwork.solve() (flow_models.py:337-350: ii_assemble(a), ii_assemble(L) with Constant f, g,
+ * ii_convert, LUSolver.solve) behind ONE call -- the same kernels as gnx_assemble_mixed +
+ * gnx_rhs_eliminate_mixed + gnx_schur_solve + gnx_edge_backsub_mixed with bit-identical results; it exists
+ * because four host round trips cost more than the GPU needs for a 2 M-dof step.
+ *   vals [nnz] out (NULL: no assembly);  b [N] out, x [N] out;  cond / rsrc / ftot [E], P [B], work: scratch
+ *   as for the separate calls;  schur_net: the network the Schur plan was built for (== net on one GPU);
+ *   side_stream != NULL: the solve chain runs on it and overlaps the assembly on `stream`; ev_fork / ev_join
+ *   are two CUDA events of the caller used to fork and join the streams (everything is ordered on `stream`
+ *   when the call returns);  resid_host / info_host as in gnx_schur_solve (non-NULL synchronises);
+ *   ex != NULL (edge-partitioned network, ex->epoch > 0): cond / rsrc / ftot are ignored, the scalars travel
+ *   through the gather buffers and the Schur kernel reads ex->peers_host[ex->rank].  n <= 10. */
+int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const int32_t* rowptr, double* vals,
+                   double f_const, double g_const, const double* pbc_out, const double* pbc_node, double* b,
+                   double* x, const gnx_network_t* schur_net, const gnx_schur_plan_t* plan, double* cond,
+                   double* rsrc, double* ftot, double* P, double* work, double rtol, int32_t max_iter,
+                   int32_t warm, const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join,
+                   void* side_stream, void* stream);
 
 /* ---------------- primal model: HydraulicNetwork (flow_models.py:53-126) ---------------- */
 

@@ -19,7 +19,7 @@ def run(name, pos, edges, n):
     lam = x[dn.lam_off:]
     def schur(max_iter):
         ms.lib.gnx_schur_solve(dn.schur_net_ref(), C.byref(plan), 1.0, d["cond"].data_ptr(), d["rsrc"].data_ptr(), d["ftot"].data_ptr(),
-                               b[dn.lam_off:].data_ptr(), None, d["P"].data_ptr(), lam.data_ptr(), work.data_ptr(), 1e-13, max_iter, 0, 0, 0,
+                               b[dn.lam_off:].data_ptr(), None, d["P"].data_ptr(), lam.data_ptr(), work.data_ptr(), 1e-13, max_iter, 0, 0, 0, None,
                                None, None, torch.cuda.current_stream().cuda_stream)
     out = {"case": name, "B": dn.B, "core": hp.nc, "iterations": info.cg_iterations, "ctas": info.cg_batches}
     for mi in (1, 101, 100000):

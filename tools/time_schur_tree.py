@@ -18,7 +18,7 @@ for levels in (12, 13, 14, 15):
     d = ms._bufs(); plan, _, work, hp = ms.schur_plan(); lam = x[dn.lam_off:]
     def schur():
         ms.lib.gnx_schur_solve(dn.schur_net_ref(), C.byref(plan), 1.0, d["cond"].data_ptr(), d["rsrc"].data_ptr(), d["ftot"].data_ptr(),
-                               b[dn.lam_off:].data_ptr(), None, d["P"].data_ptr(), lam.data_ptr(), work.data_ptr(), 1e-13, 10, 0, 0, 0,
+                               b[dn.lam_off:].data_ptr(), None, d["P"].data_ptr(), lam.data_ptr(), work.data_ptr(), 1e-13, 10, 0, 0, 0, None,
                                None, None, torch.cuda.current_stream().cuda_stream)
     for _ in range(3): schur()
     torch.cuda.synchronize(); ts = []
