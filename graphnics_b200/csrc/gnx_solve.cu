@@ -590,7 +590,7 @@ constexpr size_t SCH_SMEM = 3 * GNX_TOP_MAX * sizeof(double);
 //                  CTA is read over distributed shared memory and a level costs one hardware cluster
 //                  barrier -- a whole tree of up to 16*2048 bifurcations then needs no grid barrier.
 template <bool CLUSTER, int ROWS>
-__device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double* sr, double* sw) {
+__device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double* sr, double* sw, long long* tick = nullptr) {
   const gnx_schur_plan_t& pl = a.plan;
   const int tid = threadIdx.x, T = blockDim.x;
   cg::cluster_group cluster = cg::this_cluster();
@@ -603,13 +603,18 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
     return p[tc & (S - 1)];
   };
   auto lsync = [&]() { if (CLUSTER) cluster.sync(); else __syncthreads(); };
-  int32_t node[ROWS], lev[ROWS], ptop[ROWS], k0[ROWS], k1[ROWS];
+  // sd[] holds 1/d of a finished node (all a parent and the down-sweep need), sr[] its r, then its solution;
+  // sw[] the link weight to the parent.  The first two top children of a node sit in registers (a binary
+  // tree has no more), further ones are re-read from the plan: a level of the up-sweep then costs shared
+  // memory reads, a handful of FMAs, ONE reciprocal and a barrier -- no global load, no second division.
+  int32_t node[ROWS], lev[ROWS], ptop[ROWS], k0[ROWS], k1[ROWS], c0[ROWS], c1[ROWS], nct[ROWS];
   double d[ROWS], r[ROWS], w[ROWS];
 #pragma unroll
   for (int q = 0; q < ROWS; ++q) {
     const int32_t li = tid + q * T;
     const int32_t ti = base + li;
     lev[q] = -1; node[q] = 0; ptop[q] = -1; k0[q] = k1[q] = 0; d[q] = 1.0; r[q] = 0.0; w[q] = 0.0;
+    c0[q] = c1[q] = -1; nct[q] = 0;
     if (li < S && ti < pl.nt) {
       const int32_t i = pl.top_nodes[ti];
       node[q] = i;
@@ -618,47 +623,62 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
       if (par >= 0) { ptop[q] = pl.top_of[par]; w[q] = -a.cond[a.eidx(pl.pedge[i])]; }
       k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
       double di = __ldcg(a.d + i), ri = __ldcg(a.r + i);
-      for (int32_t k = k0[q]; k < k1[q]; ++k) {             // children below the top part: final
+      for (int32_t k = k0[q]; k < k1[q]; ++k) {
         const int32_t c = pl.ch_idx[k];
-        if (pl.top_of[c] < 0) {
+        const int32_t tc = pl.top_of[c];
+        if (tc < 0) {                                        // child below the top part: final in global memory
           const double wc = -a.cond[a.eidx(pl.pedge[c])];
           const double t = wc / __ldcg(a.d + c);
           di -= wc * t;
           ri -= t * __ldcg(a.r + c);
+        } else {
+          if (nct[q] == 0) c0[q] = tc; else if (nct[q] == 1) c1[q] = tc;
+          ++nct[q];
         }
       }
       d[q] = di; r[q] = ri;
-      sd[li] = di; sr[li] = ri; sw[li] = w[q];
+      sr[li] = ri; sw[li] = w[q];
+      if (nct[q] == 0) sd[li] = 1.0 / di;                    // no top children: final already
     }
   }
   lsync();
+  if (tick) tick[0] = clock64();
+  // contribution of top child tc to its parent: d -= w (w/d_c), r -= (w/d_c) r_c
+  auto fold = [&](int q, int32_t tc) {
+    const double wc = rd(sw, tc);
+    const double t = wc * rd(sd, tc);
+    d[q] -= wc * t;
+    r[q] -= t * rd(sr, tc);
+  };
   for (int l = pl.l_split + 1; l < pl.nl; ++l) {            // up: level l_split has no top children
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
-      if (lev[q] == l) {
-        for (int32_t k = k0[q]; k < k1[q]; ++k) {
-          const int32_t tc = pl.top_of[pl.ch_idx[k]];      // L1 hits: fetched in the prologue
-          if (tc >= 0) {
-            const double wc = rd(sw, tc);
-            const double t = wc / rd(sd, tc);
-            d[q] -= wc * t;
-            r[q] -= t * rd(sr, tc);
+      if (lev[q] == l && nct[q] > 0) {
+        fold(q, c0[q]);
+        if (nct[q] > 1) fold(q, c1[q]);
+        if (nct[q] > 2) {                                    // rare: third and later top children, from the plan
+          int seen = 0;
+          for (int32_t k = k0[q]; k < k1[q]; ++k) {
+            const int32_t tc = pl.top_of[pl.ch_idx[k]];
+            if (tc >= 0 && ++seen > 2) fold(q, tc);
           }
         }
         const int32_t li = tid + q * T;
-        sd[li] = d[q]; sr[li] = r[q];
+        sd[li] = 1.0 / d[q]; sr[li] = r[q];
       }
     }
     lsync();
   }
+  if (tick) tick[1] = clock64();
   for (int l = pl.nl - 1; l >= pl.l_split; --l) {           // down: sr[] turns into the solution
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
       if (lev[q] == l) {
+        const int32_t li = tid + q * T;
         double ri = r[q];
         if (ptop[q] >= 0) ri -= w[q] * rd(sr, ptop[q]);
-        const double xi = ri / d[q];
-        sr[tid + q * T] = xi;
+        const double xi = ri * sd[li];
+        sr[li] = xi;
         a.P[node[q]] = xi;
         if (a.lam_out) a.lam_out[node[q]] = xi * a.inv_sigma;
       }
@@ -980,6 +1000,8 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
   auto gsync = [&]() { sch_sync<MODE>(); };
   gnx_pdl_wait();                                 // the edge scalars come from the elimination kernel
+  long long tick[4] = {0, 0, 0, 0};               // SM cycles of block 0: phase 0 | top prologue | up | down (diagnostic, scal[5..7])
+  const long long tick0 = clock64();
   if (a.wait_flags) {                             // ... and, edge-partitioned, from the other ranks' over NVLink
     if ((int)threadIdx.x < a.wait_world) {
       if (blockIdx.x == 0)
@@ -1051,7 +1073,9 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
     if (MODE == SCH_CLUSTER) {                  // whole tree in one cluster's distributed shared memory
       if (pl.nt > 0) top_solve<true, GNX_TOP_MAX / CL_T>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
     } else {
-      if (blockIdx.x == 0 && pl.nt > 0) top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
+      tick[0] = clock64();
+      if (blockIdx.x == 0 && pl.nt > 0) top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+      tick[3] = clock64();
       if (pl.l_split > 0) gsync();
     }
   } else {                                       // a core exists: l_split == nl, no top part
@@ -1140,6 +1164,9 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
     const double tol2 = a.rtol * a.rtol * bb_final;
     a.scal[0] = tol2; a.scal[1] = (rr_final <= tol2) ? 1.0 : 0.0; a.scal[2] = (double)it;
     a.scal[3] = rr_final; a.scal[4] = bb_final;
+    a.scal[5] = (double)(tick[0] - tick0);        // wait for peers + phase 0 + wide rake levels
+    a.scal[6] = (double)(tick[1] - tick[0]);      // top part: prologue (plan + edge scalars -> shared memory)
+    a.scal[7] = (double)(tick[3] - tick[1]);      // top part: up + down sweeps
   }
 }
 

@@ -32,13 +32,15 @@ def test_struct_layouts_match_c(tmp_path):
     from graphnics_b200 import _lib
     from graphnics_b200.coefficients import gnx_program_t
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "graphnics_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
-                    'sizeof(gnx_network_t),sizeof(gnx_mixed_coeffs_t),sizeof(gnx_schur_plan_t),sizeof(gnx_program_t));return 0;}\n')
+    prog.write_text('#include <stdio.h>\n#include "graphnics_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                    'sizeof(gnx_network_t),sizeof(gnx_mixed_coeffs_t),sizeof(gnx_schur_plan_t),sizeof(gnx_program_t),'
+                    'sizeof(gnx_exchange_t),sizeof(gnx_primal_coeffs_t));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_lib.gnx_network_t), C.sizeof(_lib.gnx_mixed_coeffs_t),
-                     C.sizeof(_lib.gnx_schur_plan_t), C.sizeof(gnx_program_t)]
+                     C.sizeof(_lib.gnx_schur_plan_t), C.sizeof(gnx_program_t), C.sizeof(_lib.gnx_exchange_t),
+                     C.sizeof(_lib.gnx_primal_coeffs_t)]
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():

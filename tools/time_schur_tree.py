@@ -7,7 +7,7 @@ import numpy as np, torch
 from graphnics_b200.device import DeviceNetwork
 from graphnics_b200.engine import MixedSystem
 from graphnics_b200.synthetic import murray_tree
-for levels in (12, 13, 14, 15):
+for levels in (11, 12, 13, 14, 15):
     pos, edges, _, _ = murray_tree(levels, gdim=2)
     dn = DeviceNetwork(pos, edges, 2); ms = MixedSystem(dn)
     co = ms.coeffs(np.ones(dn.E))
@@ -25,5 +25,8 @@ for levels in (12, 13, 14, 15):
     for _ in range(10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); schur(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
+    torch.cuda.synchronize()
+    scal = work[work.numel() - 8:].cpu().numpy()          # block 0's SM cycles (gnx_solve.cu: scal[5..7])
     print(json.dumps({"levels": levels, "B": dn.B, "ctas": info.cg_batches, "top_S": plan.top_S, "l_split": plan.l_split,
-                      "us": min(ts) * 1e3}), flush=True)
+                      "us": min(ts) * 1e3, "cycles_phase0_and_wide_levels": scal[5], "cycles_top_prologue": scal[6],
+                      "cycles_top_sweeps": scal[7]}), flush=True)
