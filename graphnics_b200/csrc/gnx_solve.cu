@@ -1172,6 +1172,31 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
 
 static int g_sch_blocks_per_sm = -1, g_sch_sms = 0, g_sch_cluster_max = 0;
 
+// Cooperative launch that is ALSO a programmatic dependent launch (the grid may become resident while the
+// elimination kernel drains; it starts with gnx_pdl_wait()).  Falls back to a plain cooperative launch, once
+// and for good, if the driver refuses the combination.
+template <int MODE>
+static cudaError_t launch_coop(const SchurArgs& a, int blocks, size_t smem, cudaStream_t st) {
+  static int pdl_ok = -1;
+  if (pdl_ok < 0) pdl_ok = gnx_pdl_enabled() ? 1 : 0;
+  if (pdl_ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(SCH_T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, schur_solve_kernel<MODE>, a);
+    if (err == cudaSuccess) return err;
+    cudaGetLastError();
+    pdl_ok = 0;
+  }
+  SchurArgs copy = a;
+  void* args[] = {&copy};
+  return cudaLaunchCooperativeKernel((void*)schur_solve_kernel<MODE>, dim3(blocks), dim3(SCH_T), args, smem, st);
+}
+
 static int sch_init() {
   if (g_sch_blocks_per_sm >= 0) return GNX_OK;
   int dev = 0, coop = 0, per_sm = 0;
@@ -1269,8 +1294,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
       return GNX_ERR_CUDA;
     }
     want = plan->na;
-    void* args[] = {&a};
-    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<SCH_GRID_TL>, dim3(want), dim3(SCH_T), args, TL_SMEM, st));
+    GNX_CUDA(launch_coop<SCH_GRID_TL>(a, want, TL_SMEM, st));
   } else if (want <= 2 && !cluster_top) {
     GNX_CUDA(gnx_launch_dependent(schur_solve_kernel<SCH_SINGLE>, dim3(1), dim3(SCH_T), SCH_SMEM, st, a));
     GNX_LAUNCH_CHECK();
@@ -1300,8 +1324,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
     GNX_CUDA(cudaLaunchKernelEx(&cfg, schur_solve_kernel<SCH_CLUSTER>, a));
     want = -want;                                  // reported as negative: cluster
   } else {
-    void* args[] = {&a};
-    GNX_CUDA(cudaLaunchCooperativeKernel((void*)schur_solve_kernel<SCH_GRID>, dim3(want), dim3(SCH_T), args, SCH_SMEM, st));
+    GNX_CUDA(launch_coop<SCH_GRID>(a, want, SCH_SMEM, st));
   }
   if (!resid_host && !info_host) return GNX_OK;              // fully asynchronous
   double scal[8];

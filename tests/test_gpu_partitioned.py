@@ -18,7 +18,8 @@ def _tree(levels):
 
 
 @pytest.mark.parametrize("name,n,world", [("tree7", 3, 2), ("tree7", 3, 4), ("honeycomb_4_4", 2, 3),
-                                          ("rand2", 4, 2), ("arterial_tree_N7", 1, 4), ("tree9", 0, 4)])
+                                          ("rand2", 4, 2), ("arterial_tree_N7", 1, 4), ("tree9", 0, 4),
+                                          ("honeycomb48", 0, 2)])     # core > 2048 rows: replicated two-level PCG
 def test_partitioned_solve_matches_monolithic_lu(name, n, world):
     import torch
     from graphnics_b200.device import DeviceNetwork
@@ -27,6 +28,9 @@ def test_partitioned_solve_matches_monolithic_lu(name, n, world):
         pos, edges = _tree(int(name[4:]))
     elif name.startswith("rand"):
         pos, edges = random_graph(int(name[4:]), V=20, extra=5)
+    elif name == "honeycomb48":
+        from graphnics_b200.generators import honeycomb
+        pos, edges = honeycomb(48, 48, mesh=False)._graph_arrays()
     else:
         pos, edges = golden_arrays(name)
     om = oracle.build_mesh(pos, edges, n)
@@ -68,6 +72,8 @@ def test_partitioned_solve_matches_monolithic_lu(name, n, world):
     for dn, ms, co, bl, idx in ranks:
         x, info = ms.solve(co, bl, exchange=exchange, eliminated=True)
         assert info.cg_converged
+        if name == "honeycomb48":
+            assert ms.schur_plan()[3].agg is not None and info.cg_batches == 128
         x = x.cpu().numpy()
         for lo, hi in ((0, dn.p_off), (dn.p_off, dn.lam_off), (dn.lam_off, ms.N)):
             ref = x_ref[idx][lo:hi]

@@ -41,8 +41,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     out["digest"] = hashlib.sha1(vals.cpu().numpy().tobytes() + b.cpu().numpy().tobytes() + x.cpu().numpy().tobytes()).hexdigest()[:16]
     print(json.dumps(out))
 else:
-    for lv, n in ((11, 9), (17, 7), (12, 4)):
-        for vals in (("1", "1", "0"), ("1", "1", "1"), ("1", "1", "2")):
+    for lv, n in ((11, 9), (14, 6), (17, 7)):
+        for vals in (("1", "1", "0"), ("1", "1", "1")):
             r = subprocess.run([sys.executable, __file__, "child", str(lv), str(n)],
                                env=dict(os.environ, **dict(zip(KEYS, vals))), capture_output=True, text=True)
             print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-800:], flush=True)
