@@ -6,7 +6,9 @@ multipliers lambda are replicated.  Assembly, right-hand side, per-edge eliminat
 back-substitution run on the local edges only (the rank's SUBDOMAIN matrix / vector: q and p rows
 are complete, lambda rows hold the local incidences, the global rows are their sum over ranks).
 The one exchange of a solve is an all-gather of the three edge scalars (conductance, source, total
-divergence: 24 bytes per edge of the whole network); the graph-level Schur solve is then replicated
+divergence: 24 bytes per edge of the whole network) -- peer stores over NVLink from inside the
+elimination kernel, synchronised by flag words inside the Schur kernel (engine.MixedSystem._p2p_setup;
+NCCL all_gather_into_tensor as the fallback); the graph-level Schur solve is then replicated
 -- identical inputs and a deterministic kernel give bit-identical multipliers on every rank, so no
 Krylov dot product or halo ever crosses NVLink.
 """
@@ -141,7 +143,10 @@ def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_l
                "config": config_dict(levels, n, pm.E_glob, N, {
                    "parallelism": f"edge-partitioned x{world} (contiguous equal edge ranges), replicated Schur solve, "
                                   f"one exchange of 24 B/edge per solve",
-                   "exchange": ("peer stores over NVLink fused into the elimination kernel + one cross-GPU barrier"
+                   "exchange": (("peer stores over NVLink fused into the elimination kernel, flag words signalled and "
+                                 "awaited inside the Schur kernel (no collective, no barrier kernel)"
+                                 if ms._p2p and ms._p2p.get("flags") else
+                                 "peer stores over NVLink fused into the elimination kernel + one cross-GPU barrier kernel")
                                 if ms.exchange_mode == "p2p" else
                                 f"NCCL all_gather_into_tensor ({getattr(ms, '_p2p_error', '')})"),
                    "edges_per_rank": dn.E, "ndofs_per_rank": N_loc, "bifurcations": dn.B}),
