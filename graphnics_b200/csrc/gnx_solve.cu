@@ -278,33 +278,51 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
   if (!FUSED_RHS) tile_load_b<CPT, BULK>(c, b, ts);
   __syncthreads();
   tile_wait<CPT, BULK, !FUSED_RHS>(ts);
-  if (FUSED_RHS) {
-    if (c.active) {
-      const int32_t u = net.edges[2 * c.e], v = net.edges[2 * c.e + 1];
-      const int32_t tlast = (c.kk0 + CPT == m) ? m : c.kk0 + CPT - 1;
-      for (int32_t j = c.kk0; j <= tlast; ++j) {               // edge-local node j (u -> v), cells j-1 | j
-        const double hl = j > 0 ? sH[cbH + j - 1] : 0.0, hr = j < m ? sH[cbH + j] : 0.0;
-        double val = rhs.gc * (hl + hr) * 0.5;
-        if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val += rhs.pbc_node[u];     // edge OUT of a boundary node: BOUN_IN
-        if (j == m && net.bix[v] < 0 && rhs.pbc_out) val -= rhs.pbc_out[c.e];     // edge INTO a boundary node: BOUN_OUT
-        sG[qb + __ldg(net.loc + (c.flip ? m - j : j))] = val;
-        if (j < m) sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = rhs.fc * hr;
-      }
-    }
-    tile_store<CPT, BULK>(c, ts, rhs.b);
-  }
   double F[CPT], H[CPT];
   double sumF = 0.0, sumG = 0.0, sumH = 0.0;
+  if (FUSED_RHS) {
+    // the thread that eliminates cells kk0 .. kk0+CPT-1 also PRODUCES their right-hand side entries: they go to
+    // shared memory only to leave as b (bulk store) and stay in registers for the elimination
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) {
-    const int32_t kk = c.kk0 + i;
-    F[i] = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
-    H[i] = sH[cbH + kk];
-    sumG += sG[qb + __ldg(net.loc + (c.flip ? m - kk : kk))];
-    sumF += F[i];
-    sumH += H[i];
+    for (int i = 0; i < CPT; ++i) { H[i] = sH[cbH + c.kk0 + i]; F[i] = 0.0; }
+    if (c.active) {
+      const int32_t u = net.edges[2 * c.e], v = net.edges[2 * c.e + 1];
+      double hl = c.kk0 > 0 ? sH[cbH + c.kk0 - 1] : 0.0;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {                          // edge-local node j (u -> v), cells j-1 | j
+        const int32_t j = c.kk0 + i;
+        const double hr = H[i];
+        double val = rhs.gc * (hl + hr) * 0.5;
+        if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val += rhs.pbc_node[u];     // edge OUT of a boundary node: BOUN_IN
+        sG[qb + __ldg(net.loc + (c.flip ? m - j : j))] = val;
+        const double fv = rhs.fc * hr;
+        sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = fv;
+        F[i] = fv * inv_sigma;
+        sumG += val;
+        hl = hr;
+      }
+      if (c.kk0 + CPT == m) {                                  // the edge's last thread also owns node m
+        double val = rhs.gc * (hl + 0.0) * 0.5;
+        if (net.bix[v] < 0 && rhs.pbc_out) val -= rhs.pbc_out[c.e];               // edge INTO a boundary node: BOUN_OUT
+        sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = val;
+        sumG += val;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { sumF += F[i]; sumH += H[i]; }
+    tile_store<CPT, BULK>(c, ts, rhs.b);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int32_t kk = c.kk0 + i;
+      F[i] = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
+      H[i] = sH[cbH + kk];
+      sumG += sG[qb + __ldg(net.loc + (c.flip ? m - kk : kk))];
+      sumF += F[i];
+      sumH += H[i];
+    }
+    if (c.kk0 + CPT == m) sumG += sG[qb + __ldg(net.loc + (c.flip ? 0 : m))];
   }
-  if (c.kk0 + CPT == m) sumG += sG[qb + __ldg(net.loc + (c.flip ? 0 : m))];
   const int segT = m / CPT;
   double tot;
   const double incl = gnx_seg_incl_scan(sumF, segT, sh, &tot);
