@@ -86,8 +86,19 @@ class MixedSystem:
         E = self.dn.E
         if torch.is_tensor(value):
             return value.to(device=self.dev, dtype=torch.float64).contiguous().reshape(E)
-        arr = np.broadcast_to(np.asarray(value, dtype=np.float64), (E,)).copy()
-        return torch.from_numpy(arr).to(self.dev)
+        # host data: through a pinned staging buffer, asynchronous on the current stream (two buffers
+        # alternate; a buffer is reused only once the upload that last read it has run)
+        st = self.__dict__.get("_edge_stage")
+        if st is None:
+            st = self._edge_stage = {"bufs": [torch.empty(E, dtype=torch.float64).pin_memory() for _ in range(2)],
+                                     "evs": [torch.cuda.Event(), torch.cuda.Event()], "k": 0}
+        k = st["k"] = st["k"] ^ 1
+        st["evs"][k].synchronize()
+        buf = st["bufs"][k]
+        buf.numpy()[:] = np.asarray(value, dtype=np.float64)
+        out = buf.to(self.dev, non_blocking=True)
+        st["evs"][k].record()
+        return out
 
     def coeffs(self, a_edge, k_edge=None, sigma=1.0):
         a = self.edge_array(a_edge)

@@ -76,6 +76,50 @@ class FenicsGraph(nx.DiGraph):
         dn = DeviceNetwork(pos, edges, n)
         return Mesh1D(dn), CellMarker(dn)
 
+    # edge-structure mutators drop the cached list of edge attribute dictionaries (edge_attribute_array)
+    def _drop_edge_cache(self):
+        self.__dict__["_edge_dicts"] = None
+
+    def add_edge(self, u, v, **attr):
+        self._drop_edge_cache()
+        return super().add_edge(u, v, **attr)
+
+    def add_edges_from(self, ebunch, **attr):
+        self._drop_edge_cache()
+        return super().add_edges_from(ebunch, **attr)
+
+    def add_weighted_edges_from(self, ebunch, weight="weight", **attr):
+        self._drop_edge_cache()
+        return super().add_weighted_edges_from(ebunch, weight=weight, **attr)
+
+    def remove_edge(self, u, v):
+        self._drop_edge_cache()
+        return super().remove_edge(u, v)
+
+    def remove_edges_from(self, ebunch):
+        self._drop_edge_cache()
+        return super().remove_edges_from(ebunch)
+
+    def remove_node(self, n):
+        self._drop_edge_cache()
+        return super().remove_node(n)
+
+    def remove_nodes_from(self, nodes):
+        self._drop_edge_cache()
+        return super().remove_nodes_from(nodes)
+
+    def clear(self):
+        self._drop_edge_cache()
+        return super().clear()
+
+    def clear_edges(self):
+        self._drop_edge_cache()
+        return super().clear_edges()
+
+    def update(self, edges=None, nodes=None):
+        self._drop_edge_cache()
+        return super().update(edges=edges, nodes=nodes)
+
     def make_mesh(self, n=1):
         """Generates and stores the mesh with 2^n cells per edge (fenics_graph.py:102-129)."""
         pos, edges = self._graph_arrays()
@@ -179,8 +223,12 @@ class FenicsGraph(nx.DiGraph):
         """[E] float array of a (constant-per-edge) attribute; Constants / floats / constant UFL.
         Objects shared by many edges (one `Constant` for the whole graph is the common case) are
         converted once."""
-        # same order as self.edges(): by source node, then successor insertion order
-        vals = [d.get(key, default) for nbrs in self._succ.values() for d in nbrs.values()]
+        # same order as self.edges(): by source node, then successor insertion order.  The attribute
+        # dictionaries themselves are stable objects: the list of them is kept while the edge count stands.
+        dicts = self.__dict__.get("_edge_dicts")
+        if dicts is None:                                   # dropped by every method that adds / removes edges
+            dicts = self.__dict__["_edge_dicts"] = [d for nbrs in self._succ.values() for d in nbrs.values()]
+        vals = [d.get(key, default) for d in dicts]
         if vals and vals.count(vals[0]) == len(vals):                     # one shared object / one value
             vals, rep = vals[:1], len(vals)
         else:

@@ -56,6 +56,19 @@ class _MixedSpaces:
     def sizes(self):
         return [self.m + 1] * self.E + [self.E * self.m] + [1] * self.B
 
+    _offsets = {}
+
+    def offsets(self):
+        """block offsets into the monolithic vector ([len+1] int64), cached per (E, m, B)"""
+        key = (self.E, self.m, self.B)
+        off = _MixedSpaces._offsets.get(key)
+        if off is None:
+            E, m, B = key
+            q = np.arange(E + 1, dtype=np.int64) * (m + 1)
+            p_end = q[-1] + E * m
+            off = _MixedSpaces._offsets[key] = np.concatenate([q, p_end + np.arange(B + 1, dtype=np.int64)])
+        return off
+
     def role(self, i):
         if i < self.E:
             return "q_edge", i
@@ -241,7 +254,9 @@ class MixedHydraulicNetwork:
         vals = torch.empty(ms.nnz, dtype=torch.float64, device=ms.dev)
         b = torch.empty(ms.N, dtype=torch.float64, device=ms.dev)
         qp = ii_Function(W, data=torch.empty(ms.N, dtype=torch.float64, device=ms.dev))
-        _, self.solve_info = ms.assemble_rhs_solve(co, vals, b, qp.tensor(), L.rhs_kwargs())
+        # a network without cycles has no Krylov part: nothing to report, nothing to wait for
+        tree = ms.dn.B == 0 or ms.schur_plan()[3].nc == 0
+        _, self.solve_info = ms.assemble_rhs_solve(co, vals, b, qp.tensor(), L.rhs_kwargs(), sync=not tree)
         self.A, self.b = AssembledMatrix(ms, vals, co, "mixed"), AssembledVector(ms, b)
         qp.touch()
         return qp

@@ -239,8 +239,11 @@ class ii_Function(list):
 
     def __init__(self, W, data=None, net=None):
         net = net if net is not None else getattr(W, "net", None)
-        sizes = W.sizes() if hasattr(W, "sizes") else [V.dim() for V in W]
-        self._offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        if hasattr(W, "offsets"):
+            self._offsets = W.offsets()
+        else:
+            sizes = W.sizes() if hasattr(W, "sizes") else [V.dim() for V in W]
+            self._offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         N = int(self._offsets[-1])
         if net is None and len(W):
             net = getattr(W[0].mesh(), "_dn", None)
@@ -249,7 +252,7 @@ class ii_Function(list):
         self._store = {"version": 0}
         self._vector = Vector(self._data, self._store)
         self._W, self._net = W, net
-        super().__init__([None] * len(sizes))
+        super().__init__([None] * (len(self._offsets) - 1))
 
     def _make(self, i):
         V = self._W[i]
