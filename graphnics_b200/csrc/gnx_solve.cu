@@ -1030,8 +1030,8 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
       for (;;) {
         asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= a.wait_epoch) break;
-        __nanosleep(64);
-        if (++spins > (1u << 25)) __trap();       // seconds: a rank is missing -- fail instead of hanging the GPU
+        __nanosleep(spins < 4096 ? 32 : 2000);    // ranks run in step: poll fast first, then patiently
+        if (++spins > (1u << 25)) __trap();       // about a minute: a rank is missing -- fail instead of hanging the GPU
       }
     }
     __syncthreads();
