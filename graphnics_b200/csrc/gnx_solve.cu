@@ -705,6 +705,95 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
   }
 }
 
+// Diagonal and right-hand side of the Schur row of bifurcation bi (gather over its incident edges, no atomics)
+__device__ __forceinline__ void schur_row(const SchurArgs& a, int32_t bi, double& diag, double& rhs) {
+  const gnx_network_t& net = a.net;
+  const int32_t node = net.bif_nodes[bi];
+  diag = 0.0;
+  rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : (a.b_node ? a.b_node[node] * a.inv_sigma : 0.0);
+  for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
+    const int32_t code = net.inc_edge[k];
+    const int32_t e = code >> 1, end = code & 1;
+    const int64_t ei = a.eidx(e);
+    const double c = a.cond[ei];
+    diag += c;
+    rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Blocked rake (plan.nb > 0): a block is a complete subtree of <= GNX_BLK_MAX raked nodes, one per thread.
+// blk_up builds the Schur rows of its nodes, sweeps the block leaf-to-root out of shared memory (block
+// barriers only) and leaves the FINAL diagonal / right-hand side of every node in a.d / a.r (the block root's are what the top part folds in); blk_down,
+// two grid barriers later, turns them into the solution top-down, the root's parent read from a.P.
+// sd / sr / sw: GNX_BLK_MAX doubles each.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void blk_up(const SchurArgs& a, int32_t b, double* sd, double* sr, double* sw) {
+  const gnx_schur_plan_t& pl = a.plan;
+  const int tid = threadIdx.x;
+  const int32_t p0 = pl.blk_ptr[b], nn = pl.blk_ptr[b + 1] - p0;
+  const int32_t lmin = pl.blk_lv[2 * b], lmax = pl.blk_lv[2 * b + 1];
+  int32_t node = 0, lev = -1, k0 = 0, k1 = 0, c0 = -1, c1 = -1, nct = 0;
+  double d = 1.0, r = 0.0;
+  if (tid < nn) {
+    node = pl.blk_nodes[p0 + tid];
+    lev = pl.level_of[node];
+    sw[tid] = pl.parent[node] >= 0 ? -a.cond[a.eidx(pl.pedge[node])] : 0.0;
+    k0 = pl.ch_ptr[node]; k1 = pl.ch_ptr[node + 1];
+    nct = k1 - k0;                                           // a block is a complete subtree: all children inside
+    if (nct > 0) c0 = pl.blk_pos[pl.ch_idx[k0]];
+    if (nct > 1) c1 = pl.blk_pos[pl.ch_idx[k0 + 1]];
+    schur_row(a, node, d, r);
+    sr[tid] = r;
+    if (nct == 0) sd[tid] = 1.0 / d;
+  }
+  __syncthreads();
+  auto fold = [&](int32_t c) {
+    const double wc = sw[c];
+    const double t = wc * sd[c];
+    d -= wc * t;
+    r -= t * sr[c];
+  };
+  for (int l = lmin + 1; l <= lmax; ++l) {
+    if (lev == l && nct > 0) {
+      fold(c0);
+      if (nct > 1) fold(c1);
+      for (int32_t k = k0 + 2; k < k1; ++k) fold(pl.blk_pos[pl.ch_idx[k]]);
+      sd[tid] = 1.0 / d; sr[tid] = r;
+    }
+    __syncthreads();
+  }
+  if (tid < nn) { a.d[node] = d; a.r[node] = r; }
+  __syncthreads();                                           // shared memory is reused by the next block
+}
+
+__device__ __forceinline__ void blk_down(const SchurArgs& a, int32_t b, double* sr) {
+  const gnx_schur_plan_t& pl = a.plan;
+  const int tid = threadIdx.x;
+  const int32_t p0 = pl.blk_ptr[b], nn = pl.blk_ptr[b + 1] - p0;
+  const int32_t lmin = pl.blk_lv[2 * b], lmax = pl.blk_lv[2 * b + 1];
+  int32_t node = 0, lev = -1, par = -1, ppos = -1;
+  double d = 1.0, r = 0.0, w = 0.0;
+  if (tid < nn) {
+    node = pl.blk_nodes[p0 + tid];
+    lev = pl.level_of[node];
+    par = pl.parent[node];
+    if (par >= 0) { ppos = pl.blk_pos[par]; w = -a.cond[a.eidx(pl.pedge[node])]; }
+    d = __ldcg(a.d + node); r = __ldcg(a.r + node);
+  }
+  for (int l = lmax; l >= lmin; --l) {
+    if (lev == l) {
+      double ri = r;
+      if (par >= 0) ri -= w * (ppos >= 0 ? sr[ppos] : __ldcg(a.P + par));
+      const double xi = ri / d;
+      sr[tid] = xi;
+      a.P[node] = xi;
+      if (a.lam_out) a.lam_out[node] = xi * a.inv_sigma;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // Cluster-resident Jacobi-PCG on the core (SCH_CLUSTER with an ELL plan): the CG of a cyclic
 // network is a chain of hundreds of tiny dependent steps, so what matters is the latency of one
@@ -1067,24 +1156,31 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   };
 
   // ---- phase 0: Schur diagonal and right-hand side (one thread per bifurcation, gather)
-  for (int32_t bi = t0; bi < pl.B; bi += stride) {
-    const int32_t node = net.bif_nodes[bi];
-    double diag = 0.0, rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : (a.b_node ? a.b_node[node] * a.inv_sigma : 0.0);
-    for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
-      const int32_t code = net.inc_edge[k];
-      const int32_t e = code >> 1, end = code & 1;
-      const int64_t ei = a.eidx(e);
-      const double c = a.cond[ei];
-      diag += c;
-      rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
+  // (blocked rake: the blocks build their own rows, CTA 0 those of the top part -- no barrier in between)
+  if (pl.nb > 0) {
+    if (blockIdx.x == 0)
+      for (int32_t ti = threadIdx.x; ti < pl.nt; ti += blockDim.x) {
+        const int32_t bi = pl.top_nodes[ti];
+        double diag, rhs;
+        schur_row(a, bi, diag, rhs);
+        a.d[bi] = diag; a.r[bi] = rhs;
+      }
+  } else {
+    for (int32_t bi = t0; bi < pl.B; bi += stride) {
+      double diag, rhs;
+      schur_row(a, bi, diag, rhs);
+      a.d[bi] = diag; a.r[bi] = rhs;
     }
-    a.d[bi] = diag;
-    a.r[bi] = rhs;
+    gsync();
   }
-  gsync();
 
   // ---- phase 1: rake up (level 0 has no children by construction)
-  for (int l = 1; l < pl.l_split; ++l) { up(l, t0, stride); gsync(); }
+  if (pl.nb > 0) {                                 // blocked rake: whole subtrees per CTA, ONE grid barrier
+    for (int32_t b = blockIdx.x; b < pl.nb; b += nblk) blk_up(a, b, top_sh, top_sh + GNX_BLK_MAX, top_sh + 2 * GNX_BLK_MAX);
+    gsync();
+  } else {
+    for (int l = 1; l < pl.l_split; ++l) { up(l, t0, stride); gsync(); }
+  }
   double rr_final = 0.0, bb_final = 0.0;
   int it = 0;
   if (pl.nc == 0) {
@@ -1177,7 +1273,11 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
     if (pl.nl > 0) gsync();
   }
   // ---- phase 3: rake down
-  for (int l = pl.l_split - 1; l >= 0; --l) { down(l, t0, stride); if (l > 0) gsync(); }
+  if (pl.nb > 0) {
+    for (int32_t b = blockIdx.x; b < pl.nb; b += nblk) { blk_down(a, b, top_sh); __syncthreads(); }
+  } else {
+    for (int l = pl.l_split - 1; l >= 0; --l) { down(l, t0, stride); if (l > 0) gsync(); }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double tol2 = a.rtol * a.rtol * bb_final;
     a.scal[0] = tol2; a.scal[1] = (rr_final <= tol2) ? 1.0 : 0.0; a.scal[2] = (double)it;
@@ -1259,7 +1359,9 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
                                  (plan->top_S & (plan->top_S - 1)) == 0 && plan->top_S >= CL_T));
   GNX_CHECK_ARG(plan->nc == 0 || plan->l_split == plan->nl);
   GNX_CHECK_ARG(plan->nt == 0 || (plan->top_nodes && plan->top_of && plan->level_of));
-  GNX_CHECK_ARG(plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
+  GNX_CHECK_ARG(plan->nb > 0 || plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
+  GNX_CHECK_ARG(plan->nb == 0 || (plan->nb > 0 && plan->nc == 0 && plan->top_S == 0 && plan->blk_ptr && plan->blk_nodes &&
+                                  plan->blk_pos && plan->blk_lv && plan->level_of && plan->B > GNX_TOP_MAX));
   GNX_CHECK_ARG(plan->ell_w == 0 || (plan->ell_w <= 8 && plan->ell_col && plan->ell_edge && plan->ell_R > 0 &&
                                     plan->ell_R <= CL_RMAX && (int64_t)plan->ell_R * CL_CTAS >= plan->nc));
   GNX_CHECK_ARG(plan->nl == 0 || (plan->lvl_nodes && plan->parent && plan->pedge && plan->ch_ptr && plan->ch_idx));

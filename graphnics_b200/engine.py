@@ -267,6 +267,12 @@ class MixedSystem:
                 while 16 * top_S < dn.B:
                     top_S *= 2
             top, top_of, level_of = hp.top_arrays(l_split)
+            blocks = None
+            if hp.nc == 0 and top_S == 0 and dn.B > _lib.TOP_MAX and os.environ.get("GNX_SCHUR_BLOCKS", "1") != "0":
+                # big forest: whole subtrees of <= 1024 nodes per CTA instead of one grid barrier per wide level
+                blocks = hp.block_arrays(cap=_lib.BLK_MAX, top_max=_lib.TOP_MAX)
+                if blocks is not None:
+                    top, top_of, level_of, l_split = blocks["top_nodes"], blocks["top_of"], blocks["level_of"], blocks["l_top"]
             s.B, s.nl, s.l_split, s.nc, s.nnzc, s.nt = dn.B, len(hp.levels), l_split, hp.nc, hp.nnzc, len(top)
             for i, v in enumerate(lvl_ptr):
                 s.lvl_ptr[i] = int(v)
@@ -275,6 +281,10 @@ class MixedSystem:
             s.na = agg["na"] if agg is not None else 0
             extra = () if agg is None else (("agg_ptr", agg["agg_ptr"]), ("col_agg", agg["col_agg"]),
                                             ("cut_ptr", agg["cut_ptr"]), ("cut_k", agg["cut_k"]))
+            s.nb = blocks["nb"] if blocks is not None else 0
+            if blocks is not None:
+                extra += tuple((k, blocks[k]) for k in ("blk_ptr", "blk_nodes", "blk_pos", "blk_lv"))
+            hp.blocks = blocks
             for name, arr in extra + (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
                               ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),

@@ -149,6 +149,57 @@ class SchurPlan:
         top_of[top] = np.arange(len(top), dtype=np.int32)
         return top, top_of, level_of
 
+    def block_arrays(self, cap=1024, top_max=2048):
+        """Blocked rake of a forest (nc == 0): the raked nodes are split into maximal subtrees of <= cap
+        nodes (BLOCKS: complete subtrees, so all of a block's children are inside it; one CTA sweeps a block
+        out of shared memory with block barriers only) and the UPPER part (nodes whose subtree is larger),
+        which takes the place of the level-defined top part.  Two grid barriers then replace one per wide
+        level.  Returns None when it does not apply (a core exists, or the upper part exceeds top_max),
+        else dict(nb, blk_ptr [nb+1], blk_nodes, blk_pos [B] (-1: upper), blk_lv [2 nb] (lowest, highest
+        rake level in the block), top_nodes, top_of [B], level_of [B], l_top (lowest level of the upper part))."""
+        if self.nc != 0 or not self.levels:
+            return None
+        B, nl = self.B, len(self.levels)
+        level_of = np.full(B, nl, dtype=np.int32)
+        for l, nodes in enumerate(self.levels):
+            level_of[nodes] = l
+        parent = self.parent.astype(np.int64)
+        size = np.ones(B, dtype=np.int64)
+        for nodes in self.levels:                            # children sit on strictly lower levels
+            par = parent[nodes]
+            has = par >= 0
+            np.add.at(size, par[has], size[nodes[has]])
+        upper = size > cap
+        top = np.nonzero(upper)[0]
+        if len(top) > top_max:
+            return None
+        # block roots: subtree fits, the parent's does not (or there is no parent)
+        par_big = np.where(parent >= 0, upper[np.maximum(parent, 0)], True)
+        root = (~upper) & par_big
+        blk_of = -np.ones(B, dtype=np.int64)
+        roots = np.nonzero(root)[0]
+        blk_of[roots] = np.arange(len(roots))
+        for nodes in reversed(self.levels):                  # top-down: a non-root node inherits its parent's block
+            inner = nodes[(~upper[nodes]) & (~root[nodes])]
+            blk_of[inner] = blk_of[parent[inner]]
+        inb = np.nonzero(blk_of >= 0)[0]
+        assert len(inb) + len(top) == B
+        order = np.lexsort((level_of[inb], blk_of[inb]))     # by block, then by level
+        blk_nodes = inb[order]
+        counts = np.bincount(blk_of[inb], minlength=len(roots))
+        blk_ptr = np.concatenate([[0], np.cumsum(counts)])
+        blk_pos = -np.ones(B, dtype=np.int64)
+        blk_pos[blk_nodes] = np.arange(len(blk_nodes)) - np.repeat(blk_ptr[:-1], counts)
+        lv = level_of[blk_nodes]
+        blk_lv = np.stack([lv[blk_ptr[:-1]], lv[blk_ptr[1:] - 1]], axis=1).ravel()
+        top = top[np.argsort(level_of[top], kind="stable")]
+        top_of = -np.ones(B, dtype=np.int32)
+        top_of[top] = np.arange(len(top), dtype=np.int32)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        return dict(nb=len(roots), blk_ptr=i32(blk_ptr), blk_nodes=i32(blk_nodes), blk_pos=i32(blk_pos),
+                    blk_lv=i32(blk_lv), top_nodes=i32(top), top_of=top_of, level_of=level_of,
+                    l_top=int(level_of[top].min()) if len(top) else nl)
+
     def aggregate_core(self, pos, na=128):
         """Coarse space of the two-level preconditioner (additive: Jacobi + piecewise-constant coarse
         correction): the core is cut into `na` compact, equally sized aggregates by recursive coordinate

@@ -249,6 +249,7 @@ int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, 
 #define GNX_MAX_LEVELS 64
 #define GNX_TOP_MAX 2048
 #define GNX_AGG_MAX 128
+#define GNX_BLK_MAX 1024
 typedef struct gnx_schur_plan {
   int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level of the TOP part, core size */
   int32_t nnzc, nt;                    /* off-diagonal entries of the core matrix; #nodes in levels >= l_split
@@ -282,6 +283,15 @@ typedef struct gnx_schur_plan {
   const int32_t* col_agg;              /* [nnzc] aggregate of the column of every core entry */
   const int32_t* cut_ptr;              /* [na*na+1] cut_k[cut_ptr[I*na+J] ..): core entries coupling aggregate I to J != I */
   const int32_t* cut_k;
+  /* Blocked rake of a large forest (nb > 0, nc == 0): the raked nodes outside the top part form nb BLOCKS,
+   * maximal complete subtrees of <= GNX_BLK_MAX nodes, each swept by one CTA out of shared memory; the top
+   * part (top_nodes, <= GNX_TOP_MAX nodes) is then the set of nodes with larger subtrees and l_split its
+   * lowest rake level.  Two grid barriers replace one per wide level. */
+  int32_t nb, reserved;
+  const int32_t* blk_ptr;              /* [nb+1] block b = blk_nodes[blk_ptr[b] .. blk_ptr[b+1]) */
+  const int32_t* blk_nodes;
+  const int32_t* blk_pos;              /* [B] position of a node inside its block, -1 for top-part nodes */
+  const int32_t* blk_lv;               /* [2*nb] lowest and highest rake level of a block */
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

@@ -221,6 +221,12 @@ def _big_graph(name):
         from graphnics_b200.generators import honeycomb
         G = honeycomb(40, 40, mesh=False)
         return G._graph_arrays()
+    if name == "rtree":                       # unbalanced random tree, B > 2048: blocked rake with uneven blocks
+        rng = np.random.default_rng(4)
+        nn = 12000
+        par = np.array([rng.integers(0, k) for k in range(1, nn)])
+        edges = np.stack([par, np.arange(1, nn)], 1)
+        return rng.normal(size=(nn, 2)) * 30.0, edges
     if name == "honeycomb70":                 # B ~ 10k > 8192: two-level PCG, one CTA per aggregate
         from graphnics_b200.generators import honeycomb
         G = honeycomb(70, 70, mesh=False)
@@ -249,7 +255,7 @@ def _big_graph(name):
 
 
 @pytest.mark.parametrize("name,n", [("tree14", 2), ("honeycomb40", 1), ("lollipop", 1), ("honeycomb70", 1),
-                                    ("lollipop9k", 1)])
+                                    ("lollipop9k", 1), ("rtree", 1)])
 def test_solve_large_graphs(eng, name, n):
     """systems whose Schur solve needs the cooperative multi-CTA kernel (B > 2048)"""
     import torch
@@ -273,8 +279,9 @@ def test_solve_large_graphs(eng, name, n):
     np.testing.assert_allclose(vals.cpu().numpy(), A.data, rtol=1e-12, atol=1e-300)
     x, info = ms.solve_checked(co, vals, torch.from_numpy(b).cuda())
     plan = ms.schur_plan()[3]
-    if name == "tree14":
+    if name in ("tree14", "rtree"):
         assert plan.nc == 0 and info.cg_iterations == 0
+        assert plan.blocks is not None and plan.blocks["nb"] > 1          # blocked rake
     if name == "honeycomb40":
         assert plan.nc == dn.B and info.cg_iterations > 10
     if name == "lollipop":

@@ -163,3 +163,92 @@ def test_two_level_aggregates(na):
     assert its < jac, (its, jac)
     # the plan's own model (direct core solve) still works on the renumbered core
     assert np.allclose(plan.solve_host(cond, diag, rhs), ref, rtol=1e-9, atol=1e-11)
+
+
+def _blocked_rake_model(plan, ba, cond, diag, rhs):
+    """numpy model of the blocked rake (gnx_solve.cu: blk_up -> top part -> blk_down)"""
+    d = np.array(diag, dtype=np.float64); r = np.array(rhs, dtype=np.float64)
+    w = np.where(plan.pedge >= 0, -np.asarray(cond)[np.maximum(plan.pedge, 0)], 0.0)
+    lev = ba["level_of"]
+    kids = lambda i: plan.ch_idx[plan.ch_ptr[i]:plan.ch_ptr[i + 1]]
+    # blocks, independently of each other: only in-block children are touched
+    for b in range(ba["nb"]):
+        nodes = ba["blk_nodes"][ba["blk_ptr"][b]:ba["blk_ptr"][b + 1]]
+        assert list(lev[nodes]) == sorted(lev[nodes])
+        inside = set(nodes.tolist())
+        for i in nodes:
+            for c in kids(i):
+                assert c in inside
+                d[i] -= w[c] * w[c] / d[c]; r[i] -= w[c] * r[c] / d[c]
+    # upper part, level by level
+    x = np.zeros(plan.B)
+    top = ba["top_nodes"]
+    for i in top:                                           # sorted by level
+        for c in kids(i):
+            d[i] -= w[c] * w[c] / d[c]; r[i] -= w[c] * r[c] / d[c]
+    for i in top[::-1]:
+        p = plan.parent[i]
+        x[i] = (r[i] - (w[i] * x[p] if p >= 0 else 0.0)) / d[i]
+    for b in range(ba["nb"]):
+        nodes = ba["blk_nodes"][ba["blk_ptr"][b]:ba["blk_ptr"][b + 1]]
+        for i in nodes[::-1]:
+            p = plan.parent[i]
+            x[i] = (r[i] - (w[i] * x[p] if p >= 0 else 0.0)) / d[i]
+    return x
+
+
+def _random_tree(nn, seed, chain=0.0):
+    rng = np.random.default_rng(seed)
+    par = np.array([rng.integers(max(0, k - 1 if rng.random() < chain else 0), k) for k in range(1, nn)])
+    edges = np.stack([par, np.arange(1, nn)], 1)
+    pos = rng.normal(size=(nn, 2))
+    return pos, edges
+
+
+@pytest.mark.parametrize("name,cap,top_max", [("tree13", 1024, 2048), ("tree10", 100, 64), ("rtree", 300, 2048),
+                                              ("rchain", 128, 4096), ("forest", 50, 500)])
+def test_blocked_rake_plan(name, cap, top_max):
+    if name.startswith("tree"):
+        pos, edges = murray_tree(int(name[4:]), gdim=2)[:2]
+    elif name == "rtree":
+        pos, edges = _random_tree(6000, 1)
+    elif name == "rchain":
+        pos, edges = _random_tree(5000, 2, chain=0.9)
+    else:                                                   # several trees side by side
+        parts, off = [], 0
+        for k in range(5):
+            p, e = _random_tree(400 + 100 * k, 10 + k)
+            parts.append((p, e + off)); off += len(p)
+        pos = np.vstack([p for p, _ in parts]); edges = np.vstack([e for _, e in parts])
+    edges = np.asarray(edges)
+    t = host_tables(len(pos), edges)
+    bix, B = t["bix"], t["B"]
+    rng = np.random.default_rng(5)
+    cond = rng.uniform(0.5, 2.0, size=len(edges))
+    S, diag = _schur(edges, bix, B, cond)
+    rhs = rng.normal(size=B)
+    plan = SchurPlan(edges, bix, B)
+    ba = plan.block_arrays(cap=cap, top_max=top_max)
+    if plan.nc != 0:
+        assert ba is None
+        return
+    assert ba is not None, "upper part larger than expected"
+    sizes = np.diff(ba["blk_ptr"])
+    assert ba["nb"] == len(sizes) and sizes.min() >= 1 and sizes.max() <= cap
+    assert len(ba["top_nodes"]) <= top_max and sizes.sum() + len(ba["top_nodes"]) == B
+    in_blk = ba["blk_pos"] >= 0
+    assert in_blk.sum() == sizes.sum() and not in_blk[ba["top_nodes"]].any()
+    assert np.array_equal(np.sort(np.concatenate([ba["blk_nodes"], ba["top_nodes"]])), np.arange(B))
+    # the root of a block is the only node whose parent lies outside it (or is missing)
+    for b in range(ba["nb"]):
+        nodes = ba["blk_nodes"][ba["blk_ptr"][b]:ba["blk_ptr"][b + 1]]
+        inside = set(nodes.tolist())
+        outside = [i for i in nodes if plan.parent[i] < 0 or plan.parent[i] not in inside]
+        assert len(outside) == 1 and outside[0] == nodes[-1]
+        assert ba["blk_lv"][2 * b] == ba["level_of"][nodes[0]] and ba["blk_lv"][2 * b + 1] == ba["level_of"][nodes[-1]]
+        assert np.array_equal(ba["blk_pos"][nodes], np.arange(len(nodes)))
+    if len(ba["top_nodes"]):
+        assert ba["l_top"] == ba["level_of"][ba["top_nodes"]].min()
+    x = _blocked_rake_model(plan, ba, cond, diag, rhs)
+    ref = spla.spsolve(S.tocsc(), rhs)
+    assert np.allclose(x, ref, rtol=1e-9, atol=1e-11)
