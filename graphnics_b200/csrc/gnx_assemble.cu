@@ -10,7 +10,7 @@
 extern "C" int64_t gnx_mixed_ndofs(const gnx_network_t* net) { return gnx_mixed_dims(*net).N; }
 extern "C" int64_t gnx_mixed_nnz(const gnx_network_t* net) { return gnx_mixed_dims(*net).nnz; }
 
-constexpr int MODE_PATTERN = GNX_MODE_PATTERN, MODE_VALUES = GNX_MODE_VALUES;
+constexpr int MODE_PATTERN = GNX_MODE_PATTERN;
 
 // One thread per matrix row (row logic in gnx_index.h, shared with the host index self-check).
 template <int MODE>

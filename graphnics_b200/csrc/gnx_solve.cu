@@ -177,12 +177,12 @@ __device__ __forceinline__ void tile_load_h(const TileCtx& c, const double* __re
       gnx_mbar_expect_tx(&ts.bar_h, gnx_bulk_body_bytes(c.hbase, ncell));
       gnx_bulk_stream_in(ts.H, h, c.hbase, ncell, &ts.bar_h);
     }
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int r = 0; r < CPT; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) ts.H[i] = h[c.hbase + i];
+    for (int r = 0; r < CPT; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < ncell) ts.H[i] = h[c.hbase + i];
+    }
   }
 }
 template <int CPT, bool BULK>
@@ -194,17 +194,17 @@ __device__ __forceinline__ void tile_load_b(const TileCtx& c, const double* __re
       gnx_bulk_stream_in(ts.F, b, c.pbase, ncell, &ts.bar);
       gnx_bulk_stream_in(ts.G, b, c.qbase, nq, &ts.bar);
     }
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int r = 0; r < CPT; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) ts.F[i] = b[c.pbase + i];
-  }
+    for (int r = 0; r < CPT; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < ncell) ts.F[i] = b[c.pbase + i];
+    }
 #pragma unroll
-  for (int r = 0; r < CPT + 1; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < nq) ts.G[i] = b[c.qbase + i];
+    for (int r = 0; r < CPT + 1; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < nq) ts.G[i] = b[c.qbase + i];
+    }
   }
 }
 // after the __syncthreads() that follows tile_load (it publishes the barrier's initialisation and the
@@ -225,18 +225,18 @@ __device__ __forceinline__ void tile_store(const TileCtx& c, TileSmem<CPT>& ts, 
     gnx_bulk_stream_out(ts.G, out, c.qbase, nq);
     gnx_bulk_stream_out(ts.F, out, c.pbase, ncell);
     if (threadIdx.x == 0) gnx_bulk_commit();
-    return;
-  }
-  __syncthreads();
+  } else {
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < CPT + 1; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < nq) out[c.qbase + i] = ts.G[i];
-  }
+    for (int r = 0; r < CPT + 1; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < nq) out[c.qbase + i] = ts.G[i];
+    }
 #pragma unroll
-  for (int r = 0; r < CPT; ++r) {
-    const int32_t i = threadIdx.x + r * ET_T;
-    if (i < ncell) out[c.pbase + i] = ts.F[i];
+    for (int r = 0; r < CPT; ++r) {
+      const int32_t i = threadIdx.x + r * ET_T;
+      if (i < ncell) out[c.pbase + i] = ts.F[i];
+    }
   }
 }
 template <bool BULK> __device__ __forceinline__ void tile_store_done() {
@@ -1100,7 +1100,6 @@ template <int MODE>
 __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel(SchurArgs a) {
   extern __shared__ double top_sh[];             // 3 * GNX_TOP_MAX doubles (dynamic, opt-in > 48 KB)
   __shared__ double red[2][3 * 32];
-  const gnx_network_t& net = a.net;
   const gnx_schur_plan_t& pl = a.plan;
   const int nblk = gridDim.x;
   const int32_t stride = nblk * blockDim.x;
