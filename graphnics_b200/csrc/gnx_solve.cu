@@ -1,6 +1,7 @@
 // Saddle-point solve for the mixed network system: exact per-edge elimination (two segmented
 // scans over the cells of every edge) -> SPD graph-level Schur system on the bifurcation
-// multipliers -> Jacobi-PCG (2 fused kernels / iteration, CUDA-graph replay, device-side
+// multipliers, solved by ONE persistent kernel (exact rake of the tree-like parts, level by level or
+// in subtree blocks; PCG on the cyclic core -- Jacobi, or two-level for large cores; device-side
 // convergence) -> back-substitution.  Replaces ii_convert + LUSolver(A,"mumps").solve
 // (graphnics/flowmodels/flow_models.py:344-348, time_stepping.py:187-192).
 //
@@ -44,9 +45,9 @@ __device__ __forceinline__ EdgeFrame edge_frame(const gnx_network_t& net, const 
 // ------------------------------------------------------------------------------------
 // Where the edge scalars of (local) edge e go.  Single GPU: three local arrays.  Edge-partitioned
 // network: straight into the all-gather buffer of EVERY rank -- peer stores over NVLink issued by
-// the thread that holds the value (graphnics_b200/parallel.py maps the peers' buffers with
-// torch symmetric memory), so the collective is fused into the elimination kernel and only a
-// cross-GPU barrier is left between it and the Schur kernel.
+// the thread that holds the value (graphnics_b200/engine.py maps the peers' buffers with
+// torch symmetric memory), so the collective is fused into the elimination kernel; the Schur kernel
+// opens with the flag exchange that tells the ranks the scalars have landed (gnx_exchange_t).
 constexpr int GNX_MAX_PEERS = 8;
 struct EdgeOut {
   double* base[GNX_MAX_PEERS];        // destination buffers (n = 1: base[0] = cond)
@@ -113,10 +114,11 @@ edge_eliminate_kernel(gnx_network_t net, GnxMixedDims d, const double* __restric
 // ------------------------------------------------------------------------------------
 // Edge-tile kernels (m <= 1024): a block owns TILE = 256*CPT cells = TILE/m whole edges.  The
 // three contiguous global ranges of the tile (p-block of b, q-block of b, cell lengths) are
-// streamed into shared memory with coalesced loads -- that is where all the memory-level
-// parallelism comes from -- and every permuted access (Gray-code cell order, first-encounter
-// vertex order, edge orientation) happens in shared memory.  A thread owns CPT consecutive cells:
-// serial prefix in registers + block-segmented scan of the thread totals.
+// brought into shared memory by the copy engine (cp.async.bulk, gnx_tma.cuh; or by coalesced loads
+// of the block) -- that is where all the memory-level parallelism comes from -- and every permuted
+// access (Gray-code cell order, first-encounter vertex order, edge orientation) happens in shared
+// memory.  A thread owns CPT consecutive cells: serial prefix in registers + block-segmented scan
+// of the thread totals.  Outputs leave the same way (staged at their dof slots, one bulk store per range).
 // ------------------------------------------------------------------------------------
 constexpr int ET_T = 256;
 
