@@ -63,7 +63,8 @@ class MixedSystem:
         self.dn = dn
         self.group = group           # torch.distributed process group of a partitioned network
         # how a partitioned solve gathers the edge scalars: "p2p" = peer stores fused into the elimination
-        # kernel (torch symmetric memory maps the peers' buffers) + one cross-GPU barrier; "nccl" = one
+        # kernel (torch symmetric memory maps the peers' buffers), synchronised by flag words inside the Schur
+        # kernel (gnx_exchange_t); "nccl" = one
         # all_gather_into_tensor; "auto" = p2p when symmetric memory can be set up, else nccl
         self.exchange_mode = exchange
         self._p2p = None
