@@ -158,6 +158,7 @@ def run_reference(args):
     levels = TREE_LEVELS + grow
     pos, edges = tree_arrays(levels)
     n = max(TREE_N - grow, 4)
+    n = min(n, int(os.environ.get("GNX_BENCH_REF_MAX_N", n)))      # (tests: a smaller sample)
     step, N = oracle_step_factory(pos, edges, n)
     t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
     while t * (args.steps + args.warmup) > 240.0 and n > 4:       # bounded sample
