@@ -37,6 +37,7 @@ class gnx_mixed_coeffs_t(C.Structure):
 MAX_LEVELS = 64
 TOP_MAX = 2048
 BLK_MAX = 1024                # GNX_BLK_MAX: nodes of a rake block (one CTA, one node per thread)
+SUB_PER_AGG = int(os.environ.get("GNX_SCHUR_SUB", "8"))   # fine aggregates per coarse one (1: coarse level only)
 AGG_MAX = 128                 # GNX_AGG_MAX: aggregates (= CTAs) of the two-level PCG
 TWO_LEVEL_MIN_CORE = int(os.environ.get("GNX_TWO_LEVEL_MIN_CORE", "2048"))   # smaller cores: one CTA or one cluster, plain Jacobi
 
@@ -52,8 +53,9 @@ class gnx_schur_plan_t(C.Structure):
         ("ell_w", C.c_int32), ("ell_R", C.c_int32), ("top_S", C.c_int32), ("na", C.c_int32),
         ("ell_col", C.c_void_p), ("ell_edge", C.c_void_p),
         ("agg_ptr", C.c_void_p), ("col_agg", C.c_void_p), ("cut_ptr", C.c_void_p), ("cut_k", C.c_void_p),
-        ("nb", C.c_int32), ("reserved", C.c_int32),
+        ("nb", C.c_int32), ("ns", C.c_int32),
         ("blk_ptr", C.c_void_p), ("blk_nodes", C.c_void_p), ("blk_pos", C.c_void_p), ("blk_lv", C.c_void_p),
+        ("sub_ptr", C.c_void_p), ("row_sub", C.c_void_p),
     ]
 
 

@@ -514,6 +514,7 @@ struct SchurArgs {
   double *xc, *rc, *zc, *wc, *p0, *p1, *dg;   // [nc]
   double *cval;                               // [nnzc]
   double *Eg, *sE;                            // two-level PCG: coarse matrix [na*na], aggregate sums of r [na]
+  double *s1, *dE;                            // fine aggregates [na*ns]: sums of r, diagonal of W1^T S W1
   double *part[5];                            // [nblk] each
   double *scal;                               // [8]: tol2, converged, iterations, rr, bb
   double rtol;
@@ -537,7 +538,7 @@ struct SchurArgs {
 extern "C" int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan) {
   if (!plan) return 0;
   const int64_t nval = plan->ell_w > 0 ? (int64_t)plan->ell_w * plan->nc : 0;
-  const int64_t coarse = plan->na > 0 ? (int64_t)plan->na * plan->na + plan->na : 0;
+  const int64_t coarse = plan->na > 0 ? (int64_t)plan->na * plan->na + plan->na + 2 * (int64_t)GNX_SUB_MAX : 0;
   return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 8 + coarse;
 }
 
@@ -922,22 +923,25 @@ __device__ __forceinline__ void core_pcg_cluster(const SchurArgs& a, double* sm,
 }
 
 // ------------------------------------------------------------------------------------
-// Two-level PCG on a large core (cooperative grid, plan.na CTAs, CTA J owns the rows of aggregate J).
-// Jacobi alone needs O(diameter) iterations on a lattice-like core (2499 on the 200 x 200 honeycomb);
-// the additive coarse correction  M^-1 = D^-1 + W (W^T S W)^-1 W^T  over na <= 128 compact aggregates
-// (W = their indicator vectors) removes the smooth error Jacobi cannot reach (608 iterations there).
-// It costs no extra grid barrier:
-//  * the coarse matrix E = W^T S W (na x na) is summed once per solve over fixed lists (row J by CTA J),
+// Multilevel-additive PCG on a large core (cooperative grid, plan.na CTAs, CTA J owns the rows of coarse
+// aggregate J).  Jacobi alone needs O(diameter) iterations on a lattice-like core (2476 on the 200 x 200
+// honeycomb); the preconditioner
+//     M^-1 = D^-1 + W1 diag(W1^T S W1)^-1 W1^T + W2 (W2^T S W2)^-1 W2^T
+// over na * ns fine and na <= 128 coarse aggregates (W = their indicator vectors; a coarse aggregate is the
+// union of ns fine ones) removes the smooth error Jacobi cannot reach: 579 iterations with the coarse level
+// alone, ~340 with both.  It costs no extra grid barrier:
+//  * the coarse matrix E = W2^T S W2 (na x na) is summed once per solve over fixed lists (row J by CTA J),
 //    and EVERY CTA inverts it by Gauss-Jordan in its own shared memory -- the same arithmetic in the same
-//    order, so all CTAs hold the same bits and the inverse never travels;
-//  * per iteration CTA J publishes s_J = sum of r over its rows together with its dot-product partials
-//    (the barrier of the existing all-reduce), every CTA then forms y = E^-1 s and s.y redundantly, and
-//    the preconditioned residual is never stored whole: z_j = r_j/d_j + y[aggregate(j)] is rebuilt by
-//    whoever reads it.
-// Shared memory: E^-1 [na][na+1] | s | y | pivot row | pivot column | 8 x na partials.
+//    order, so all CTAs hold the same bits and the inverse never travels; the fine level only needs the
+//    diagonal of W1^T S W1 (one number per fine aggregate, summed by one warp);
+//  * per iteration CTA J publishes the sums of r over its fine aggregates (one warp each) and their total
+//    together with its dot-product partials (the barrier of the existing all-reduce), every CTA then forms
+//    y1 = s1 / dE, y2 = E^-1 s2 and s1.y1 + s2.y2 redundantly, and the preconditioned residual is never
+//    stored whole: z_j = r_j/d_j + y1[fine(j)] + y2[coarse(j)] is rebuilt by whoever reads it.
+// Shared memory: E^-1 [na][na+1] | s2 | y2 | pivot row | pivot column | 8 x na partials | y1 | 1/dE.
 // ------------------------------------------------------------------------------------
 constexpr int AGG_LD = GNX_AGG_MAX + 1;          // odd leading dimension: column walks are conflict-free
-constexpr size_t TL_SMEM = ((size_t)GNX_AGG_MAX * AGG_LD + 12 * GNX_AGG_MAX) * sizeof(double);
+constexpr size_t TL_SMEM = ((size_t)GNX_AGG_MAX * AGG_LD + 12 * GNX_AGG_MAX + 2 * GNX_SUB_MAX) * sizeof(double);
 
 template <class Gather>
 __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm, double (*red)[3 * 32], Gather gather,
@@ -950,8 +954,53 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   double* const rk = y_sh + GNX_AGG_MAX;
   double* const ck = rk + GNX_AGG_MAX;
   double* const part8 = ck + GNX_AGG_MAX;
+  double* const y1_sh = part8 + 8 * GNX_AGG_MAX;
+  double* const dEi_sh = y1_sh + GNX_SUB_MAX;
   const int32_t r0 = pl.agg_ptr[J], r1 = pl.agg_ptr[J + 1];
+  const int ns = pl.ns > 1 ? pl.ns : 1, nf = na * ns, lg = __ffs(ns) - 1;       // fine aggregates per coarse one
   cg::grid_group grid = cg::this_grid();
+  // sums of r over my fine aggregates and their total -> a.s1, a.sE; with_dE: also the fine diagonal of
+  // W1^T S W1.  All 32 warps work: 32/ns warps share a fine aggregate (lane- and warp-strided rows), partials
+  // are combined in a fixed order.  Block-wide.
+  auto sub_sums = [&](bool with_dE) {
+    __syncthreads();                               // this CTA's rc (dg, cval) are written
+    const int w = tid >> 5, lane = tid & 31, nw = T >> 5;
+    const int wps = nw / ns;                       // warps per fine aggregate (ns <= 32)
+    if (w < wps * ns) {
+      const int32_t f = J * ns + w / wps;
+      const int32_t i0 = ns > 1 ? pl.sub_ptr[f] : r0, i1 = ns > 1 ? pl.sub_ptr[f + 1] : r1;
+      double sr = 0.0, sd = 0.0;
+      for (int32_t i = i0 + (w % wps) * 32 + lane; i < i1; i += 32 * wps) {
+        sr += __ldcg(a.rc + i);
+        if (with_dE) {
+          double t = __ldcg(a.dg + i);
+          for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k)
+            if (pl.col_agg[k] == f) t += __ldcg(a.cval + k);
+          sd += t;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(GNX_FULL, sr, o);
+        sd += __shfl_xor_sync(GNX_FULL, sd, o);
+      }
+      if (lane == 0) { part8[w] = sr; part8[64 + w] = sd; }
+    }
+    __syncthreads();
+    if (tid < ns) {
+      double sr = 0.0, sd = 0.0;
+      for (int q = 0; q < wps; ++q) { sr += part8[tid * wps + q]; sd += part8[64 + tid * wps + q]; }
+      part8[128 + tid] = sr;
+      a.s1[J * ns + tid] = sr;
+      if (with_dE) a.dE[J * ns + tid] = sd;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w2 = 0; w2 < ns; ++w2) t += part8[128 + w2];
+      a.sE[J] = t;
+    }
+  };
 
   // ---- raked children, matrix values, residual of the initial guess; row sums for the coarse diagonal
   double acc[3] = {0.0, 0.0, 0.0};
@@ -988,13 +1037,13 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
     double off = 0.0;
     for (int32_t K = 0; K < na; ++K) if (K != J) off += rk[K];
     rk[J] = v2[1] - off;
-    a.sE[J] = v2[0];
   }
   __syncthreads();
   for (int32_t K = tid; K < na; K += T) a.Eg[J * na + K] = rk[K];
+  sub_sums(true);
   {
     double* const part[3] = {a.part[0], a.part[1], a.part[2]};
-    grid_allreduce<SCH_GRID, 3>(acc, part, na, red[0]);          // its grid barrier publishes Eg and sE
+    grid_allreduce<SCH_GRID, 3>(acc, part, na, red[0]);          // its grid barrier publishes Eg, sE, s1 and dE
   }
   // ---- every CTA: E -> E^-1 in shared memory (in-place Gauss-Jordan; E is SPD, no pivoting).
   // Thread t owns column t & 127 of rows (t >> 7) + 8 u.
@@ -1002,6 +1051,8 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   constexpr int RSTEP = SCH_T / GNX_AGG_MAX;
   if (cj < na)
     for (int i = ci0; i < na; i += RSTEP) Ei[i * AGG_LD + cj] = __ldcg(a.Eg + i * na + cj);
+  if (ns > 1)
+    for (int f = tid; f < nf; f += T) dEi_sh[f] = 1.0 / __ldcg(a.dE + f);
   __syncthreads();
   for (int k = 0; k < na; ++k) {
     if (tid < na) { rk[tid] = Ei[k * AGG_LD + tid]; ck[tid] = Ei[tid * AGG_LD + k]; }
@@ -1022,6 +1073,14 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   // y = E^-1 s (all of it, every CTA), returns s.y
   auto coarse = [&]() -> double {
     for (int32_t K = tid; K < na; K += T) s_sh[K] = __ldcg(a.sE + K);
+    double fine = 0.0;                            // s1 . y1 (my share)
+    if (ns > 1)
+      for (int f = tid; f < nf; f += T) {
+        const double sf = __ldcg(a.s1 + f);
+        const double yf = sf * dEi_sh[f];
+        y1_sh[f] = yf;
+        fine += sf * yf;
+      }
     __syncthreads();
     double pv = 0.0;
     if (cj < na) {
@@ -1030,13 +1089,13 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
     }
     part8[ci0 * GNX_AGG_MAX + cj] = pv;
     __syncthreads();
-    double sg[1] = {0.0};
+    double sg[1] = {fine};
     if (tid < na) {
       double y = 0.0;
 #pragma unroll
       for (int q = 0; q < RSTEP; ++q) y += part8[q * GNX_AGG_MAX + tid];
       y_sh[tid] = y;
-      sg[0] = y * s_sh[tid];
+      sg[0] += y * s_sh[tid];
     }
     block_allreduce<1>(sg, red[1]);
     __syncthreads();                              // red[1] is the next reduction's buffer, too
@@ -1054,11 +1113,14 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
     const double yJ = y_sh[J];
     double pw[1] = {0.0};
     for (int32_t i = r0 + tid; i < r1; i += T) {
-      const double pi = (a.zc[i] + yJ) + beta * p_old[i];
+      const double yi = ns > 1 ? yJ + y1_sh[pl.row_sub[i]] : yJ;
+      const double pi = (a.zc[i] + yi) + beta * p_old[i];
       double wi = a.dg[i] * pi;
       for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k) {
         const int32_t j = pl.ccol[k];
-        wi += a.cval[k] * ((__ldcg(a.zc + j) + y_sh[pl.col_agg[k]]) + beta * __ldcg(p_old + j));
+        const int32_t cs = pl.col_agg[k];                     // fine aggregate of the column
+        const double yj = ns > 1 ? y_sh[cs >> lg] + y1_sh[cs] : y_sh[cs];
+        wi += a.cval[k] * ((__ldcg(a.zc + j) + yj) + beta * __ldcg(p_old + j));
       }
       p_new[i] = pi;
       a.wc[i] = wi;
@@ -1069,16 +1131,17 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
       grid_allreduce<SCH_GRID, 1>(pw, part, na, red[1]);
     }
     const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
-    double v3[3] = {0.0, 0.0, 0.0};               // r.D^-1 r, r.r, sum of r over my aggregate
+    double v3[2] = {0.0, 0.0};                    // r.D^-1 r, r.r
     for (int32_t i = r0 + tid; i < r1; i += T) {
       a.xc[i] += alpha * p_new[i];
       const double ri = a.rc[i] - alpha * a.wc[i];
       const double zi = ri / a.dg[i];
       a.rc[i] = ri; a.zc[i] = zi;
-      v3[0] += ri * zi; v3[1] += ri * ri; v3[2] += ri;
+      v3[0] += ri * zi; v3[1] += ri * ri;
     }
-    block_allreduce<3>(v3, red[0]);
-    if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; a.sE[J] = v3[2]; }
+    block_allreduce<2>(v3, red[0]);
+    if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; }
+    sub_sums(false);
     grid.sync();
     double t2[2] = {0.0, 0.0};
     for (int i = tid; i < na; i += T) { t2[0] += __ldcg(a.part[0] + i); t2[1] += __ldcg(a.part[1] + i); }
@@ -1369,6 +1432,9 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   GNX_CHECK_ARG(plan->nc == 0 || (plan->core_nodes && plan->crp && plan->ccol && plan->cedge && plan->ch_ptr));
   GNX_CHECK_ARG(plan->na == 0 || (plan->na >= 2 && plan->na <= GNX_AGG_MAX && plan->na <= plan->nc && plan->agg_ptr &&
                                   plan->col_agg && plan->cut_ptr && plan->cut_k));
+  GNX_CHECK_ARG(plan->na == 0 || plan->ns <= 1 ||
+                (plan->ns <= 32 && (plan->ns & (plan->ns - 1)) == 0 && (int64_t)plan->na * plan->ns <= GNX_SUB_MAX &&
+                 plan->sub_ptr && plan->row_sub));
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = sch_init()) return rc;
   SchurArgs a;
@@ -1383,7 +1449,8 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   a.cval = w; w += plan->nnzc;
   for (int k = 0; k < 5; ++k) { a.part[k] = w; w += 2048; }
   a.scal = w; w += 8;
-  a.Eg = w; w += (int64_t)plan->na * plan->na; a.sE = w;
+  a.Eg = w; w += (int64_t)plan->na * plan->na; a.sE = w; w += plan->na;
+  a.s1 = w; w += GNX_SUB_MAX; a.dE = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
   a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_world = 0;

@@ -250,7 +250,7 @@ class MixedSystem:
                 # large cyclic core: two-level PCG, aggregates cut by coordinate bisection of the node positions
                 node_of = np.empty(dn.B, dtype=np.int64)
                 node_of[bix_h[bix_h >= 0]] = np.nonzero(bix_h >= 0)[0]
-                agg = hp.aggregate_core(dn.pos.cpu().numpy()[node_of], na=_lib.AGG_MAX)
+                agg = hp.aggregate_core(dn.pos.cpu().numpy()[node_of], na=_lib.AGG_MAX, ns=_lib.SUB_PER_AGG)
             lvl_ptr, lvl_nodes = hp.level_arrays()
             keep = {}
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
@@ -280,8 +280,10 @@ class MixedSystem:
             ell_w, ell_R, ell_col, ell_edge = hp.ell_arrays()
             s.ell_w, s.ell_R, s.top_S = ell_w, ell_R, top_S
             s.na = agg["na"] if agg is not None else 0
+            s.ns = agg["ns"] if agg is not None else 0
             extra = () if agg is None else (("agg_ptr", agg["agg_ptr"]), ("col_agg", agg["col_agg"]),
-                                            ("cut_ptr", agg["cut_ptr"]), ("cut_k", agg["cut_k"]))
+                                            ("cut_ptr", agg["cut_ptr"]), ("cut_k", agg["cut_k"]),
+                                            ("sub_ptr", agg["sub_ptr"]), ("row_sub", agg["row_sub"]))
             s.nb = blocks["nb"] if blocks is not None else 0
             if blocks is not None:
                 extra += tuple((k, blocks[k]) for k in ("blk_ptr", "blk_nodes", "blk_pos", "blk_lv"))

@@ -200,21 +200,31 @@ class SchurPlan:
                     blk_lv=i32(blk_lv), top_nodes=i32(top), top_of=top_of, level_of=level_of,
                     l_top=int(level_of[top].min()) if len(top) else nl)
 
-    def aggregate_core(self, pos, na=128):
-        """Coarse space of the two-level preconditioner (additive: Jacobi + piecewise-constant coarse
-        correction): the core is cut into `na` compact, equally sized aggregates by recursive coordinate
-        bisection of the node positions `pos` [B, gdim] (positions only steer the QUALITY of the
-        aggregates; any partition gives a symmetric positive definite preconditioner), and the core is
-        RENUMBERED so that every aggregate is a contiguous range of core rows (one CTA per aggregate in
-        the kernel).  Sets self.agg = dict(na, agg_ptr [na+1], col_agg [nnzc] aggregate of every CSR
-        column, cut_ptr [na*na+1], cut_k: the CSR entries that couple aggregate I to J != I, grouped by
-        (I, J) in a fixed order -- the coarse matrix is summed over these lists, deterministically)."""
+    def aggregate_core(self, pos, na=128, ns=8):
+        """Coarse spaces of the multilevel-additive preconditioner of the core PCG
+            M^-1 = D^-1 + W1 diag(W1^T S W1)^-1 W1^T + W2 (W2^T S W2)^-1 W2^T
+        (W1 / W2: indicator vectors of na*ns fine / na coarse aggregates, every coarse aggregate being the
+        union of ns fine ones): the core is cut by recursive coordinate bisection of the node positions
+        `pos` [B, gdim] into na*ns compact, equally sized fine aggregates (positions only steer the QUALITY
+        of the aggregates; any partition gives a symmetric positive definite preconditioner), and the core
+        is RENUMBERED fine aggregate by fine aggregate, so that fine and coarse aggregates are contiguous
+        row ranges (one CTA per coarse aggregate in the kernel).  na, ns powers of two.  Sets self.agg =
+        dict(na, ns, agg_ptr [na+1], sub_ptr [na*ns+1], row_sub [nc] / col_agg [nnzc]: FINE aggregate of a row
+        / of the column of a CSR entry (coarse = fine // ns), cut_ptr [na*na+1], cut_k: the CSR entries that
+        couple coarse aggregate I to J != I, grouped by (I, J) in a fixed order -- the coarse matrix is summed
+        over these lists, deterministically)."""
         nc = self.nc
         na = int(min(na, nc))
+        while na & (na - 1):
+            na &= na - 1                                      # power of two
+        ns = int(ns)
+        while ns > 1 and na * ns > nc:
+            ns //= 2
+        nf = na * ns
         p = np.asarray(pos, dtype=np.float64)[self.core_nodes]
         owner = np.zeros(nc, dtype=np.int64)
-        todo = [(np.arange(nc), na, 0)]
-        while todo:
+        todo = [(np.arange(nc), nf, 0)]
+        while todo:                                           # halving: fine parts [J*ns, (J+1)*ns) make up coarse part J
             idx, k, base = todo.pop()
             if k == 1:
                 owner[idx] = base
@@ -240,16 +250,19 @@ class SchurPlan:
         self.ccol = newpos[self.ccol[src]].astype(np.int32)
         self.cedge = self.cedge[src].astype(np.int32)
         self.crp = new_crp.astype(np.int32)
-        agg_of = owner[order]
-        agg_ptr = np.concatenate([[0], np.cumsum(np.bincount(agg_of, minlength=na))]).astype(np.int32)
+        row_sub = owner[order]
+        sub_ptr = np.concatenate([[0], np.cumsum(np.bincount(row_sub, minlength=nf))]).astype(np.int32)
+        agg_ptr = sub_ptr[::ns].copy()
         rows = np.repeat(np.arange(nc), np.diff(self.crp))
-        I, J = agg_of[rows], agg_of[self.ccol]
+        col_sub = row_sub[self.ccol]
+        I, J = row_sub[rows] // ns, col_sub // ns
         cut = np.nonzero(I != J)[0]
         key = I[cut] * na + J[cut]
         o = np.argsort(key, kind="stable")
         cut_k = cut[o].astype(np.int32)
         cut_ptr = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=na * na))]).astype(np.int32)
-        self.agg = dict(na=na, agg_ptr=agg_ptr, agg_of=agg_of.astype(np.int32), col_agg=J.astype(np.int32),
+        self.agg = dict(na=na, ns=ns, agg_ptr=agg_ptr, sub_ptr=sub_ptr, row_sub=row_sub.astype(np.int32),
+                        agg_of=(row_sub // ns).astype(np.int32), col_agg=col_sub.astype(np.int32),
                         cut_ptr=cut_ptr, cut_k=cut_k if len(cut_k) else np.zeros(1, dtype=np.int32))
         return self.agg
 

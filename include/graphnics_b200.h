@@ -250,6 +250,7 @@ int gnx_schur_build(const gnx_network_t* net, double sigma, const double* cond, 
 #define GNX_TOP_MAX 2048
 #define GNX_AGG_MAX 128
 #define GNX_BLK_MAX 1024
+#define GNX_SUB_MAX 1024
 typedef struct gnx_schur_plan {
   int32_t B, nl, l_split, nc;          /* unknowns, rake levels, first level of the TOP part, core size */
   int32_t nnzc, nt;                    /* off-diagonal entries of the core matrix; #nodes in levels >= l_split
@@ -276,22 +277,26 @@ typedef struct gnx_schur_plan {
   int32_t na;                          /* > 0: two-level preconditioner, the core rows are grouped into na aggregates */
   const int32_t* ell_col;              /* [ell_w*nc] */
   const int32_t* ell_edge;             /* [ell_w*nc] graph edge whose -cond is the entry, -1 = padding */
-  /* Two-level PCG on a large core (na > 0, 2 <= na <= GNX_AGG_MAX; cooperative grid of na CTAs, one per
-   * aggregate): preconditioner  M^-1 = D^-1 + W (W^T S W)^-1 W^T  with W the piecewise-constant
-   * indicator vectors of the aggregates.  Core rows are numbered aggregate by aggregate. */
+  /* Multilevel-additive PCG on a large core (na > 0, 2 <= na <= GNX_AGG_MAX; cooperative grid of na CTAs, one
+   * per coarse aggregate): preconditioner  M^-1 = D^-1 + W1 diag(W1^T S W1)^-1 W1^T + W2 (W2^T S W2)^-1 W2^T
+   * with W1 / W2 the piecewise-constant indicator vectors of the na*ns fine / na coarse aggregates
+   * (na*ns <= GNX_SUB_MAX, ns a power of two <= 32).  Core rows are numbered fine aggregate by fine aggregate. */
   const int32_t* agg_ptr;              /* [na+1] core rows of aggregate J = agg_ptr[J] .. agg_ptr[J+1]) */
-  const int32_t* col_agg;              /* [nnzc] aggregate of the column of every core entry */
+  const int32_t* col_agg;              /* [nnzc] FINE aggregate of the column of every core entry (coarse = fine / ns) */
   const int32_t* cut_ptr;              /* [na*na+1] cut_k[cut_ptr[I*na+J] ..): core entries coupling aggregate I to J != I */
   const int32_t* cut_k;
   /* Blocked rake of a large forest (nb > 0, nc == 0): the raked nodes outside the top part form nb BLOCKS,
    * maximal complete subtrees of <= GNX_BLK_MAX nodes, each swept by one CTA out of shared memory; the top
    * part (top_nodes, <= GNX_TOP_MAX nodes) is then the set of nodes with larger subtrees and l_split its
    * lowest rake level.  Two grid barriers replace one per wide level. */
-  int32_t nb, reserved;
+  int32_t nb;
+  int32_t ns;                          /* multilevel PCG: every coarse aggregate is the union of ns fine ones (1: coarse level only) */
   const int32_t* blk_ptr;              /* [nb+1] block b = blk_nodes[blk_ptr[b] .. blk_ptr[b+1]) */
   const int32_t* blk_nodes;
   const int32_t* blk_pos;              /* [B] position of a node inside its block, -1 for top-part nodes */
   const int32_t* blk_lv;               /* [2*nb] lowest and highest rake level of a block */
+  const int32_t* sub_ptr;              /* [na*ns+1] core rows of the fine aggregates (ns > 1) */
+  const int32_t* row_sub;              /* [nc] fine aggregate of a core row (ns > 1) */
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

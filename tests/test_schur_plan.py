@@ -73,8 +73,10 @@ def test_plan_solves_schur_system(name):
 
 def _two_level_pcg(plan, agg, cond, diag, rhs, rtol=1e-13, max_iter=5000):
     """numpy model of core_pcg_twolevel (gnx_solve.cu): the coarse matrix comes from the plan's cut lists
-    and row sums exactly as the kernel sums it, z = D^-1 r + W E^-1 W^T r is never stored whole."""
-    nc, na = plan.nc, agg["na"]
+    and row sums, the fine-level diagonal from row_sub / col_agg, exactly as the kernel sums them;
+    z = D^-1 r + W1 dE^-1 W1^T r + W2 E^-1 W2^T r is never stored whole."""
+    nc, na, ns = plan.nc, agg["na"], agg["ns"]
+    nf = na * ns
     rows = np.repeat(np.arange(nc), np.diff(plan.crp))
     cval = -np.asarray(cond)[plan.cedge]
     dg = np.asarray(diag)[plan.core_nodes]
@@ -87,13 +89,26 @@ def _two_level_pcg(plan, agg, cond, diag, rhs, rtol=1e-13, max_iter=5000):
                 ks = agg["cut_k"][agg["cut_ptr"][I * na + J]:agg["cut_ptr"][I * na + J + 1]]
                 E[I, J] = cval[ks].sum() if len(ks) else 0.0
         E[I, I] = rowsum[agg["agg_ptr"][I]:agg["agg_ptr"][I + 1]].sum() - E[I].sum()
-    agg_of = np.repeat(np.arange(na), np.diff(agg["agg_ptr"]))
-    W = sp.csr_matrix((np.ones(nc), (np.arange(nc), agg_of)), shape=(nc, na))
-    assert np.allclose(E, (W.T @ S @ W).toarray(), rtol=1e-12, atol=1e-12 * abs(E).max())
+    row_sub, col_sub = agg["row_sub"], agg["col_agg"]
+    assert np.array_equal(row_sub, np.repeat(np.arange(nf), np.diff(agg["sub_ptr"])))
+    assert np.array_equal(agg["agg_ptr"], agg["sub_ptr"][::ns]) and np.array_equal(col_sub, row_sub[plan.ccol])
+    same = col_sub == row_sub[rows]
+    dE = np.bincount(row_sub, weights=dg, minlength=nf) + np.bincount(row_sub[rows][same], weights=cval[same], minlength=nf)
+    agg_of = row_sub // ns
+    W2 = sp.csr_matrix((np.ones(nc), (np.arange(nc), agg_of)), shape=(nc, na))
+    W1 = sp.csr_matrix((np.ones(nc), (np.arange(nc), row_sub)), shape=(nc, nf))
+    assert np.allclose(E, (W2.T @ S @ W2).toarray(), rtol=1e-12, atol=1e-12 * abs(E).max())
+    assert np.allclose(dE, (W1.T @ S @ W1).diagonal(), rtol=1e-12)
     Ei = np.linalg.inv(E)
     b = np.asarray(rhs)[plan.core_nodes]
+
+    def prec(r):
+        s1 = np.bincount(row_sub, weights=r, minlength=nf)
+        s2 = s1.reshape(na, ns).sum(axis=1)
+        y1 = (s1 / dE) if ns > 1 else np.zeros(nf)
+        return r / dg + y1[row_sub] + (Ei @ s2)[agg_of]
     x = np.zeros(nc); r = b.copy()
-    z = r / dg + (Ei @ (W.T @ r))[agg_of]
+    z = prec(r)
     p = z.copy(); rz = r @ z; bb = b @ b
     for it in range(1, max_iter + 1):
         w = S @ p
@@ -101,7 +116,7 @@ def _two_level_pcg(plan, agg, cond, diag, rhs, rtol=1e-13, max_iter=5000):
         x += al * p; r -= al * w
         if r @ r <= rtol * rtol * bb:
             return x, it, S
-        z = r / dg + (Ei @ (W.T @ r))[agg_of]
+        z = prec(r)
         rzn = r @ z
         p = z + (rzn / rz) * p
         rz = rzn
@@ -121,8 +136,8 @@ def _jacobi_pcg_iters(S, b, rtol=1e-13, max_iter=20000):
     return max_iter
 
 
-@pytest.mark.parametrize("na", [2, 7, 32])
-def test_two_level_aggregates(na):
+@pytest.mark.parametrize("na,ns", [(2, 1), (8, 1), (32, 1), (8, 4), (32, 8)])
+def test_two_level_aggregates(na, ns):
     """aggregate_core: balanced contiguous aggregates, renumbered core CSR = permuted original, cut lists
     give W^T S W, and the two-level PCG reaches the direct solution in fewer iterations than Jacobi"""
     from graphnics_b200.generators import honeycomb
@@ -144,8 +159,8 @@ def test_two_level_aggregates(na):
     old_nodes = plan.core_nodes.copy()
     node_of = np.empty(B, dtype=np.int64)
     node_of[bix[bix >= 0]] = np.nonzero(bix >= 0)[0]
-    agg = plan.aggregate_core(pos[node_of], na=na)
-    assert agg["na"] == na and agg["agg_ptr"][0] == 0 and agg["agg_ptr"][-1] == plan.nc
+    agg = plan.aggregate_core(pos[node_of], na=na, ns=ns)
+    assert agg["na"] == na and agg["ns"] == ns and agg["agg_ptr"][0] == 0 and agg["agg_ptr"][-1] == plan.nc
     sizes = np.diff(agg["agg_ptr"])
     assert sizes.min() >= 1 and sizes.max() - sizes.min() <= 1 + int(np.log2(na))
     assert sorted(plan.core_nodes.tolist()) == sorted(old_nodes.tolist())
@@ -155,7 +170,7 @@ def test_two_level_aggregates(na):
     P = sp.csr_matrix((np.ones(plan.nc), (perm, np.arange(plan.nc))), shape=(plan.nc, plan.nc))
     assert abs(P @ before @ P.T - after).max() == 0.0
     agg_of = np.repeat(np.arange(na), sizes)
-    assert np.array_equal(agg["col_agg"], agg_of[plan.ccol])
+    assert np.array_equal(agg["col_agg"] // ns, agg_of[plan.ccol])
     x, its, S = _two_level_pcg(plan, agg, cond, diag, rhs)
     ref = spla.spsolve(S_full.tocsc(), rhs)
     assert np.allclose(x, ref[plan.core_nodes], rtol=1e-9, atol=1e-11)
