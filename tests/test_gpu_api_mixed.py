@@ -115,24 +115,24 @@ def test_mixed_hydraulic():
 
 
 def sympy_hydraulic_manufactured_solution(G, Ainv, Res):
-    """tests/test_time_stepping.py:47-60"""
+    """tests/test_time_stepping.py:47-60: q = t sin(2*3.14 x), p = cos(2*3.14 x) (p does not depend on t),
+    g = Ainv q_t + Res q + p_x, f = q_x, all as `Expression(ccode, degree=2, t=0)`"""
     import sympy as sym
     from graphnics_b200 import Expression
-    x, t_, x_ = sym.symbols("x[0] t x_")
-    q = sym.sin(2 * sym.pi * x) + sym.cos(2 * sym.pi * t_)
-    f = q.diff(x)
-    dsp = -Res * q - Ainv * q.diff(t_)
-    p_ = sym.integrate(dsp, (x, 0, x_))
-    p = p_.subs(x_, x)
-    g = 0
-    q, p, f, g = [sym.printing.ccode(func) for func in [q, p, f, g]]
-    q, p, f, g = [Expression(func, degree=2, t=0) for func in [q, p, f, g]]
+    x, t = sym.symbols("x[0] t")
+    q = t * sym.sin(2 * 3.14 * x)
+    p = sym.cos(2 * 3.14 * x)
+    g = Ainv * sym.diff(q, t) + Res * q + sym.diff(p, x)
+    f = sym.diff(q, x)
+    q, p, f, g = [Expression(sym.printing.ccode(expr), degree=2, t=0) for expr in (q, p, f, g)]
     return q, p, f, g
 
 
 @pytest.mark.parametrize("scheme", ["IE", "CN"])
 def test_time_stepping_mixed_hydraulic(scheme):
-    """tests/test_time_stepping.py:98-136 (the reference only runs IE: "TODO: Test with CN")"""
+    """tests/test_time_stepping.py:98-136 with the reference's own data and bounds (error_q < 1e-1,
+    error_p < 1e-1; the reference only runs IE: "TODO: Test with CN"), then every stored state against the
+    oracle's literal replay of the loop"""
     from graphnics_b200 import (line_graph, Constant, TimeDepMixedHydraulicNetwork, time_stepping_stokes,
                                 FunctionSpace, project, errornorm)
     G = line_graph(2)
@@ -158,31 +158,20 @@ def test_time_stepping_mixed_hydraulic(scheme):
     pa = project(p, FunctionSpace(G.mesh, "CG", 2))
     error_q = errornorm(qh, qa)
     error_p = errornorm(ph, pa)
-    # The reference asserts error_q < 1e-1 here.  A literal replay of its loop (t_steps-1 = 9 implicit
-    # Euler steps of dt = 0.1 from a zero state, data clock running to 0.9875) lands on mean(q) = 0.80
-    # against the exact 1.0 at t = T -- the scalar model Ainv Q' + Res Q = F(t) gives the same 0.801 --
-    # so the bound cannot hold for the algorithm as written; FEniCS is not available to see what the
-    # reference really produces ("known deviations").  We assert the replayed value and that
-    # the scheme converges with more steps.
-    if scheme == "IE":
-        assert error_q < 0.25 and error_p < 2.5
-        qps40 = time_stepping_stokes(TimeDepMixedHydraulicNetwork(G, f=f, g=g, p_bc=p, Ainv=Ainv), Constant(0),
-                                     t_steps=40, T=T, t_step_scheme=scheme)
-        q.t = T
-        assert errornorm(qps40[-1][0], project(q, FunctionSpace(G.mesh, "CG", 3))) < 1e-1
-        q.t = p.t = f.t = g.t = 0      # the oracle replay below starts its clocks at 0
+    if scheme == "IE":                 # the reference's assertions, unchanged
+        assert error_q < 1e-1, f"Large error in time stepping mixed hydraulic model, error_q={error_q:1.1e}"
+        assert error_p < 1e-1, f"Large error in time stepping mixed hydraulic model, error_p={error_p:1.1e}"
+    else:                              # CN: the flux is as good; the pressure (a multiplier) oscillates
+        assert error_q < 1e-1
 
     # every stored state against the oracle's literal restatement of the loop (quirks included)
-    pi = np.pi
+    w = 2 * 3.14
     om = oracle.build_mesh(np.array([[0.0, 0.0], [1.0, 0.0]]), np.array([[0, 1]]), 5)
     TC = lambda fn: oracle.TimeCoef(fn, degree=2, clock="attr")
-    fo = TC(lambda x, tt: 2 * pi * np.cos(2 * pi * x[..., 0]))
-    def p_fn(x, tt):
-        X = x[..., 0]
-        # p = int_0^x (-Res q - Ainv dq/dt) dx
-        return (-Res * ((1 - np.cos(2 * pi * X)) / (2 * pi) + X * np.cos(2 * pi * tt))
-                + Ainv * 2 * pi * np.sin(2 * pi * tt) * X)
-    xs = oracle.time_stepping("mixed", om, f=fo, g=0.0, p_bc=TC(p_fn), Res=float(Res), Ainv=float(Ainv),
+    fo = TC(lambda x, tt: tt * w * np.cos(w * x[..., 0]))
+    go = TC(lambda x, tt: Ainv * np.sin(w * x[..., 0]) + Res * tt * np.sin(w * x[..., 0]) - w * np.sin(w * x[..., 0]))
+    po = TC(lambda x, tt: np.cos(w * x[..., 0]))
+    xs = oracle.time_stepping("mixed", om, f=fo, g=go, p_bc=po, Res=float(Res), Ainv=float(Ainv),
                               t_steps=t_steps, T=T, scheme=scheme, project=True)
     assert len(xs) == len(qps)
     for k, (xo, qpk) in enumerate(zip(xs, qps)):
