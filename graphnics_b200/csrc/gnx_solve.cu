@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 #include "gnx_common.cuh"
 #include "gnx_tma.cuh"
+#include "gnx_asm_tile.cuh"
 namespace cg = cooperative_groups;
 
 struct EdgeFrame {
@@ -120,6 +121,26 @@ edge_eliminate_kernel(gnx_network_t net, GnxMixedDims d, const double* __restric
 // memory.  A thread owns CPT consecutive cells: serial prefix in registers + block-segmented scan
 // of the thread totals.  Outputs leave the same way (staged at their dof slots, one bulk store per range).
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// The per-cell arithmetic of the edge-tile kernels with every rounding spelled out: the chain kernels and the
+// persistent step kernel (which recomputes instead of re-reading, and has a Constant-zero-data fast path) must
+// produce the same bits, so no expression is left to the compiler's choice of FMA contraction.
+// ------------------------------------------------------------------------------------
+// right cell of node j: a h_j (2 q_j + q_{j+1}) / 6 with q_{j+1} = q_j + F_j
+__device__ __forceinline__ double gnx_mq_right(double a, double h, double q, double F) {
+  return __dmul_rn(__dmul_rn(__dmul_rn(a, h), __fma_rn(3.0, q, F)), 1.0 / 6.0);
+}
+// + left cell: a h_{j-1} (q_{j-1} + 2 q_j) / 6 with q_{j-1} = q_j - F_{j-1}
+__device__ __forceinline__ double gnx_mq_left(double mq, double a, double hl, double q, double fl) {
+  return __fma_rn(__dmul_rn(__dmul_rn(a, hl), __fma_rn(3.0, q, -fl)), 1.0 / 6.0, mq);
+}
+// running sum of h_k (cumF_k + cumF_{k+1}) / 2
+__device__ __forceinline__ double gnx_s2_step(double s2, double h, double cum, double F) {
+  return __fma_rn(__dmul_rn(h, __dadd_rn(__dadd_rn(cum, cum), F)), 0.5, s2);
+}
+__device__ __forceinline__ double gnx_edge_cond(double a, double L) { return __ddiv_rn(1.0, __dmul_rn(a, L)); }
+__device__ __forceinline__ double gnx_edge_rsrc(double a, double sumG, double s2) { return __fma_rn(-a, s2, sumG); }
+
 constexpr int ET_T = 256;
 
 struct TileCtx {
@@ -139,14 +160,14 @@ template <int CPT> struct TileSmem {
 };
 
 template <int CPT>
-__device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxMixedDims& d) {
+__device__ __forceinline__ TileCtx tile_ctx_at(const gnx_network_t& net, const GnxMixedDims& d, int32_t tile, int32_t ltid) {
   constexpr int TILE = ET_T * CPT;
   TileCtx c;
   c.m = d.m;
   const int32_t G = TILE >> net.n;
-  c.e0 = blockIdx.x * G;
+  c.e0 = tile * G;
   c.nE = min(G, net.E - c.e0);
-  const int32_t k0 = threadIdx.x * CPT;
+  const int32_t k0 = ltid * CPT;
   int32_t le = k0 >> net.n;
   c.active = le < c.nE;
   c.le = c.active ? le : c.nE - 1;
@@ -160,10 +181,14 @@ __device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxM
   return c;
 }
 template <int CPT, bool BULK>
-__device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxMixedDims& d) {
-  TileCtx c = tile_ctx<CPT>(net, d);
+__device__ __forceinline__ TileCtx tile_ctx_at(const gnx_network_t& net, const GnxMixedDims& d, int32_t tile, int32_t ltid) {
+  TileCtx c = tile_ctx_at<CPT>(net, d, tile, ltid);
   if (BULK) { c.shp = (int32_t)(c.pbase & 1); c.shq = (int32_t)(c.qbase & 1); c.shh = (int32_t)(c.hbase & 1); }
   return c;
+}
+template <int CPT, bool BULK>
+__device__ __forceinline__ TileCtx tile_ctx(const gnx_network_t& net, const GnxMixedDims& d) {
+  return tile_ctx_at<CPT, BULK>(net, d, (int32_t)blockIdx.x, (int32_t)threadIdx.x);
 }
 
 // Tile inputs -> shared memory.  BULK: thread 0 hands the contiguous ranges to the copy engine, completion
@@ -294,18 +319,19 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
       for (int i = 0; i < CPT; ++i) {                          // edge-local node j (u -> v), cells j-1 | j
         const int32_t j = c.kk0 + i;
         const double hr = H[i];
-        double val = rhs.gc * (hl + hr) * 0.5;
-        if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val += rhs.pbc_node[u];     // edge OUT of a boundary node: BOUN_IN
+        // (explicitly rounded: the persistent step kernel recomputes these values and must get the same bits)
+        double val = __dmul_rn(__dmul_rn(rhs.gc, __dadd_rn(hl, hr)), 0.5);
+        if (j == 0 && net.bix[u] < 0 && rhs.pbc_node) val = __dadd_rn(val, rhs.pbc_node[u]);     // edge OUT of a boundary node: BOUN_IN
         sG[qb + __ldg(net.loc + (c.flip ? m - j : j))] = val;
-        const double fv = rhs.fc * hr;
+        const double fv = __dmul_rn(rhs.fc, hr);
         sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = fv;
-        F[i] = fv * inv_sigma;
+        F[i] = __dmul_rn(fv, inv_sigma);
         sumG += val;
         hl = hr;
       }
       if (c.kk0 + CPT == m) {                                  // the edge's last thread also owns node m
-        double val = rhs.gc * (hl + 0.0) * 0.5;
-        if (net.bix[v] < 0 && rhs.pbc_out) val -= rhs.pbc_out[c.e];               // edge INTO a boundary node: BOUN_OUT
+        double val = __dmul_rn(__dmul_rn(rhs.gc, __dadd_rn(hl, 0.0)), 0.5);
+        if (net.bix[v] < 0 && rhs.pbc_out) val = __dsub_rn(val, rhs.pbc_out[c.e]);               // edge INTO a boundary node: BOUN_OUT
         sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = val;
         sumG += val;
       }
@@ -317,7 +343,7 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
       const int32_t kk = c.kk0 + i;
-      F[i] = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kk : kk)] * inv_sigma : 0.0;
+      F[i] = c.active ? __dmul_rn(sF[cbF + gnx_gray(c.flip ? m - 1 - kk : kk)], inv_sigma) : 0.0;
       H[i] = sH[cbH + kk];
       sumG += sG[qb + __ldg(net.loc + (c.flip ? m - kk : kk))];
       sumF += F[i];
@@ -331,12 +357,12 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
   double cum = incl - sumF;                       // cumF at the first cell of this thread
   double s2 = 0.0;
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) { s2 += H[i] * (cum + cum + F[i]) * 0.5; cum += F[i]; }
+  for (int i = 0; i < CPT; ++i) { s2 = gnx_s2_step(s2, H[i], cum, F[i]); cum = __dadd_rn(cum, F[i]); }
   double acc[3] = {s2, sumG, sumH};
   gnx_seg_sum<3>(acc, segT, sh);
   if (c.active && c.kk0 == 0) {
     const double a = a_edge[c.e];
-    out.put(c.e, 1.0 / (a * acc[2]), acc[1] - a * acc[0], tot);
+    out.put(c.e, gnx_edge_cond(a, acc[2]), gnx_edge_rsrc(a, acc[1], acc[0]), tot);
   }
   if (FUSED_RHS) tile_store_done<BULK>();
 }
@@ -1161,16 +1187,16 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
 template <int MODE> struct SchThreads { static constexpr int value = SCH_T; };
 template <> struct SchThreads<SCH_CLUSTER> { static constexpr int value = CL_T; };
 
+// The whole Schur solve as a device function: the body of schur_solve_kernel<MODE>, and -- MODE == SCH_SINGLE,
+// executed by CTA 0 -- the middle phase of the persistent step kernel (step_resident_kernel below).
+// top_sh: 3 * GNX_TOP_MAX doubles of shared memory, red: 2 x 96 doubles.
 template <int MODE>
-__global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel(SchurArgs a) {
-  extern __shared__ double top_sh[];             // 3 * GNX_TOP_MAX doubles (dynamic, opt-in > 48 KB)
-  __shared__ double red[2][3 * 32];
+__device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, double (*red)[3 * 32]) {
   const gnx_schur_plan_t& pl = a.plan;
-  const int nblk = gridDim.x;
+  const int nblk = MODE == SCH_SINGLE ? 1 : gridDim.x;       // (one CTA of a larger grid in the persistent step kernel)
   const int32_t stride = nblk * blockDim.x;
-  const int32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t t0 = (MODE == SCH_SINGLE ? 0 : blockIdx.x * blockDim.x) + threadIdx.x;
   auto gsync = [&]() { sch_sync<MODE>(); };
-  gnx_pdl_wait();                                 // the edge scalars come from the elimination kernel
   long long tick[4] = {0, 0, 0, 0};               // SM cycles of block 0: phase 0 | top prologue | up | down (diagnostic, scal[5..7])
   const long long tick0 = clock64();
   if (a.wait_flags) {                             // ... and, edge-partitioned, from the other ranks' over NVLink
@@ -1352,6 +1378,14 @@ __global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(SchThreads<MODE>::value, 1) schur_solve_kernel(SchurArgs a) {
+  extern __shared__ double top_sh[];             // 3 * GNX_TOP_MAX doubles (dynamic, opt-in > 48 KB)
+  __shared__ double red[2][3 * 32];
+  gnx_pdl_wait();                                 // the edge scalars come from the elimination kernel
+  schur_body<MODE>(a, top_sh, red);
+}
+
 static int g_sch_blocks_per_sm = -1, g_sch_sms = 0, g_sch_cluster_max = 0;
 
 // Cooperative launch that is ALSO a programmatic dependent launch (the grid may become resident while the
@@ -1406,14 +1440,11 @@ static int sch_init() {
   return GNX_OK;
 }
 
-// P holds the initial guess of the core unknowns on entry when warm != 0.
-// resid_host[0] = ||r||/||rhs|| of the core system (recurrence residual; 0 for a pure tree),
-// info_host[3] = {CG iterations, converged, grid blocks}.  Asynchronous when both are NULL.
-extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
-                               const double* cond, const double* rsrc, const double* ftot,
-                               const double* b_lam, const double* b_node, double* P, double* lam_out, double* work,
-                               double rtol, int32_t max_iter, int32_t warm, int32_t chunk, int32_t rank_stride,
-                               const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* stream) {
+// argument checks + kernel argument block of a Schur solve (shared by gnx_schur_solve and the persistent step)
+static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
+                           const double* cond, const double* rsrc, const double* ftot, const double* b_lam,
+                           const double* b_node, double* P, double* lam_out, double* work, double rtol, int32_t max_iter,
+                           int32_t warm, int32_t chunk, int32_t rank_stride, const gnx_exchange_t* ex) {
   GNX_CHECK_ARG(net && plan && cond && rsrc && ftot && P && work && sigma != 0.0 && rtol > 0 && max_iter > 0);
   GNX_CHECK_ARG(plan->B == net->B && plan->B > 0 && plan->nl >= 0 && plan->nl <= GNX_MAX_LEVELS);
   GNX_CHECK_ARG(plan->l_split >= 0 && plan->l_split <= plan->nl && plan->nc >= 0 && plan->nc <= plan->B);
@@ -1435,9 +1466,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   GNX_CHECK_ARG(plan->na == 0 || plan->ns <= 1 ||
                 (plan->ns <= 32 && (plan->ns & (plan->ns - 1)) == 0 && (int64_t)plan->na * plan->ns <= GNX_SUB_MAX &&
                  plan->sub_ptr && plan->row_sub));
-  cudaStream_t st = (cudaStream_t)stream;
   if (int rc = sch_init()) return rc;
-  SchurArgs a;
   a.net = *net; a.plan = *plan;
   a.inv_sigma = 1.0 / sigma;
   a.cond = cond; a.rsrc = rsrc; a.ftot = ftot; a.b_lam = b_lam; a.b_node = b_node; a.P = P; a.lam_out = lam_out;
@@ -1464,6 +1493,40 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
       a.sig_flags[k] = reinterpret_cast<long long*>(ex->peers_host[k] + (int64_t)ex->world * 3 * ex->chunk) + ex->rank;
     }
   }
+  return GNX_OK;
+}
+
+// resid_host[0] = ||r||/||rhs|| of the core system (recurrence residual; 0 for a pure tree),
+// info_host[3] = {CG iterations, converged, grid blocks (< 0: one cluster)}.  Asynchronous when both are NULL.
+static int schur_report(const SchurArgs& a, int want, double* resid_host, int32_t* info_host, cudaStream_t st) {
+  if (!resid_host && !info_host) return GNX_OK;              // fully asynchronous
+  double scal[8];
+  GNX_CUDA(cudaMemcpyAsync(scal, a.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GNX_CUDA(cudaStreamSynchronize(st));
+  const double bb = scal[4];
+  const double rel = bb > 0 ? sqrt(scal[3] / bb) : 0.0;
+  if (resid_host) resid_host[0] = rel;
+  const int done = scal[1] != 0.0;
+  if (info_host) { info_host[0] = (int32_t)scal[2]; info_host[1] = done; info_host[2] = want; }
+  if (!done) {
+    gnx_set_error("schur CG: no convergence in %d iterations (rel. resid %.3e)", (int)scal[2], rel);
+    return GNX_ERR_NOCONV;
+  }
+  return GNX_OK;
+}
+
+// P holds the initial guess of the core unknowns on entry when warm != 0.
+extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
+                               const double* cond, const double* rsrc, const double* ftot,
+                               const double* b_lam, const double* b_node, double* P, double* lam_out, double* work,
+                               double rtol, int32_t max_iter, int32_t warm, int32_t chunk, int32_t rank_stride,
+                               const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SchurArgs a;
+  if (int rc = schur_args_fill(a, net, plan, sigma, cond, rsrc, ftot, b_lam, b_node, P, lam_out, work, rtol, max_iter,
+                               warm, chunk, rank_stride, ex)) return rc;
+  const bool cluster_top = plan->top_S > 0;
+  const int64_t B = plan->B, nc = plan->nc;
   // CTAs: enough threads for the widest phase.  <= 2 CTAs' worth runs as one CTA; a system with a
   // Krylov core (hundreds of barriers) runs as ONE CLUSTER when that gives every thread <= 32 rows;
   // everything else (wide rake levels of a large tree: few barriers, lots of rows) as a cooperative grid.
@@ -1514,20 +1577,7 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   } else {
     GNX_CUDA(launch_coop<SCH_GRID>(a, want, SCH_SMEM, st));
   }
-  if (!resid_host && !info_host) return GNX_OK;              // fully asynchronous
-  double scal[8];
-  GNX_CUDA(cudaMemcpyAsync(scal, a.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GNX_CUDA(cudaStreamSynchronize(st));
-  const double bb = scal[4];
-  const double rel = bb > 0 ? sqrt(scal[3] / bb) : 0.0;
-  if (resid_host) resid_host[0] = rel;
-  const int done = scal[1] != 0.0;
-  if (info_host) { info_host[0] = (int32_t)scal[2]; info_host[1] = done; info_host[2] = want; }   // CTAs (< 0: one cluster)
-  if (!done) {
-    gnx_set_error("schur CG: no convergence in %d iterations (rel. resid %.3e)", (int)scal[2], rel);
-    return GNX_ERR_NOCONV;
-  }
-  return GNX_OK;
+  return schur_report(a, want, resid_host, info_host, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1600,7 +1650,7 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   const double Pv = bv >= 0 ? P[bv] : 0.0;
   const double a = a_edge[c.e];
   const double kv = k_edge ? k_edge[c.e] : 0.0;
-  const double q0 = cond[c.e] * (Pu - Pv + rsrc[c.e]);
+  const double q0 = __dmul_rn(cond[c.e], __dadd_rn(__dsub_rn(Pu, Pv), rsrc[c.e]));
   __syncthreads();
   tile_wait<CPT, BULK, true>(ts);
   const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
@@ -1612,7 +1662,7 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     const int32_t kk = c.kk0 + i;
     ps[i] = cbF + gnx_gray(c.flip ? m - 1 - kk : kk);
     qs[i] = qb + __ldg(net.loc + (c.flip ? m - kk : kk));
-    F[i] = c.active ? sF[ps[i]] * inv_sigma : 0.0;
+    F[i] = c.active ? __dmul_rn(sF[ps[i]], inv_sigma) : 0.0;
     H[i] = sH[cbH + kk];
     Gq[i] = c.active ? sG[qs[i]] : 0.0;
     sumF += F[i];
@@ -1620,7 +1670,7 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   double Fl = 0.0, Hl = 1.0;                       // cell left of my first node
   if (c.kk0 > 0) {
     const int32_t kl = c.kk0 - 1;
-    Fl = c.active ? sF[cbF + gnx_gray(c.flip ? m - 1 - kl : kl)] * inv_sigma : 0.0;
+    Fl = c.active ? __dmul_rn(sF[cbF + gnx_gray(c.flip ? m - 1 - kl : kl)], inv_sigma) : 0.0;
     Hl = sH[cbH + kl];
   }
   const int segT = m / CPT;
@@ -1631,18 +1681,18 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
   double sumD = 0.0;
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
-    q[i] = q0 + cum;
-    double mq = a * H[i] * (3.0 * q[i] + F[i]) * (1.0 / 6.0);                      // h_j (2 q_j + q_{j+1})/6
+    q[i] = __dadd_rn(q0, cum);
+    double mq = gnx_mq_right(a, H[i], q[i], F[i]);                                 // h_j (2 q_j + q_{j+1})/6
     const bool has_left = (i > 0) || (c.kk0 > 0);
     const double fl = i > 0 ? F[i - 1] : Fl, hl = i > 0 ? H[i - 1] : Hl;
-    if (has_left) mq += a * hl * (3.0 * q[i] - fl) * (1.0 / 6.0);                  // h_{j-1}(q_{j-1} + 2 q_j)/6
+    if (has_left) mq = gnx_mq_left(mq, a, hl, q[i], fl);                           // h_{j-1}(q_{j-1} + 2 q_j)/6
     if (kv != 0.0) {                                                               // stiffness (NetworkStokes)
-      mq -= kv * F[i] / H[i];
-      if (has_left) mq += kv * fl / hl;
+      mq = __dsub_rn(mq, __ddiv_rn(__dmul_rn(kv, F[i]), H[i]));
+      if (has_left) mq = __dadd_rn(mq, __ddiv_rn(__dmul_rn(kv, fl), hl));
     }
-    D[i] = Gq[i] - mq;
+    D[i] = __dsub_rn(Gq[i], mq);
     sumD += D[i];
-    cum += F[i];
+    cum = __dadd_rn(cum, F[i]);
   }
   const double inclD = gnx_seg_incl_scan(sumD, segT, sh, &totD);
   double cd = Pu + (inclD - sumD);
@@ -1652,9 +1702,9 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
     for (int i = 0; i < CPT; ++i) {
       cd += D[i];
       sG[qs[i]] = q[i];
-      sF[ps[i]] = cd * inv_sigma;
+      sF[ps[i]] = __dmul_rn(cd, inv_sigma);
     }
-    if (c.kk0 + CPT == m) sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = q0 + totF;
+    if (c.kk0 + CPT == m) sG[qb + __ldg(net.loc + (c.flip ? 0 : m))] = __dadd_rn(q0, totF);
   }
   tile_store<CPT, BULK>(c, ts, x);
   tile_store_done<BULK>();
@@ -1690,4 +1740,642 @@ extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_
   }
   GNX_LAUNCH_CHECK();
   return GNX_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Persistent step kernel: right-hand side + elimination -> Schur solve -> back-substitution in ONE
+// cooperative launch, one CTA per SM, for networks whose cell lengths fit the GPU's shared memory
+// (<= RS_MAX_TILES tiles of 1024 cells per SM: 1.2 M cells on 148 SMs -- the C2 benchmark size).
+//
+// The three-kernel chain above is latency-bound at that size: every kernel boundary costs a launch and a
+// fresh round of global loads, and the back-substitution re-reads what the elimination just had in shared
+// memory.  Here a CTA (4 sub-blocks of 256 threads, each working on one tile at a time with its own
+// named barrier) keeps the cell lengths of ITS tiles resident in shared memory for the whole solve:
+//   phase 1  all tiles' lengths requested from the copy engine at once (one mbarrier per tile); per tile the
+//            right-hand side is produced in shared memory, leaves as b (two bulk stores) and is eliminated
+//            -> three scalars per edge;  the CTA then arrives on a global counter (release);
+//   phase 2  CTA 0 waits for the counter (acquire) and runs the Schur solve (schur_body<SCH_SINGLE>: the
+//            flag exchange with the other ranks of a partitioned network, rake / core PCG, multipliers);
+//            every other CTA meanwhile ASSEMBLES the CSR values (the solver never reads them: a_form /
+//            ii_assemble of the step, flow_models.py:343) -- the row code of mixed_values_tile_kernel, 512-cell
+//            tiles dealt round-robin to the sub-blocks, each range leaving as one bulk store -- and then parks
+//            on a flag word: the latency-bound graph-level solve hides under the step's largest stream of bytes;
+//   phase 3  back-substitution out of the resident lengths (Constant data: the right-hand side entries are
+//            recomputed, not re-read), the solution tile leaves as two bulk stores.
+// Per-thread arithmetic is that of edge_eliminate_tile_kernel<4,true,true>, edge_backsub_tile_kernel<4,true>
+// and mixed_values_tile_kernel<2,true,STIFF>, operation for operation: b, x and the CSR values are
+// bit-identical to the chain's.  HBM traffic of the step: h once (8 B/cell; the assembly's second look at it
+// is an L2 hit) + b, x (16 B/dof) and the values (64 B/cell) written, nothing re-read.
+// ------------------------------------------------------------------------------------
+constexpr int RS_T = 1024;                       // threads per CTA
+constexpr int RS_SUB = RS_T / ET_T;              // sub-blocks per CTA
+constexpr int RS_CPT = 4;
+constexpr int RS_TILE = ET_T * RS_CPT;           // cells per tile
+constexpr int RS_MIN_N = 6;                      // 2^6 .. 2^10 cells per edge: <= 16 edges per tile
+constexpr int RS_MAX_G = RS_TILE >> RS_MIN_N;    // edges per tile
+constexpr int RS_MAX_TILES = 8;                  // resident tiles per CTA
+constexpr int RS_HSLOT = RS_TILE + 2;            // doubles per resident tile (+ parity shift)
+constexpr int RS_FSLOT = RS_TILE + 2;
+constexpr int RS_GSLOT = RS_TILE + ET_T + 2;
+constexpr int RS_ACPT = 2;                       // cells per thread of the in-kernel assembly tiles
+constexpr int RS_ATILE = ASM_T * RS_ACPT;
+constexpr int RS_AQ = 5 * RS_ATILE + 3 * (RS_ATILE >> RS_MIN_N) + 8;      // staged q-row range of an assembly tile (n >= RS_MIN_N)
+constexpr int RS_STAGE = RS_AQ + 3 * RS_ATILE + 4;                        // + its p-row range; or the p | q range of b / x
+static_assert(ASM_T == ET_T, "assembly and solve tiles share the 256-thread sub-blocks");
+static_assert(RS_STAGE >= RS_FSLOT + RS_GSLOT, "a solve tile fits the staging area of a sub-block");
+static_assert(RS_SUB * RS_STAGE >= 3 * GNX_TOP_MAX, "the Schur phase of CTA 0 reuses the staging area");
+static_assert((RS_HSLOT % 2) == 0 && (RS_FSLOT % 2) == 0 && (RS_STAGE % 2) == 0 && (RS_AQ % 2) == 0, "16-byte aligned slots");
+
+// what a tile's threads need to know about an edge, gathered ONCE per step into shared memory (the chain of
+// dependent global loads edges -> bix -> p_bc costs a DRAM round trip per hop when the L2 is cold)
+struct __align__(16) RsEdge {
+  double a, pin, pout;                           // mass coefficient; boundary data at the u / v end (flags say whether they apply)
+  double q0, Pu;                                 // phase 3: flux at node 0, pressure at node u
+  int32_t bu, bv, flags, pad;                    // bifurcation index of the ends (-1: boundary); bit 0 flip, 1 pin, 2 pout
+};
+
+struct StepArgs {
+  gnx_network_t net;
+  GnxMixedDims d;
+  const double* a_edge;
+  const double* k_edge;
+  double inv_sigma;
+  ConstRhs rhs;
+  EdgeOut out;
+  const double *cond, *rsrc;                     // this rank's edge scalars where the back-substitution finds them
+  const double* P;
+  double* x;
+  double* vals;                                  // CSR values (NULL: no assembly)
+  double sigma;
+  int32_t nb_tiles, tiles_per_cta;
+  unsigned long long* sync;                      // [0] arrival counter (reset by CTA 0), [1] epoch of the last finished Schur phase,
+  unsigned long long epoch;                      // [2..9] globaltimer stamps of CTA 0 (diagnostic)
+};
+
+__device__ __forceinline__ unsigned long long rs_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int32_t gnx_blocks_dev(int64_t n, int t) { return (int32_t)((n + t - 1) / t); }
+__device__ __forceinline__ void rs_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(ET_T) : "memory"); }
+
+// gnx_seg_incl_scan / gnx_seg_sum for a 256-thread sub-block (same combination order, named barrier)
+__device__ __forceinline__ double rs_seg_incl_scan(double v, int seg, double* sh, double* total, int ltid, int bid) {
+  const int lane = ltid & 31;
+  const int w = seg < 32 ? seg : 32;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(GNX_FULL, v, o, w);
+    if (o < w && (lane & (w - 1)) >= o) v += t;
+  }
+  if (seg <= 32) {
+    *total = __shfl_sync(GNX_FULL, v, w - 1, w);
+    return v;
+  }
+  const int wid = ltid >> 5;
+  const int wps = seg >> 5;
+  rs_bar(bid);
+  if (lane == 31) sh[wid] = v;
+  rs_bar(bid);
+  const int w0 = wid & ~(wps - 1);
+  double t = (lane < wps) ? sh[w0 + lane] : 0.0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double u = __shfl_up_sync(GNX_FULL, t, o);
+    if (o < wps && lane >= o) t += u;
+  }
+  *total = __shfl_sync(GNX_FULL, t, wps - 1);
+  const int me = wid - w0;
+  const double before = __shfl_sync(GNX_FULL, t, me > 0 ? me - 1 : 0);
+  return me > 0 ? v + before : v;
+}
+template <int K>
+__device__ __forceinline__ void rs_seg_sum(double (&v)[K], int seg, double* sh, int ltid, int bid) {
+  const int lane = ltid & 31;
+  const int w = seg < 32 ? seg : 32;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(GNX_FULL, v[k], o, w);
+      if (o < w) v[k] += t;
+    }
+  }
+  if (seg <= 32) return;
+  const int wid = ltid >> 5;
+  const int wps = seg >> 5;
+  const int w0 = wid & ~(wps - 1);
+  rs_bar(bid);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k * 32 + wid] = v[k];
+  }
+  rs_bar(bid);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = (lane < wps) ? sh[k * 32 + w0 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(GNX_FULL, t, o);
+    v[k] = t;
+  }
+}
+
+// tile geometry without touching global memory (the orientation comes from the edge record)
+__device__ __forceinline__ TileCtx rs_tile_ctx(const gnx_network_t& net, const GnxMixedDims& d, int32_t tile, int32_t ltid,
+                                               const RsEdge* rec) {
+  TileCtx c;
+  c.m = d.m;
+  const int32_t G = RS_TILE >> net.n;
+  c.e0 = tile * G;
+  c.nE = min(G, net.E - c.e0);
+  const int32_t k0 = ltid * RS_CPT;
+  const int32_t le = k0 >> net.n;
+  c.active = le < c.nE;
+  c.le = c.active ? le : c.nE - 1;
+  c.e = c.e0 + c.le;
+  c.kk0 = k0 & (c.m - 1);
+  c.flip = rec[c.le].flags & 1;
+  c.pbase = d.p_off + (int64_t)c.e0 * c.m;
+  c.hbase = (int64_t)c.e0 * c.m;
+  c.qbase = (int64_t)c.e0 * (c.m + 1);
+  c.shp = (int32_t)(c.pbase & 1); c.shq = (int32_t)(c.qbase & 1); c.shh = (int32_t)(c.hbase & 1);
+  return c;
+}
+
+// staged range -> out[base .. base+len) by the sub-block's first thread (odd ends: its second warp)
+__device__ __forceinline__ void rs_put(const double* st, double* __restrict__ out, int64_t b0, int32_t len, int ltid) {
+  const int32_t sh = (int32_t)(b0 & 1);
+  const int32_t rest = len - sh;
+  if (ltid == 0) {
+    const int32_t body = rest > 0 ? (rest & ~1) : 0;
+    if (body > 0) gnx_bulk_s2g(out + b0 + sh, st + 2 * sh, (uint32_t)body * 8u);
+  }
+  if (ltid == 32) {
+    if (sh && len > 0) out[b0] = st[1];
+    if (rest > 0 && (rest & 1)) out[b0 + len - 1] = st[sh + len - 1];
+  }
+}
+__device__ __forceinline__ void rs_tile_store(const TileCtx& c, const double* sF, const double* sG, double* __restrict__ out,
+                                              int ltid, int bid) {
+  gnx_fence_async_smem();
+  rs_bar(bid);
+  rs_put(sG, out, c.qbase, c.nE * (c.m + 1), ltid);
+  rs_put(sF, out, c.pbase, c.nE * c.m, ltid);
+  if (ltid == 0) gnx_bulk_commit();
+}
+
+// right-hand side entry of edge-local node j (cells j-1 | j) for Constant data: what edge_eliminate_tile_kernel
+// <FUSED_RHS> stages at q dof j -- recomputed with the same, explicitly rounded, operations wherever it is needed
+// (the chain rounds these values by storing them; a recomputation must not be contracted into its consumer)
+__device__ __forceinline__ double rs_rhs_node(const StepArgs& s, const RsEdge& r, int32_t j, double hl, double hr) {
+  double val = __dmul_rn(__dmul_rn(s.rhs.gc, __dadd_rn(hl, hr)), 0.5);
+  if (j == 0 && (r.flags & 2)) val = __dadd_rn(val, r.pin);
+  return val;
+}
+
+// ZFG: f = g = 0 (boundary data only, the common steady case): every F is +0, every q-row entry of b is +0 except
+// at boundary ends; the general code then adds and multiplies zeros -- the fast path skips exactly those
+// operations (x + 0 = x, x * 0 = +0 for the positive lengths and finite data involved), so it yields the same bits.
+template <bool ZFG>
+__device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t tile, int ltid, int bid, const double* sH,
+                                                  double* sF, double* sG, double* sh, const RsEdge* rec, const int32_t* sloc) {
+  constexpr int CPT = RS_CPT;
+  const TileCtx c = rs_tile_ctx(s.net, s.d, tile, ltid, rec);
+  const RsEdge& r = rec[c.le];
+  const int32_t m = c.m;
+  const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
+  double F[CPT], H[CPT];
+  double sumF = 0.0, sumG = 0.0, sumH = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) { H[i] = sH[cbH + c.kk0 + i]; F[i] = 0.0; }
+  if (ZFG) {
+    // b tile: zeros, then the boundary ends
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) sF[RS_FSLOT - 1 - (ltid + i * ET_T)] = 0.0;     // (covers [2, RS_FSLOT); slots 0, 1 below)
+#pragma unroll
+    for (int i = 0; i < CPT + 1; ++i) sG[ltid + i * ET_T] = 0.0;
+    if (ltid < 2) { sF[ltid] = 0.0; sG[RS_GSLOT - 1 - ltid] = 0.0; }
+    rs_bar(bid);
+    if (c.active && c.kk0 == 0 && (r.flags & 2)) { const double v0 = __dadd_rn(0.0, r.pin); sG[qb + sloc[c.flip ? m : 0]] = v0; sumG += v0; }
+    if (c.active && c.kk0 + CPT == m && (r.flags & 4)) { const double vm = __dsub_rn(0.0, r.pout); sG[qb + sloc[c.flip ? 0 : m]] = vm; sumG += vm; }
+  } else if (c.active) {
+    double hl = c.kk0 > 0 ? sH[cbH + c.kk0 - 1] : 0.0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int32_t j = c.kk0 + i;
+      const double hr = H[i];
+      const double val = rs_rhs_node(s, r, j, hl, hr);
+      sG[qb + sloc[c.flip ? m - j : j]] = val;
+      const double fv = __dmul_rn(s.rhs.fc, hr);
+      sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = fv;
+      F[i] = __dmul_rn(fv, s.inv_sigma);
+      sumG += val;
+      hl = hr;
+    }
+    if (c.kk0 + CPT == m) {
+      double val = __dmul_rn(__dmul_rn(s.rhs.gc, __dadd_rn(hl, 0.0)), 0.5);
+      if (r.flags & 4) val = __dsub_rn(val, r.pout);
+      sG[qb + sloc[c.flip ? 0 : m]] = val;
+      sumG += val;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) { sumF += F[i]; sumH += H[i]; }
+  rs_tile_store(c, sF, sG, s.rhs.b, ltid, bid);
+  const int segT = m / CPT;
+  if (ZFG) {
+    double acc[2] = {sumG, sumH};
+    rs_seg_sum<2>(acc, segT, sh, ltid, bid);
+    if (c.active && c.kk0 == 0) s.out.put(c.e, gnx_edge_cond(r.a, acc[1]), gnx_edge_rsrc(r.a, acc[0], 0.0), 0.0);
+    return;
+  }
+  double tot;
+  const double incl = rs_seg_incl_scan(sumF, segT, sh, &tot, ltid, bid);
+  double cum = incl - sumF;
+  double s2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) { s2 = gnx_s2_step(s2, H[i], cum, F[i]); cum = __dadd_rn(cum, F[i]); }
+  double acc[3] = {s2, sumG, sumH};
+  rs_seg_sum<3>(acc, segT, sh, ltid, bid);
+  if (c.active && c.kk0 == 0) s.out.put(c.e, gnx_edge_cond(r.a, acc[2]), gnx_edge_rsrc(r.a, acc[1], acc[0]), tot);
+}
+
+template <bool ZFG>
+__device__ __forceinline__ void rs_backsub_tile(const StepArgs& s, int32_t tile, int ltid, int bid, const double* sH,
+                                                double* sF, double* sG, double* sh, const RsEdge* rec, const int32_t* sloc) {
+  constexpr int CPT = RS_CPT;
+  const TileCtx c = rs_tile_ctx(s.net, s.d, tile, ltid, rec);
+  const RsEdge& r = rec[c.le];
+  const int32_t m = c.m;
+  const double Pu = r.Pu, a = r.a, q0 = r.q0;
+  const double kv = s.k_edge ? s.k_edge[c.e] : 0.0;
+  const double inv_sigma = s.inv_sigma;
+  const int32_t cbF = c.le * m + c.shp, cbH = c.le * m + c.shh, qb = c.le * (m + 1) + c.shq;
+  int32_t ps[CPT];
+  double F[CPT], H[CPT], Gq[CPT];
+  double sumF = 0.0;
+  double Fl = 0.0, Hl = 1.0;
+  double hl = 0.0;
+  if (c.kk0 > 0) {
+    Hl = sH[cbH + c.kk0 - 1];
+    hl = Hl;
+    if (!ZFG) Fl = c.active ? __dmul_rn(__dmul_rn(s.rhs.fc, Hl), inv_sigma) : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int32_t kk = c.kk0 + i;
+    ps[i] = cbF + gnx_gray(c.flip ? m - 1 - kk : kk);
+    H[i] = sH[cbH + kk];
+    if (ZFG) {
+      F[i] = 0.0;
+      Gq[i] = (c.active && kk == 0 && (r.flags & 2)) ? __dadd_rn(0.0, r.pin) : 0.0;
+    } else {
+      F[i] = c.active ? __dmul_rn(__dmul_rn(s.rhs.fc, H[i]), inv_sigma) : 0.0;
+      Gq[i] = c.active ? rs_rhs_node(s, r, kk, hl, H[i]) : 0.0;
+      hl = H[i];
+      sumF += F[i];
+    }
+  }
+  const int segT = m / CPT;
+  double totF = 0.0, totD;
+  double cum = 0.0;
+  if (!ZFG) {
+    const double inclF = rs_seg_incl_scan(sumF, segT, sh, &totF, ltid, bid);
+    cum = inclF - sumF;
+  }
+  double q[CPT], D[CPT];
+  double sumD = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    q[i] = ZFG ? q0 : __dadd_rn(q0, cum);
+    double mq = gnx_mq_right(a, H[i], q[i], F[i]);
+    const bool has_left = (i > 0) || (c.kk0 > 0);
+    const double fl = i > 0 ? F[i - 1] : Fl, hlft = i > 0 ? H[i - 1] : Hl;
+    if (has_left) mq = gnx_mq_left(mq, a, hlft, q[i], fl);
+    if (!ZFG && kv != 0.0) {
+      mq = __dsub_rn(mq, __ddiv_rn(__dmul_rn(kv, F[i]), H[i]));
+      if (has_left) mq = __dadd_rn(mq, __ddiv_rn(__dmul_rn(kv, fl), hlft));
+    }
+    D[i] = __dsub_rn(Gq[i], mq);
+    sumD += D[i];
+    if (!ZFG) cum = __dadd_rn(cum, F[i]);
+  }
+  const double inclD = rs_seg_incl_scan(sumD, segT, sh, &totD, ltid, bid);
+  double cd = Pu + (inclD - sumD);
+  if (ZFG) {
+    // the flux is constant along an edge: fill the edge's q range, no numbering lookups
+    for (int32_t le = 0; le < c.nE; ++le) {
+      const double qe = rec[le].q0;
+      double* const dst = sG + le * (m + 1) + c.shq;
+      for (int32_t t = ltid; t <= m; t += ET_T) dst[t] = qe;
+    }
+  }
+  if (c.active) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      cd += D[i];
+      if (!ZFG) sG[qb + sloc[c.flip ? m - (c.kk0 + i) : c.kk0 + i]] = q[i];
+      sF[ps[i]] = __dmul_rn(cd, inv_sigma);
+    }
+    if (!ZFG && c.kk0 + CPT == m) sG[qb + sloc[c.flip ? 0 : m]] = __dadd_rn(q0, totF);
+  }
+  rs_tile_store(c, sF, sG, s.x, ltid, bid);
+}
+
+// CSR values of assembly tile `atile` (RS_ATILE cells = whole edges): mixed_values_tile_kernel<2,true,STIFF> for a
+// 256-thread sub-block
+template <bool STIFF>
+__device__ __forceinline__ void rs_assemble_tile(const StepArgs& s, int32_t atile, int ltid, int bid, double* stage) {
+  constexpr int CPT = RS_ACPT;
+  constexpr int TILE = RS_ATILE;
+  const gnx_network_t& net = s.net;
+  double* const stage_p = stage + RS_AQ;
+  const int32_t m = s.d.m, n = net.n;
+  const int32_t G = TILE >> n;
+  const int32_t e0 = atile * G;
+  const int32_t nE = min(G, net.E - e0);
+  const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + net.ebif_prefix[e0];
+  const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + net.ebif_prefix[e0 + nE];
+  const int64_t pbase = s.d.p_nnz_off + 3 * (int64_t)e0 * m;
+  const int32_t psh = (int32_t)(pbase & 1);
+  const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
+  const int32_t k0 = (ltid >> 5) * (32 * CPT) + (ltid & 31);
+  const double sg = s.sigma;
+  AsmEdge E;
+  int32_t cur = -1;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int32_t k = k0 + 32 * i;
+    const int32_t le = k >> n;
+    if (le >= nE) break;
+    const int32_t t = k & (m - 1);
+    if (le != cur) {
+      cur = le;
+      const int32_t e = e0 + le;
+      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+      E.flip = u > v;
+      E.blo1 = net.bix[E.flip ? v : u] >= 0;
+      E.bhi1 = net.bix[E.flip ? u : v] >= 0;
+      E.a = s.a_edge[e];
+      E.kk = (STIFF && s.k_edge) ? s.k_edge[e] : 0.0;
+      E.sgn = E.flip ? -sg : sg;
+      E.he = net.h + (int64_t)e * m;
+      E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
+    }
+    const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
+    if (t == m - 1) asm_qrow<STIFF>(stage, tab, E, m, m, sg);
+    const int32_t slot = psh + 3 * (le * m + gnx_gray(t));
+    const bool up = (f >> 17) & 1;
+    stage_p[slot] = up ? -E.sgn : E.sgn;
+    stage_p[slot + 1] = up ? E.sgn : -E.sgn;
+    stage_p[slot + 2] = 0.0;
+  }
+  gnx_fence_async_smem();
+  rs_bar(bid);
+  rs_put(stage, s.vals, base, (int32_t)(end - base), ltid);
+  rs_put(stage_p, s.vals, pbase, 3 * nE * m, ltid);
+  if (ltid == 0) { gnx_bulk_commit(); gnx_bulk_wait_read(); }
+  rs_bar(bid);                                      // the staging area is free again
+}
+
+// phase 2 of a CTA that does not run the Schur solve: assembly tiles and lambda rows, dealt round-robin over the
+// `nsub` assembling sub-blocks of the grid (this one is number g)
+__device__ __forceinline__ void rs_assemble(const StepArgs& s, int32_t g, int32_t nsub, int ltid, int bid, double* stage) {
+  const int32_t Ga = RS_ATILE >> s.net.n;
+  const int32_t nb_asm = gnx_blocks_dev(s.net.E, Ga);
+  const int32_t nb_lam = s.net.B > 0 ? gnx_blocks_dev(s.net.B, ASM_T) : 0;
+  for (int32_t t = g; t < nb_asm + nb_lam; t += nsub) {
+    if (t < nb_asm) {
+      if (s.k_edge) rs_assemble_tile<true>(s, t, ltid, bid, stage);
+      else rs_assemble_tile<false>(s, t, ltid, bid, stage);
+    } else {
+      const int64_t r = s.d.lam_off + (int64_t)(t - nb_asm) * ASM_T + ltid;
+      if (r < s.d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(s.net, s.d, r, s.a_edge, s.k_edge, 1.0, s.sigma, nullptr, nullptr, s.vals);
+    }
+  }
+}
+
+__device__ __forceinline__ void rs_spin_ge(const unsigned long long* p, unsigned long long want) {
+  unsigned long long v;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v >= want) break;
+    __nanosleep(spins < 64 ? 20 : 200);
+    if (++spins > (1u << 24)) __trap();            // seconds: a CTA is missing -- fail instead of hanging the GPU
+  }
+}
+
+__global__ void __launch_bounds__(RS_T, 1)
+step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ SchurArgs a) {
+  extern __shared__ __align__(16) double rs_sm[];
+  __shared__ double red[2][3 * 32];
+  __shared__ double sh_sub[RS_SUB][3 * 32];
+  __shared__ __align__(8) uint64_t hbar[RS_MAX_TILES];
+  const int tid = threadIdx.x, sub = tid / ET_T, ltid = tid % ET_T, bid = 1 + sub;
+  const gnx_network_t& net = s.net;
+  const int32_t m = s.d.m;
+  // dynamic shared memory: resident cell lengths | staging (4 sub-blocks) | edge records | SubMesh numbering table
+  double* const Hres = rs_sm;
+  double* const stage = rs_sm + (size_t)s.tiles_per_cta * RS_HSLOT;
+  RsEdge* const recs = reinterpret_cast<RsEdge*>(stage + RS_SUB * RS_STAGE);
+  int32_t* const sloc = reinterpret_cast<int32_t*>(recs + s.tiles_per_cta * RS_MAX_G);
+  double* const sF = stage + sub * RS_STAGE;
+  double* const sG = sF + RS_FSLOT;
+  const int32_t G = RS_TILE >> net.n;
+  const bool zfg = s.rhs.fc == 0.0 && s.rhs.gc == 0.0 && !s.k_edge;
+  int32_t nmine = 0;
+  for (int32_t t = blockIdx.x; t < s.nb_tiles; t += gridDim.x) ++nmine;
+  // ---- phase 1: every tile's cell lengths in flight at once ...
+  if (tid == 0) {
+    if (blockIdx.x == 0) s.sync[2] = rs_now();
+    for (int32_t k = 0; k < nmine; ++k) {
+      const int32_t tile = blockIdx.x + k * gridDim.x;
+      const int32_t e0 = tile * G, nE = min(G, net.E - e0);
+      const int64_t hbase = (int64_t)e0 * m;
+      gnx_mbar_init(&hbar[k], 1);
+      gnx_mbar_expect_tx(&hbar[k], gnx_bulk_body_bytes(hbase, nE * m));
+      gnx_bulk_stream_in(Hres + (size_t)k * RS_HSLOT, net.h, hbase, nE * m, &hbar[k]);
+    }
+  }
+  // ... and, beside them, what the tiles need to know about their edges (one thread per edge: the dependent
+  // loads edges -> bix -> boundary data run for all edges of the CTA at once) and the numbering table
+  for (int32_t idx = tid; idx < nmine * G; idx += RS_T) {
+    const int32_t k = idx / G, le = idx - k * G;
+    const int32_t e = (blockIdx.x + k * gridDim.x) * G + le;
+    if (e < net.E) {
+      RsEdge r;
+      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+      r.bu = net.bix[u]; r.bv = net.bix[v];
+      r.flags = (u > v ? 1 : 0) | ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
+      r.a = s.a_edge[e];
+      r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
+      r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
+      r.q0 = 0.0; r.Pu = 0.0; r.pad = 0;
+      recs[k * RS_MAX_G + le] = r;
+    }
+  }
+  for (int32_t i = tid; i <= m; i += RS_T) sloc[i] = net.loc[i];
+  for (int64_t r = s.d.lam_off + (int64_t)blockIdx.x * RS_T + tid; r < s.d.N; r += (int64_t)gridDim.x * RS_T) s.rhs.b[r] = 0.0;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) s.sync[8] = rs_now();
+  const bool dbg = blockIdx.x == 1 && tid == 0;    // diagnostic stamps of an ordinary CTA: sync[16..]
+  if (dbg) s.sync[16] = rs_now();
+  for (int32_t k = sub; k < nmine; k += RS_SUB) {
+    gnx_mbar_wait(&hbar[k], 0);
+    if (dbg) s.sync[17 + (k >= RS_SUB ? 2 : 0)] = rs_now();
+    if (k >= RS_SUB) {                             // the staging area still feeds the bulk stores of my previous tile
+      if (ltid == 0) gnx_bulk_wait_read();
+      rs_bar(bid);
+    }
+    if (zfg) rs_eliminate_tile<true>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+                                     recs + k * RS_MAX_G, sloc);
+    else rs_eliminate_tile<false>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+                                  recs + k * RS_MAX_G, sloc);
+    if (dbg) s.sync[18 + (k >= RS_SUB ? 2 : 0)] = rs_now();
+  }
+  if (ltid == 0) gnx_bulk_wait_read();
+  if (dbg) s.sync[21] = rs_now();
+  if (s.out.n > 1) __threadfence_system();          // edge scalars stored into the other ranks' buffers
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(s.sync, 1ull);
+  }
+  // ---- phase 2: the graph-level solve on CTA 0, the CSR values on all the others
+  double* const astage = stage + sub * RS_STAGE;
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      s.sync[3] = rs_now();
+      rs_spin_ge(s.sync, gridDim.x);
+      s.sync[0] = 0ull;                            // nobody touches the counter again in this launch
+      s.sync[4] = rs_now();
+    }
+    __syncthreads();
+    schur_body<SCH_SINGLE>(a, stage, red);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(s.sync + 1), "l"(s.epoch) : "memory");
+      s.sync[5] = rs_now();
+    }
+    if (s.vals && gridDim.x == 1) rs_assemble(s, sub, RS_SUB, ltid, bid, astage);     // (a one-CTA grid has nobody else)
+  } else {
+    if (dbg) s.sync[22] = rs_now();
+    if (s.vals) rs_assemble(s, (blockIdx.x - 1) * RS_SUB + sub, (gridDim.x - 1) * RS_SUB, ltid, bid, astage);
+    if (dbg) s.sync[23] = rs_now();
+    if (tid == 0) rs_spin_ge(s.sync + 1, s.epoch);
+    if (dbg) s.sync[24] = rs_now();
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) s.sync[6] = rs_now();
+  // ---- phase 3: back-substitution out of the resident lengths; first the edges' end pressures (one thread per edge)
+  for (int32_t idx = tid; idx < nmine * G; idx += RS_T) {
+    const int32_t k = idx / G, le = idx - k * G;
+    const int32_t e = (blockIdx.x + k * gridDim.x) * G + le;
+    if (e < net.E) {
+      RsEdge& r = recs[k * RS_MAX_G + le];
+      const double Pu = r.bu >= 0 ? __ldcg(s.P + r.bu) : 0.0;
+      const double Pv = r.bv >= 0 ? __ldcg(s.P + r.bv) : 0.0;
+      r.Pu = Pu;
+      r.q0 = __dmul_rn(__ldcg(s.cond + e), __dadd_rn(__dsub_rn(Pu, Pv), __ldcg(s.rsrc + e)));
+    }
+  }
+  __syncthreads();
+  if (dbg) s.sync[25] = rs_now();
+  for (int32_t k = sub; k < nmine; k += RS_SUB) {
+    if (k >= RS_SUB) {
+      if (ltid == 0) gnx_bulk_wait_read();
+      rs_bar(bid);
+    }
+    if (zfg) rs_backsub_tile<true>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+                                   recs + k * RS_MAX_G, sloc);
+    else rs_backsub_tile<false>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+                                recs + k * RS_MAX_G, sloc);
+    if (dbg) s.sync[26 + (k >= RS_SUB ? 1 : 0)] = rs_now();
+  }
+  if (ltid == 0) gnx_bulk_wait_read();
+  if (dbg) s.sync[28] = rs_now();
+  if (blockIdx.x == 0 && tid == 0) s.sync[7] = rs_now();
+}
+
+static size_t rs_smem_bytes(int tiles_per_cta, int m) {
+  return ((size_t)tiles_per_cta * RS_HSLOT + (size_t)RS_SUB * RS_STAGE) * sizeof(double) +
+         (size_t)tiles_per_cta * RS_MAX_G * sizeof(RsEdge) + (((size_t)m + 1 + 3) & ~(size_t)3) * sizeof(int32_t);
+}
+
+static int rs_enabled() {             // tuning / A-B knob: GNX_STEP_RESIDENT=0 keeps the three-kernel chain
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GNX_STEP_RESIDENT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+// 1 if the persistent kernel can run this step (else the caller uses the kernel chain)
+int gnx_step_resident_applies(const gnx_network_t* net, const gnx_schur_plan_t* plan, const double* b, const double* x,
+                              const unsigned long long* sync) {
+  if (!rs_enabled() || !sync || !plan || net->B <= 0 || net->n < RS_MIN_N || net->n > 10) return 0;
+  if (plan->B > 2 * SCH_T || plan->na > 0 || plan->top_S > 0 || plan->nb > 0) return 0;     // one-CTA Schur solve only
+  if (!edge_bulk(net->h, b, x)) return 0;
+  if (sch_init() != GNX_OK) return 0;
+  const int G = RS_TILE >> net->n;
+  const int nb_tiles = gnx_blocks(net->E, G);
+  const int grid = nb_tiles < g_sch_sms ? nb_tiles : g_sch_sms;
+  return gnx_blocks(nb_tiles, grid) <= RS_MAX_TILES;
+}
+
+int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const, double g_const,
+                             const double* pbc_out, const double* pbc_node, double* b, double* x,
+                             const gnx_network_t* schur_net, const gnx_schur_plan_t* plan, double* cond, double* rsrc,
+                             double* ftot, double* P, double* work, double rtol, int32_t max_iter, int32_t warm,
+                             const gnx_exchange_t* ex, unsigned long long* sync, unsigned long long epoch,
+                             double* vals, double* resid_host, int32_t* info_host, cudaStream_t st) {
+  GNX_CHECK_ARG(!vals || (net->rowtab && ((uintptr_t)vals & 15) == 0));
+  GNX_CHECK_ARG(net && co && co->a_edge && b && x && plan && P && work && sync && epoch > 0 && co->sigma != 0.0);
+  StepArgs s;
+  s.net = *net; s.d = gnx_mixed_dims(*net);
+  s.a_edge = co->a_edge; s.k_edge = co->k_edge; s.inv_sigma = 1.0 / co->sigma;
+  s.rhs = ConstRhs{f_const, g_const, pbc_out, pbc_node, b};
+  int32_t chunk = 0, stride = 0;
+  const double *gc = cond, *gr = rsrc, *gf = ftot;
+  if (ex) {
+    if (int rc = edge_out_exchange(s.out, ex, net->E)) return rc;
+    double* g = ex->peers_host[ex->rank];
+    chunk = ex->chunk; stride = 3 * ex->chunk;
+    s.cond = g + (int64_t)ex->rank * stride; s.rsrc = s.cond + chunk;
+    gc = g; gr = g + chunk; gf = g + 2 * (int64_t)chunk;
+  } else {
+    GNX_CHECK_ARG(cond && rsrc && ftot);
+    edge_out_local(s.out, cond, rsrc, ftot);
+    s.cond = cond; s.rsrc = rsrc;
+  }
+  s.P = P; s.x = x; s.vals = vals; s.sigma = co->sigma;
+  const int G = RS_TILE >> net->n;
+  s.nb_tiles = gnx_blocks(net->E, G);
+  const int grid = s.nb_tiles < g_sch_sms ? s.nb_tiles : g_sch_sms;
+  s.tiles_per_cta = gnx_blocks(s.nb_tiles, grid);
+  GNX_CHECK_ARG(s.tiles_per_cta <= RS_MAX_TILES);
+  s.sync = sync; s.epoch = epoch;
+  SchurArgs a;
+  const GnxMixedDims d = s.d;
+  if (int rc = schur_args_fill(a, schur_net, plan, co->sigma, gc, gr, gf, b + d.lam_off, nullptr, P, x + d.lam_off, work,
+                               rtol, max_iter, warm, chunk, stride, ex)) return rc;
+  const size_t smem = rs_smem_bytes(s.tiles_per_cta, 1 << net->n);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    GNX_CUDA(cudaFuncSetAttribute(step_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  // one CTA per SM and at most as many CTAs as SMs: the grid is co-resident either way; the cooperative launch
+  // makes the driver check it (GNX_STEP_COOP=0: ordinary launch, A-B knob)
+  static int coop = -1;
+  if (coop < 0) { const char* e = getenv("GNX_STEP_COOP"); coop = e ? atoi(e) : 1; }
+  if (coop) {
+    void* args[] = {(void*)&s, (void*)&a};
+    GNX_CUDA(cudaLaunchCooperativeKernel((void*)step_resident_kernel, dim3(grid), dim3(RS_T), args, smem, st));
+  } else {
+    step_resident_kernel<<<grid, RS_T, smem, st>>>(s, a);
+    GNX_LAUNCH_CHECK();
+  }
+  return schur_report(a, 1, resid_host, info_host, st);
 }

@@ -5,16 +5,35 @@
 // stream-context switches and event calls cost more than the 55 us the GPU needs for the C2 step.
 #include "gnx_common.cuh"
 
+// gnx_solve.cu: the persistent (resident-tile) step kernel
+int gnx_step_resident_applies(const gnx_network_t* net, const gnx_schur_plan_t* plan, const double* b, const double* x,
+                              const unsigned long long* sync);
+int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const, double g_const,
+                             const double* pbc_out, const double* pbc_node, double* b, double* x,
+                             const gnx_network_t* schur_net, const gnx_schur_plan_t* plan, double* cond, double* rsrc,
+                             double* ftot, double* P, double* work, double rtol, int32_t max_iter, int32_t warm,
+                             const gnx_exchange_t* ex, unsigned long long* sync, unsigned long long epoch,
+                             double* vals, double* resid_host, int32_t* info_host, cudaStream_t st);
+
 extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const int32_t* rowptr,
                               double* vals, double f_const, double g_const, const double* pbc_out,
                               const double* pbc_node, double* b, double* x, const gnx_network_t* schur_net,
                               const gnx_schur_plan_t* plan, double* cond, double* rsrc, double* ftot, double* P,
                               double* work, double rtol, int32_t max_iter, int32_t warm, const gnx_exchange_t* ex,
-                              double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join, void* side_stream, void* stream) {
+                              double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join, void* side_stream,
+                              int64_t* sync, int64_t epoch, void* stream) {
   GNX_CHECK_ARG(net && co && b && x && (ex || (cond && rsrc && ftot)));
   GNX_CHECK_ARG(!ex || (ex->epoch > 0 && ex->peers_host && ex->rank >= 0 && ex->rank < ex->world));
   GNX_CHECK_ARG(net->B == 0 || (schur_net && plan && P && work));
   cudaStream_t main_st = (cudaStream_t)stream;
+  if (sync && epoch > 0 && net->B > 0 && (!vals || (net->rowtab && ((uintptr_t)vals & 15) == 0)) &&
+      gnx_step_resident_applies(net, plan, b, x, reinterpret_cast<const unsigned long long*>(sync))) {
+    // small enough for the cell lengths to stay in shared memory: the whole step -- assembly included -- is ONE
+    // persistent kernel on the caller's stream (no second stream, no events)
+    return gnx_step_resident_launch(net, co, f_const, g_const, pbc_out, pbc_node, b, x, schur_net, plan, cond, rsrc,
+                                    ftot, P, work, rtol, max_iter, warm, ex, reinterpret_cast<unsigned long long*>(sync),
+                                    (unsigned long long)epoch, vals, resid_host, info_host, main_st);
+  }
   cudaStream_t solve_st = side_stream ? (cudaStream_t)side_stream : main_st;
   const bool fork = side_stream != nullptr && vals != nullptr;
   if (fork) {

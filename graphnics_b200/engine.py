@@ -503,6 +503,10 @@ class MixedSystem:
         plan = work = None
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
+        if getattr(self, "_step_sync", None) is None:      # arrival counter + epoch word of the persistent step kernel
+            self._step_sync = torch.zeros(32, dtype=torch.int64, device=self.dev)
+            self._step_epoch = 0
+        self._step_epoch += 1
         resid = inf = None
         if sync and dn.B > 0:
             resid = C.c_double(0.0)
@@ -517,7 +521,8 @@ class MixedSystem:
             ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]), ptr(d["P"]) if dn.B > 0 else None, ptr(work), float(rtol),
             int(max_iter), 1 if warm_start else 0, C.byref(ex) if ex is not None else None,
             C.byref(resid) if resid is not None else None, inf,
-            self._ev_ptr[0], self._ev_ptr[1], self._hi_ptr if overlap else None, current_stream()))
+            self._ev_ptr[0], self._ev_ptr[1], self._hi_ptr if overlap else None,
+            ptr(self._step_sync), self._step_epoch, current_stream()))
         if resid is not None:
             info.cg_iterations += int(inf[0])
             info.cg_converged = bool(inf[1])

@@ -340,13 +340,18 @@ int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* c
  *   are two CUDA events of the caller used to fork and join the streams (everything is ordered on `stream`
  *   when the call returns);  resid_host / info_host as in gnx_schur_solve (non-NULL synchronises);
  *   ex != NULL (edge-partitioned network, ex->epoch > 0): cond / rsrc / ftot are ignored, the scalars travel
- *   through the gather buffers and the Schur kernel reads ex->peers_host[ex->rank].  n <= 10. */
+ *   through the gather buffers and the Schur kernel reads ex->peers_host[ex->rank].  n <= 10.
+ *   sync != NULL (2 device words, zeroed ONCE by the caller) and epoch >= 1 (strictly increasing from call to
+ *   call on the same `sync`): networks whose cell lengths fit the shared memory of the GPU (<= 8 tiles of 1024
+ *   cells per SM, Schur system of <= 2048 unknowns, 2 <= n <= 10) run right-hand side + elimination -> Schur
+ *   solve -> back-substitution as ONE persistent cooperative kernel (step_resident_kernel, gnx_solve.cu) that keeps
+ *   the lengths resident between the phases; b and x are bit-identical to the kernel chain's. */
 int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const int32_t* rowptr, double* vals,
                    double f_const, double g_const, const double* pbc_out, const double* pbc_node, double* b,
                    double* x, const gnx_network_t* schur_net, const gnx_schur_plan_t* plan, double* cond,
                    double* rsrc, double* ftot, double* P, double* work, double rtol, int32_t max_iter,
                    int32_t warm, const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join,
-                   void* side_stream, void* stream);
+                   void* side_stream, int64_t* sync, int64_t epoch, void* stream);
 
 /* ---------------- primal model: HydraulicNetwork (flow_models.py:53-126) ---------------- */
 

@@ -1,0 +1,61 @@
+"""Persistent (resident-tile) step kernel on the C2 tree: CUDA-event time per step with the L2 flushed, the
+phase stamps of CTA 0 (%globaltimer: start | own tiles eliminated | all CTAs arrived | Schur done | parked CTAs
+released | end), and the same step through the three-kernel chain (GNX_STEP_RESIDENT=0 in a second process).
+  python tools/time_resident.py [levels] [n] [--no-vals]"""
+import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from graphnics_b200.device import DeviceNetwork
+from graphnics_b200.engine import MixedSystem
+from graphnics_b200.synthetic import murray_tree
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+levels = int(args[0]) if args else 11
+n = int(args[1]) if len(args) > 1 else 9
+pos, edges, _, _ = murray_tree(levels, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
+dn = DeviceNetwork(pos, edges, n)
+ms = MixedSystem(dn)
+ms.build_pattern()
+co = ms.coeffs(np.ones(dn.E))
+vals = None if "--no-vals" in sys.argv else torch.empty(ms.nnz, dtype=torch.float64, device="cuda")
+b = torch.empty(ms.N, dtype=torch.float64, device="cuda")
+x = torch.empty(ms.N, dtype=torch.float64, device="cuda")
+xq, _ = ms.dof_coordinates(False)
+kw = dict(pbc_out=ms.end_values(xq[:, 1].contiguous()), pbc_node=dn.pos[:, 1].contiguous())
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def step():
+    if vals is None:
+        ms._step_native(co, None, b, x, kw, True, sync=False)
+    else:
+        ms.assemble_rhs_solve(co, vals, b, x, kw, sync=False)
+
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+ts, stamps, stamps1 = [], [], []
+for _ in range(30):
+    flush.fill_(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); e1.record(); e1.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+    s = ms._step_sync.cpu().numpy()
+    stamps.append((s[[8, 3, 4, 5, 6, 7]] - s[2]) / 1e3)
+    stamps1.append((s[16:29] - s[2]) / 1e3)
+out = {"levels": levels, "n": n, "N": ms.N, "resident": os.environ.get("GNX_STEP_RESIDENT", "1"), "vals": vals is not None,
+       "us_per_step": {"min": float(np.min(ts)), "median": float(np.median(ts)), "max": float(np.max(ts))}}
+if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
+    st = np.median(np.asarray(stamps), axis=0)
+    out["cta0_stamps_us"] = dict(zip(["prefetched", "own_tiles_done", "all_arrived", "schur_done", "released", "end"], st.round(2).tolist()))
+    st1 = np.median(np.asarray(stamps1), axis=0)
+    out["cta1_stamps_us"] = dict(zip(["prefetched", "H0_arrived", "elim0_done", "H4_arrived", "elim4_done", "b_stores_read", "asm_start",
+                                      "asm_done", "released", "p3_prefetched", "bs0_done", "bs4_done", "end"], st1.round(2).tolist()))
+if vals is not None:
+    rr, bb = ms.residual(vals, x, b).cpu().tolist()
+    out["rel_residual"] = float(np.sqrt(rr / bb))
+print(json.dumps(out))
