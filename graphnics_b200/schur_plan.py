@@ -149,7 +149,7 @@ class SchurPlan:
         top_of[top] = np.arange(len(top), dtype=np.int32)
         return top, top_of, level_of
 
-    def block_arrays(self, cap=1024, top_max=2048):
+    def block_arrays(self, cap=1024, top_max=2048, force_upper=None, count=None):
         """Blocked rake of a forest (nc == 0): the raked nodes are split into maximal subtrees of <= cap
         nodes (BLOCKS: complete subtrees, so all of a block's children are inside it; one CTA sweeps a block
         out of shared memory with block barriers only) and the UPPER part (nodes whose subtree is larger),
@@ -170,12 +170,17 @@ class SchurPlan:
             has = par >= 0
             np.add.at(size, par[has], size[nodes[has]])
         upper = size > cap
+        if force_upper is not None:                          # (rank view: the replicated nodes always sit in the top part)
+            upper = upper | force_upper
+        in_levels = np.zeros(B, dtype=bool)
+        in_levels[np.concatenate(self.levels)] = True
+        upper &= in_levels
         top = np.nonzero(upper)[0]
         if len(top) > top_max:
             return None
         # block roots: subtree fits, the parent's does not (or there is no parent)
         par_big = np.where(parent >= 0, upper[np.maximum(parent, 0)], True)
-        root = (~upper) & par_big
+        root = (~upper) & par_big & in_levels
         blk_of = -np.ones(B, dtype=np.int64)
         roots = np.nonzero(root)[0]
         blk_of[roots] = np.arange(len(roots))
@@ -183,7 +188,7 @@ class SchurPlan:
             inner = nodes[(~upper[nodes]) & (~root[nodes])]
             blk_of[inner] = blk_of[parent[inner]]
         inb = np.nonzero(blk_of >= 0)[0]
-        assert len(inb) + len(top) == B
+        assert len(inb) + len(top) == (B if count is None else count)
         order = np.lexsort((level_of[inb], blk_of[inb]))     # by block, then by level
         blk_nodes = inb[order]
         counts = np.bincount(blk_of[inb], minlength=len(roots))
@@ -286,31 +291,87 @@ class SchurPlan:
         edge[k, rows] = self.cedge
         return w, R, col.ravel().astype(np.int32), edge.ravel().astype(np.int32)
 
-    # numpy model of the device algorithm (used by the CPU tests to pin the algebra)
-    def solve_host(self, cond, diag, rhs, core_solver=None):
-        d = np.array(diag, dtype=np.float64)
-        r = np.array(rhs, dtype=np.float64)
-        x = np.zeros(self.B)
-        w = np.where(self.pedge >= 0, -np.asarray(cond)[np.maximum(self.pedge, 0)], 0.0)
 
-        def gather(nodes):
-            for i in nodes:
-                for c in self.ch_idx[self.ch_ptr[i]:self.ch_ptr[i + 1]]:
-                    d[i] -= w[c] * w[c] / d[c]
-                    r[i] -= w[c] * r[c] / d[c]
-        for lv in self.levels:
-            gather(lv)
-        if self.nc:
-            gather(self.core_nodes)
-            import scipy.sparse as sp
-            import scipy.sparse.linalg as spla
-            rows = np.repeat(np.arange(self.nc), np.diff(self.crp))
-            S = sp.csr_matrix((-np.asarray(cond)[self.cedge], (rows, self.ccol)), shape=(self.nc, self.nc))
-            S = S + sp.diags(d[self.core_nodes])
-            x[self.core_nodes] = spla.spsolve(S.tocsc(), r[self.core_nodes]) if core_solver is None \
-                else core_solver(S, r[self.core_nodes])
-        for lv in reversed(self.levels):
-            for i in lv:
-                p = self.parent[i]
-                x[i] = (r[i] - (w[i] * x[p] if p >= 0 else 0.0)) / d[i]
-        return x
+class RankPlan(SchurPlan):
+    """One rank's view of the plan of an EDGE-PARTITIONED network.
+
+    `owner[i]` (per bifurcation) says who eliminates a raked node: rank r if every edge at node i and at all of
+    its rake descendants belongs to rank r (the whole subtree is rank-local: r builds the rows and sweeps it
+    without talking to anybody), -1 otherwise -- the REPLICATED nodes (core nodes and raked nodes that see more
+    than one rank), which every rank processes redundantly after ONE exchange: the owner of an edge at a
+    replicated node sends its three scalars, the owner of a local subtree whose parent is replicated sends the
+    subtree root's final (diagonal, right-hand side) pair.
+
+    The view keeps the global index arrays (parent, pedge, children, core) and re-levels the nodes this rank
+    works on: its local nodes keep their rake level, the replicated raked nodes follow on levels >= l_sync
+    (their height among themselves) -- so "everything below l_sync" is exactly what can be done before the
+    exchange, and the kernel's level loops need one synchronisation point.
+      ncls[B]  bit 0: replicated (row built after the exchange), bit 1: foreign (another rank's local node:
+               skipped), bit 2: local root whose (d, r) is exported
+    """
+
+    def __init__(self, hp, owner, rank, max_levels=MAX_LEVELS):
+        self.__dict__.update(hp.__dict__)
+        B = hp.B
+        owner = np.asarray(owner, dtype=np.int64)
+        self.owner, self.rank = owner, int(rank)
+        raked = np.zeros(B, dtype=bool)
+        hlevel = np.full(B, -1, dtype=np.int64)
+        for l, nodes in enumerate(hp.levels):
+            raked[nodes] = True
+            hlevel[nodes] = l
+        local = raked & (owner == rank)
+        repl = raked & (owner < 0)
+        L_loc = int(hlevel[local].max()) + 1 if local.any() else 0
+        # height of the replicated raked nodes among themselves
+        tl = np.zeros(B, dtype=np.int64)
+        parent = hp.parent.astype(np.int64)
+        for nodes in hp.levels:                               # children before parents
+            t = nodes[repl[nodes]]
+            par = parent[t]
+            ok = (par >= 0) & repl[np.maximum(par, 0)]
+            np.maximum.at(tl, par[ok], tl[t[ok]] + 1)
+        n_t = int(tl[repl].max()) + 1 if repl.any() else 0
+        if L_loc + n_t > max_levels:
+            raise ValueError("rank view needs %d rake levels (limit %d)" % (L_loc + n_t, max_levels))
+        levels = [hp.levels[l][local[hp.levels[l]]] for l in range(L_loc)]
+        rn = np.nonzero(repl)[0]
+        levels += [rn[tl[rn] == k].astype(np.int32) for k in range(n_t)]
+        self.levels = [np.ascontiguousarray(l, dtype=np.int32) for l in levels]
+        self.l_sync = L_loc
+        self.n_mine = int(local.sum() + repl.sum())          # raked nodes this rank sweeps
+        par_repl = np.where(parent >= 0, (owner[np.maximum(parent, 0)] < 0), False)
+        ncls = np.zeros(B, dtype=np.int32)
+        ncls[owner < 0] |= 1
+        ncls[(owner >= 0) & (owner != rank)] |= 2
+        ncls[local & par_repl] |= 4
+        self.ncls = ncls
+        self.repl_raked = repl
+
+    def rank_block_arrays(self, cap=1024, top_max=2048):
+        return self.block_arrays(cap=cap, top_max=top_max, force_upper=self.repl_raked, count=self.n_mine)
+
+
+def node_owners(hp, edges, bix, epart):
+    """owner[B] of RankPlan for the edge partition `epart` (rank per edge) of the network `edges`"""
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    epart = np.asarray(epart, dtype=np.int64)
+    B = hp.B
+    bu, bv = np.asarray(bix)[edges[:, 0]], np.asarray(bix)[edges[:, 1]]
+    lo = np.full(B, np.iinfo(np.int64).max)
+    hi = np.full(B, -1, dtype=np.int64)
+    for be in (bu, bv):
+        k = be >= 0
+        np.minimum.at(lo, be[k], epart[k])
+        np.maximum.at(hi, be[k], epart[k])
+    owner = np.where(lo == hi, lo, -1)
+    owner[hp.core_nodes] = -1
+    parent = hp.parent.astype(np.int64)
+    for nodes in hp.levels:                                   # a node is only as local as its children
+        par = parent[nodes]
+        has = par >= 0
+        bad = has & (owner[nodes] != owner[np.maximum(par, 0)])
+        owner[par[bad]] = -1
+    # (a parent demoted above may itself have been visited as a child already only on a LOWER level: levels
+    #  are processed bottom-up, so every demotion reaches the ancestors in the same pass)
+    return owner

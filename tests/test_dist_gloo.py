@@ -22,6 +22,7 @@ def _rank_main(rank, world, port, name, n, out):
     from _util import golden_arrays, random_graph, host_tables
     from graphnics_b200.device import partition_range
     from graphnics_b200.schur_plan import SchurPlan
+    from schur_host import solve_host
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -58,7 +59,7 @@ def _rank_main(rank, world, port, name, n, out):
         S, rhs, bix = oracle.schur_system(om, cond_g, rsrc_g, ftot_g, b[lay["lam_off"]:])
         t = host_tables(len(pos), edges)
         plan = SchurPlan(edges, t["bix"], t["B"])
-        P = plan.solve_host(cond_g, S.diagonal(), rhs)
+        P = solve_host(plan, cond_g, S.diagonal(), rhs)
         Pt = torch.from_numpy(P.copy())
         lo, hi = Pt.clone(), Pt.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)

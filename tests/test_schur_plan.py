@@ -7,6 +7,7 @@ import scipy.sparse.linalg as spla
 
 from _util import host_tables, random_graph, golden_arrays
 from graphnics_b200.schur_plan import SchurPlan
+from schur_host import solve_host
 from graphnics_b200.synthetic import murray_tree
 
 
@@ -62,7 +63,7 @@ def test_plan_solves_schur_system(name):
     for i in lv:
         p = plan.parent[i]
         assert p < 0 or level_of[p] > level_of[i]
-    x = plan.solve_host(cond, diag, rhs)
+    x = solve_host(plan, cond, diag, rhs)
     xr = spla.spsolve(S.tocsc(), rhs)
     assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
     if name.startswith("tree") or name.startswith("arterial"):
@@ -177,7 +178,7 @@ def test_two_level_aggregates(na, ns):
     jac = _jacobi_pcg_iters(S, rhs[plan.core_nodes])
     assert its < jac, (its, jac)
     # the plan's own model (direct core solve) still works on the renumbered core
-    assert np.allclose(plan.solve_host(cond, diag, rhs), ref, rtol=1e-9, atol=1e-11)
+    assert np.allclose(solve_host(plan, cond, diag, rhs), ref, rtol=1e-9, atol=1e-11)
 
 
 def _blocked_rake_model(plan, ba, cond, diag, rhs):
