@@ -56,12 +56,14 @@ class gnx_schur_plan_t(C.Structure):
         ("nb", C.c_int32), ("ns", C.c_int32),
         ("blk_ptr", C.c_void_p), ("blk_nodes", C.c_void_p), ("blk_pos", C.c_void_p), ("blk_lv", C.c_void_p),
         ("sub_ptr", C.c_void_p), ("row_sub", C.c_void_p),
+        ("l_sync", C.c_int32), ("nxl", C.c_int32), ("ncls", C.c_void_p), ("xlist", C.c_void_p),
     ]
 
 
 class gnx_exchange_t(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("chunk", C.c_int32), ("reserved", C.c_int32),
-                ("peers_host", C.POINTER(C.c_void_p)), ("epoch", C.c_int64), ("reserved2", C.c_void_p)]
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("chunk", C.c_int32), ("mode", C.c_int32),
+                ("peers_host", C.POINTER(C.c_void_p)), ("epoch", C.c_int64), ("egl", C.c_void_p),
+                ("E_glob", C.c_int32), ("B_glob", C.c_int32), ("phase", C.c_int32), ("reserved", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -100,7 +102,7 @@ PROTOTYPES = {
     "gnx_project_end_values": (_I, [_NET, _P, _P, _I, _I, _P, _P]),
     "gnx_dof_coordinates_mixed": (_I, [_NET, _P, _P, _P, _P, _P]),
     "gnx_edge_eliminate_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P]),
-    "gnx_edge_eliminate_mixed_p2p": (_I, [_NET, _CO, _P, _EX, _P]),
+    "gnx_edge_eliminate_mixed_p2p": (_I, [_NET, _CO, _P, _EX, _P, _P, _P]),
     "gnx_rhs_eliminate_mixed": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P, _EX, _P]),
     "gnx_step_mixed": (_I, [_NET, _CO, _P, _P, _D, _D, _P, _P, _P, _P, _NET, _PLAN, _P, _P, _P, _P, _P, _D, _I, _I,
                             _EX, c_f64p, c_i32p, _P, _P, _P, _P, _L, _P]),

@@ -54,7 +54,31 @@ struct EdgeOut {
   double* base[GNX_MAX_PEERS];        // destination buffers (n = 1: base[0] = cond)
   int32_t n;
   int64_t off_rsrc, off_ftot;         // offsets of the rsrc / ftot arrays relative to base (in doubles)
+  // Subtree-partitioned network (gnx_exchange mode 1): base[0] is this rank's buffer indexed by GLOBAL edge id,
+  // base[1..n) the other ranks'; egl[e] = global id of local edge e, bit 31 set if an end of the edge is a
+  // REPLICATED bifurcation -- only those scalars cross NVLink.  lcond / lrsrc [E_loc]: what the local
+  // back-substitution reads.
+  const int32_t* egl;
+  double *lcond, *lrsrc;
   __device__ __forceinline__ void put(int32_t e, double c, double r, double f) const {
+    if (egl) {
+      const int32_t g = egl[e];
+      const int32_t ge = g & 0x7fffffff;
+      lcond[e] = c; lrsrc[e] = r;
+      double* p = base[0];
+      p[ge] = c; p[off_rsrc + ge] = r; p[off_ftot + ge] = f;
+      if (g < 0) {
+#pragma unroll
+        for (int k = 1; k < GNX_MAX_PEERS; ++k) {
+          if (k < n) {
+            double* q = base[k];
+            q[ge] = c; q[off_rsrc + ge] = r; q[off_ftot + ge] = f;
+          }
+        }
+        __threadfence_system();       // (a handful of edges per rank: the fence is off every hot path)
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < GNX_MAX_PEERS; ++k) {
       if (k < n) {
@@ -423,6 +447,7 @@ static void edge_out_local(EdgeOut& out, double* cond, double* rsrc, double* fto
   for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
   out.base[0] = cond; out.n = 1;
   out.off_rsrc = rsrc - cond; out.off_ftot = ftot - cond;
+  out.egl = nullptr; out.lcond = out.lrsrc = nullptr;
 }
 
 extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
@@ -440,15 +465,28 @@ extern "C" int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixe
 
 // Edge-partitioned network (gnx_exchange): every edge scalar is stored straight into the gather buffer of
 // every rank; block of rank q at q*3*chunk, the world flag words behind the world blocks.
-static int edge_out_exchange(EdgeOut& out, const gnx_exchange_t* ex, int32_t E) {
+static int edge_out_exchange(EdgeOut& out, const gnx_exchange_t* ex, int32_t E, double* lcond = nullptr, double* lrsrc = nullptr) {
   GNX_CHECK_ARG(ex->peers_host && ex->world >= 1 && ex->world <= GNX_MAX_PEERS && ex->rank >= 0 &&
-                ex->rank < ex->world && ex->chunk >= E && ex->epoch >= 0);
+                ex->rank < ex->world && ex->epoch >= 0);
   for (int k = 0; k < GNX_MAX_PEERS; ++k) out.base[k] = nullptr;
+  out.egl = nullptr; out.lcond = out.lrsrc = nullptr;
+  out.n = ex->world;
+  if (ex->mode == 1) {               // global-indexed buffers, own first
+    GNX_CHECK_ARG(ex->egl && lcond && lrsrc && ex->E_glob >= E && ex->B_glob >= 0);
+    int k = 1;
+    for (int q = 0; q < ex->world; ++q) {
+      GNX_CHECK_ARG(ex->peers_host[q] != nullptr);
+      if (q == ex->rank) out.base[0] = ex->peers_host[q]; else out.base[k++] = ex->peers_host[q];
+    }
+    out.off_rsrc = ex->E_glob; out.off_ftot = 2 * (int64_t)ex->E_glob;
+    out.egl = ex->egl; out.lcond = lcond; out.lrsrc = lrsrc;
+    return GNX_OK;
+  }
+  GNX_CHECK_ARG(ex->chunk >= E);
   for (int k = 0; k < ex->world; ++k) {
     GNX_CHECK_ARG(ex->peers_host[k] != nullptr);
     out.base[k] = ex->peers_host[k] + (int64_t)ex->rank * 3 * ex->chunk;
   }
-  out.n = ex->world;
   out.off_rsrc = ex->chunk; out.off_ftot = 2 * (int64_t)ex->chunk;
   return GNX_OK;
 }
@@ -460,7 +498,7 @@ extern "C" int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed
   GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && net->n <= 10);
   EdgeOut out;
   if (ex) {
-    if (int rc = edge_out_exchange(out, ex, net->E)) return rc;
+    if (int rc = edge_out_exchange(out, ex, net->E, cond, rsrc)) return rc;
   } else {
     GNX_CHECK_ARG(cond && rsrc && ftot);
     edge_out_local(out, cond, rsrc, ftot);
@@ -470,10 +508,11 @@ extern "C" int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed
 }
 
 extern "C" int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
-                                            const double* b, const gnx_exchange_t* ex, void* stream) {
+                                            const double* b, const gnx_exchange_t* ex, double* cond, double* rsrc,
+                                            void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && b && net->h && co->sigma != 0.0 && ex);
   EdgeOut out;
-  if (int rc = edge_out_exchange(out, ex, net->E)) return rc;
+  if (int rc = edge_out_exchange(out, ex, net->E, cond, rsrc)) return rc;
   return launch_eliminate(net, co, b, out, (cudaStream_t)stream);
 }
 
@@ -555,6 +594,13 @@ struct SchurArgs {
   long long* sig_flags[GNX_MAX_PEERS];        // my flag word in every rank's gather buffer
   long long wait_epoch;
   int32_t wait_world;
+  // subtree-partitioned network (gnx_exchange mode 1, plan.ncls != NULL): the flag exchange happens INSIDE the
+  // solve, after the rank-local sweeps (plan.l_sync); xbuf[k] = the other ranks' buffers, where the final
+  // (d, r) of my exported subtree roots go (d at xd_off + node, r at xr_off + node, like a.d / a.r in mine)
+  double* xbuf[GNX_MAX_PEERS];
+  int32_t nx;
+  int64_t xd_off, xr_off;
+  int32_t phase;                              // 0: whole solve, flags in the kernel; 1: up to the exchange; 2: after it
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
     const int32_t r = e / chunk;
     return (int64_t)r * rank_stride + (e - r * chunk);
@@ -622,6 +668,54 @@ __device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const* pa
   block_allreduce<K>(v, sh);
 }
 
+// Diagonal and right-hand side of the Schur row of bifurcation bi (gather over its incident edges, no atomics)
+__device__ __forceinline__ void schur_row(const SchurArgs& a, int32_t bi, double& diag, double& rhs) {
+  const gnx_network_t& net = a.net;
+  const int32_t node = net.bif_nodes[bi];
+  diag = 0.0;
+  rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : (a.b_node ? a.b_node[node] * a.inv_sigma : 0.0);
+  for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
+    const int32_t code = net.inc_edge[k];
+    const int32_t e = code >> 1, end = code & 1;
+    const int64_t ei = a.eidx(e);
+    const double c = a.cond[ei];
+    diag += c;
+    rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
+  }
+}
+
+// Flag exchange between the ranks of a partitioned solve, run by the first `wait_world` threads of ONE CTA: tell every
+// rank that what I export has landed (the stores were followed by system-scope fences and a barrier), wait for all.
+__device__ __forceinline__ void sch_flag_exchange(const SchurArgs& a) {
+  if ((int)threadIdx.x < a.wait_world) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[threadIdx.x]), "l"(a.wait_epoch) : "memory");
+    const long long* f = a.wait_flags + threadIdx.x;
+    long long v;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= a.wait_epoch) break;
+      __nanosleep(spins < 4096 ? 32 : 2000);    // ranks run in step: poll fast first, then patiently
+      if (++spins > (1u << 25)) __trap();       // about a minute: a rank is missing -- fail instead of hanging the GPU
+    }
+  }
+}
+
+// The final (d, r) of my local subtree roots whose parent is replicated -> every other rank (threads of ONE CTA;
+// the values are final in MY global arrays: written before the last barrier)
+__device__ __forceinline__ void sch_export_roots(const SchurArgs& a) {
+  const gnx_schur_plan_t& pl = a.plan;
+  for (int32_t k = threadIdx.x; k < pl.nxl; k += blockDim.x) {
+    const int32_t node = pl.xlist[k];
+    const double dv = __ldcg(a.d + node), rv = __ldcg(a.r + node);
+    for (int q = 0; q < a.nx; ++q) {
+      a.xbuf[q][a.xd_off + node] = dv;
+      a.xbuf[q][a.xr_off + node] = rv;
+    }
+    __threadfence_system();
+  }
+}
+
 // The TOP part of the rake (levels >= l_split, <= GNX_TOP_MAX nodes) swept by ONE CTA: a thread
 // owns up to TOP_ROWS nodes, all plan data are fetched up front (independent loads), the running
 // diagonal / rhs / link weight live in shared memory, and a level costs one block barrier instead
@@ -636,14 +730,23 @@ constexpr size_t SCH_SMEM = 3 * GNX_TOP_MAX * sizeof(double);
 //                  [rank*S, (rank+1)*S) (S = plan.top_S, a power of two); a child / parent in another
 //                  CTA is read over distributed shared memory and a level costs one hardware cluster
 //                  barrier -- a whole tree of up to 16*2048 bifurcations then needs no grid barrier.
+// Subtree-partitioned network (plan.ncls != NULL, CLUSTER = false): the top part holds this rank's upper local nodes
+// (levels < l_sync) and ALL replicated raked nodes (levels >= l_sync).  Between the two the ranks exchange: my
+// exported roots' final (d, r) go to everybody, flags are swapped, and only then are the rows of the replicated
+// nodes built (their edges' scalars and their local children's pairs have arrived from the owners).  A replicated
+// node folds its local children -- mine or another rank's, all the same -- from global memory and keeps only
+// replicated children in registers, so every rank performs the same operations on the same bits.
+// Returns true when the solve stops at the exchange (a.phase == 1).
 template <bool CLUSTER, int ROWS>
-__device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double* sr, double* sw, long long* tick = nullptr) {
+__device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double* sr, double* sw, long long* tick = nullptr) {
   const gnx_schur_plan_t& pl = a.plan;
   const int tid = threadIdx.x, T = blockDim.x;
   cg::cluster_group cluster = cg::this_cluster();
   const int32_t S = CLUSTER ? pl.top_S : GNX_TOP_MAX;
   const int sshift = 31 - __clz(S);
   const int32_t base = CLUSTER ? (int32_t)cluster.block_rank() * S : 0;
+  const int32_t* const ncls = CLUSTER ? nullptr : pl.ncls;
+  const int l_sync = ncls ? pl.l_sync : pl.nl;
   auto rd = [&](double* arr, int32_t tc) -> double {
     if (!CLUSTER) return arr[tc];
     const double* p = cluster.map_shared_rank(arr, tc >> sshift);
@@ -656,40 +759,76 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
   // memory reads, a handful of FMAs, ONE reciprocal and a barrier -- no global load, no second division.
   int32_t node[ROWS], lev[ROWS], ptop[ROWS], k0[ROWS], k1[ROWS], c0[ROWS], c1[ROWS], nct[ROWS];
   double d[ROWS], r[ROWS], w[ROWS];
+  bool repl[ROWS];
+  // is child c of row q kept in registers / shared memory (else: final in global memory)?
+  auto top_child = [&](int q, int32_t c) -> int32_t {
+    const int32_t tc = pl.top_of[c];
+    if (tc >= 0 && repl[q] && !(ncls[c] & 1)) return -1;
+    return tc;
+  };
+  // numeric part of a row's set-up: row (from global memory, or built here for a replicated node), link weight,
+  // children below the top part folded in
+  auto numeric = [&](int q) {
+    const int32_t li = tid + q * T;
+    const int32_t i = node[q];
+    const int32_t par = pl.parent[i];
+    w[q] = par >= 0 ? -a.cond[a.eidx(pl.pedge[i])] : 0.0;
+    double di, ri;
+    if (repl[q]) schur_row(a, i, di, ri);
+    else { di = __ldcg(a.d + i); ri = __ldcg(a.r + i); }
+    nct[q] = 0; c0[q] = c1[q] = -1;
+    for (int32_t k = k0[q]; k < k1[q]; ++k) {
+      const int32_t c = pl.ch_idx[k];
+      const int32_t tc = top_child(q, c);
+      if (tc < 0) {                                        // child below the top part: final in global memory
+        const double wc = -a.cond[a.eidx(pl.pedge[c])];
+        const double t = wc / __ldcg(a.d + c);
+        di -= wc * t;
+        ri -= t * __ldcg(a.r + c);
+      } else {
+        if (nct[q] == 0) c0[q] = tc; else if (nct[q] == 1) c1[q] = tc;
+        ++nct[q];
+      }
+    }
+    d[q] = di; r[q] = ri;
+    sr[li] = ri; sw[li] = w[q];
+    if (nct[q] == 0) sd[li] = 1.0 / di;                    // no top children: final already
+  };
 #pragma unroll
   for (int q = 0; q < ROWS; ++q) {
     const int32_t li = tid + q * T;
     const int32_t ti = base + li;
     lev[q] = -1; node[q] = 0; ptop[q] = -1; k0[q] = k1[q] = 0; d[q] = 1.0; r[q] = 0.0; w[q] = 0.0;
-    c0[q] = c1[q] = -1; nct[q] = 0;
+    c0[q] = c1[q] = -1; nct[q] = 0; repl[q] = false;
     if (li < S && ti < pl.nt) {
       const int32_t i = pl.top_nodes[ti];
       node[q] = i;
       lev[q] = pl.level_of[i];
+      repl[q] = ncls && (ncls[i] & 1);
       const int32_t par = pl.parent[i];
-      if (par >= 0) { ptop[q] = pl.top_of[par]; w[q] = -a.cond[a.eidx(pl.pedge[i])]; }
+      if (par >= 0) ptop[q] = pl.top_of[par];
       k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
-      double di = __ldcg(a.d + i), ri = __ldcg(a.r + i);
-      for (int32_t k = k0[q]; k < k1[q]; ++k) {
-        const int32_t c = pl.ch_idx[k];
-        const int32_t tc = pl.top_of[c];
-        if (tc < 0) {                                        // child below the top part: final in global memory
-          const double wc = -a.cond[a.eidx(pl.pedge[c])];
-          const double t = wc / __ldcg(a.d + c);
-          di -= wc * t;
-          ri -= t * __ldcg(a.r + c);
-        } else {
-          if (nct[q] == 0) c0[q] = tc; else if (nct[q] == 1) c1[q] = tc;
-          ++nct[q];
-        }
-      }
-      d[q] = di; r[q] = ri;
-      sr[li] = ri; sw[li] = w[q];
-      if (nct[q] == 0) sd[li] = 1.0 / di;                    // no top children: final already
+      if (!repl[q]) numeric(q);
     }
   }
   lsync();
   if (tick) tick[0] = clock64();
+  // the exchange, between the last local and the first replicated level
+  auto exchange = [&]() -> bool {
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q)
+      if (lev[q] >= 0 && !repl[q] && (ncls[node[q]] & 4)) { a.d[node[q]] = d[q]; a.r[node[q]] = r[q]; }
+    lsync();
+    if (a.phase != 2) sch_export_roots(a);
+    lsync();
+    if (a.phase == 1) return true;
+    if (a.phase == 0) { sch_flag_exchange(a); lsync(); }
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q)
+      if (lev[q] >= 0 && repl[q]) numeric(q);
+    lsync();
+    return false;
+  };
   // contribution of top child tc to its parent: d -= w (w/d_c), r -= (w/d_c) r_c
   auto fold = [&](int q, int32_t tc) {
     const double wc = rd(sw, tc);
@@ -697,7 +836,9 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
     d[q] -= wc * t;
     r[q] -= t * rd(sr, tc);
   };
-  for (int l = pl.l_split + 1; l < pl.nl; ++l) {            // up: level l_split has no top children
+  for (int l = pl.l_split; l < pl.nl; ++l) {               // up
+    if (ncls && l == l_sync) { if (exchange()) return true; }
+    if (l == pl.l_split) continue;                          // the lowest top level has no top children
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
       if (lev[q] == l && nct[q] > 0) {
@@ -706,7 +847,7 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
         if (nct[q] > 2) {                                    // rare: third and later top children, from the plan
           int seen = 0;
           for (int32_t k = k0[q]; k < k1[q]; ++k) {
-            const int32_t tc = pl.top_of[pl.ch_idx[k]];
+            const int32_t tc = ncls ? top_child(q, pl.ch_idx[k]) : pl.top_of[pl.ch_idx[k]];
             if (tc >= 0 && ++seen > 2) fold(q, tc);
           }
         }
@@ -716,6 +857,7 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
     }
     lsync();
   }
+  if (ncls && l_sync >= pl.nl) { if (exchange()) return true; }     // (no replicated raked node)
   if (tick) tick[1] = clock64();
   for (int l = pl.nl - 1; l >= pl.l_split; --l) {           // down: sr[] turns into the solution
 #pragma unroll
@@ -732,22 +874,7 @@ __device__ __forceinline__ void top_solve(const SchurArgs& a, double* sd, double
     }
     lsync();
   }
-}
-
-// Diagonal and right-hand side of the Schur row of bifurcation bi (gather over its incident edges, no atomics)
-__device__ __forceinline__ void schur_row(const SchurArgs& a, int32_t bi, double& diag, double& rhs) {
-  const gnx_network_t& net = a.net;
-  const int32_t node = net.bif_nodes[bi];
-  diag = 0.0;
-  rhs = a.b_lam ? -a.b_lam[bi] * a.inv_sigma : (a.b_node ? a.b_node[node] * a.inv_sigma : 0.0);
-  for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) {
-    const int32_t code = net.inc_edge[k];
-    const int32_t e = code >> 1, end = code & 1;
-    const int64_t ei = a.eidx(e);
-    const double c = a.cond[ei];
-    diag += c;
-    rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
-  }
+  return false;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1199,18 +1326,22 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
   auto gsync = [&]() { sch_sync<MODE>(); };
   long long tick[4] = {0, 0, 0, 0};               // SM cycles of block 0: phase 0 | top prologue | up | down (diagnostic, scal[5..7])
   const long long tick0 = clock64();
-  if (a.wait_flags) {                             // ... and, edge-partitioned, from the other ranks' over NVLink
-    if ((int)threadIdx.x < a.wait_world) {
-      if (blockIdx.x == 0)
-        asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[threadIdx.x]), "l"(a.wait_epoch) : "memory");
+  // subtree-partitioned network: local sweeps first, ONE exchange at level l_sync, replicated nodes after it
+  const int32_t* const ncls = pl.ncls;
+  const bool part = ncls != nullptr;
+  const int l_sync = part ? pl.l_sync : pl.nl;
+  if (a.wait_flags && !part) {                    // replicated solve: the edge scalars of ALL ranks, over NVLink
+    if (blockIdx.x == 0) {
+      sch_flag_exchange(a);
+    } else if ((int)threadIdx.x < a.wait_world) {
       const long long* f = a.wait_flags + threadIdx.x;
       long long v;
       unsigned spins = 0;
       for (;;) {
         asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= a.wait_epoch) break;
-        __nanosleep(spins < 4096 ? 32 : 2000);    // ranks run in step: poll fast first, then patiently
-        if (++spins > (1u << 25)) __trap();       // about a minute: a rank is missing -- fail instead of hanging the GPU
+        __nanosleep(spins < 4096 ? 32 : 2000);
+        if (++spins > (1u << 25)) __trap();
       }
     }
     __syncthreads();
@@ -1245,31 +1376,49 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
     }
   };
 
+  auto row_to_global = [&](int32_t bi) {
+    double diag, rhs;
+    schur_row(a, bi, diag, rhs);
+    a.d[bi] = diag; a.r[bi] = rhs;
+  };
   // ---- phase 0: Schur diagonal and right-hand side (one thread per bifurcation, gather)
-  // (blocked rake: the blocks build their own rows, CTA 0 those of the top part -- no barrier in between)
-  if (pl.nb > 0) {
-    if (blockIdx.x == 0)
+  // (blocked rake: the blocks build their own rows, CTA 0 those of the top part -- no barrier in between;
+  //  partitioned: only my local nodes now, the replicated ones after the exchange)
+  if (pl.nb > 0 || a.phase == 2) {
+    if (blockIdx.x == 0 && pl.nc == 0)
       for (int32_t ti = threadIdx.x; ti < pl.nt; ti += blockDim.x) {
         const int32_t bi = pl.top_nodes[ti];
-        double diag, rhs;
-        schur_row(a, bi, diag, rhs);
-        a.d[bi] = diag; a.r[bi] = rhs;
+        if (!part || !(ncls[bi] & 1)) row_to_global(bi);
       }
+  } else if (part) {
+    for (int32_t idx = t0; idx < pl.lvl_ptr[l_sync]; idx += stride) row_to_global(pl.lvl_nodes[idx]);
+    gsync();
   } else {
-    for (int32_t bi = t0; bi < pl.B; bi += stride) {
-      double diag, rhs;
-      schur_row(a, bi, diag, rhs);
-      a.d[bi] = diag; a.r[bi] = rhs;
-    }
+    for (int32_t bi = t0; bi < pl.B; bi += stride) row_to_global(bi);
     gsync();
   }
 
   // ---- phase 1: rake up (level 0 has no children by construction)
   if (pl.nb > 0) {                                 // blocked rake: whole subtrees per CTA, ONE grid barrier
-    for (int32_t b = blockIdx.x; b < pl.nb; b += nblk) blk_up(a, b, top_sh, top_sh + GNX_BLK_MAX, top_sh + 2 * GNX_BLK_MAX);
+    if (a.phase != 2)
+      for (int32_t b = blockIdx.x; b < pl.nb; b += nblk) blk_up(a, b, top_sh, top_sh + GNX_BLK_MAX, top_sh + 2 * GNX_BLK_MAX);
     gsync();
-  } else {
-    for (int l = 1; l < pl.l_split; ++l) { up(l, t0, stride); gsync(); }
+  } else if (a.phase != 2) {
+    const int lend = pl.l_split < l_sync ? pl.l_split : l_sync;       // (a forest's top part starts at or below l_sync)
+    for (int l = 1; l < lend; ++l) { up(l, t0, stride); gsync(); }
+  }
+  if (part && pl.nc > 0) {
+    // a core exists: no top part; the exchange sits between the local and the replicated levels of the grid sweep
+    if (a.phase != 2 && blockIdx.x == 0) sch_export_roots(a);
+    if (a.phase == 1) return;
+    if (a.phase == 0) {
+      if (blockIdx.x == 0) { __syncthreads(); sch_flag_exchange(a); }
+      gsync();
+    }
+    for (int32_t idx = pl.lvl_ptr[l_sync] + t0; idx < pl.lvl_ptr[pl.nl]; idx += stride) row_to_global(pl.lvl_nodes[idx]);
+    for (int32_t i = t0; i < pl.nc; i += stride) row_to_global(pl.core_nodes[i]);
+    gsync();
+    for (int l = l_sync; l < pl.nl; ++l) { up(l, t0, stride); gsync(); }
   }
   double rr_final = 0.0, bb_final = 0.0;
   int it = 0;
@@ -1280,6 +1429,7 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
       tick[0] = clock64();
       if (blockIdx.x == 0 && pl.nt > 0) top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
       tick[3] = clock64();
+      if (a.phase == 1) return;                  // (partitioned, emulated ranks / NCCL: stop at the exchange)
       if (pl.l_split > 0) gsync();
     }
   } else {                                       // a core exists: l_split == nl, no top part
@@ -1457,6 +1607,7 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   GNX_CHECK_ARG(plan->nb > 0 || plan->nt == plan->lvl_ptr[plan->nl] - plan->lvl_ptr[plan->l_split]);
   GNX_CHECK_ARG(plan->nb == 0 || (plan->nb > 0 && plan->nc == 0 && plan->top_S == 0 && plan->blk_ptr && plan->blk_nodes &&
                                   plan->blk_pos && plan->blk_lv && plan->level_of && plan->B > GNX_TOP_MAX));
+  GNX_CHECK_ARG(plan->ncls == nullptr || plan->nc == 0 || plan->l_split == plan->nl);
   GNX_CHECK_ARG(plan->ell_w == 0 || (plan->ell_w <= 8 && plan->ell_col && plan->ell_edge && plan->ell_R > 0 &&
                                     plan->ell_R <= CL_RMAX && (int64_t)plan->ell_R * CL_CTAS >= plan->nc));
   GNX_CHECK_ARG(plan->nl == 0 || (plan->lvl_nodes && plan->parent && plan->pedge && plan->ch_ptr && plan->ch_idx));
@@ -1483,7 +1634,31 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
   a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_world = 0;
-  if (ex && ex->epoch > 0) {
+  a.nx = 0; a.xd_off = a.xr_off = 0; a.phase = 0;
+  for (int k = 0; k < GNX_MAX_PEERS; ++k) a.xbuf[k] = nullptr;
+  const bool subtree = ex && ex->mode == 1;
+  GNX_CHECK_ARG(subtree == (plan->ncls != nullptr));
+  if (subtree) {
+    // global-indexed buffers [cond | rsrc | ftot (E_glob each) | d | r (B_glob each) | world flag words]; the
+    // caller passes cond / rsrc / ftot = my buffer's arrays; d and r of the sweep live in it as well
+    GNX_CHECK_ARG(ex->peers_host && ex->world >= 1 && ex->world <= GNX_MAX_PEERS && ex->rank >= 0 && ex->rank < ex->world &&
+                  ex->peers_host[ex->rank] && ex->B_glob == plan->B && ex->E_glob == net->E && chunk == 0 &&
+                  ex->phase >= 0 && ex->phase <= 2 && (ex->phase != 0 || ex->epoch > 0));
+    GNX_CHECK_ARG(plan->l_sync >= 0 && plan->l_sync <= plan->nl && plan->nxl >= 0 && (plan->nxl == 0 || plan->xlist) &&
+                  plan->top_S == 0 && (plan->nc > 0 || plan->l_split <= plan->l_sync));
+    GNX_CHECK_ARG(cond == ex->peers_host[ex->rank]);
+    const int64_t flag_off = 3 * (int64_t)ex->E_glob + 2 * (int64_t)ex->B_glob;
+    a.xd_off = 3 * (int64_t)ex->E_glob; a.xr_off = a.xd_off + ex->B_glob;
+    a.d = ex->peers_host[ex->rank] + a.xd_off; a.r = ex->peers_host[ex->rank] + a.xr_off;
+    a.phase = ex->phase;
+    for (int k = 0; k < ex->world; ++k) {
+      GNX_CHECK_ARG(ex->peers_host[k] != nullptr);
+      if (k != ex->rank) a.xbuf[a.nx++] = ex->peers_host[k];
+      a.sig_flags[k] = reinterpret_cast<long long*>(ex->peers_host[k] + flag_off) + ex->rank;
+    }
+    a.wait_flags = reinterpret_cast<const long long*>(ex->peers_host[ex->rank] + flag_off);
+    a.wait_epoch = ex->epoch; a.wait_world = ex->world;
+  } else if (ex && ex->epoch > 0) {
     GNX_CHECK_ARG(ex->peers_host && ex->world >= 1 && ex->world <= GNX_MAX_PEERS && ex->rank >= 0 &&
                   ex->rank < ex->world && ex->peers_host[ex->rank] && ex->chunk == chunk);
     a.wait_flags = reinterpret_cast<const long long*>(ex->peers_host[ex->rank] + (int64_t)ex->world * 3 * ex->chunk);
@@ -1530,7 +1705,8 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
   // CTAs: enough threads for the widest phase.  <= 2 CTAs' worth runs as one CTA; a system with a
   // Krylov core (hundreds of barriers) runs as ONE CLUSTER when that gives every thread <= 32 rows;
   // everything else (wide rake levels of a large tree: few barriers, lots of rows) as a cooperative grid.
-  int want = (int)((B + SCH_T - 1) / SCH_T);
+  const int64_t nrows = plan->ncls ? (int64_t)plan->lvl_ptr[plan->nl] + nc : B;     // partitioned: what THIS rank sweeps
+  int want = (int)((nrows + SCH_T - 1) / SCH_T);
   const int cap = g_sch_sms * g_sch_blocks_per_sm;
   if (want > cap) want = cap;
   if (want > 2048) want = 2048;
@@ -2315,7 +2491,8 @@ static int rs_enabled() {             // tuning / A-B knob: GNX_STEP_RESIDENT=0 
 int gnx_step_resident_applies(const gnx_network_t* net, const gnx_schur_plan_t* plan, const double* b, const double* x,
                               const unsigned long long* sync) {
   if (!rs_enabled() || !sync || !plan || net->B <= 0 || net->n < RS_MIN_N || net->n > 10) return 0;
-  if (plan->B > 2 * SCH_T || plan->na > 0 || plan->top_S > 0 || plan->nb > 0) return 0;     // one-CTA Schur solve only
+  const int64_t nrows = plan->ncls ? (int64_t)plan->lvl_ptr[plan->nl] + plan->nc : plan->B;
+  if (nrows > 2 * SCH_T || plan->na > 0 || plan->top_S > 0 || plan->nb > 0) return 0;       // one-CTA Schur solve only
   if (!edge_bulk(net->h, b, x)) return 0;
   if (sch_init() != GNX_OK) return 0;
   const int G = RS_TILE >> net->n;
@@ -2338,7 +2515,13 @@ int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t*
   s.rhs = ConstRhs{f_const, g_const, pbc_out, pbc_node, b};
   int32_t chunk = 0, stride = 0;
   const double *gc = cond, *gr = rsrc, *gf = ftot;
-  if (ex) {
+  if (ex && ex->mode == 1) {                     // subtree partition: global-indexed buffer, local copies for phase 3
+    GNX_CHECK_ARG(cond && rsrc && ex->phase == 0);
+    if (int rc = edge_out_exchange(s.out, ex, net->E, cond, rsrc)) return rc;
+    double* g = ex->peers_host[ex->rank];
+    s.cond = cond; s.rsrc = rsrc;
+    gc = g; gr = g + ex->E_glob; gf = g + 2 * (int64_t)ex->E_glob;
+  } else if (ex) {
     if (int rc = edge_out_exchange(s.out, ex, net->E)) return rc;
     double* g = ex->peers_host[ex->rank];
     chunk = ex->chunk; stride = 3 * ex->chunk;

@@ -24,6 +24,7 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
                               int64_t* sync, int64_t epoch, void* stream) {
   GNX_CHECK_ARG(net && co && b && x && (ex || (cond && rsrc && ftot)));
   GNX_CHECK_ARG(!ex || (ex->epoch > 0 && ex->peers_host && ex->rank >= 0 && ex->rank < ex->world));
+  GNX_CHECK_ARG(!ex || ex->mode == 0 || (cond && rsrc));
   GNX_CHECK_ARG(net->B == 0 || (schur_net && plan && P && work));
   cudaStream_t main_st = (cudaStream_t)stream;
   if (sync && epoch > 0 && net->B > 0 && (!vals || (net->rowtab && ((uintptr_t)vals & 15) == 0)) &&
@@ -47,7 +48,16 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
   if (int rc = gnx_rhs_eliminate_mixed(net, co, f_const, g_const, pbc_out, pbc_node, b, cond, rsrc, ftot, ex,
                                        solve_st)) return rc;
   int32_t chunk = 0, stride = 0;
-  if (ex) {                                     // the scalars of ALL edges, as the ranks stored them into my buffer
+  if (ex && ex->mode == 1) {                    // subtree partition: local sweeps, one exchange inside the Schur kernel
+    GNX_CHECK_ARG(cond && rsrc && ex->phase == 0);
+    if (net->B > 0) {
+      double* g = ex->peers_host[ex->rank];
+      double* lam = x + gnx_mixed_dims(*net).lam_off;
+      if (int rc = gnx_schur_solve(schur_net, plan, co->sigma, g, g + ex->E_glob, g + 2 * (int64_t)ex->E_glob,
+                                   b + gnx_mixed_dims(*net).lam_off, nullptr, P, lam, work, rtol, max_iter, warm, 0, 0, ex,
+                                   resid_host, info_host, solve_st)) return rc;
+    }
+  } else if (ex) {                              // the scalars of ALL edges, as the ranks stored them into my buffer
     double* g = ex->peers_host[ex->rank];
     chunk = ex->chunk; stride = 3 * ex->chunk;
     cond = g + (int64_t)ex->rank * stride;      // my own block: what the back-substitution reads

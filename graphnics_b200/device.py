@@ -123,7 +123,7 @@ class DeviceNetwork:
     `self.glob` keeps the whole network's tables for the (replicated) Schur solve.
     """
 
-    def __init__(self, pos, edges, n, device=None, with_mf=True, part=None):
+    def __init__(self, pos, edges, n, device=None, with_mf=True, part=None, epart=None):
         lib = _lib.require_device()
         self.device = torch.device(device if device is not None else "cuda")
         dev = self.device
@@ -137,15 +137,25 @@ class DeviceNetwork:
         self.part = part
         self.glob = None
         with torch.cuda.device(dev):
+            self.edge_ids = None
             if part is not None:
                 rank, world = part
                 self.E_glob = int(edges_all.shape[0])
-                self.e0, self.e1, self.chunk = partition_range(self.E_glob, rank, world)
-                if self.e1 <= self.e0:
-                    raise ValueError("empty edge range: more ranks than edges")
                 self.edges_glob = edges_all
                 self.glob = _Tables(lib, edges_all, self.V, dev)
-                self.edges = edges_all[self.e0:self.e1].contiguous()
+                if epart is None:
+                    # contiguous equal index ranges, edge scalars of ALL edges gathered, replicated Schur solve
+                    self.e0, self.e1, self.chunk = partition_range(self.E_glob, rank, world)
+                    if self.e1 <= self.e0:
+                        raise ValueError("empty edge range: more ranks than edges")
+                    self.edges = edges_all[self.e0:self.e1].contiguous()
+                else:
+                    # arbitrary edge set (partition.partition_edges: subtrees): rank-local rake, small exchange
+                    self.epart = np.ascontiguousarray(epart, dtype=np.int32)
+                    self.edge_ids = np.nonzero(self.epart == rank)[0].astype(np.int64)
+                    if len(self.edge_ids) == 0:
+                        raise ValueError("rank %d owns no edge" % rank)
+                    self.edges = edges_all[torch.from_numpy(self.edge_ids).to(dev)].contiguous()
             else:
                 self.edges = edges_all
             self.E = int(self.edges.shape[0])

@@ -77,6 +77,8 @@ class MixedSystem:
         self._plan = None
         self._solve_bufs = None
         self._red_work = None
+        self.subtree = dn.part is not None and dn.edge_ids is not None     # gnx_exchange mode 1
+        self._xch = None             # subtree mode: exchange buffers of all ranks + epoch
 
     # ---- helpers -------------------------------------------------------------------------
     def _f64(self, *shape):
@@ -226,7 +228,7 @@ class MixedSystem:
             d = {}
             d["cond"], d["rsrc"], d["ftot"] = self._f64(E), self._f64(E), self._f64(E)
             d["P"] = torch.zeros(B, dtype=torch.float64, device=self.dev)
-            if dn.part is not None:
+            if dn.part is not None and not self.subtree:
                 # edge scalars of the WHOLE network, gathered from all ranks (equal chunks; the tail of
                 # the last chunk is padding).  The per-rank source buffers are chunk-sized too.
                 # Layout: per rank one block [cond | rsrc | ftot] of 3*chunk doubles -> ONE collective.
@@ -244,7 +246,14 @@ class MixedSystem:
             from .schur_plan import SchurPlan
             dn = self.dn
             bix_h = dn.bix.cpu().numpy()
-            hp = SchurPlan(dn.schur_edges_host(), bix_h, dn.B, max_levels=_lib.MAX_LEVELS)
+            hp = getattr(dn, "host_plan", None)            # (the partitioner's plan of the whole network, if it made one)
+            if hp is None:
+                hp = SchurPlan(dn.schur_edges_host(), bix_h, dn.B, max_levels=_lib.MAX_LEVELS)
+            view = None
+            if getattr(self, "subtree", False):
+                from .schur_plan import RankPlan, node_owners
+                owner = node_owners(hp, dn.schur_edges_host(), bix_h, dn.epart)
+                hp = view = RankPlan(hp, owner, dn.part[0], max_levels=_lib.MAX_LEVELS)
             agg = None
             if hp.nc > _lib.TWO_LEVEL_MIN_CORE and os.environ.get("GNX_SCHUR_TWO_LEVEL", "1") != "0":
                 # large cyclic core: two-level PCG, aggregates cut by coordinate bisection of the node positions
@@ -269,9 +278,12 @@ class MixedSystem:
                     top_S *= 2
             top, top_of, level_of = hp.top_arrays(l_split)
             blocks = None
-            if hp.nc == 0 and top_S == 0 and dn.B > _lib.TOP_MAX and os.environ.get("GNX_SCHUR_BLOCKS", "1") != "0":
+            n_swept = dn.B if view is None else view.n_mine
+            if hp.nc == 0 and top_S == 0 and n_swept > _lib.TOP_MAX and dn.B > _lib.TOP_MAX and \
+                    os.environ.get("GNX_SCHUR_BLOCKS", "1") != "0":
                 # big forest: whole subtrees of <= 1024 nodes per CTA instead of one grid barrier per wide level
-                blocks = hp.block_arrays(cap=_lib.BLK_MAX, top_max=_lib.TOP_MAX)
+                blocks = (hp.block_arrays(cap=_lib.BLK_MAX, top_max=_lib.TOP_MAX) if view is None else
+                          view.rank_block_arrays(cap=_lib.BLK_MAX, top_max=_lib.TOP_MAX))
                 if blocks is not None:
                     top, top_of, level_of, l_split = blocks["top_nodes"], blocks["top_of"], blocks["level_of"], blocks["l_top"]
             s.B, s.nl, s.l_split, s.nc, s.nnzc, s.nt = dn.B, len(hp.levels), l_split, hp.nc, hp.nnzc, len(top)
@@ -288,6 +300,22 @@ class MixedSystem:
             if blocks is not None:
                 extra += tuple((k, blocks[k]) for k in ("blk_ptr", "blk_nodes", "blk_pos", "blk_lv"))
             hp.blocks = blocks
+            s.l_sync, s.nxl = len(hp.levels), 0
+            if view is not None:
+                if hp.nc == 0 and l_split > view.l_sync:
+                    raise ValueError("subtree partition: %d replicated bifurcations do not fit the top part (%d)"
+                                     % (int(view.repl_raked.sum()), _lib.TOP_MAX))
+                xlist = np.nonzero(view.ncls & 4)[0]
+                s.l_sync, s.nxl = view.l_sync, len(xlist)
+                extra += (("ncls", view.ncls), ("xlist", xlist))
+                # local edge -> global id, bit 31: an end is a replicated bifurcation (the scalars cross NVLink)
+                eg = dn.schur_edges_host()[dn.edge_ids]
+                bu, bv = bix_h[eg[:, 0]], bix_h[eg[:, 1]]
+                rep = (np.where(bu >= 0, view.owner[np.maximum(bu, 0)] < 0, False) |
+                       np.where(bv >= 0, view.owner[np.maximum(bv, 0)] < 0, False))
+                egl = dn.edge_ids.astype(np.int64) | np.where(rep, 1 << 31, 0)
+                self._egl = torch.from_numpy(egl.astype(np.uint32).view(np.int32)).to(self.dev)
+                self._xedges = dn.edge_ids[rep]            # what this rank exports (NCCL fallback packs these)
             for name, arr in extra + (("lvl_nodes", lvl_nodes), ("parent", hp.parent), ("pedge", hp.pedge),
                               ("ch_ptr", hp.ch_ptr), ("ch_idx", hp.ch_idx), ("core_nodes", hp.core_nodes),
                               ("crp", hp.crp), ("ccol", hp.ccol), ("cedge", hp.cedge),
@@ -347,6 +375,146 @@ class MixedSystem:
         ex.epoch = p2p["step"] if p2p["flags"] else 0      # 0: separate barrier kernel (GNX_P2P_BARRIER=1)
         return k, ex
 
+    # ---- subtree-partitioned solve (gnx_exchange mode 1) --------------------------------------
+    def xch_words(self):
+        """doubles of one exchange buffer: [cond | rsrc | ftot (E_glob each) | d | r (B each) | world flag words]"""
+        dn = self.dn
+        return 3 * dn.E_glob + 2 * dn.B + dn.part[1]
+
+    def xch_attach(self, slots):
+        """ranks emulated in ONE process (tests): slots[k][r] = exchange buffer k of rank r on this device"""
+        world = self.dn.part[1]
+        ptrs = [(C.c_void_p * world)(*[int(t.data_ptr()) for t in slot]) for slot in slots]
+        self._xch = dict(bufs=[slot[self.dn.part[0]] for slot in slots], ptrs=ptrs, step=0, mode="emulated", keep=slots)
+
+    def _xch_setup(self):
+        """two exchange buffers (alternating per solve) mapped into every rank: torch symmetric memory; without
+        peer access each rank keeps plain buffers and the exported values travel by one NCCL all-gather
+        between the two halves of the Schur solve"""
+        if self._xch is not None:
+            return self._xch
+        import torch.distributed as dist
+        dn = self.dn
+        rank, world = dn.part
+        group = self.group if self.group is not None else dist.group.WORLD
+        nw = self.xch_words()
+        try:
+            if self.exchange_mode == "nccl" or world > 8:
+                raise RuntimeError("NCCL exchange requested")
+            import torch.distributed._symmetric_memory as symm
+            bufs, hdls, ptrs = [], [], []
+            for _ in range(2):
+                t = symm.empty(nw, dtype=torch.float64, device=self.dev)
+                t.zero_()
+                torch.cuda.synchronize(self.dev)           # flags are zero before any peer can reach them
+                h = symm.rendezvous(t, group)
+                bufs.append(t); hdls.append(h)
+                ptrs.append((C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]))
+            for h in hdls:
+                h.barrier(channel=0)
+            torch.cuda.synchronize(self.dev)
+            self._xch = dict(bufs=bufs, hdls=hdls, ptrs=ptrs, step=0, mode="p2p")
+            self.exchange_mode = "p2p"
+        except Exception as ex:
+            if self.exchange_mode == "p2p":
+                raise
+            self._p2p_error = repr(ex)
+            self.exchange_mode = "nccl"
+            bufs = [torch.zeros(nw, dtype=torch.float64, device=self.dev) for _ in range(2)]
+            ptrs = [(C.c_void_p * 1)(int(t.data_ptr())) for t in bufs]
+            # positions (in a buffer) of what every rank exports: its edges at replicated bifurcations, its roots
+            plan = self.schur_plan()[3]
+            owner, E, B = plan.owner, dn.E_glob, dn.B
+            eg = dn.schur_edges_host()
+            bix_h = dn.bix.cpu().numpy()
+            bu, bv = bix_h[eg[:, 0]], bix_h[eg[:, 1]]
+            rep = (np.where(bu >= 0, owner[np.maximum(bu, 0)] < 0, False) | np.where(bv >= 0, owner[np.maximum(bv, 0)] < 0, False))
+            par = plan.parent.astype(np.int64)
+            root = (owner >= 0) & np.where(par >= 0, owner[np.maximum(par, 0)] < 0, False)
+            pos = []
+            for q in range(world):
+                xe = np.nonzero(rep & (dn.epart == q))[0]
+                xn = np.nonzero(root & (owner == q))[0]
+                pos.append(np.concatenate([xe, E + xe, 2 * E + xe, 3 * E + xn, 3 * E + B + xn]).astype(np.int64))
+            L = max(len(p_) for p_ in pos)
+            self._xch = dict(bufs=bufs, ptrs=ptrs, step=0, mode="nccl", group=group,
+                             pos=[torch.from_numpy(p_).to(self.dev) for p_ in pos], L=max(L, 1),
+                             send=torch.zeros(max(L, 1), dtype=torch.float64, device=self.dev),
+                             recv=torch.zeros(world * max(L, 1), dtype=torch.float64, device=self.dev))
+        return self._xch
+
+    def _xch_desc(self, xc, k, phase):
+        dn = self.dn
+        ex = _lib.gnx_exchange_t()
+        if xc["mode"] == "nccl":
+            ex.world, ex.rank = 1, 0
+        else:
+            ex.rank, ex.world = dn.part
+        ex.chunk, ex.mode = 0, 1
+        ex.peers_host = xc["ptrs"][k]
+        ex.epoch = xc["step"]
+        ex.egl = self._egl.data_ptr()
+        ex.E_glob, ex.B_glob, ex.phase = dn.E_glob, dn.B, phase
+        return ex
+
+    def _xch_nccl(self, xc, buf):
+        """the exchange by collective: everybody's exported values into everybody's buffer"""
+        import torch.distributed as dist
+        rank, world = self.dn.part
+        L = xc["L"]
+        mine = xc["pos"][rank]
+        xc["send"][: len(mine)] = buf[mine]
+        dist.all_gather_into_tensor(xc["recv"], xc["send"], group=xc["group"])
+        for q in range(world):
+            if q != rank and len(xc["pos"][q]):
+                buf[xc["pos"][q]] = xc["recv"][q * L: q * L + len(xc["pos"][q])]
+
+    def _solve_subtree(self, co, b, x, rtol, max_iter, warm_start, info, sync, cr, xphase):
+        """local elimination + local rake -> ONE exchange -> replicated top -> local down-sweep + back-substitution.
+        xphase None: the whole solve (flags inside the Schur kernel over NVLink peer mappings, or NCCL between
+        two kernel launches); 1 / 2: the two halves on their own (ranks emulated in one process)."""
+        dn = self.dn
+        d = self._bufs()
+        st = current_stream()
+        plan, _, work, _ = self.schur_plan()
+        xc = self._xch_setup()
+        if xphase in (None, 1):
+            xc["step"] += 1
+        k = (xc["step"] - 1) & 1
+        buf = xc["bufs"][k]
+        E_g = dn.E_glob
+        lam = x[dn.lam_off:]
+        phases = ([0] if xc["mode"] == "p2p" else [1, 2]) if xphase is None else [xphase]
+        for ph in phases:
+            ex = self._xch_desc(xc, k, ph)
+            if ph in (0, 1):
+                if cr is not None:
+                    check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, ptr(d["cond"]), ptr(d["rsrc"]),
+                                                           ptr(d["ftot"]), C.byref(ex), st))
+                else:
+                    check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), C.byref(ex), ptr(d["cond"]),
+                                                                ptr(d["rsrc"]), st))
+            elif xc["mode"] == "nccl" and xphase is None:
+                self._xch_nccl(xc, buf)
+            args = (dn.schur_net_ref(), C.byref(plan), co.sigma, ptr(buf), ptr(buf[E_g:]), ptr(buf[2 * E_g:]),
+                    ptr(b[dn.lam_off:]), None, ptr(d["P"]), ptr(lam), ptr(work), float(rtol), int(max_iter),
+                    1 if warm_start else 0, 0, 0, C.byref(ex))
+            if sync and ph != 1:
+                resid = C.c_double(0.0)
+                inf = (C.c_int32 * 3)()
+                check(self.lib.gnx_schur_solve(*args, C.byref(resid), inf, st))
+                info.cg_iterations += int(inf[0])
+                info.cg_converged = bool(inf[1])
+                info.cg_batches += int(inf[2])
+                info.cg_rel_resid = float(resid.value)
+            else:
+                check(self.lib.gnx_schur_solve(*args, None, None, st))
+            if ph == 1:
+                continue
+            check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                                  ptr(d["P"]), ptr(x), st))
+        return x, info
+
     def eliminate(self, co, b):
         """phase 1: per-edge scans -> edge scalars (device only, no sync)."""
         d = self._bufs()
@@ -366,7 +534,7 @@ class MixedSystem:
         return out
 
     def solve(self, co, b, x=None, rtol=1e-13, max_iter=100000, warm_start=False, info=None, sync=True,
-              exchange=None, eliminated=False, const_rhs=None):
+              exchange=None, eliminated=False, const_rhs=None, xphase=None):
         """x = A^{-1} b for the operator described by `co` (never forms A): edge elimination ->
         one persistent Schur kernel (rake + core PCG) -> back-substitution.
         sync=False: nothing returns to the host; `info` is not filled.
@@ -379,6 +547,15 @@ class MixedSystem:
         info = info if info is not None else SolveInfo()
         x = x if x is not None else self._f64(self.N)
         st = current_stream()
+        if self.subtree and dn.B > 0:
+            if const_rhs is not None and dn.n > 10:
+                self.rhs(out=b, **const_rhs)
+                const_rhs = None
+            cr = None
+            if const_rhs is not None:
+                cr = (float(const_rhs.get("f_const", 0.0)), float(const_rhs.get("g_const", 0.0)),
+                      ptr(const_rhs.get("pbc_out")), ptr(const_rhs.get("pbc_node")), ptr(b))
+            return self._solve_subtree(co, b, x, rtol, max_iter, warm_start, info, sync, cr, xphase)
         p2p = None
         if dn.part is not None and exchange is None and not eliminated and dn.B > 0:
             p2p = self._p2p_setup()
@@ -458,9 +635,14 @@ class MixedSystem:
         fused = rhs_kwargs.get("f_nodal") is None and rhs_kwargs.get("g_nodal") is None and self.dn.n <= 10
         if fused:                                  # Constant f, g: the elimination kernel produces b itself
             solve_kw = dict(solve_kw, const_rhs={k: v for k, v in rhs_kwargs.items() if k not in ("f_nodal", "g_nodal")})
-        if fused and x is not None and not solve_kw.get("eliminated") and solve_kw.get("exchange") is None:
+        if fused and x is not None and not solve_kw.get("eliminated") and solve_kw.get("exchange") is None \
+                and solve_kw.get("xphase") is None:
             p2p = None
-            if self.dn.part is not None and self.dn.B > 0:
+            if self.subtree and self.dn.B > 0:
+                xc = self._xch_setup()
+                if xc["mode"] == "p2p":
+                    return self._step_native(co, vals, b, x, solve_kw.pop("const_rhs"), overlap, xch=xc, **solve_kw)
+            elif self.dn.part is not None and self.dn.B > 0:
                 p2p = self._p2p_setup()
             if self.dn.part is None or (p2p is not None and p2p["flags"]):
                 return self._step_native(co, vals, b, x, solve_kw.pop("const_rhs"), overlap, p2p=p2p, **solve_kw)
@@ -486,7 +668,7 @@ class MixedSystem:
         return out
 
     def _step_native(self, co, vals, b, x, const_rhs, overlap, rtol=1e-13, max_iter=100000, warm_start=False,
-                     info=None, sync=True, p2p=None, **_):
+                     info=None, sync=True, p2p=None, xch=None, **_):
         """the whole step behind ONE library call (gnx_step_mixed): same kernels, streams and events as the
         Python-sequenced path above, a fraction of its host time"""
         dn = self.dn
@@ -514,6 +696,9 @@ class MixedSystem:
         ex = None
         if p2p is not None:
             _, ex = self._exchange(p2p)
+        if xch is not None:
+            xch["step"] += 1
+            ex = self._xch_desc(xch, (xch["step"] - 1) & 1, 0)
         check(self.lib.gnx_step_mixed(
             dn.net_ref(), co.ref(), ptr(self.rowptr), ptr(vals), float(const_rhs.get("f_const", 0.0)),
             float(const_rhs.get("g_const", 0.0)), ptr(const_rhs.get("pbc_out")), ptr(const_rhs.get("pbc_node")), ptr(b),

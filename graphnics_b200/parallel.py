@@ -27,23 +27,55 @@ __all__ = ["PartitionedMixed", "run_partitioned_bench", "global_residual"]
 
 
 class PartitionedMixed:
-    """the mixed system of the whole network, this rank's share"""
+    """the mixed system of the whole network, this rank's share.
 
-    def __init__(self, pos, edges, n, rank=None, world=None, device=None, group=None, exchange="auto"):
+    partition="subtree" (default): edges are dealt by partition.partition_edges -- whole subtrees of the rake forest
+    per rank, so a rank eliminates and rakes its part without communication and only the few replicated bifurcations
+    at the top of the tree (plus the edges at them) take part in the one exchange of a solve.
+    partition="range": contiguous equal index ranges, every edge's scalars gathered, Schur solve replicated (round 1)."""
+
+    def __init__(self, pos, edges, n, rank=None, world=None, device=None, group=None, exchange="auto",
+                 partition="subtree"):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
-        self.dn = DeviceNetwork(pos, edges, n, device=device, part=(self.rank, self.world))
+        epart = plan = None
+        if partition == "subtree" and self.world > 1:
+            from .partition import partition_edges
+            epart, plan = partition_edges(np.asarray(edges), len(pos), self.world)
+        self.dn = DeviceNetwork(pos, edges, n, device=device, part=(self.rank, self.world), epart=epart)
+        if plan is not None:
+            self.dn.host_plan = plan
         self.ms = MixedSystem(self.dn, group=group, exchange=exchange)
+        if epart is not None:
+            try:
+                self.ms.schur_plan()
+            except ValueError:                       # replicated set too large for the top part: round-1 layout
+                self.dn = DeviceNetwork(pos, edges, n, device=device, part=(self.rank, self.world))
+                self.ms = MixedSystem(self.dn, group=group, exchange=exchange)
         self.E_glob, self.m = self.dn.E_glob, self.dn.m
         self.N_glob = self.E_glob * (2 * self.m + 1) + self.dn.B
 
+    def edge_ids(self):
+        """global ids of this rank's edges, ascending"""
+        dn = self.dn
+        return dn.edge_ids if dn.edge_ids is not None else np.arange(dn.e0, dn.e1, dtype=np.int64)
+
     def local_dofs_of_global(self):
         """indices into the monolithic GLOBAL vector of this rank's local vector [q_loc | p_loc | lambda]"""
-        dn, m = self.dn, self.m
-        q = np.arange(dn.e0 * (m + 1), dn.e1 * (m + 1))
-        p = self.E_glob * (m + 1) + np.arange(dn.e0 * m, dn.e1 * m)
-        lam = self.E_glob * (2 * m + 1) + np.arange(dn.B)
+        m = self.m
+        e = self.edge_ids()
+        q = (e[:, None] * (m + 1) + np.arange(m + 1)[None, :]).ravel()
+        p = self.E_glob * (m + 1) + (e[:, None] * m + np.arange(m)[None, :]).ravel()
+        lam = self.E_glob * (2 * m + 1) + np.arange(self.dn.B)
         return np.concatenate([q, p, lam])
+
+    def valid_multipliers(self):
+        """bifurcations whose multiplier this rank computes: its local nodes and the replicated ones (all of them with
+        the range partition)"""
+        if not self.ms.subtree or self.dn.B == 0:
+            return np.arange(self.dn.B)
+        v = self.ms.schur_plan()[3]
+        return np.nonzero((v.owner == self.rank) | (v.owner < 0))[0]
 
 
 def global_residual(ms, vals, x, b, group=None):

@@ -215,23 +215,38 @@ int gnx_edge_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t*
  * kernel is left.  epoch must grow from solve to solve on a buffer; epoch = 0: no flags, the caller
  * separates the two kernels with its own cross-GPU barrier.  world <= 8. */
 typedef struct gnx_exchange {
-  int32_t world, rank, chunk, reserved;
+  int32_t world, rank, chunk, mode;   /* mode 0: gathered blocks as described above; mode 1: see below */
   double* const* peers_host;   /* [world], host array of device addresses */
   int64_t epoch;
-  void* reserved2;
+  /* mode 1 -- SUBTREE-ALIGNED partition (graphnics_b200/partition.py; north_star: "edge-balanced subtrees"): a rank owns
+   * an arbitrary set of edges, egl[e] = global id of its local edge e with bit 31 set when an end of the edge is a
+   * REPLICATED bifurcation.  Every rank's buffer is indexed by GLOBAL ids:
+   *   [cond | rsrc | ftot (E_glob doubles each) | d | r (B_glob each) | world 64-bit flag words].
+   * A rank eliminates, builds the Schur rows of and rakes the bifurcations whose whole subtree it owns WITHOUT any
+   * communication; only the scalars of edges at replicated bifurcations (bit 31) and the final (d, r) pair of every
+   * local subtree root under a replicated parent (gnx_schur_plan_t.xlist) are stored into all buffers over NVLink.  The
+   * ONE flag exchange of a solve then happens inside the Schur kernel at rake level plan.l_sync; the replicated
+   * bifurcations (the top of the tree: 2^k - 1 for a binary tree on 2^k ranks) are processed redundantly, bit-identically.
+   * phase: 0 = the whole solve in one kernel, flags inside (epoch > 0); 1 = up to the exchange (stores to the peers
+   * done, no flags); 2 = from the exchange on -- 1 and 2 let a caller put its own collective / barrier in between
+   * (NCCL fallback, ranks emulated in one process). */
+  const int32_t* egl;
+  int32_t E_glob, B_glob, phase, reserved;
 } gnx_exchange_t;
 
 /* L_form with Constant f / g (what the steady models use: boundary data + constants) and the elimination
  * in ONE kernel: b [N] is an OUTPUT, bit-identical to gnx_assemble_rhs_mixed(net, NULL, NULL, f_const,
  * g_const, pbc_out, pbc_node, b).  Saves a launch and the 8 B/dof read of b.  n <= 10.
- * ex != NULL selects the edge-partitioned output (cond / rsrc / ftot are then ignored). */
+ * ex != NULL selects the edge-partitioned output (mode 0: cond / rsrc / ftot are ignored; mode 1: cond / rsrc [E] receive
+ * the local copies the back-substitution reads). */
 int gnx_rhs_eliminate_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
                             double g_const, const double* pbc_out, const double* pbc_node, double* b,
                             double* cond, double* rsrc, double* ftot, const gnx_exchange_t* ex, void* stream);
 
-/* Edge-partitioned network: gnx_edge_eliminate_mixed with the collective fused in (see gnx_exchange). */
+/* Edge-partitioned network: gnx_edge_eliminate_mixed with the collective fused in (see gnx_exchange; cond / rsrc:
+ * mode 1 only, may be NULL in mode 0). */
 int gnx_edge_eliminate_mixed_p2p(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
-                                 const gnx_exchange_t* ex, void* stream);
+                                 const gnx_exchange_t* ex, double* cond, double* rsrc, void* stream);
 
 /* Graph-level Schur system S P = r on the B bifurcation unknowns (node gather, no atomics),
  * as explicit arrays -- inspection / tests; gnx_schur_solve builds the same quantities itself.
@@ -297,6 +312,14 @@ typedef struct gnx_schur_plan {
   const int32_t* blk_lv;               /* [2*nb] lowest and highest rake level of a block */
   const int32_t* sub_ptr;              /* [na*ns+1] core rows of the fine aggregates (ns > 1) */
   const int32_t* row_sub;              /* [nc] fine aggregate of a core row (ns > 1) */
+  /* One rank's view of the plan of a subtree-partitioned network (gnx_exchange mode 1; schur_plan.RankPlan), ncls != NULL:
+   * lvl_nodes / top_nodes / blocks hold the nodes THIS rank sweeps -- its local ones on levels < l_sync, the
+   * replicated raked ones on levels >= l_sync (l_split <= l_sync when nc == 0); parent / pedge / children / core arrays
+   * stay global.  ncls[B]: bit 0 replicated, bit 1 another rank's local node, bit 2 local root whose final (d, r) is
+   * exported; xlist[nxl]: those roots. */
+  int32_t l_sync, nxl;
+  const int32_t* ncls;
+  const int32_t* xlist;
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

@@ -162,3 +162,93 @@ def test_partitioned_primal_solve_matches_monolithic_lu(name, n, world):
         xi = x[ps.p_off + pv_loc[interior]]
         ri = x_ref[lay["p_off"] + pv_glob[interior]]
         assert np.linalg.norm(xi - ri) <= 1e-8 * max(np.linalg.norm(ri), 1e-30)
+
+
+def _case(name):
+    if name.startswith("tree"):
+        return _tree(int(name[4:]))
+    if name.startswith("rand"):
+        return random_graph(int(name[4:]), V=20, extra=5)
+    if name == "lollipop":
+        from test_partition import _lollipop
+        return _lollipop()
+    if name == "honeycomb48":
+        from graphnics_b200.generators import honeycomb
+        return honeycomb(48, 48, mesh=False)._graph_arrays()
+    return golden_arrays(name)
+
+
+@pytest.mark.parametrize("name,n,world", [("tree7", 3, 2), ("tree7", 6, 4), ("tree12", 1, 8), ("tree13", 0, 4), ("tree14", 0, 2),
+                                          ("arterial_tree_N7", 2, 3), ("rand2", 4, 2), ("lollipop", 2, 4),
+                                          ("honeycomb_4_4", 2, 3), ("honeycomb48", 0, 2)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_subtree_partitioned_solve_matches_monolithic_lu(name, n, world, fused):
+    """gnx_exchange mode 1 with the ranks played in one process: every rank eliminates and rakes ITS subtrees, stores
+    what it exports straight into the other ranks' buffers (phase 1 of all ranks), then every rank processes the
+    replicated bifurcations and sweeps down (phase 2).  Each rank's share of the solution against the oracle's LU."""
+    import torch
+    from graphnics_b200.parallel import PartitionedMixed
+    pos, edges = _case(name)
+    om = oracle.build_mesh(pos, edges, n)
+    lay = oracle.mixed_layout(om)
+    E = len(edges)
+    rng = np.random.default_rng(3)
+    Res = rng.uniform(0.5, 2.0, size=E)
+    lin = oracle.Coef(lambda x: 1.0 + 2.0 * x[..., 0] - 0.5 * x[..., 1], 1)
+    A = oracle.assemble_mixed(om, Res)
+    if fused:                                 # Constant data: the elimination kernel produces b
+        b = oracle.assemble_mixed_rhs(om, f=0.75, g=-1.25, p_bc=lin, project=False)
+    else:
+        g = oracle.Coef(lambda x: np.sin(3 * x[..., 0]) + x[..., 1], 1)
+        f = oracle.Coef(lambda x: np.cos(2 * x[..., 1]) - x[..., 0], 1)
+        b = oracle.assemble_mixed_rhs(om, f=f, g=g, p_bc=lin, project=False)
+    x_ref = oracle.lu_solve(A, b)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    pms = [PartitionedMixed(pos, edges, n, rank=r, world=world) for r in range(world)]
+    assert all(pm.ms.subtree for pm in pms)
+    nw = pms[0].ms.xch_words()
+    slots = [[torch.full((nw,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(world)] for _ in range(2)]
+    ranks = []
+    for pm in pms:
+        ms, dn = pm.ms, pm.dn
+        ms.xch_attach(slots)
+        idx = pm.local_dofs_of_global()
+        co = ms.coeffs(Res[pm.edge_ids()])
+        xq, _ = ms.dof_coordinates(False)
+        xqh = xq.cpu().numpy()
+        if fused:
+            kw = dict(const_rhs=dict(f_const=0.75, g_const=-1.25, pbc_out=ms.end_values(dev(lin(xqh))), pbc_node=dev(lin(pos))))
+            bl = torch.full((ms.N,), float("nan"), dtype=torch.float64, device="cuda")
+        else:
+            kw = {}
+            bl = ms.rhs(dev(f(xqh)), dev(g(xqh)), ms.end_values(dev(lin(xqh))), dev(lin(pos)))
+        x = torch.full((ms.N,), float("nan"), dtype=torch.float64, device="cuda")
+        ranks.append((pm, co, bl, x, kw, idx))
+    for rep in range(3):                      # repeated solves alternate the two buffers
+        for pm, co, bl, x, kw, idx in ranks:
+            pm.ms.solve(co, bl, x=x, xphase=1, sync=False, **kw)
+        infos = [pm.ms.solve(co, bl, x=x, xphase=2, **kw)[1] for pm, co, bl, x, kw, idx in ranks]
+    lam_all = []
+    for (pm, co, bl, x, kw, idx), info in zip(ranks, infos):
+        dn = pm.dn
+        assert info.cg_converged
+        xh = x.cpu().numpy()
+        np.testing.assert_allclose(bl.cpu().numpy()[:dn.lam_off], b[idx][:dn.lam_off], rtol=1e-12, atol=1e-14)
+        for lo, hi in ((0, dn.p_off), (dn.p_off, dn.lam_off)):
+            ref = x_ref[idx][lo:hi]
+            assert np.linalg.norm(xh[lo:hi] - ref) <= 1e-8 * max(np.linalg.norm(ref), 1e-30), (name, world, pm.rank, lo)
+        v = pm.valid_multipliers()
+        lam, lam_ref = xh[dn.lam_off:][v], x_ref[lay["lam_off"]:][v]
+        assert np.linalg.norm(lam - lam_ref) <= 1e-8 * max(np.linalg.norm(lam_ref), 1e-30)
+        lam_all.append((v, xh[dn.lam_off:]))
+    # every multiplier is computed somewhere; replicated ones carry identical bits on every rank
+    seen = np.zeros(om.B, dtype=int)
+    for v, _ in lam_all:
+        seen[v] += 1
+    assert (seen >= 1).all()
+    repl = np.nonzero(seen == world)[0]
+    for v, lam in lam_all[1:]:
+        assert np.array_equal(lam[repl].view(np.int64), lam_all[0][1][repl].view(np.int64))
+    plan0 = pms[0].ms.schur_plan()[3]
+    if name.startswith("tree"):
+        assert int((plan0.owner < 0).sum()) <= 2 * world        # a handful of replicated bifurcations
