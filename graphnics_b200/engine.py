@@ -576,7 +576,7 @@ class MixedSystem:
             if cr is not None:
                 check(self.lib.gnx_rhs_eliminate_mixed(dn.net_ref(), co.ref(), *cr, None, None, None, C.byref(ex), st))
             else:
-                check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), C.byref(ex), st))
+                check(self.lib.gnx_edge_eliminate_mixed_p2p(dn.net_ref(), co.ref(), ptr(b), C.byref(ex), None, None, st))
             if ex.epoch == 0:
                 p2p["hdls"][k].barrier(channel=0)
             g = p2p["bufs"][k]
