@@ -8,19 +8,23 @@ edge = 1 048 064 cells, N = 2 099 198 mixed DOFs), reported as MDOF/s.
 One "step" = what `MixedHydraulicNetwork.solve()` does after the mesh exists
 (graphnics/flowmodels/flow_models.py:337-350): assemble the monolithic CSR values, assemble the
 right-hand side, solve.  Mesh, CSR pattern and solver workspaces are built once, outside the timed
-region (SURVEY.md 8d "built once").
+region, and reported as `built_once_ms` (SURVEY.md 8d "built once").
 
   value        device-resident inputs, CUDA events around every step (L2 flushed between steps)
   e2e          the user-facing call `MixedHydraulicNetwork(G, p_bc=...).solve()` +
                `qp.vector().get_local()` : host (numpy) coefficient data in, host solution out
   roofline     the step's dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  parity       the timed step's b / x against the CPU oracle on the same workload
   cpu_baseline the numpy/scipy oracle (oracle/, the CPU restatement of the reference path) on the
                same workload on this box's host cores
+  at_scale     the same kernels where HBM, not latency, is the limit (N > 1: BASELINE.json configs[4], the
+               ~100 M-DOF tree across the GPUs)
 `--impl reference` times that CPU restatement alone (the real reference needs FEniCS + fenics_ii +
 PETSc/MUMPS, none of which can be installed offline -- DESIGN.md).
+N > 1 (torchrun, one rank per GPU): weak scaling, one more tree generation per doubling, the tree cut into
+subtrees (graphnics_b200/partition.py).
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -36,6 +40,9 @@ if ROOT not in sys.path:
 
 METRIC = "MDOF/s (assemble+solve) MixedHydraulicNetwork on synthetic tree"
 TREE_LEVELS, TREE_N = 11, 9
+SCALE_LEVELS, SCALE_N = 16, 7          # at_scale at N GPUs: 16 + log2(N) generations, 2^7 cells per edge (N = 8: C5)
+# SURVEY.md 8(d) per-unit algorithmic bytes: assembly ~110 B/cell, edge-scan elimination ~32 B/DOF
+ASM_B_PER_CELL, ELIM_B_PER_DOF = 110, 32
 
 
 def peaks():
@@ -112,8 +119,35 @@ def config_dict(levels, n, E, N, extra=None):
     return d
 
 
+def step_stats(ts):
+    ts = np.asarray(ts, dtype=np.float64)
+    return {"min": float(ts.min()), "median": float(np.median(ts)), "max": float(ts.max()), "mean": float(ts.mean())}
+
+
+def count_launches(fn, reps):
+    """kernels launched by `reps` calls of fn, counted by CUPTI (torch.profiler) on a replay outside the timed
+    region: (total, {kernel name: launches per call})"""
+    try:
+        import torch
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            if ev.device_type is not None and "cuda" in str(ev.device_type).lower() and not ev.name.lower().startswith("memcpy") \
+                    and not ev.name.lower().startswith("memset"):
+                names[ev.name] = names.get(ev.name, 0) + 1
+        total = int(sum(names.values()))
+        return total, {k[:90]: v / reps for k, v in sorted(names.items())}
+    except Exception as ex:                      # no CUPTI on this box: say so instead of inventing a number
+        return None, {"unavailable": repr(ex)[:200]}
+
+
 # --------------------------------------------------------------------------------------------
-# CPU restatement (oracle) -- cpu_baseline and --impl reference
+# CPU restatement (oracle) -- cpu_baseline, parity and --impl reference
 # --------------------------------------------------------------------------------------------
 def oracle_step_factory(pos, edges, n):
     import oracle
@@ -125,27 +159,53 @@ def oracle_step_factory(pos, edges, n):
         A = oracle.assemble_mixed(om, 1.0)
         b = oracle.assemble_mixed_rhs(om, p_bc=pbc, project=False)
         return oracle.lu_solve(A, b)
+    step.om = om
     return step, N
 
 
 def cpu_baseline(pos, edges, budget_s=20.0):
-    """oracle on the full workload if it fits the budget, else on a coarser refinement."""
+    """oracle on the full workload if it fits the budget, else on a coarser refinement.  Returns the baseline
+    record and (n, x) of the last oracle solve for the parity check."""
     n = TREE_N
     while True:
         step, N = oracle_step_factory(pos, edges, n)
-        t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
+        t0 = time.perf_counter(); x = step(); t = time.perf_counter() - t0
         if t <= budget_s or n <= 4:
             break
         n -= 2
     reps = max(1, min(3, int(budget_s / max(t, 1e-3)) - 1))
     ts = [t]
     for _ in range(reps):
-        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); x = step(); ts.append(time.perf_counter() - t0)
     best = min(ts)
-    return {"value": N / best / 1e6, "unit": "MDOF/s", "cores": 1, "kind": "port",
-            "sample": f"numpy/scipy oracle (COO->CSR assembly + SuperLU), same tree, 2^{n} cells/edge, N={N}, "
-                      f"best of {len(ts)} runs, {best:.2f} s per assemble+solve",
-            "seconds_per_step": best}
+    rec = {"value": N / best / 1e6, "unit": "MDOF/s", "cores": 1, "kind": "port",
+           "sample": f"numpy/scipy oracle (COO->CSR assembly + SuperLU), same tree, 2^{n} cells/edge, N={N}, "
+                     f"best of {len(ts)} runs, {best:.2f} s per assemble+solve",
+           "seconds_per_step": best}
+    return rec, (n, x, step.om)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def parity_block(om, x_ref, route, xg, bg=None, rowptr=None, colidx=None, vals=None):
+    """the timed step's result against the oracle (tests/test_gpu_bench_configs.py asserts the same quantities)"""
+    import oracle
+    lay = oracle.mixed_layout(om)
+    out = {"oracle": route,
+           "rel_l2_q": rel(xg[:lay["p_off"]], x_ref[:lay["p_off"]]),
+           "rel_l2_p": rel(xg[lay["p_off"]:lay["lam_off"]], x_ref[lay["p_off"]:lay["lam_off"]]),
+           "rel_l2_lam": rel(xg[lay["lam_off"]:], x_ref[lay["lam_off"]:])}
+    if bg is not None:
+        b_ref = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda x: x[..., 1], 1), project=False)
+        out["rhs_max_abs_diff"] = float(np.abs(bg - b_ref).max())
+    if vals is not None:
+        A = oracle.assemble_mixed(om, 1.0)
+        out["pattern_equal"] = bool(np.array_equal(rowptr, A.indptr) and np.array_equal(colidx, A.indices))
+        out["values_max_rel_diff"] = float(np.abs(vals - A.data).max() / np.abs(A.data).max())
+    out["ok"] = bool(max(out["rel_l2_q"], out["rel_l2_p"], out["rel_l2_lam"]) <= 1e-8 and out.get("pattern_equal", True))
+    return out
 
 
 def run_reference(args):
@@ -167,10 +227,10 @@ def run_reference(args):
         t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
     for _ in range(args.warmup):
         step()
-    t0 = time.perf_counter()
+    ts = []
     for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
     val = N / dt / 1e6
     E_full = len(edges)
     full_N = E_full * (2 * (1 << TREE_N) + 1) + (E_full - 1) // 2
@@ -179,7 +239,12 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MDOF/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict(levels, TREE_N, len(edges), full_N, {"sample_n": n, "sample_ndofs": N}),
+           "config": config_dict(levels, TREE_N, len(edges), full_N,
+                                 {"sample_n": n, "sample_ndofs": N, "same_workload": bool(n == TREE_N),
+                                  "note": None if n == TREE_N else
+                                  f"bounded sample: the same tree at 2^{n} instead of 2^{TREE_N} cells per edge -- the "
+                                  f"per-DOF throughput of a COARSER refinement, not the GPU arm's workload"}),
+           "ms_per_step_stats": step_stats(np.asarray(ts) * 1e3),
            "cpu_baseline": {"value": val, "unit": "MDOF/s", "cores": 1, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -188,6 +253,22 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def timed_steps(torch, fn, reps, warm, flush):
+    host_us = []
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); t0 = time.perf_counter(); fn(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts, host_us
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -195,7 +276,6 @@ def run_gpu(args):
     from graphnics_b200.engine import MixedSystem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -209,15 +289,21 @@ def run_gpu(args):
         os.dup2(2, 1)
         sys.stdout = os.fdopen(keep, "w", buffering=1)
         dist.init_process_group("nccl", device_id=dev)
-    if world > 1:
-        from graphnics_b200.parallel import run_partitioned_bench
-        return run_partitioned_bench(args, METRIC, config_dict, peaks, ClockSampler)
+        return run_partitioned(args, dev)
 
     pos, edges = tree_arrays()
     n = TREE_N
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     dn = DeviceNetwork(pos, edges, n, device=dev)
+    torch.cuda.synchronize()
+    t_mesh = time.perf_counter() - t0
     ms = MixedSystem(dn)
-    ms.build_pattern()
+    t0 = time.perf_counter(); ms.build_pattern(); torch.cuda.synchronize(); t_pat = time.perf_counter() - t0
+    t0 = time.perf_counter(); ms.schur_plan(); torch.cuda.synchronize(); t_plan = time.perf_counter() - t0
+    built_once = {"mesh_tables_ms": t_mesh * 1e3, "csr_pattern_ms": t_pat * 1e3, "schur_plan_host_ms": t_plan * 1e3,
+                  "total_ms": (t_mesh + t_pat + t_plan) * 1e3,
+                  "note": "first call in the process: includes CUDA context / module load; not part of the step"}
     N, nnz, NC = ms.N, ms.nnz, dn.num_cells
     Res_host = np.ones(dn.E)
     co = ms.coeffs(Res_host)
@@ -228,44 +314,31 @@ def run_gpu(args):
     pbc_out = ms.end_values(xq[:, 1].contiguous())
     pbc_node = dn.pos[:, 1].contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
     rhs_kw = dict(pbc_out=pbc_out, pbc_node=pbc_node)
 
     def step():
         ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=not args.no_overlap, sync=False)
 
-    host_us = []          # host time to enqueue one call (no synchronisation inside)
-
     def timed(fn, reps, warm, do_flush=True):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            if do_flush:
-                flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); t0 = time.perf_counter(); fn(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
-            e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return ts
+        return timed_steps(torch, fn, reps, warm, flush if do_flush else None)[0]
 
     # ---- headline: K timed steps
     clocks = ClockSampler(local).start()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    ts, host_us = timed_steps(torch, step, args.steps, max(args.warmup, 3), flush)
     torch.cuda.synchronize()
-    ts = timed(step, args.steps, 0)
-    torch.cuda.synchronize()
-    host_enqueue_us = float(np.median(host_us))
     ms_per_step = float(np.sum(ts) / args.steps)
     value = N / (ms_per_step * 1e-3) / 1e6
+    resident = bool(int(ms.lib.gnx_step_is_resident()))
+    launches, launch_names = count_launches(step, args.steps)
 
-    # ---- accuracy of what was timed (monolithic residual of the assembled system)
+    # ---- accuracy of what was timed: monolithic residual + (below) the oracle
     rr, bb = ms.residual(vals, x, b).cpu().tolist()
     rel_resid = float(np.sqrt(rr / bb))
+    x_timed, b_timed = x.cpu().numpy(), b.cpu().numpy()
+    vals_timed = vals.cpu().numpy()
 
     # ---- per-kernel breakdown (each kernel alone, L2 flushed) and roofline
+    import ctypes
     bufs = ms._bufs()
     kernels = {}
 
@@ -273,7 +346,10 @@ def run_gpu(args):
         t = float(np.mean(timed(fn, 10, 3)))
         kernels[name] = {"ms": t, "algorithmic_bytes": int(bytes_), "GBps": bytes_ / t / 1e6}
 
-    k("mixed_values_kernel (assembly)", lambda: ms.assemble(co, out=vals), 8 * nnz + 8 * NC)
+    step_bytes_survey = ASM_B_PER_CELL * NC + ELIM_B_PER_DOF * N
+    step_bytes_moved = 8 * nnz + 8 * NC + 2 * 8 * N                 # values + h once + b, x written (nothing re-read)
+    k("step kernel(s) as timed (assemble + rhs + solve)", step, step_bytes_survey)
+    k("mixed_values_tile_kernel (assembly alone)", lambda: ms.assemble(co, out=vals), 8 * nnz + 8 * NC)
     k("mixed_rhs_kernel", lambda: ms.rhs(None, None, pbc_out, pbc_node, out=b), 8 * N)
     k("edge_eliminate_kernel", lambda: ms.lib.gnx_edge_eliminate_mixed(
         dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
@@ -287,14 +363,19 @@ def run_gpu(args):
     k("edge_backsub_kernel", lambda: ms.lib.gnx_edge_backsub_mixed(
         dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["P"].data_ptr(), x.data_ptr(), torch.cuda.current_stream().cuda_stream), 2 * 8 * N + 8 * NC)
-    k("eliminate+schur+backsub (solve, 3 launches)", lambda: ms.solve(co, b, x=x, sync=False), 3 * 8 * N + 2 * 8 * NC)
+    k("eliminate+schur+backsub (kernel chain, 3 launches)", lambda: ms.solve(co, b, x=x, sync=False), 3 * 8 * N + 2 * 8 * NC)
     y = torch.empty_like(x)
     spmv_bytes = 12 * nnz + 4 * (N + 1) + 16 * N
     k("spmv_kernel (not in the step; Krylov building block)", lambda: ms.spmv(vals, x, y), spmv_bytes)
     k("reference point: torch copy_ of N doubles (not in the step)", lambda: y.copy_(x), 16 * N)
     hbm, peak_src = peaks()
-    dom = max((kk for kk in kernels if "not in the step" not in kk and "(solve" not in kk and "latency" not in kk),
-              key=lambda kk: kernels[kk]["ms"])
+    if resident:
+        dom = "step kernel(s) as timed (assemble + rhs + solve)"
+        dom_name = "step_resident_kernel (ONE persistent kernel: rhs + elimination | Schur solve + CSR assembly | back-substitution)"
+    else:
+        dom = max((kk for kk in kernels if "not in the step" not in kk and "chain" not in kk and "latency" not in kk
+                   and "as timed" not in kk), key=lambda kk: kernels[kk]["ms"])
+        dom_name = dom
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
     traffic, tsrc = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -302,31 +383,50 @@ def run_gpu(args):
         with open(tp) as fh:
             tj = json.load(fh)
         for key, rec in tj.get("kernels", {}).items():
-            if key in dom:
+            if key in dom_name:
                 traffic, tsrc = rec["dram_bytes_read"] + rec["dram_bytes_write"], tj.get("source")
-    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
-            "frac": kernels[dom]["GBps"] / hbm, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src}
+    roof = {"bound": "hbm", "kernel": dom_name, "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
+            "frac": kernels[dom]["GBps"] / hbm, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+            "algorithmic_bytes": kernels[dom]["algorithmic_bytes"],
+            "algorithmic_bytes_rule": (f"SURVEY.md 8(d): assembly {ASM_B_PER_CELL} B/cell x {NC} cells + edge-scan elimination "
+                                       f"{ELIM_B_PER_DOF} B/DOF x {N} DOFs" if resident else "see DESIGN.md section 4"),
+            "bytes_the_kernel_has_to_move": int(step_bytes_moved) if resident else None,
+            "ms": kernels[dom]["ms"]}
 
     # ---- the same kernels where HBM, not launch latency, is the limit: a 17-generation tree, 2^7 cells per
     #      edge (33.7 M DOFs, 1.1 GB of CSR values; every array is many times the 126 MB L2)
     at_scale = kernels_at_scale(hbm, timed)
 
     # ---- e2e through the drop-in Python API, host data in / host solution out
-    e2e = e2e_python_api(pos, edges, n, dn, args)
+    e2e = e2e_python_api(pos, edges, n, args)
     clk = clocks.stop()
 
     out = {"metric": METRIC, "value": value, "unit": "MDOF/s", "n_gpus": 1, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(TREE_LEVELS, n, dn.E, N, {"nnz": nnz, "bifurcations": dn.B}),
-           "rel_residual": rel_resid, "gpu_launches": 4 * args.steps, "host_enqueue_us_per_step": host_enqueue_us,
+           "ms_per_step_stats": step_stats(ts), "built_once_ms": built_once,
+           "rel_residual": rel_resid, "gpu_launches": launches, "gpu_launches_per_step": launch_names,
+           "gpu_launches_how": "CUPTI (torch.profiler) kernel records of a replay of the same K steps after the timed region",
+           "host_enqueue_us_per_step": float(np.median(host_us)),
            "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
-           "streams": ("1 (kernels back to back)" if args.no_overlap else
-                       "2: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute on a "
-                       "high-priority stream; joined before the step's end event"), "kernels": kernels, "roofline": roof,
-           "at_scale": at_scale, "e2e": e2e, "clocks": clk}
+           "step_path": ("ONE persistent cooperative kernel (cell lengths resident in shared memory; CSR assembly on the SMs "
+                         "that wait for the one-CTA Schur phase)" if resident else
+                         ("kernel chain on one stream" if args.no_overlap else
+                          "kernel chain: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute "
+                          "on a high-priority stream")),
+           "kernels": kernels, "roofline": roof, "at_scale": at_scale, "e2e": e2e, "clocks": clk}
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(pos, edges)
+        out["cpu_baseline"], (n_or, x_or, om) = cpu_baseline(pos, edges)
+        import oracle
+        if n_or == n:
+            out["parity"] = parity_block(om, x_or, "LU (SuperLU) of the oracle's assembled matrix, same tree, same refinement",
+                                         x_timed, b_timed, ms.rowptr.cpu().numpy(), ms.colidx.cpu().numpy(), vals_timed)
+        else:                                    # the LU was too slow for the budget here: elimination route at full size
+            om = oracle.build_mesh(pos, edges, n)
+            b_ref = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda xx: xx[..., 1], 1), project=False)
+            out["parity"] = parity_block(om, oracle.solve_by_elimination(om, b_ref, 1.0),
+                                         "oracle elimination route (oracle/elimination.py)", x_timed, b_timed)
     print(json.dumps(out))
 
 
@@ -380,18 +480,24 @@ def kernels_at_scale(hbm, timed, levels=17, n=7):
     return out
 
 
-def e2e_python_api(pos, edges, n, dn, args):
-    """`MixedHydraulicNetwork(G, p_bc=Expression("x[1]")).solve()` on a FenicsGraph, then the solution
-    copied to the host -- wall clock around a synchronised region."""
-    import torch
+def api_graph(pos, edges, n, comm=None):
     import graphnics_b200 as gn
     G = gn.FenicsGraph()
     G.add_nodes_from((i, {"pos": p}) for i, p in enumerate(pos.tolist()))
     G.add_edges_from(map(tuple, edges.tolist()))
-    G.make_mesh(n)                       # built once (not timed), like the reference benchmark
+    G.make_mesh(n, comm=comm)            # built once (not timed), like the reference benchmark
     res = gn.Constant(1.0)
     for e in G.edges():
         G.edges[e]["Res"] = res
+    return G
+
+
+def e2e_python_api(pos, edges, n, args, comm=None):
+    """`MixedHydraulicNetwork(G, p_bc=Expression("x[1]")).solve()` on a FenicsGraph, then the solution
+    copied to the host -- wall clock around a synchronised region (max over ranks when partitioned)."""
+    import torch
+    import graphnics_b200 as gn
+    G = api_graph(pos, edges, n, comm)
     p_bc = gn.Expression("x[1]", degree=2)
 
     def step():
@@ -402,16 +508,233 @@ def e2e_python_api(pos, edges, n, dn, args):
     for _ in range(max(args.warmup, 3)):
         xh = step()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    if comm:
+        import torch.distributed as dist
+        dist.barrier()
+    ts = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         xh = step()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
+    n_local, E_local = xh.size, G._dn.E
+    if comm:
+        import torch.distributed as dist
+        t = torch.tensor([dt, float(n_local), float(E_local)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, n_sum, E_sum = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        world = dist.get_world_size()
+        m = 1 << n
+        N = len(edges) * (2 * m + 1) + G._dn.B
+        h2d, d2h = int(8 * E_sum + 2 * 1024 * world), int(8 * n_sum)
+    else:
+        N, h2d, d2h = n_local, int(8 * E_local + 2 * 1024), int(8 * n_local)
+    return {"value": N / dt / 1e6, "unit": "MDOF/s", "ms_per_step": dt * 1e3, "ms_per_step_stats": step_stats(np.asarray(ts) * 1e3),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "timer": "wall clock (perf_counter) around synchronised region" + (", max over ranks" if comm else ""),
+            "call": ("G.make_mesh(n, comm=True) once; per step MixedHydraulicNetwork(G, p_bc=Expression('x[1]')).solve(); "
+                     "qp.vector().get_local()  (the rank-local part, like PETSc under MPI)" if comm else
+                     "MixedHydraulicNetwork(G, p_bc=Expression('x[1]')).solve(); qp.vector().get_local()")}
+
+
+# --------------------------------------------------------------------------------------------
+# N > 1: one rank per GPU
+# --------------------------------------------------------------------------------------------
+def assemble_global(pm, pieces, lam_pieces, owner):
+    """rank 0: the monolithic global vector from the ranks' local [q | p] blocks and multiplier blocks"""
+    world, m, E = pm.world, pm.m, pm.E_glob
+    B = pm.dn.B
+    x = np.full(pm.N_glob, np.nan)
+    epart = pm.dn.epart if pm.dn.edge_ids is not None else None
+    for r in range(world):
+        if epart is not None:
+            e = np.nonzero(epart == r)[0]
+        else:
+            from graphnics_b200.device import partition_range
+            e0, e1, _ = partition_range(E, r, world)
+            e = np.arange(e0, e1)
+        q = (e[:, None] * (m + 1) + np.arange(m + 1)[None, :]).ravel()
+        p = E * (m + 1) + (e[:, None] * m + np.arange(m)[None, :]).ravel()
+        loc = pieces[r]
+        x[q] = loc[: len(q)]
+        x[p] = loc[len(q): len(q) + len(p)]
+        lam = lam_pieces[r]
+        mine = np.arange(B) if owner is None else np.nonzero((owner == r) | ((owner < 0) & (r == 0)))[0]
+        x[E * (2 * m + 1) + mine] = lam[mine]
+    return x
+
+
+def partitioned_case(torch, dist, dev, levels, n, args, flush, reps, warm):
+    """one weak-scaling workload: build, time, residual; returns (record, pm, tensors)"""
+    from graphnics_b200.parallel import PartitionedMixed, global_residual
+    pos, edges = tree_arrays(levels)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    pm = PartitionedMixed(pos, edges, n, device=dev, exchange=os.environ.get("GNX_EXCHANGE", "auto"),
+                          partition=os.environ.get("GNX_PARTITION", "subtree"))
+    dn, ms = pm.dn, pm.ms
+    ms.build_pattern()
+    ms.schur_plan()
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / args.steps
-    N = xh.size
-    return {"value": N / dt / 1e6, "unit": "MDOF/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(8 * dn.E + 2 * 1024), "d2h_bytes_per_step": int(8 * N),
-            "timer": "wall clock (perf_counter) around synchronised region",
-            "call": "MixedHydraulicNetwork(G, p_bc=Expression('x[1]')).solve(); qp.vector().get_local()"}
+    t_build = time.perf_counter() - t0
+    N_loc, nnz_loc = ms.N, ms.nnz
+    co = ms.coeffs(torch.ones(dn.E, dtype=torch.float64, device=dev))
+    vals = torch.empty(nnz_loc, dtype=torch.float64, device=dev)
+    b = torch.empty(N_loc, dtype=torch.float64, device=dev)
+    x = torch.zeros(N_loc, dtype=torch.float64, device=dev)
+    xq, _ = ms.dof_coordinates(False)
+    pbc_out = ms.end_values(xq[:, 1].contiguous())
+    pbc_node = dn.pos[:, 1].contiguous()
+    del xq
+    ms._xq = None
+    rhs_kw = dict(pbc_out=pbc_out, pbc_node=pbc_node)
+    overlap = not getattr(args, "no_overlap", False)
+
+    def step():
+        ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=overlap, sync=False)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ts, host_us = [], []
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); t0 = time.perf_counter(); step(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor(ts, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # per step: the slowest rank
+    ts_max = t.cpu().numpy()
+    rel_resid = global_residual(ms, vals, x, b)
+    hp = ms.schur_plan()[3]
+    rec = {"levels": levels, "n": n, "edges": pm.E_glob, "ndofs": pm.N_glob, "ms_per_step": float(ts_max.mean()),
+           "ms_per_step_stats": step_stats(ts_max), "rel_residual": rel_resid, "edges_per_rank": dn.E,
+           "ndofs_per_rank": N_loc, "bifurcations": dn.B,
+           "replicated_bifurcations": int((hp.owner < 0).sum()) if ms.subtree else dn.B,
+           "built_once_ms": t_build * 1e3, "host_enqueue_us_per_step": float(np.median(host_us)),
+           "per_rank_bytes": {"survey_8d": int(ASM_B_PER_CELL * dn.num_cells + ELIM_B_PER_DOF * N_loc),
+                              "moved_by_the_kernel_chain": int(8 * (nnz_loc + dn.num_cells) + 8 * N_loc +
+                                                               2 * 8 * (N_loc + dn.num_cells) + 8 * N_loc)}}
+    return rec, pm, (co, vals, b, x, step)
+
+
+def run_partitioned(args, dev):
+    import torch
+    import torch.distributed as dist
+    from graphnics_b200.parallel import gather_to_root
+    world, rank = dist.get_world_size(), dist.get_rank()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    grow = int(np.ceil(np.log2(world)))
+    hbm, peak_src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    clocks = ClockSampler(local).start() if rank == 0 else None
+
+    # ---- headline: C2 per rank (weak scaling)
+    levels, n = TREE_LEVELS + grow, TREE_N
+    rec, pm, (co, vals, b, x, step) = partitioned_case(torch, dist, dev, levels, n, args, flush, args.steps, max(args.warmup, 3))
+    ms, dn = pm.ms, pm.dn
+    launches, launch_names = count_launches(step, args.steps)
+    resident = bool(int(ms.lib.gnx_step_is_resident()))
+    # parity: rank 0 gathers the solution and compares it with the oracle's elimination route on the WHOLE tree
+    pieces = gather_to_root(x[:dn.lam_off])
+    lam_pieces = gather_to_root(x[dn.lam_off:])
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        import oracle
+        pos, edges = tree_arrays(levels)
+        om = oracle.build_mesh(pos, edges, n)
+        b_ref = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda xx: xx[..., 1], 1), project=False)
+        x_ref = oracle.solve_by_elimination(om, b_ref, 1.0)
+        owner = ms.schur_plan()[3].owner if ms.subtree else None
+        xg = assemble_global(pm, pieces, lam_pieces, owner)
+        parity = parity_block(om, x_ref, "oracle elimination route (oracle/elimination.py) on the whole N-GPU tree; "
+                                         "the ranks' pieces gathered on rank 0", xg)
+        del om, x_ref, xg
+    del pieces, lam_pieces
+    dist.barrier()
+
+    # ---- e2e through the drop-in API on the partitioned graph
+    pos, edges = tree_arrays(levels)
+    e2e = e2e_python_api(pos, edges, n, args, comm=True)
+    del co, vals, b, x, step, pm, ms, dn
+    torch.cuda.empty_cache()
+
+    # ---- at scale: 16 + log2(world) generations, 2^7 cells per edge (world = 8: BASELINE.json configs[4], 135 M DOFs)
+    srec, spm, (sco, svals, sb, sx, sstep) = partitioned_case(torch, dist, dev, SCALE_LEVELS + grow, SCALE_N, args, None, 10, 3)
+    sms, sdn = spm.ms, spm.dn
+    srec["MDOF_per_s"] = srec["ndofs"] / srec["ms_per_step"] / 1e3
+    srec["per_rank_GBps_survey_bytes"] = srec["per_rank_bytes"]["survey_8d"] / srec["ms_per_step"] / 1e6
+    srec["per_rank_frac_of_measured_hbm_peak"] = srec["per_rank_GBps_survey_bytes"] / hbm
+    srec["per_rank_GBps_moved_bytes"] = srec["per_rank_bytes"]["moved_by_the_kernel_chain"] / srec["ms_per_step"] / 1e6
+    srec["workload"] = (f"binary tree, {SCALE_LEVELS + grow} generations, E={srec['edges']}, 2^{SCALE_N} cells/edge, "
+                        f"N={srec['ndofs']} across {world} GPUs (L2 not flushed: every array is >> L2)")
+    # oracle check that does not depend on the refinement: with f = g = 0 the multipliers and the (constant) flux of
+    # every edge are the graph-level Kirchhoff solution, whatever the number of cells -- compare with the oracle
+    # on the same tree at 2 cells per edge
+    lam_all = gather_to_root(sx[sdn.lam_off:])
+    q0_all = gather_to_root(sx[:sdn.p_off].reshape(sdn.E, sdn.m + 1)[:, 0].contiguous())
+    if rank == 0 and not args.no_cpu:
+        import oracle
+        pos2, edges2 = tree_arrays(SCALE_LEVELS + grow)
+        om = oracle.build_mesh(pos2, edges2, 1)
+        b_ref = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda xx: xx[..., 1], 1), project=False)
+        x_ref = oracle.solve_by_elimination(om, b_ref, 1.0)
+        lay = oracle.mixed_layout(om)
+        owner = sms.schur_plan()[3].owner if sms.subtree else None
+        lam = np.full(sdn.B, np.nan)
+        qe = np.full(spm.E_glob, np.nan)
+        for r in range(world):
+            mine = np.arange(sdn.B) if owner is None else np.nonzero((owner == r) | ((owner < 0) & (r == 0)))[0]
+            lam[mine] = lam_all[r][mine]
+            e = np.nonzero(sdn.epart == r)[0] if sdn.edge_ids is not None else None
+            if e is None:
+                from graphnics_b200.device import partition_range
+                e0, e1, _ = partition_range(spm.E_glob, r, world)
+                e = np.arange(e0, e1)
+            qe[e] = q0_all[r]
+        srec["oracle_sample"] = {"what": "multipliers and per-edge flux vs the oracle on the same tree at 2 cells/edge "
+                                         "(refinement-independent for f = g = 0)",
+                                 "rel_l2_lam": rel(lam, x_ref[lay["lam_off"]:]),
+                                 "rel_l2_q_edge": rel(qe, x_ref[:lay["p_off"]].reshape(len(edges2), 3)[:, 0])}
+        srec["oracle_sample"]["ok"] = bool(max(srec["oracle_sample"]["rel_l2_lam"], srec["oracle_sample"]["rel_l2_q_edge"]) <= 1e-8)
+    dist.barrier()
+    clk = clocks.stop() if clocks is not None else None
+    if rank == 0:
+        N = rec["ndofs"]
+        ms_per_step = rec["ms_per_step"]
+        out = {"metric": METRIC, "value": N / (ms_per_step * 1e-3) / 1e6, "unit": "MDOF/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": config_dict(levels, n, rec["edges"], N, {
+                   "parallelism": (f"edge-partitioned x{world}: one subtree per rank (partition.py), rank-local elimination and "
+                                   f"rake, {rec['replicated_bifurcations']} replicated bifurcations, ONE exchange per solve "
+                                   f"(edges at replicated bifurcations + local subtree roots)"),
+                   "exchange": "peer stores over NVLink + flag words inside the kernel" if sms.exchange_mode == "p2p"
+                               else f"NCCL all-gather between two launches ({getattr(sms, '_p2p_error', '')})",
+                   "edges_per_rank": rec["edges_per_rank"], "ndofs_per_rank": rec["ndofs_per_rank"],
+                   "bifurcations": rec["bifurcations"]}),
+               "ms_per_step_stats": rec["ms_per_step_stats"], "built_once_ms": {"total_ms": rec["built_once_ms"]},
+               "rel_residual": rec["rel_residual"], "gpu_launches": launches, "gpu_launches_per_step": launch_names,
+               "gpu_launches_how": "CUPTI (torch.profiler) kernel records of a replay of the same K steps on rank 0",
+               "host_enqueue_us_per_step": rec["host_enqueue_us_per_step"],
+               "step_path": "ONE persistent cooperative kernel per rank, the exchange inside it" if resident else "kernel chain",
+               "parity": parity,
+               "roofline": {"bound": "hbm", "kernel": "per-rank step (assemble + rhs + eliminate + Schur + back-substitute)",
+                            "achieved": rec["per_rank_bytes"]["survey_8d"] / ms_per_step / 1e6, "peak": hbm, "unit": "GB/s",
+                            "frac": rec["per_rank_bytes"]["survey_8d"] / ms_per_step / 1e6 / hbm, "traffic": None,
+                            "peak_source": peak_src,
+                            "algorithmic_bytes_rule": f"SURVEY.md 8(d): {ASM_B_PER_CELL} B/cell + {ELIM_B_PER_DOF} B/DOF, per rank"},
+               "at_scale": srec, "e2e": e2e, "clocks": clk}
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -420,9 +743,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / oracle parity legs (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true",
-                    help="run the step's kernels back to back on one stream (default: CSR assembly overlaps the solve)")
+                    help="kernel chain only: run the step's kernels back to back on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

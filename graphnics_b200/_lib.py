@@ -106,6 +106,7 @@ PROTOTYPES = {
     "gnx_rhs_eliminate_mixed": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P, _EX, _P]),
     "gnx_step_mixed": (_I, [_NET, _CO, _P, _P, _D, _D, _P, _P, _P, _P, _NET, _PLAN, _P, _P, _P, _P, _P, _D, _I, _I,
                             _EX, c_f64p, c_i32p, _P, _P, _P, _P, _L, _P]),
+    "gnx_step_is_resident": (_I, []),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
     "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _EX, c_f64p, c_i32p, _P]),

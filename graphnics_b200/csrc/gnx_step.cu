@@ -15,6 +15,9 @@ int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t*
                              const gnx_exchange_t* ex, unsigned long long* sync, unsigned long long epoch,
                              double* vals, double* resid_host, int32_t* info_host, cudaStream_t st);
 
+static int g_last_step_resident = 0;
+extern "C" int gnx_step_is_resident(void) { return g_last_step_resident; }
+
 extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const int32_t* rowptr,
                               double* vals, double f_const, double g_const, const double* pbc_out,
                               const double* pbc_node, double* b, double* x, const gnx_network_t* schur_net,
@@ -31,10 +34,12 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
       gnx_step_resident_applies(net, plan, b, x, reinterpret_cast<const unsigned long long*>(sync))) {
     // small enough for the cell lengths to stay in shared memory: the whole step -- assembly included -- is ONE
     // persistent kernel on the caller's stream (no second stream, no events)
+    g_last_step_resident = 1;
     return gnx_step_resident_launch(net, co, f_const, g_const, pbc_out, pbc_node, b, x, schur_net, plan, cond, rsrc,
                                     ftot, P, work, rtol, max_iter, warm, ex, reinterpret_cast<unsigned long long*>(sync),
                                     (unsigned long long)epoch, vals, resid_host, info_host, main_st);
   }
+  g_last_step_resident = 0;
   cudaStream_t solve_st = side_stream ? (cudaStream_t)side_stream : main_st;
   const bool fork = side_stream != nullptr && vals != nullptr;
   if (fork) {

@@ -120,12 +120,32 @@ class FenicsGraph(nx.DiGraph):
         self._drop_edge_cache()
         return super().update(edges=edges, nodes=nodes)
 
-    def make_mesh(self, n=1):
-        """Generates and stores the mesh with 2^n cells per edge (fenics_graph.py:102-129)."""
+    def make_mesh(self, n=1, comm=None):
+        """Generates and stores the mesh with 2^n cells per edge (fenics_graph.py:102-129).
+
+        comm (beyond the reference, which is serial): True or a torch.distributed process group -- the network is
+        EDGE-PARTITIONED over the group's ranks, one GPU each (partition.partition_edges: whole subtrees per rank);
+        this rank meshes its own edges only, the models built on the graph solve the global problem together, and
+        `qp.vector().get_local()` returns the process-local part like a PETSc vector under MPI does
+        (`G.local_edges`: global indices of the edges this rank holds, ascending)."""
         pos, edges = self._graph_arrays()
         self.geom_dim = pos.shape[1]
         self.num_edges = len(edges)
-        self._dn = DeviceNetwork(pos, edges, n)
+        self._group = None
+        self.local_edges = None
+        if comm is not None and comm is not False:
+            import torch.distributed as dist
+            group = None if comm is True else comm
+            world = dist.get_world_size(group)
+            if world > 1:
+                from .partition import partition_edges
+                epart, plan = partition_edges(edges, len(pos), world)
+                self._dn = DeviceNetwork(pos, edges, n, part=(dist.get_rank(group), world), epart=epart)
+                self._dn.host_plan = plan
+                self._group = group if group is not None else dist.group.WORLD
+                self.local_edges = self._dn.edge_ids
+        if self.local_edges is None:
+            self._dn = DeviceNetwork(pos, edges, n)
         self._systems = {}
         self.mesh = self._dn._host_mesh()
         self.mf = CellMarker(self._dn)
@@ -227,8 +247,11 @@ class FenicsGraph(nx.DiGraph):
         # dictionaries themselves are stable objects: the list of them is kept while the edge count stands.
         dicts = self.__dict__.get("_edge_dicts")
         if dicts is None:                                   # dropped by every method that adds / removes edges
-            dicts = self.__dict__["_edge_dicts"] = [d for nbrs in self._succ.values() for d in nbrs.values()]
-        vals = [d.get(key, default) for d in dicts]
+            dicts = [d for nbrs in self._succ.values() for d in nbrs.values()]
+            if getattr(self, "local_edges", None) is not None:          # partitioned: this rank's edges only
+                dicts = [dicts[i] for i in self.local_edges]
+            self.__dict__["_edge_dicts"] = dicts
+        vals = [d.get(key, default) for d in dicts]           # (values are re-read on every solve: a user may change them)
         if vals and vals.count(vals[0]) == len(vals):                     # one shared object / one value
             vals, rep = vals[:1], len(vals)
         else:

@@ -35,7 +35,7 @@ def _system(G, kind):
         raise RuntimeError("call G.make_mesh() before building a model")
     if kind not in G._systems:
         if kind == "mixed":
-            G._systems[kind] = MixedSystem(G._dn)
+            G._systems[kind] = MixedSystem(G._dn, group=getattr(G, "_group", None))
         else:
             from ..engine_primal import PrimalSystem
             G._systems[kind] = PrimalSystem(G._dn)
@@ -109,6 +109,29 @@ class _LazyArgs:
         return (self.fn(V) for V in self.W)
 
 
+def _coef_key(cc):
+    """what a compiled coefficient evaluates to depends on its program and the CURRENT parameter values only"""
+    if cc.user is not None:
+        return None
+    if cc.is_constant:
+        return ("const", cc.const_value())
+    return (tuple(cc._code), tuple(float(cc.ufl.params[s]) for s in cc._pslots), cc.degree)
+
+
+def _cached(ms, slot, cc, make):
+    """boundary data derived from an Expression (projected end values, node values) are kept on the system while the
+    expression and its parameters (e.g. `.t`) stand: a steady solve repeated on the same graph, or a time loop with
+    time-independent p_bc, does not launch the projection again"""
+    key = _coef_key(cc)
+    hit = ms.__dict__.get(slot)
+    if key is not None and hit is not None and hit[0] == key:
+        return hit[1]
+    val = make()
+    if key is not None:
+        ms.__dict__[slot] = (key, val)
+    return val
+
+
 # ------------------------------------------------------------------------------------------
 # form handles
 # ------------------------------------------------------------------------------------------
@@ -170,7 +193,7 @@ class _MixedLForm:
             c = pbc.const_value()
             self.pbc_out = None if c == 0.0 else torch.full((dn.E,), c, dtype=torch.float64, device=dn.device)
         else:
-            self.pbc_out = ms.project_end_values(pbc)
+            self.pbc_out = _cached(ms, "_pbc_out_cache", pbc, lambda: ms.project_end_values(pbc))
         self._pbc = pbc
 
     def rhs_kwargs(self):
@@ -179,7 +202,7 @@ class _MixedLForm:
         pbc = as_coefficient(self.model.p_bc)
         pbc_node = None
         if not (pbc.is_constant and pbc.const_value() == 0.0):
-            pbc_node = pbc.eval_device(ms.dn.pos)
+            pbc_node = _cached(ms, "_pbc_node_cache", pbc, lambda: pbc.eval_device(ms.dn.pos))
         return dict(f_nodal=self.f_nodal, g_nodal=self.g_nodal, pbc_out=self.pbc_out, pbc_node=pbc_node,
                     f_const=self.f_const, g_const=self.g_const)
 
@@ -253,7 +276,9 @@ class MixedHydraulicNetwork:
         ms.build_pattern()
         vals = torch.empty(ms.nnz, dtype=torch.float64, device=ms.dev)
         b = torch.empty(ms.N, dtype=torch.float64, device=ms.dev)
-        qp = ii_Function(W, data=torch.empty(ms.N, dtype=torch.float64, device=ms.dev))
+        # (partitioned network: the multipliers of other ranks' local bifurcations are not computed here -- zero)
+        alloc = torch.empty if ms.dn.part is None else torch.zeros
+        qp = ii_Function(W, data=alloc(ms.N, dtype=torch.float64, device=ms.dev))
         # a network without cycles has no Krylov part: nothing to report, nothing to wait for
         tree = ms.dn.B == 0 or ms.schur_plan()[3].nc == 0
         _, self.solve_info = ms.assemble_rhs_solve(co, vals, b, qp.tensor(), L.rhs_kwargs(), sync=not tree)

@@ -1,16 +1,18 @@
 """Edge-partitioned multi-GPU execution of the mixed model: one process per GPU,
 torch.distributed (NCCL) for the plumbing.
 
-A rank owns a contiguous range of edges and with it, exclusively, their q and p unknowns; the
-multipliers lambda are replicated.  Assembly, right-hand side, per-edge elimination and
-back-substitution run on the local edges only (the rank's SUBDOMAIN matrix / vector: q and p rows
-are complete, lambda rows hold the local incidences, the global rows are their sum over ranks).
-The one exchange of a solve is an all-gather of the three edge scalars (conductance, source, total
-divergence: 24 bytes per edge of the whole network) -- peer stores over NVLink from inside the
-elimination kernel, synchronised by flag words inside the Schur kernel (engine.MixedSystem._p2p_setup;
-NCCL all_gather_into_tensor as the fallback); the graph-level Schur solve is then replicated
--- identical inputs and a deterministic kernel give bit-identical multipliers on every rank, so no
-Krylov dot product or halo ever crosses NVLink.
+A rank owns a set of edges (partition.py: whole subtrees of the rake forest) and with it, exclusively, their q and
+p unknowns.  Assembly, right-hand side, per-edge elimination and back-substitution run on the local edges only
+(the rank's SUBDOMAIN matrix / vector: q and p rows are complete, lambda rows hold the local incidences, the
+global rows are their sum over ranks).  The graph-level Schur system is raked rank-locally wherever a whole
+subtree sits on one rank; the ONE exchange of a solve carries the three scalars of the edges at REPLICATED
+bifurcations and the final (diagonal, right-hand side) pair of every local subtree root -- peer stores over NVLink
+from inside the kernels, synchronised by flag words inside the Schur kernel (engine.MixedSystem._xch_setup; one
+NCCL all-gather between two kernel launches as the fallback).  The replicated bifurcations (2^k - 1 for a binary
+tree on 2^k ranks; everything for a network without tree-like parts) are processed redundantly: identical inputs
+and a deterministic kernel give bit-identical multipliers on every rank, so no Krylov dot product or halo crosses
+NVLink.  partition="range" keeps round 1's layout (contiguous index ranges, all edge scalars gathered, whole Schur
+solve replicated).
 """
 import json
 import os
@@ -23,7 +25,7 @@ import torch.distributed as dist
 from .device import DeviceNetwork, partition_range
 from .engine import MixedSystem
 
-__all__ = ["PartitionedMixed", "run_partitioned_bench", "global_residual"]
+__all__ = ["PartitionedMixed", "global_residual", "gather_to_root"]
 
 
 class PartitionedMixed:
@@ -97,104 +99,17 @@ def global_residual(ms, vals, x, b, group=None):
     return (rr / bb) ** 0.5 if bb > 0 else rr ** 0.5
 
 
-def run_partitioned_bench(args, metric, config_dict, peaks, ClockSampler, tree_levels=11, n=9):
-    """bench.py --gpus N (N > 1): weak scaling -- the tree grows by one generation per doubling of
-    the GPU count, every rank keeps ~2047 edges x 2^9 cells."""
-    from .synthetic import murray_tree
-    world, rank = dist.get_world_size(), dist.get_rank()
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    levels = tree_levels + int(np.ceil(np.log2(world)))
-    pos, edges, _, _ = murray_tree(levels, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
-    pm = PartitionedMixed(pos, edges, n, device=dev, exchange=os.environ.get("GNX_EXCHANGE", "auto"))
-    dn, ms = pm.dn, pm.ms
-    ms.build_pattern()
-    ms.schur_plan()
-    N_loc, nnz_loc = ms.N, ms.nnz
-    res_host = torch.ones(dn.E, dtype=torch.float64).pin_memory()
-    co = ms.coeffs(res_host.to(dev))
-    vals = torch.empty(nnz_loc, dtype=torch.float64, device=dev)
-    b = torch.empty(N_loc, dtype=torch.float64, device=dev)
-    x = torch.empty(N_loc, dtype=torch.float64, device=dev)
-    xq, _ = ms.dof_coordinates(False)
-    pbc_out = ms.end_values(xq[:, 1].contiguous())
-    pbc_node = dn.pos[:, 1].contiguous()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    rhs_kw = dict(pbc_out=pbc_out, pbc_node=pbc_node)
-    overlap = not getattr(args, "no_overlap", False)
-
-    def step():
-        ms.assemble_rhs_solve(co, vals, b, x, rhs_kw, overlap=overlap, sync=False)
-
-    clocks = ClockSampler(local).start() if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    tot = 0.0
-    host_us = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); t0 = time.perf_counter(); step(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
-        e1.synchronize()
-        tot += e0.elapsed_time(e1)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([tot], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t[0]) / args.steps
-    rel_resid = global_residual(ms, vals, x, b)
-
-    # e2e: host coefficient data in, host solution out, wall clock, max over ranks
-    xh = torch.empty(N_loc, dtype=torch.float64).pin_memory()
-
-    def e2e_step():
-        co2 = ms.coeffs(res_host.to(dev, non_blocking=True))
-        ms.assemble_rhs_solve(co2, vals, b, x, rhs_kw, overlap=overlap, sync=False)
-        xh.copy_(x, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    for _ in range(3):
-        e2e_step()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    clk = clocks.stop() if clocks is not None else None
-    hp = ms.schur_plan()[3]
-    if rank == 0:
-        hbm, peak_src = peaks()
-        N = pm.N_glob
-        out = {"metric": metric, "value": N / (ms_per_step * 1e-3) / 1e6, "unit": "MDOF/s", "n_gpus": world,
-               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": config_dict(levels, n, pm.E_glob, N, {
-                   "parallelism": f"edge-partitioned x{world} (contiguous equal edge ranges), replicated Schur solve, "
-                                  f"one exchange of 24 B/edge per solve",
-                   "exchange": (("peer stores over NVLink fused into the elimination kernel, flag words signalled and "
-                                 "awaited inside the Schur kernel (no collective, no barrier kernel)"
-                                 if ms._p2p and ms._p2p.get("flags") else
-                                 "peer stores over NVLink fused into the elimination kernel + one cross-GPU barrier kernel")
-                                if ms.exchange_mode == "p2p" else
-                                f"NCCL all_gather_into_tensor ({getattr(ms, '_p2p_error', '')})"),
-                   "edges_per_rank": dn.E, "ndofs_per_rank": N_loc, "bifurcations": dn.B}),
-               "rel_residual": rel_resid, "gpu_launches": 4 * args.steps,
-               "host_enqueue_us_per_step": float(np.median(host_us)),
-               "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
-               "roofline": {"bound": "hbm", "kernel": "per-rank step (assemble + rhs + eliminate + back-substitute)",
-                            "achieved": (8 * (nnz_loc + dn.num_cells) + 8 * N_loc + 2 * 8 * (N_loc + dn.num_cells)
-                                         + 8 * N_loc) / ms_per_step / 1e6,
-                            "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src},
-               "e2e": {"value": N / float(dt[0]) / 1e6, "unit": "MDOF/s", "ms_per_step": float(dt[0]) * 1e3,
-                       "h2d_bytes_per_step": int(8 * dn.E) * world, "d2h_bytes_per_step": int(8 * N_loc) * world,
-                       "timer": "wall clock, max over ranks",
-                       "call": "per rank: pinned Res -> device, assemble + rhs + solve, local solution -> pinned host"},
-               "clocks": clk}
-        out["roofline"]["frac"] = out["roofline"]["achieved"] / hbm
-        print(json.dumps(out))
-    dist.barrier()
-    dist.destroy_process_group()
+def gather_to_root(t, group=None):
+    """the (differently sized) 1-D device tensors of all ranks on rank 0, as a list of host arrays (None elsewhere)"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s_[0]) for s_ in sizes]
+    pad = torch.zeros(max(sizes), dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, out, dst=0, group=group)
+    if rank != 0:
+        return None
+    return [o[:k].cpu().numpy() for o, k in zip(out, sizes)]

@@ -376,6 +376,9 @@ int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const
                    int32_t warm, const gnx_exchange_t* ex, double* resid_host, int32_t* info_host, void* ev_fork, void* ev_join,
                    void* side_stream, int64_t* sync, int64_t epoch, void* stream);
 
+/* 1 if the last gnx_step_mixed call of this process ran as the persistent kernel, 0 if as the kernel chain (reporting) */
+int gnx_step_is_resident(void);
+
 /* ---------------- primal model: HydraulicNetwork (flow_models.py:53-126) ---------------- */
 
 /* Operator  [ diag(a_c h_c)  s G ; -s G^T  0 ]  on  W = [DG0(mesh) | CG1(mesh)]  (q dof = global
