@@ -57,6 +57,7 @@ class gnx_schur_plan_t(C.Structure):
         ("blk_ptr", C.c_void_p), ("blk_nodes", C.c_void_p), ("blk_pos", C.c_void_p), ("blk_lv", C.c_void_p),
         ("sub_ptr", C.c_void_p), ("row_sub", C.c_void_p),
         ("l_sync", C.c_int32), ("nxl", C.c_int32), ("ncls", C.c_void_p), ("xlist", C.c_void_p),
+        ("top_rec", C.c_void_p),
     ]
 
 

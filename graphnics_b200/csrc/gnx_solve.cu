@@ -611,7 +611,7 @@ extern "C" int64_t gnx_schur_work_doubles(const gnx_schur_plan_t* plan) {
   if (!plan) return 0;
   const int64_t nval = plan->ell_w > 0 ? (int64_t)plan->ell_w * plan->nc : 0;
   const int64_t coarse = plan->na > 0 ? (int64_t)plan->na * plan->na + plan->na + 2 * (int64_t)GNX_SUB_MAX : 0;
-  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 8 + coarse;
+  return 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048 + 32 + coarse;
 }
 
 // All-reduce of K values over the block with ONE barrier.  `sh` holds K*32 doubles; callers
@@ -682,6 +682,17 @@ __device__ __forceinline__ void schur_row(const SchurArgs& a, int32_t bi, double
     diag += c;
     rhs += end ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
   }
+}
+
+// The index data schur_row(bi) walks (never written during a solve), touched ahead of time: a replicated node's row
+// can only be built after the exchange, and by then these dependent loads are L1 / L2 hits instead of a chain of
+// cold misses on the solve's critical path.  Returns a checksum (the caller keeps it alive).
+__device__ __forceinline__ int32_t schur_row_warm(const SchurArgs& a, int32_t bi) {
+  const gnx_network_t& net = a.net;
+  const int32_t node = net.bif_nodes[bi];
+  int32_t acc = node;
+  for (int32_t k = net.inc_ptr[node]; k < net.inc_ptr[node + 1]; ++k) acc ^= net.inc_edge[k];
+  return acc;
 }
 
 // Flag exchange between the ranks of a partitioned solve, run by the first `wait_world` threads of ONE CTA: tell every
@@ -768,13 +779,49 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   };
   // numeric part of a row's set-up: row (from global memory, or built here for a replicated node), link weight,
   // children below the top part folded in
+  const int4* const trec = CLUSTER ? nullptr : reinterpret_cast<const int4*>(pl.top_rec);
+  // the same from the row's packed record (plan.top_rec): one 64-byte load, then every scalar it names at once
+  auto numeric_rec = [&](int q) {
+    const int32_t li = tid + q * T;
+    const int4 r0 = __ldg(trec + 4 * (base + li)), r1 = __ldg(trec + 4 * (base + li) + 1);
+    const int4 r2 = __ldg(trec + 4 * (base + li) + 2), r3 = __ldg(trec + 4 * (base + li) + 3);
+    const int32_t i = r0.x;
+    w[q] = r0.w >= 0 ? -a.cond[a.eidx(r0.w)] : 0.0;
+    double di = 0.0;
+    double ri = a.b_lam ? -a.b_lam[i] * a.inv_sigma : (a.b_node ? a.b_node[r2.w] * a.inv_sigma : 0.0);
+    const int32_t inc[4] = {r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (inc[k] >= 0) {
+        const int64_t ei = a.eidx(inc[k] >> 1);
+        const double c = a.cond[ei];
+        di += c;
+        ri += (inc[k] & 1) ? (c * a.rsrc[ei] + a.ftot[ei]) : (-c * a.rsrc[ei]);
+      }
+    }
+    const int32_t bc[2] = {r1.w, r2.x}, be[2] = {r2.y, r2.z};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (bc[k] >= 0) {                                     // child below the top part: final in global memory
+        const double wc = -a.cond[a.eidx(be[k])];
+        const double t = wc / __ldcg(a.d + bc[k]);
+        di -= wc * t;
+        ri -= t * __ldcg(a.r + bc[k]);
+      }
+    }
+    c0[q] = r1.x; c1[q] = r1.y; nct[q] = r1.z;
+    d[q] = di; r[q] = ri;
+    sr[li] = ri; sw[li] = w[q];
+    if (nct[q] == 0) sd[li] = 1.0 / di;
+  };
   auto numeric = [&](int q) {
+    if (trec && !(nct[q] & (1 << 30))) { numeric_rec(q); return; }
     const int32_t li = tid + q * T;
     const int32_t i = node[q];
     const int32_t par = pl.parent[i];
     w[q] = par >= 0 ? -a.cond[a.eidx(pl.pedge[i])] : 0.0;
     double di, ri;
-    if (repl[q]) schur_row(a, i, di, ri);
+    if (repl[q] || trec) schur_row(a, i, di, ri);          // (with records nobody has built the top rows beforehand)
     else { di = __ldcg(a.d + i); ri = __ldcg(a.r + i); }
     nct[q] = 0; c0[q] = c1[q] = -1;
     for (int32_t k = k0[q]; k < k1[q]; ++k) {
@@ -801,32 +848,52 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     lev[q] = -1; node[q] = 0; ptop[q] = -1; k0[q] = k1[q] = 0; d[q] = 1.0; r[q] = 0.0; w[q] = 0.0;
     c0[q] = c1[q] = -1; nct[q] = 0; repl[q] = false;
     if (li < S && ti < pl.nt) {
-      const int32_t i = pl.top_nodes[ti];
-      node[q] = i;
-      lev[q] = pl.level_of[i];
-      repl[q] = ncls && (ncls[i] & 1);
-      const int32_t par = pl.parent[i];
-      if (par >= 0) ptop[q] = pl.top_of[par];
-      k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
-      if (!repl[q]) numeric(q);
+      if (trec) {
+        const int4 r0 = __ldg(trec + 4 * ti), r1 = __ldg(trec + 4 * ti + 1);
+        node[q] = r0.x; lev[q] = r0.y; ptop[q] = r0.z;
+        nct[q] = r1.z;                                       // (bit 30: numeric() takes the generic path for this row)
+        repl[q] = ncls && (ncls[r0.x] & 1);
+        if (r1.z & (1 << 30)) { k0[q] = pl.ch_ptr[r0.x]; k1[q] = pl.ch_ptr[r0.x + 1]; }
+        if (!repl[q]) numeric(q);
+      } else {
+        const int32_t i = pl.top_nodes[ti];
+        node[q] = i;
+        lev[q] = pl.level_of[i];
+        repl[q] = ncls && (ncls[i] & 1);
+        const int32_t par = pl.parent[i];
+        if (par >= 0) ptop[q] = pl.top_of[par];
+        k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
+        if (!repl[q]) numeric(q);
+        else {                                             // warm the index data of the row built after the exchange
+          int32_t acc = schur_row_warm(a, i) ^ (par >= 0 ? pl.pedge[i] : 0);
+          for (int32_t k = k0[q]; k < k1[q]; ++k) { const int32_t c = pl.ch_idx[k]; acc ^= pl.top_of[c] ^ ncls[c] ^ pl.pedge[c]; }
+          if (acc == 0x7fffffff) sw[li] = 0.0;             // (never true in practice: keeps the loads alive)
+        }
+      }
     }
   }
   lsync();
   if (tick) tick[0] = clock64();
+  auto stamp = [&](int k) { if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[8 + k] = (double)(t & 0xffffffffffull); } };
+  stamp(1);
   // the exchange, between the last local and the first replicated level
   auto exchange = [&]() -> bool {
+    stamp(2);
 #pragma unroll
     for (int q = 0; q < ROWS; ++q)
       if (lev[q] >= 0 && !repl[q] && (ncls[node[q]] & 4)) { a.d[node[q]] = d[q]; a.r[node[q]] = r[q]; }
     lsync();
     if (a.phase != 2) sch_export_roots(a);
     lsync();
+    stamp(3);
     if (a.phase == 1) return true;
     if (a.phase == 0) { sch_flag_exchange(a); lsync(); }
+    stamp(4);
 #pragma unroll
     for (int q = 0; q < ROWS; ++q)
       if (lev[q] >= 0 && repl[q]) numeric(q);
     lsync();
+    stamp(5);
     return false;
   };
   // contribution of top child tc to its parent: d -= w (w/d_c), r -= (w/d_c) r_c
@@ -859,6 +926,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   }
   if (ncls && l_sync >= pl.nl) { if (exchange()) return true; }     // (no replicated raked node)
   if (tick) tick[1] = clock64();
+  stamp(6);
   for (int l = pl.nl - 1; l >= pl.l_split; --l) {           // down: sr[] turns into the solution
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
@@ -874,6 +942,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     }
     lsync();
   }
+  stamp(7);
   return false;
 }
 
@@ -1326,6 +1395,7 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
   auto gsync = [&]() { sch_sync<MODE>(); };
   long long tick[4] = {0, 0, 0, 0};               // SM cycles of block 0: phase 0 | top prologue | up | down (diagnostic, scal[5..7])
   const long long tick0 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[8] = (double)(t & 0xffffffffffull); }
   // subtree-partitioned network: local sweeps first, ONE exchange at level l_sync, replicated nodes after it
   const int32_t* const ncls = pl.ncls;
   const bool part = ncls != nullptr;
@@ -1384,15 +1454,18 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
   // ---- phase 0: Schur diagonal and right-hand side (one thread per bifurcation, gather)
   // (blocked rake: the blocks build their own rows, CTA 0 those of the top part -- no barrier in between;
   //  partitioned: only my local nodes now, the replicated ones after the exchange)
+  const bool top_rows_later = pl.top_rec != nullptr && pl.nc == 0 && MODE != SCH_CLUSTER;   // top_solve builds them from the records
   if (pl.nb > 0 || a.phase == 2) {
-    if (blockIdx.x == 0 && pl.nc == 0)
+    if (blockIdx.x == 0 && pl.nc == 0 && !top_rows_later)
       for (int32_t ti = threadIdx.x; ti < pl.nt; ti += blockDim.x) {
         const int32_t bi = pl.top_nodes[ti];
         if (!part || !(ncls[bi] & 1)) row_to_global(bi);
       }
-  } else if (part) {
-    for (int32_t idx = t0; idx < pl.lvl_ptr[l_sync]; idx += stride) row_to_global(pl.lvl_nodes[idx]);
-    gsync();
+  } else if (part || top_rows_later) {
+    // (levels are contiguous in lvl_nodes: everything below the exchange level / below the top part)
+    const int32_t lim = pl.lvl_ptr[top_rows_later ? (pl.l_split < l_sync ? pl.l_split : l_sync) : l_sync];
+    for (int32_t idx = t0; idx < lim; idx += stride) row_to_global(pl.lvl_nodes[idx]);
+    if (lim > 0) gsync();
   } else {
     for (int32_t bi = t0; bi < pl.B; bi += stride) row_to_global(bi);
     gsync();
@@ -1628,7 +1701,7 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   a.p0 = w; w += nc; a.p1 = w; w += nc; a.dg = w; w += nc;
   a.cval = w; w += plan->nnzc;
   for (int k = 0; k < 5; ++k) { a.part[k] = w; w += 2048; }
-  a.scal = w; w += 8;
+  a.scal = w; w += 32;                          // [0..7] status, [8..] %globaltimer stamps of CTA 0 (diagnostic)
   a.Eg = w; w += (int64_t)plan->na * plan->na; a.sE = w; w += plan->na;
   a.s1 = w; w += GNX_SUB_MAX; a.dE = w;
   a.rtol = rtol; a.max_iter = max_iter; a.warm = warm;
@@ -2413,7 +2486,9 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
   }
   if (ltid == 0) gnx_bulk_wait_read();
   if (dbg) s.sync[21] = rs_now();
-  if (s.out.n > 1) __threadfence_system();          // edge scalars stored into the other ranks' buffers
+  // (scalars stored into other ranks' buffers were followed by a system-scope fence of the storing thread, EdgeOut::put;
+  //  the gathered layout of mode 0 stores ALL of them remotely: one fence per thread there)
+  if (s.out.n > 1 && !s.out.egl) __threadfence_system();
   __syncthreads();
   if (tid == 0) {
     __threadfence();

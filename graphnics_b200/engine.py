@@ -301,6 +301,11 @@ class MixedSystem:
                 extra += tuple((k, blocks[k]) for k in ("blk_ptr", "blk_nodes", "blk_pos", "blk_lv"))
             hp.blocks = blocks
             s.l_sync, s.nxl = len(hp.levels), 0
+            if len(top) and top_S == 0 and hp.nc == 0:
+                from .schur_plan import top_records
+                g = dn.glob if dn.glob is not None else dn
+                extra += (("top_rec", top_records(hp, top, top_of, level_of, g.inc_ptr.cpu().numpy(), g.inc_edge.cpu().numpy(),
+                                                  g._bif_nodes.cpu().numpy(), None if view is None else view.ncls).ravel()),)
             if view is not None:
                 if hp.nc == 0 and l_split > view.l_sync:
                     raise ValueError("subtree partition: %d replicated bifurcations do not fit the top part (%d)"

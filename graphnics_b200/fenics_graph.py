@@ -152,11 +152,18 @@ class FenicsGraph(nx.DiGraph):
         self.record_bifurcation_and_boundary_nodes()
         self.assign_tangents()
 
+    def _held_edges(self):
+        """the (u, v) pairs whose mesh this process holds, in device order (all edges unless partitioned)"""
+        ev = list(self.edges())
+        if getattr(self, "local_edges", None) is not None:
+            ev = [ev[i] for i in self.local_edges]
+        return ev
+
     def make_submeshes(self):
         """Per-edge submeshes and vertex tag functions (fenics_graph.py:132-156)."""
         if self._dn is None:
             raise RuntimeError("call make_mesh() first")
-        for i, (u, v) in enumerate(self.edges):
+        for i, (u, v) in enumerate(self._held_edges()):
             self.edges[u, v]["submesh"] = SubMesh(self._dn, i)
             self.edges[u, v]["vf"] = VertexMarker(self._dn, i)
 
@@ -182,41 +189,36 @@ class FenicsGraph(nx.DiGraph):
             self.bifurcation_ixs, self.boundary_ixs = bif, bnd
         self.num_bifurcations = len(self.bifurcation_ixs)
 
+    def _edge_length_array(self):
+        """[E] Euclidean edge lengths in G.edges() order (from the device when the whole graph is meshed here)"""
+        if self._dn is not None and getattr(self, "local_edges", None) is None:
+            return self._dn.elen.cpu().numpy()
+        pos, edges = self._graph_arrays()
+        return np.sqrt(((pos[edges[:, 1]] - pos[edges[:, 0]]) ** 2).sum(axis=1))
+
     def compute_edge_lengths(self):
-        """fenics_graph.py:187-198"""
-        if self._dn is not None:
-            L = self._dn.elen.cpu().numpy()
-            for i, e in enumerate(self.edges()):
-                self.edges()[e]["length"] = float(L[i])
-        else:
-            for e in self.edges():
-                v1, v2 = e
-                self.edges()[e]["length"] = np.linalg.norm(
-                    np.asarray(self.nodes()[v2]["pos"]) - np.asarray(self.nodes()[v1]["pos"]))
+        """edges[e]["length"] = |pos[v] - pos[u]| (fenics_graph.py:187-198)"""
+        for e, length in zip(self.edges(), self._edge_length_array().tolist()):
+            self.edges[e]["length"] = length
 
     def compute_vertex_degrees(self):
-        """Weighted vertex degrees l_v/2 (fenics_graph.py:200-226)."""
-        try:
-            e = list(self.edges())[0]
-            self.edges()[e]["length"]
-        except KeyError:
+        """nodes[v]["degree"] = half the total length of the edges at v; degree_min / degree_max
+        (fenics_graph.py:200-226)"""
+        _, edges = self._graph_arrays()
+        if any("length" not in d for _, _, d in self.edges(data=True)):
             self.compute_edge_lengths()
-        for v in self.nodes():
-            l_v = 0
-            for e in self.in_edges(v):
-                l_v += self.edges()[e]["length"]
-            for e in self.out_edges(v):
-                l_v += self.edges()[e]["length"]
-            self.nodes()[v]["degree"] = l_v / 2
-        degrees = nx.get_node_attributes(self, "degree")
-        self.degree_min = min(degrees.values())
-        self.degree_max = max(degrees.values())
+        length = np.asarray([d["length"] for _, _, d in self.edges(data=True)], dtype=np.float64)
+        half = 0.5 * (np.bincount(edges[:, 0], weights=length, minlength=len(self)) +
+                      np.bincount(edges[:, 1], weights=length, minlength=len(self)))
+        for v, hv in zip(self.nodes(), half.tolist()):
+            self.nodes[v]["degree"] = hv
+        self.degree_min, self.degree_max = float(half.min()), float(half.max())
 
     def assign_tangents(self):
         """Unit tangent of every edge (fenics_graph.py:230-253): edges[e]['tangent'], G.tangents,
         G.tangent."""
         tang = self._dn.tangents.cpu().numpy()
-        for i, (u, v) in enumerate(self.edges()):
+        for i, (u, v) in enumerate(self._held_edges()):
             self.edges[u, v]["tangent"] = tang[i]
         self.tangents = list(nx.get_edge_attributes(self, "tangent").items())
         self.tangent = _TangentField(self)
@@ -235,8 +237,23 @@ class FenicsGraph(nx.DiGraph):
         return int((tu == BOUN_IN).sum() + (tv == BOUN_IN).sum()), int((tu == BOUN_OUT).sum() + (tv == BOUN_OUT).sum())
 
     def mark_edge_vfs(self, node_ixs, tag_in, tag_out):
-        """Kept for API parity (fenics_graph.py:280-311): tags are produced by gnx_vertex_tables."""
-        return None
+        """Tag, in the vertex markers of the per-edge submeshes, the end of every edge that goes INTO a node of
+        `node_ixs` with tag_in and the start of every edge that goes OUT of one with tag_out
+        (fenics_graph.py:280-311).  The reference finds the end by an exact coordinate search in the submesh; the
+        SubMesh-local number of an edge's ends is known in closed form here (device.submesh_numbering).
+        `make_submeshes()` produces the default tags on the GPU (gnx_vertex_tables); this method lets user code
+        re-tag on the host view the way it can with the reference."""
+        if self._dn is None:
+            raise RuntimeError("call make_mesh() first")
+        dn = self._dn
+        vf, loc, m = dn.vf_host(), dn.loc_host, dn.m
+        wanted = set(int(v) for v in node_ixs)
+        for i, (u, v) in enumerate(self._held_edges()):
+            first, last = (loc[m], loc[0]) if u > v else (loc[0], loc[m])      # SubMesh-local ids of the u / v end
+            if v in wanted:
+                vf[i, last] = tag_in
+            if u in wanted:
+                vf[i, first] = tag_out
 
     # ---- helpers used by the models -------------------------------------------------------------
     def edge_attribute_array(self, key, default=1.0):
@@ -274,66 +291,71 @@ class FenicsGraph(nx.DiGraph):
         return np.repeat(out, rep) if rep > 1 else out
 
 
-class GlobalFlux(UserExpression):
-    """Vector flux = scalar flux * tangent (fenics_graph.py:314-351)."""
+class _EdgewiseExpression(UserExpression):
+    """expression on the global mesh defined edge by edge: a cell belongs to edge `mf[cell]`"""
 
-    def __init__(self, G, qs, **kwargs):
-        if not isinstance(qs, list):
-            qs = [qs]
-        self.G, self.qs = G, qs
+    def __init__(self, G, **kwargs):
+        self.G = G
+        self._tangent = np.asarray([t for _, t in G.tangents], dtype=np.float64)      # [E, gdim]
         super().__init__(**kwargs)
 
+    def _edge(self, cell):
+        return self.G.mf[cell.index]
+
+
+class GlobalFlux(_EdgewiseExpression):
+    """vector flux = scalar flux of the edge times its unit tangent (fenics_graph.py:314-351);
+    `qs`: one function per edge, or a single function on the global mesh"""
+
+    def __init__(self, G, qs, **kwargs):
+        self.qs = qs if isinstance(qs, list) else [qs]
+        super().__init__(G, **kwargs)
+
     def eval_cell(self, values, x, cell):
-        edge = self.G.mf[cell.index]
-        tangent = self.G.tangents[edge][1]
-        qval = self.qs[edge](x) if len(self.qs) > 1 else self.qs[0](x)
-        for k in range(self.G.geom_dim):
-            values[k] = qval * tangent[k]
+        e = self._edge(cell)
+        q = self.qs[e if len(self.qs) > 1 else 0]
+        values[: self.G.geom_dim] = q(x) * self._tangent[e]
 
     def value_shape(self):
         return (self.G.geom_dim,)
 
 
-class GlobalCrossectionFlux(UserExpression):
-    """Scalar flux on the global mesh from the per-edge fluxes (fenics_graph.py:354-375)."""
+class GlobalCrossectionFlux(_EdgewiseExpression):
+    """the per-edge scalar fluxes as one scalar field on the global mesh (fenics_graph.py:354-375)"""
 
     def __init__(self, G, qs, **kwargs):
-        self.G, self.qs = G, qs
-        super().__init__(**kwargs)
+        self.qs = qs
+        super().__init__(G, **kwargs)
 
     def eval_cell(self, values, x, cell):
-        values[0] = self.qs[self.G.mf[cell.index]](x)
+        values[0] = self.qs[self._edge(cell)](x)
 
     def value_shape(self):
         return ()
 
 
-class TangentFunction(UserExpression):
-    """Tangent expression (fenics_graph.py:378-401); the kernels never call it."""
+class TangentFunction(_EdgewiseExpression):
+    """unit tangent of the edge a cell lies on (fenics_graph.py:378-401); the kernels never call it"""
 
     def __init__(self, G, degree, **kwargs):
-        self.G, self.degree = G, degree
-        super().__init__(**kwargs)
+        self.degree = degree
+        super().__init__(G, **kwargs)
 
     def eval_cell(self, values, x, cell):
-        edge = self.G.mf[cell.index]
-        for k in range(self.G.geom_dim):
-            values[k] = self.G.tangents[edge][1][k]
+        values[: self.G.geom_dim] = self._tangent[self._edge(cell)]
 
     def value_shape(self):
         return (self.G.geom_dim,)
 
 
 def copy_from_nx_graph(G_nx):
-    """Deep copy of an nx.Graph as FenicsGraph (fenics_graph.py:404-434)."""
+    """FenicsGraph with the nodes, edges (in `G_nx.edges()` order -- that fixes the direction an undirected graph's
+    edges get) and attributes of a networkx graph; attribute dictionaries are copied, values shared
+    (fenics_graph.py:404-434)"""
     G = FenicsGraph()
     G.graph.update(G_nx.graph)
-    G.add_nodes_from((n, d.copy()) for n, d in G_nx._node.items())
-    for u, v in G_nx.edges():
-        G.add_edge(u, v)
-    for e in G.edges():
-        for key, val in G_nx.edges()[e].items():
-            G.edges()[e][key] = val
+    G.add_nodes_from((v, dict(attrs)) for v, attrs in G_nx.nodes(data=True))
+    G.add_edges_from((u, v, dict(attrs)) for u, v, attrs in G_nx.edges(data=True))
     return G
 
 

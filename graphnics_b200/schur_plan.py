@@ -292,6 +292,59 @@ class SchurPlan:
         return w, R, col.ravel().astype(np.int32), edge.ravel().astype(np.int32)
 
 
+def top_records(hp, top, top_of, level_of, inc_ptr, inc_edge, bif_nodes, ncls=None):
+    """Packed per-row records of the top part (gnx_schur_plan_t.top_rec, [nt, 16] int32): everything the one-CTA sweep
+    needs to know about a top node in ONE 64-byte load instead of a chain of dependent look-ups --
+      0 node (bifurcation index)   1 rake level   2 top position of the parent (-1)   3 edge to the parent (-1)
+      4, 5 top positions of the first two children kept in shared memory (-1)         6 number of such children
+      7, 8 the first two children folded from global memory (-1)    9, 10 their edges     11 graph node
+      12..15 incident edges as (edge << 1 | end) in incidence-list order (-1 unused)
+    bit 30 of entry 6 marks a row that does not fit (more than two children of a kind, more than four incident
+    edges): the kernel then walks the generic arrays for it.  Rank views (ncls given): a replicated node keeps only
+    replicated children in shared memory, local children -- of any rank -- are folded from global memory."""
+    nt = len(top)
+    rec = -np.ones((nt, 16), dtype=np.int64)
+    top = np.asarray(top, dtype=np.int64)
+    rec[:, 0] = top
+    rec[:, 1] = np.asarray(level_of)[top]
+    par = hp.parent[top].astype(np.int64)
+    rec[:, 2] = np.where(par >= 0, np.asarray(top_of)[np.maximum(par, 0)], -1)
+    rec[:, 3] = np.where(par >= 0, hp.pedge[top], -1)
+    rec[:, 6] = 0
+    gnode = np.asarray(bif_nodes, dtype=np.int64)[top]
+    rec[:, 11] = gnode
+    ch_ptr, ch_idx = hp.ch_ptr.astype(np.int64), hp.ch_idx.astype(np.int64)
+    slow = np.zeros(nt, dtype=bool)
+    nkids = ch_ptr[top + 1] - ch_ptr[top]
+    n_in, n_out = np.zeros(nt, dtype=np.int64), np.zeros(nt, dtype=np.int64)
+    for j in range(int(nkids.max()) if nt else 0):          # j-th child of every row that has one
+        has = nkids > j
+        c = ch_idx[np.where(has, ch_ptr[top] + j, 0)]
+        tc = np.asarray(top_of)[c].astype(np.int64)
+        if ncls is not None:                                 # replicated row, local child: from global memory
+            tc = np.where((ncls[top] & 1).astype(bool) & ~(ncls[c] & 1).astype(bool), -1, tc)
+        inside = has & (tc >= 0)
+        outside = has & (tc < 0)
+        for k in (0, 1):
+            put = inside & (n_in == k)
+            rec[put, 4 + k] = tc[put]
+            put = outside & (n_out == k)
+            rec[put, 7 + k] = c[put]
+            rec[put, 9 + k] = hp.pedge[c[put]]
+        slow |= (inside & (n_in >= 2)) | (outside & (n_out >= 2))
+        n_in += inside
+        n_out += outside
+    rec[:, 6] = n_in
+    inc_ptr, inc_edge = np.asarray(inc_ptr, dtype=np.int64), np.asarray(inc_edge, dtype=np.int64)
+    deg = inc_ptr[gnode + 1] - inc_ptr[gnode]
+    slow |= deg > 4
+    for j in range(4):
+        has = deg > j
+        rec[has, 12 + j] = inc_edge[inc_ptr[gnode[has]] + j]
+    rec[slow, 6] |= 1 << 30
+    return np.ascontiguousarray(rec, dtype=np.int32)
+
+
 class RankPlan(SchurPlan):
     """One rank's view of the plan of an EDGE-PARTITIONED network.
 

@@ -320,6 +320,10 @@ typedef struct gnx_schur_plan {
   int32_t l_sync, nxl;
   const int32_t* ncls;
   const int32_t* xlist;
+  /* [nt][16] packed records of the top part (schur_plan.top_records; NULL: the sweep walks the generic arrays): node,
+   * level, parent's top position, parent edge, two shared-memory children, their count (bit 30: row does not fit the
+   * record), two global-memory children and their edges, graph node, four incident edges (edge << 1 | end) */
+  const int32_t* top_rec;
 } gnx_schur_plan_t;
 
 /* The whole Schur solve as ONE persistent kernel (a single CTA for small systems, a cooperative

@@ -15,14 +15,25 @@ from graphnics_b200.synthetic import murray_tree
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 levels = int(args[0]) if args else 11
 n = int(args[1]) if len(args) > 1 else 9
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:                      # torchrun: `levels` is the single-GPU tree, one more generation per doubling
+    import torch.distributed as dist
+    from graphnics_b200.parallel import PartitionedMixed
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    levels += int(np.ceil(np.log2(world)))
 pos, edges, _, _ = murray_tree(levels, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
-dn = DeviceNetwork(pos, edges, n)
-ms = MixedSystem(dn)
+if world > 1:
+    pm = PartitionedMixed(pos, edges, n, partition=os.environ.get("GNX_PARTITION", "subtree"))
+    dn, ms = pm.dn, pm.ms
+else:
+    dn = DeviceNetwork(pos, edges, n)
+    ms = MixedSystem(dn)
 ms.build_pattern()
 co = ms.coeffs(np.ones(dn.E))
 vals = None if "--no-vals" in sys.argv else torch.empty(ms.nnz, dtype=torch.float64, device="cuda")
 b = torch.empty(ms.N, dtype=torch.float64, device="cuda")
-x = torch.empty(ms.N, dtype=torch.float64, device="cuda")
+x = torch.zeros(ms.N, dtype=torch.float64, device="cuda")
 xq, _ = ms.dof_coordinates(False)
 kw = dict(pbc_out=ms.end_values(xq[:, 1].contiguous()), pbc_node=dn.pos[:, 1].contiguous())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -38,7 +49,7 @@ def step():
 for _ in range(5):
     step()
 torch.cuda.synchronize()
-ts, stamps, stamps1 = [], [], []
+ts, stamps, stamps1, stamps2 = [], [], [], []
 for _ in range(30):
     flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,6 +58,10 @@ for _ in range(30):
     s = ms._step_sync.cpu().numpy()
     stamps.append((s[[8, 3, 4, 5, 6, 7]] - s[2]) / 1e3)
     stamps1.append((s[16:29] - s[2]) / 1e3)
+    if ms.dn.B > 0:
+        w = ms.schur_plan()[2]
+        sc = w[-32 - ((ms.schur_plan()[0].na ** 2 + ms.schur_plan()[0].na + 2 * 1024) if ms.schur_plan()[0].na else 0):][:32].cpu().numpy()
+        stamps2.append((sc[9:16] - sc[8]) / 1e3)
 out = {"levels": levels, "n": n, "N": ms.N, "resident": os.environ.get("GNX_STEP_RESIDENT", "1"), "vals": vals is not None,
        "us_per_step": {"min": float(np.min(ts)), "median": float(np.median(ts)), "max": float(np.max(ts))}}
 if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
@@ -55,7 +70,18 @@ if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
     st1 = np.median(np.asarray(stamps1), axis=0)
     out["cta1_stamps_us"] = dict(zip(["prefetched", "H0_arrived", "elim0_done", "H4_arrived", "elim4_done", "b_stores_read", "asm_start",
                                       "asm_done", "released", "p3_prefetched", "bs0_done", "bs4_done", "end"], st1.round(2).tolist()))
-if vals is not None:
+if stamps2:
+    out["schur_stamps_us"] = dict(zip(["prologue", "local_up", "exported", "flags", "repl_rows", "up_done", "down_done"],
+                                      np.median(np.asarray(stamps2), axis=0).round(2).tolist()))
+if vals is not None and world == 1:
     rr, bb = ms.residual(vals, x, b).cpu().tolist()
     out["rel_residual"] = float(np.sqrt(rr / bb))
-print(json.dumps(out))
+if world > 1:
+    out["rank"] = dist.get_rank()
+    for r in range(world):
+        if r == dist.get_rank():
+            print(json.dumps(out), flush=True)
+        dist.barrier()
+    dist.destroy_process_group()
+else:
+    print(json.dumps(out))
