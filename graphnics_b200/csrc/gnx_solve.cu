@@ -602,6 +602,7 @@ struct SchurArgs {
   int64_t xd_off, xr_off;
   int32_t phase;                              // 0: whole solve, flags in the kernel; 1: up to the exchange; 2: after it
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
+    if (chunk == 2147483647) return e;          // (uniform: everything but the gathered layout -- no integer division)
     const int32_t r = e / chunk;
     return (int64_t)r * rank_stride + (e - r * chunk);
   }
@@ -666,6 +667,18 @@ __device__ __forceinline__ void grid_allreduce(double (&v)[K], double* const* pa
   }
   __syncthreads();                            // sh reuse
   block_allreduce<K>(v, sh);
+}
+
+// 1/x to within an ulp or two: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps = 4 dependent FMAs, where the
+// correctly rounded division is a ~30-instruction dependent chain -- and one reciprocal sits on the critical path of
+// EVERY level of the one-CTA rake.  Deterministic; x is a positive, finite Schur diagonal.
+__device__ __forceinline__ double gnx_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = __fma_rn(-x, y, 1.0);
+  y = __fma_rn(y, e, y);
+  e = __fma_rn(-x, y, 1.0);
+  return __fma_rn(y, e, y);
 }
 
 // Diagonal and right-hand side of the Schur row of bifurcation bi (gather over its incident edges, no atomics)
@@ -780,6 +793,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   // numeric part of a row's set-up: row (from global memory, or built here for a replicated node), link weight,
   // children below the top part folded in
   const int4* const trec = CLUSTER ? nullptr : reinterpret_cast<const int4*>(pl.top_rec);
+  if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[16] = (double)(t & 0xffffffffffull); }
   // the same from the row's packed record (plan.top_rec): one 64-byte load, then every scalar it names at once
   auto numeric_rec = [&](int q) {
     const int32_t li = tid + q * T;
@@ -812,7 +826,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     c0[q] = r1.x; c1[q] = r1.y; nct[q] = r1.z;
     d[q] = di; r[q] = ri;
     sr[li] = ri; sw[li] = w[q];
-    if (nct[q] == 0) sd[li] = 1.0 / di;
+    if (nct[q] == 0) sd[li] = gnx_rcp(di);
   };
   auto numeric = [&](int q) {
     if (trec && !(nct[q] & (1 << 30))) { numeric_rec(q); return; }
@@ -839,7 +853,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     }
     d[q] = di; r[q] = ri;
     sr[li] = ri; sw[li] = w[q];
-    if (nct[q] == 0) sd[li] = 1.0 / di;                    // no top children: final already
+    if (nct[q] == 0) sd[li] = gnx_rcp(di);                    // no top children: final already
   };
 #pragma unroll
   for (int q = 0; q < ROWS; ++q) {
@@ -872,6 +886,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
       }
     }
   }
+  if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[17] = (double)(t & 0xffffffffffull); }
   lsync();
   if (tick) tick[0] = clock64();
   auto stamp = [&](int k) { if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[8 + k] = (double)(t & 0xffffffffffull); } };
@@ -919,7 +934,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
           }
         }
         const int32_t li = tid + q * T;
-        sd[li] = 1.0 / d[q]; sr[li] = r[q];
+        sd[li] = gnx_rcp(d[q]); sr[li] = r[q];
       }
     }
     lsync();
@@ -970,7 +985,7 @@ __device__ __forceinline__ void blk_up(const SchurArgs& a, int32_t b, double* sd
     if (nct > 1) c1 = pl.blk_pos[pl.ch_idx[k0 + 1]];
     schur_row(a, node, d, r);
     sr[tid] = r;
-    if (nct == 0) sd[tid] = 1.0 / d;
+    if (nct == 0) sd[tid] = gnx_rcp(d);
   }
   __syncthreads();
   auto fold = [&](int32_t c) {
@@ -984,7 +999,7 @@ __device__ __forceinline__ void blk_up(const SchurArgs& a, int32_t b, double* sd
       fold(c0);
       if (nct > 1) fold(c1);
       for (int32_t k = k0 + 2; k < k1; ++k) fold(pl.blk_pos[pl.ch_idx[k]]);
-      sd[tid] = 1.0 / d; sr[tid] = r;
+      sd[tid] = gnx_rcp(d); sr[tid] = r;
     }
     __syncthreads();
   }
@@ -1500,7 +1515,12 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
       if (pl.nt > 0) top_solve<true, GNX_TOP_MAX / CL_T>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX);
     } else {
       tick[0] = clock64();
-      if (blockIdx.x == 0 && pl.nt > 0) top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+      // (one row per thread when the top part fits: half the per-thread state of the general two-row sweep --
+      //  at 64 registers per thread that is the difference between spilling and not)
+      if (blockIdx.x == 0 && pl.nt > 0) {
+        if (pl.nt <= SCH_T) top_solve<false, 1>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+        else top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+      }
       tick[3] = clock64();
       if (a.phase == 1) return;                  // (partitioned, emulated ranks / NCCL: stop at the exchange)
       if (pl.l_split > 0) gsync();
@@ -2020,7 +2040,8 @@ constexpr int RS_T = 1024;                       // threads per CTA
 constexpr int RS_SUB = RS_T / ET_T;              // sub-blocks per CTA
 constexpr int RS_CPT = 4;
 constexpr int RS_TILE = ET_T * RS_CPT;           // cells per tile
-constexpr int RS_MIN_N = 6;                      // 2^6 .. 2^10 cells per edge: <= 16 edges per tile
+constexpr int RS_MIN_N = 6;                      // 2^6 .. 2^9 cells per edge: <= 16 edges per solve tile,
+constexpr int RS_MAX_N = 9;                      // whole edges in a 512-cell assembly tile
 constexpr int RS_MAX_G = RS_TILE >> RS_MIN_N;    // edges per tile
 constexpr int RS_MAX_TILES = 8;                  // resident tiles per CTA
 constexpr int RS_HSLOT = RS_TILE + 2;            // doubles per resident tile (+ parity shift)
@@ -2565,7 +2586,7 @@ static int rs_enabled() {             // tuning / A-B knob: GNX_STEP_RESIDENT=0 
 // 1 if the persistent kernel can run this step (else the caller uses the kernel chain)
 int gnx_step_resident_applies(const gnx_network_t* net, const gnx_schur_plan_t* plan, const double* b, const double* x,
                               const unsigned long long* sync) {
-  if (!rs_enabled() || !sync || !plan || net->B <= 0 || net->n < RS_MIN_N || net->n > 10) return 0;
+  if (!rs_enabled() || !sync || !plan || net->B <= 0 || net->n < RS_MIN_N || net->n > RS_MAX_N) return 0;
   const int64_t nrows = plan->ncls ? (int64_t)plan->lvl_ptr[plan->nl] + plan->nc : plan->B;
   if (nrows > 2 * SCH_T || plan->na > 0 || plan->top_S > 0 || plan->nb > 0) return 0;       // one-CTA Schur solve only
   if (!edge_bulk(net->h, b, x)) return 0;

@@ -59,14 +59,79 @@ class TimeDepMixedHydraulicNetwork(MixedHydraulicNetwork):
         return _MassVectorForm(self, u, coeff)
 
 
+def _cell_means(dn, coef):
+    """L2 projection onto DG0 of the global mesh = cell means (global cell order), Simpson on every cell
+    (midpoint / trapezoid for degree <= 1 data)"""
+    import torch
+    c = dn.cells.long()
+    xa, xb = dn.coords[c[:, 0]], dn.coords[c[:, 1]]
+    pts = torch.stack([xa, 0.5 * (xa + xb), xb], dim=1).reshape(-1, dn.gdim).contiguous()
+    ci = np.repeat(np.arange(dn.num_cells), 3) if coef.user is not None else None
+    v = coef.eval_device(pts, pts_per_edge=3 * dn.m, tangents=dn.tangents, cell_index=ci).reshape(-1, 3)
+    if coef.degree <= 1:
+        return v[:, 1] if coef.degree == 0 else 0.5 * (v[:, 0] + v[:, 2])
+    return (v[:, 0] + 4.0 * v[:, 1] + v[:, 2]) / 6.0
+
+
 def _as_state(model, qp0):
-    """initial state as a monolithic device vector in W layout (:147-165)"""
+    """initial state as a monolithic device vector in W layout (time_stepping.py:147-165): None (zero), an
+    ii_Function on model.W, or -- like the reference, which projects component by component (:162-165) -- a
+    list with one entry per space of W: Functions on W[i] are copied, Constants / numbers / Expressions / UFL
+    are projected (per-edge CG1: consistent-mass L2 projection, the kernel L_form uses; DG0: cell means; Real: the
+    value of a Constant; CG1 on the global mesh of the primal model: nodal interpolation)."""
+    import torch
+    from ..coefficients import as_coefficient
+    from ..function import Function
     W = model.W
     if qp0 is None:
         return ii_Function(W)
     if isinstance(qp0, ii_Function):
         return qp0.copy()
-    raise TypeError("qp0 must be None or an ii_Function on model.W")
+    if not isinstance(qp0, (list, tuple)) or len(qp0) != len(W):
+        raise TypeError("qp0 must be None, an ii_Function on model.W or a list with one entry per space of model.W")
+    sys_ = model._system()
+    dn = sys_.dn
+    out = ii_Function(W)
+    x = out.tensor()
+    off = W.offsets() if hasattr(W, "offsets") else np.concatenate([[0], np.cumsum([V.dim() for V in W])])
+
+    def put(i, comp, make):
+        if isinstance(comp, Function):
+            x[int(off[i]):int(off[i + 1])].copy_(comp.vector().tensor)
+        else:
+            x[int(off[i]):int(off[i + 1])].copy_(make(as_coefficient(comp)))
+
+    if hasattr(W, "role"):                                   # mixed model: [q_0 .. q_{E-1} | p | lambda_0 ..]
+        E, m = dn.E, dn.m
+        whole = {}                                           # one projection per distinct object, every edge's slice from it
+
+        def q_block(i):
+            def make(cc, i=i):
+                key = id(qp0[i])
+                if key not in whole:
+                    whole[key] = sys_.project_coefficient(cc)
+                return whole[key][i * (m + 1):(i + 1) * (m + 1)]
+            return make
+        if all(qp0[i] is qp0[0] for i in range(E)) and not isinstance(qp0[0], Function):
+            x[: E * (m + 1)].copy_(sys_.project_coefficient(as_coefficient(qp0[0])))
+        else:
+            for i in range(E):
+                put(i, qp0[i], q_block(i))
+        put(E, qp0[E], lambda cc: _cell_means(dn, cc))
+        for k in range(dn.B):
+            comp = qp0[E + 1 + k]
+            if isinstance(comp, Function):
+                put(E + 1 + k, comp, None)
+            else:
+                cc = as_coefficient(comp)
+                if not cc.is_constant:
+                    raise NotImplementedError("a Real-space component of qp0 must be a Constant, a number or a Function")
+                x[int(off[E + 1 + k])] = cc.const_value()
+    else:                                                    # primal model: [DG0(mesh) | CG1(mesh)]
+        put(0, qp0[0], lambda cc: _cell_means(dn, cc))
+        put(1, qp0[1], lambda cc: cc.eval_device(dn.coords))
+    out.touch() if hasattr(out, "touch") else None
+    return out
 
 
 def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step_scheme="IE",

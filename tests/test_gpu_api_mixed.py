@@ -177,3 +177,49 @@ def test_time_stepping_mixed_hydraulic(scheme):
     for k, (xo, qpk) in enumerate(zip(xs, qps)):
         xg = qpk.vector().get_local()
         assert np.linalg.norm(xg - xo) <= 1e-8 * max(np.linalg.norm(xo), 1e-30), (scheme, k)
+
+
+def test_time_stepping_initial_state_given_as_a_list_of_components():
+    """qp0 as the reference takes it (time_stepping.py:162-165): one entry per space of W, projected component-wise"""
+    from graphnics_b200 import (line_graph, Constant, Expression, TimeDepMixedHydraulicNetwork, TimeDepHydraulicNetwork,
+                                time_stepping_stokes)
+    G = line_graph(3)
+    G.make_mesh(4)
+    G.make_submeshes()
+    Ainv, Res, T, t_steps = 2.0, 3.0, 0.5, 5
+    for e in G.edges():
+        G.edges()[e]["Res"] = Res
+    q0 = Expression("sin(x[0])", degree=2)
+    p0 = Expression("1 + x[0]", degree=1)
+    model = TimeDepMixedHydraulicNetwork(G, p_bc=Expression("x[0]", degree=2), Ainv=Ainv)
+    E, B = 2, 1
+    qps = time_stepping_stokes(model, Constant(0), t_steps=t_steps, T=T, qp0=[q0] * E + [p0] + [Constant(0.25)] * B)
+    pos = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    om = oracle.build_mesh(pos, np.array([[0, 1], [1, 2]]), 4)
+    lay = oracle.mixed_layout(om)
+    x0 = np.zeros(lay["N"])
+    x0[:lay["p_off"]] = oracle.project_p1_edges(om, oracle.Coef(lambda x: np.sin(x[..., 0]), 2)).ravel()
+    mid = om.coords[om.cells].mean(axis=1)
+    x0[lay["p_off"]:lay["lam_off"]] = 1.0 + mid[:, 0]                 # cell means of a linear function
+    x0[lay["lam_off"]:] = 0.25
+    np.testing.assert_allclose(qps[0].vector().get_local(), x0, rtol=1e-12, atol=1e-14)
+    xs = oracle.time_stepping("mixed", om, p_bc=oracle.Coef(lambda x: x[..., 0], 2), Res=Res, Ainv=Ainv, t_steps=t_steps,
+                              T=T, x0=x0, scheme="IE")
+    for k in range(t_steps):
+        xg = qps[k].vector().get_local()
+        assert np.linalg.norm(xg - xs[k]) <= 1e-8 * np.linalg.norm(xs[k]), k
+    # primal model: [DG0 flux | CG1 pressure]
+    G.make_mesh(4)
+    modelp = TimeDepHydraulicNetwork(G, p_bc=Expression("x[0]", degree=2), Res=Constant(Res), Ainv=Constant(Ainv))
+    qps = time_stepping_stokes(modelp, Constant(0), t_steps=t_steps, T=T, qp0=[q0, p0], t_step_scheme="CN")
+    layp = oracle.primal_layout(om)
+    x0 = np.zeros(layp["N"])
+    xa, xb = om.coords[om.cells[:, 0]][:, 0], om.coords[om.cells[:, 1]][:, 0]
+    x0[:layp["p_off"]] = (np.sin(xa) + 4 * np.sin(0.5 * (xa + xb)) + np.sin(xb)) / 6.0
+    x0[layp["p_off"]:] = 1.0 + om.coords[:, 0]
+    np.testing.assert_allclose(qps[0].vector().get_local(), x0, rtol=1e-12, atol=1e-14)
+    xs = oracle.time_stepping("primal", om, p_bc=oracle.Coef(lambda x: x[..., 0], 2), Res=Res, Ainv=Ainv, t_steps=t_steps,
+                              T=T, x0=x0, scheme="CN")
+    for k in range(t_steps):
+        xg = qps[k].vector().get_local()
+        assert np.linalg.norm(xg - xs[k]) <= 1e-8 * np.linalg.norm(xs[k]), k

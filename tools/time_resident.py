@@ -51,7 +51,8 @@ for _ in range(5):
 torch.cuda.synchronize()
 ts, stamps, stamps1, stamps2 = [], [], [], []
 for _ in range(30):
-    flush.fill_(1)
+    if "--no-flush" not in sys.argv:
+        flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); step(); e1.record(); e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
@@ -61,7 +62,7 @@ for _ in range(30):
     if ms.dn.B > 0:
         w = ms.schur_plan()[2]
         sc = w[-32 - ((ms.schur_plan()[0].na ** 2 + ms.schur_plan()[0].na + 2 * 1024) if ms.schur_plan()[0].na else 0):][:32].cpu().numpy()
-        stamps2.append((sc[9:16] - sc[8]) / 1e3)
+        stamps2.append((np.concatenate([sc[16:18], sc[9:16]]) - sc[8]) / 1e3)
 out = {"levels": levels, "n": n, "N": ms.N, "resident": os.environ.get("GNX_STEP_RESIDENT", "1"), "vals": vals is not None,
        "us_per_step": {"min": float(np.min(ts)), "median": float(np.median(ts)), "max": float(np.max(ts))}}
 if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
@@ -71,7 +72,7 @@ if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
     out["cta1_stamps_us"] = dict(zip(["prefetched", "H0_arrived", "elim0_done", "H4_arrived", "elim4_done", "b_stores_read", "asm_start",
                                       "asm_done", "released", "p3_prefetched", "bs0_done", "bs4_done", "end"], st1.round(2).tolist()))
 if stamps2:
-    out["schur_stamps_us"] = dict(zip(["prologue", "local_up", "exported", "flags", "repl_rows", "up_done", "down_done"],
+    out["schur_stamps_us"] = dict(zip(["top_solve_entry", "rows_ready_thread0", "prologue", "local_up", "exported", "flags", "repl_rows", "up_done", "down_done"],
                                       np.median(np.asarray(stamps2), axis=0).round(2).tolist()))
 if vals is not None and world == 1:
     rr, bb = ms.residual(vals, x, b).cpu().tolist()
