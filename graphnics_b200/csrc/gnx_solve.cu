@@ -595,7 +595,7 @@ struct SchurArgs {
   long long wait_epoch;
   int32_t wait_world;
   // subtree-partitioned network (gnx_exchange mode 1, plan.ncls != NULL): the flag exchange happens INSIDE the
-  // solve, after the rank-local sweeps (plan.l_sync); xbuf[k] = the other ranks' buffers, where the final
+  // solve, after the rank-local sweeps (plan.l_sync); xbuf[k] = rank k's buffer (NULL for me), where the final
   // (d, r) of my exported subtree roots go (d at xd_off + node, r at xr_off + node, like a.d / a.r in mine)
   double* xbuf[GNX_MAX_PEERS];
   int32_t nx;
@@ -725,18 +725,34 @@ __device__ __forceinline__ void sch_flag_exchange(const SchurArgs& a) {
   }
 }
 
-// The final (d, r) of my local subtree roots whose parent is replicated -> every other rank (threads of ONE CTA;
-// the values are final in MY global arrays: written before the last barrier)
-__device__ __forceinline__ void sch_export_roots(const SchurArgs& a) {
+// The exchange of a subtree-partitioned solve, run by the first `world` threads of ONE CTA after a barrier that
+// made my roots' final (d, r) visible in MY global arrays: thread q stores them into rank q's buffer and then
+// RELEASES its flag word there (st.release.sys orders the thread's own stores before the flag: no separate
+// system-scope fence; the edge scalars other threads sent earlier were fenced by their senders, EdgeOut::put),
+// then waits for rank q's flag in my buffer.  do_send / do_flags: phases of gnx_exchange_t.
+__device__ __forceinline__ void sch_export_roots(const SchurArgs& a, bool do_send, bool do_flags) {
   const gnx_schur_plan_t& pl = a.plan;
-  for (int32_t k = threadIdx.x; k < pl.nxl; k += blockDim.x) {
-    const int32_t node = pl.xlist[k];
-    const double dv = __ldcg(a.d + node), rv = __ldcg(a.r + node);
-    for (int q = 0; q < a.nx; ++q) {
-      a.xbuf[q][a.xd_off + node] = dv;
-      a.xbuf[q][a.xr_off + node] = rv;
+  const int q = threadIdx.x;
+  if (q >= a.wait_world) return;
+  if (do_send && a.xbuf[q]) {
+    for (int32_t k = 0; k < pl.nxl; ++k) {
+      const int32_t node = pl.xlist[k];
+      a.xbuf[q][a.xd_off + node] = __ldcg(a.d + node);
+      a.xbuf[q][a.xr_off + node] = __ldcg(a.r + node);
     }
-    __threadfence_system();
+    if (!do_flags) __threadfence_system();
+  }
+  if (do_flags) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[q]), "l"(a.wait_epoch) : "memory");
+    const long long* f = a.wait_flags + q;
+    long long v;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= a.wait_epoch) break;
+      __nanosleep(spins < 4096 ? 32 : 2000);
+      if (++spins > (1u << 25)) __trap();
+    }
   }
 }
 
@@ -898,11 +914,10 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     for (int q = 0; q < ROWS; ++q)
       if (lev[q] >= 0 && !repl[q] && (ncls[node[q]] & 4)) { a.d[node[q]] = d[q]; a.r[node[q]] = r[q]; }
     lsync();
-    if (a.phase != 2) sch_export_roots(a);
-    lsync();
     stamp(3);
+    sch_export_roots(a, a.phase != 2, a.phase == 0);
+    lsync();
     if (a.phase == 1) return true;
-    if (a.phase == 0) { sch_flag_exchange(a); lsync(); }
     stamp(4);
 #pragma unroll
     for (int q = 0; q < ROWS; ++q)
@@ -1497,12 +1512,9 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
   }
   if (part && pl.nc > 0) {
     // a core exists: no top part; the exchange sits between the local and the replicated levels of the grid sweep
-    if (a.phase != 2 && blockIdx.x == 0) sch_export_roots(a);
+    if (blockIdx.x == 0) sch_export_roots(a, a.phase != 2, a.phase == 0);
     if (a.phase == 1) return;
-    if (a.phase == 0) {
-      if (blockIdx.x == 0) { __syncthreads(); sch_flag_exchange(a); }
-      gsync();
-    }
+    if (a.phase == 0) gsync();
     for (int32_t idx = pl.lvl_ptr[l_sync] + t0; idx < pl.lvl_ptr[pl.nl]; idx += stride) row_to_global(pl.lvl_nodes[idx]);
     for (int32_t i = t0; i < pl.nc; i += stride) row_to_global(pl.core_nodes[i]);
     gsync();
@@ -1744,11 +1756,12 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
     a.xd_off = 3 * (int64_t)ex->E_glob; a.xr_off = a.xd_off + ex->B_glob;
     a.d = ex->peers_host[ex->rank] + a.xd_off; a.r = ex->peers_host[ex->rank] + a.xr_off;
     a.phase = ex->phase;
-    for (int k = 0; k < ex->world; ++k) {
+    for (int k = 0; k < ex->world; ++k) {               // (indexed by rank; my own slot stays NULL)
       GNX_CHECK_ARG(ex->peers_host[k] != nullptr);
-      if (k != ex->rank) a.xbuf[a.nx++] = ex->peers_host[k];
+      if (k != ex->rank) a.xbuf[k] = ex->peers_host[k];
       a.sig_flags[k] = reinterpret_cast<long long*>(ex->peers_host[k] + flag_off) + ex->rank;
     }
+    a.nx = ex->world;
     a.wait_flags = reinterpret_cast<const long long*>(ex->peers_host[ex->rank] + flag_off);
     a.wait_epoch = ex->epoch; a.wait_world = ex->world;
   } else if (ex && ex->epoch > 0) {
