@@ -269,6 +269,23 @@ def timed_steps(torch, fn, reps, warm, flush):
     return ts, host_us
 
 
+def pin_to_gpu_numa(local):
+    """bind this rank's host threads (and with them its pinned staging buffers, first touch) to the CPUs NVML names as
+    local to its GPU: eight ranks copying 17 MB each to the host at once otherwise share one memory controller"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -288,6 +305,7 @@ def run_gpu(args):
         keep = os.dup(1)
         os.dup2(2, 1)
         sys.stdout = os.fdopen(keep, "w", buffering=1)
+        pin_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=dev)
         return run_partitioned(args, dev)
 
@@ -466,6 +484,14 @@ def kernels_at_scale(hbm, timed, levels=17, n=7):
     k("edge_backsub_tile_kernel", lambda: ms.lib.gnx_edge_backsub_mixed(
         dn.net_ref(), co.ref(), b.data_ptr(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(),
         bufs["P"].data_ptr(), x.data_ptr(), st()), 2 * 8 * N + 8 * NC)
+    # Constant data (what the step runs): b is produced by the elimination kernel and never read again
+    import ctypes
+    k("edge_const_tile_kernel<eliminate> (rhs + elimination, Constant data)", lambda: ms.lib.gnx_rhs_eliminate_mixed(
+        dn.net_ref(), co.ref(), 0.0, 0.0, pbc_out.data_ptr(), pbc_node.data_ptr(), b.data_ptr(), bufs["cond"].data_ptr(),
+        bufs["rsrc"].data_ptr(), bufs["ftot"].data_ptr(), None, st()), 8 * N + 8 * NC)
+    k("edge_const_tile_kernel<backsub> (Constant data: b recomputed, not read)", lambda: ms.lib.gnx_edge_backsub_mixed_const(
+        dn.net_ref(), co.ref(), 0.0, 0.0, pbc_out.data_ptr(), pbc_node.data_ptr(), b.data_ptr(), bufs["cond"].data_ptr(),
+        bufs["rsrc"].data_ptr(), bufs["P"].data_ptr(), x.data_ptr(), st()), 8 * N + 8 * NC)
     k("spmv_kernel (CSR, fp64 values, int32 indices)", lambda: ms.spmv(vals, x, y), 12 * nnz + 4 * (N + 1) + 16 * N)
     # what plain library kernels reach on the same buffers: a pure write stream is bounded well below the
     # copy figure MEASURED_PEAKS.json quotes, which is the ceiling for the write-dominated assembly / rhs kernels

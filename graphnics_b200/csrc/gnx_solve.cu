@@ -427,9 +427,14 @@ static int edge_cpt() {           // tuning knob: cells per thread of the edge-t
   return cpt;
 }
 
+static bool const_tiles_apply(const gnx_network_t* net, const void* b_or_x);
+static int launch_eliminate_const(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const EdgeOut& out,
+                                  const ConstRhs& rhs, cudaStream_t st);
+
 static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                             const EdgeOut& out, cudaStream_t st, const ConstRhs* rhs = nullptr) {
   const GnxMixedDims d = gnx_mixed_dims(*net);
+  if (rhs && const_tiles_apply(net, rhs->b)) return launch_eliminate_const(net, co, out, *rhs, st);
   if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, rhs, st);
   else if (net->n == 1 || (edge_cpt() == 2 && net->n <= 9)) launch_eliminate_tile<2>(net, d, co, b, out, rhs, st);
   else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, rhs, st);
@@ -2588,6 +2593,118 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
 static size_t rs_smem_bytes(int tiles_per_cta, int m) {
   return ((size_t)tiles_per_cta * RS_HSLOT + (size_t)RS_SUB * RS_STAGE) * sizeof(double) +
          (size_t)tiles_per_cta * RS_MAX_G * sizeof(RsEdge) + (((size_t)m + 1 + 3) & ~(size_t)3) * sizeof(int32_t);
+}
+
+// ------------------------------------------------------------------------------------
+// The same per-tile functions as STREAMING kernels (one 1024-cell tile per 256-thread block) for networks too large
+// to stay resident: with Constant data the back-substitution RECOMPUTES the right-hand side entries instead of
+// re-reading b (16 B/dof of traffic less than edge_backsub_tile_kernel), and f = g = 0 takes the fast path.
+// What a tile needs to know about its edges is gathered into shared memory by one thread per edge first.
+// ------------------------------------------------------------------------------------
+template <bool ZFG, bool BACKSUB>
+__global__ void __launch_bounds__(ET_T, 4)
+edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
+  __shared__ __align__(16) double sH[RS_HSLOT];
+  __shared__ __align__(16) double sFG[RS_FSLOT + RS_GSLOT];
+  __shared__ double sh[3 * 32];
+  __shared__ RsEdge rec[RS_MAX_G];
+  __shared__ int32_t sloc[1024 + 4];
+  __shared__ __align__(8) uint64_t hbar;
+  const gnx_network_t& net = s.net;
+  const int tid = threadIdx.x;
+  const int32_t m = s.d.m;
+  if (!BACKSUB && (int32_t)blockIdx.x >= s.nb_tiles) {              // blocks past the tiles zero the lambda rows of b
+    const int64_t r = s.d.lam_off + (int64_t)(blockIdx.x - s.nb_tiles) * ET_T + tid;
+    if (r < s.d.N) s.rhs.b[r] = 0.0;
+    return;
+  }
+  if (!BACKSUB) gnx_pdl_trigger();
+  const int32_t G = RS_TILE >> net.n;
+  const int32_t e0 = blockIdx.x * G, nE = min(G, net.E - e0);
+  if (tid == 0) {                                                   // static data: in flight before the dependency wait
+    const int64_t hbase = (int64_t)e0 * m;
+    gnx_mbar_init(&hbar, 1);
+    gnx_mbar_expect_tx(&hbar, gnx_bulk_body_bytes(hbase, nE * m));
+    gnx_bulk_stream_in(sH, net.h, hbase, nE * m, &hbar);
+  }
+  for (int32_t i = tid; i <= m; i += ET_T) sloc[i] = net.loc[i];
+  if (BACKSUB) gnx_pdl_wait();                                      // P and the edge scalars come from the kernels before
+  if (tid < nE) {
+    const int32_t e = e0 + tid;
+    RsEdge r;
+    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
+    r.bu = net.bix[u]; r.bv = net.bix[v];
+    r.flags = (u > v ? 1 : 0) | ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
+    r.a = s.a_edge[e];
+    r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
+    r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
+    r.q0 = 0.0; r.Pu = 0.0; r.pad = 0;
+    if (BACKSUB) {
+      const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
+      const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
+      r.Pu = Pu;
+      r.q0 = __dmul_rn(s.cond[e], __dadd_rn(__dsub_rn(Pu, Pv), s.rsrc[e]));
+    }
+    rec[tid] = r;
+  }
+  __syncthreads();
+  gnx_mbar_wait(&hbar, 0);
+  if (BACKSUB) rs_backsub_tile<ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
+  else rs_eliminate_tile<ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
+  if (tid == 0) gnx_bulk_wait_read();
+}
+
+static bool const_tiles_apply(const gnx_network_t* net, const void* b_or_x) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GNX_CONST_TILES"); on = e ? atoi(e) : 1; }      // A-B knob
+  return on && net->n >= RS_MIN_N && net->n <= 10 && edge_bulk(net->h, b_or_x);
+}
+
+static void const_tiles_args(StepArgs& s, const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const ConstRhs& rhs) {
+  s.net = *net; s.d = gnx_mixed_dims(*net);
+  s.a_edge = co->a_edge; s.k_edge = co->k_edge; s.inv_sigma = 1.0 / co->sigma; s.sigma = co->sigma;
+  s.rhs = rhs;
+  s.cond = s.rsrc = nullptr; s.P = nullptr; s.x = nullptr; s.vals = nullptr;
+  s.nb_tiles = gnx_blocks(net->E, RS_TILE >> net->n);
+  s.tiles_per_cta = 1; s.sync = nullptr; s.epoch = 0;
+}
+
+// fused right-hand side + elimination for Constant data through the tile functions of the persistent kernel
+static int launch_eliminate_const(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const EdgeOut& out,
+                                  const ConstRhs& rhs, cudaStream_t st) {
+  StepArgs s;
+  const_tiles_args(s, net, co, rhs);
+  s.out = out;
+  const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ET_T) : 0;
+  const bool zfg = rhs.fc == 0.0 && rhs.gc == 0.0 && !co->k_edge;
+  if (zfg) edge_const_tile_kernel<true, false><<<s.nb_tiles + nb_lam, ET_T, 0, st>>>(s);
+  else edge_const_tile_kernel<false, false><<<s.nb_tiles + nb_lam, ET_T, 0, st>>>(s);
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+// Back-substitution for a right-hand side of Constant data (what gnx_rhs_eliminate_mixed produced): b is not read,
+// its entries are recomputed from f_const, g_const and the boundary data; x bit-identical to gnx_edge_backsub_mixed.
+extern "C" int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
+                                            double g_const, const double* pbc_out, const double* pbc_node, const double* b,
+                                            const double* cond, const double* rsrc, const double* P, double* x,
+                                            void* stream) {
+  GNX_CHECK_ARG(net && co && co->a_edge && cond && rsrc && x && net->h && co->sigma != 0.0);
+  GNX_CHECK_ARG(net->B == 0 || P);
+  if (net->B == 0 || !const_tiles_apply(net, x)) {
+    GNX_CHECK_ARG(b != nullptr);
+    return gnx_edge_backsub_mixed(net, co, b, cond, rsrc, P, x, stream);
+  }
+  StepArgs s;
+  const_tiles_args(s, net, co, ConstRhs{f_const, g_const, pbc_out, pbc_node, nullptr});
+  edge_out_local(s.out, nullptr, nullptr, nullptr);
+  s.cond = cond; s.rsrc = rsrc; s.P = P; s.x = x;
+  const bool zfg = f_const == 0.0 && g_const == 0.0 && !co->k_edge;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zfg) GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<true, true>, dim3(s.nb_tiles), dim3(ET_T), 0, st, s));
+  else GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<false, true>, dim3(s.nb_tiles), dim3(ET_T), 0, st, s));
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
 }
 
 static int rs_enabled() {             // tuning / A-B knob: GNX_STEP_RESIDENT=0 keeps the three-kernel chain

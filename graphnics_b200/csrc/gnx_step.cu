@@ -78,7 +78,8 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
     if (int rc = gnx_schur_solve(schur_net, plan, co->sigma, cond, rsrc, ftot, b + gnx_mixed_dims(*net).lam_off, nullptr,
                                  P, lam, work, rtol, max_iter, warm, 0, 0, nullptr, resid_host, info_host, solve_st)) return rc;
   }
-  if (int rc = gnx_edge_backsub_mixed(net, co, b, cond, rsrc, net->B > 0 ? P : nullptr, x, solve_st)) return rc;
+  if (int rc = gnx_edge_backsub_mixed_const(net, co, f_const, g_const, pbc_out, pbc_node, b, cond, rsrc,
+                                            net->B > 0 ? P : nullptr, x, solve_st)) return rc;
   if (fork) {
     GNX_CUDA(cudaEventRecord((cudaEvent_t)ev_join, solve_st));
     if (int rc = gnx_assemble_mixed(net, co, rowptr, vals, main_st)) return rc;

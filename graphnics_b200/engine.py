@@ -516,8 +516,12 @@ class MixedSystem:
                 check(self.lib.gnx_schur_solve(*args, None, None, st))
             if ph == 1:
                 continue
-            check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
-                                                  ptr(d["P"]), ptr(x), st))
+            if cr is not None:
+                check(self.lib.gnx_edge_backsub_mixed_const(dn.net_ref(), co.ref(), *cr[:4], ptr(b), ptr(d["cond"]),
+                                                            ptr(d["rsrc"]), ptr(d["P"]), ptr(x), st))
+            else:
+                check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),
+                                                      ptr(d["P"]), ptr(x), st))
         return x, info
 
     def eliminate(self, co, b):
@@ -624,8 +628,12 @@ class MixedSystem:
                 info.cg_rel_resid = float(resid.value)
             else:
                 check(self.lib.gnx_schur_solve(*args, None, None, st))
-        check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(loc_cond), ptr(loc_rsrc),
-                                              ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
+        if cr is not None and not eliminated:
+            check(self.lib.gnx_edge_backsub_mixed_const(dn.net_ref(), co.ref(), *cr[:4], ptr(b), ptr(loc_cond), ptr(loc_rsrc),
+                                                        ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
+        else:
+            check(self.lib.gnx_edge_backsub_mixed(dn.net_ref(), co.ref(), ptr(b), ptr(loc_cond), ptr(loc_rsrc),
+                                                  ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
         return x, info
 
     def assemble_rhs_solve(self, co, vals, b, x, rhs_kwargs=None, overlap=True, **solve_kw):

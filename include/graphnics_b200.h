@@ -357,6 +357,14 @@ int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* c
                            const double* cond, const double* rsrc, const double* P, double* x,
                            void* stream);
 
+/* gnx_edge_backsub_mixed for a right-hand side of Constant data (the b that gnx_rhs_eliminate_mixed produced from the
+ * same f_const, g_const, pbc_out, pbc_node): b is NOT read -- its entries are recomputed (16 B/dof of traffic less),
+ * f = g = 0 takes a fast path; x is bit-identical.  2^6 .. 2^10 cells per edge, else (or when b != NULL and the tile
+ * path does not apply) it forwards to gnx_edge_backsub_mixed. */
+int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const, double g_const,
+                                 const double* pbc_out, const double* pbc_node, const double* b, const double* cond,
+                                 const double* rsrc, const double* P, double* x, void* stream);
+
 /* One MixedHydraulicNetwork.solve() (flow_models.py:337-350: ii_assemble(a), ii_assemble(L) with Constant f, g,
  * ii_convert, LUSolver.solve) behind ONE call -- the same kernels as gnx_assemble_mixed +
  * gnx_rhs_eliminate_mixed + gnx_schur_solve + gnx_edge_backsub_mixed with bit-identical results; it exists
