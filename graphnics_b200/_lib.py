@@ -110,6 +110,7 @@ PROTOTYPES = {
     "gnx_step_is_resident": (_I, []),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
+    "gnx_schur_unconverged": (_I, [_PLAN, _P, _P]),
     "gnx_schur_solve": (_I, [_NET, _PLAN, _D, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _EX, c_f64p, c_i32p, _P]),
     "gnx_primal_ndofs": (_L, [_NET]),
     "gnx_primal_nnz": (_L, [_NET]),

@@ -1054,6 +1054,21 @@ __device__ __forceinline__ void blk_down(const SchurArgs& a, int32_t b, double* 
   }
 }
 
+// Stopping rule of the core PCG: ||r||^2 <= rtol^2 ||b||^2 -- relative to the INITIAL residual when b = 0 (a warm start
+// from a non-zero state with a zero right-hand side must still come down to x = 0, and rtol^2 * 0 could never be met) --
+// and a stagnation exit: no 10 % gain in 2000 iterations means the recurrence has hit its floor; spinning on to
+// max_iter would only burn grid barriers (the caller sees "not converged").  All CTAs evaluate it on identical bits.
+struct PcgStop {
+  double tol2, best;
+  int it_best;
+  __device__ __forceinline__ PcgStop(double rtol, double bb, double rr0) : tol2(rtol * rtol * (bb > 0.0 ? bb : rr0)), best(rr0), it_best(0) {}
+  __device__ __forceinline__ bool done(double rr, int it) {
+    if (rr <= tol2) return true;
+    if (rr < 0.9 * best) { best = rr; it_best = it; }
+    return it - it_best > 2000;
+  }
+};
+
 // ------------------------------------------------------------------------------------
 // Cluster-resident Jacobi-PCG on the core (SCH_CLUSTER with an ELL plan): the CG of a cyclic
 // network is a chain of hundreds of tiny dependent steps, so what matters is the latency of one
@@ -1129,9 +1144,9 @@ __device__ __forceinline__ void core_pcg_cluster(const SchurArgs& a, double* sm,
   cluster_allreduce<3>(acc, slotA, red[0], cluster);
   double rzc = acc[0], rzp = acc[0], rr = acc[1];
   const double bb = acc[2];
-  const double tol2 = a.rtol * a.rtol * bb;
+  PcgStop stop(a.rtol, bb, rr);
   for (; it < a.max_iter; ++it) {
-    if (rr <= tol2) break;
+    if (stop.done(rr, it)) break;
     const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
     const double* p_old = pbuf[it & 1];
     double* p_new = pbuf[(it & 1) ^ 1];
@@ -1360,10 +1375,10 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   };
   double rr = acc[1];
   const double bb = acc[2];
-  const double tol2 = a.rtol * a.rtol * bb;
+  PcgStop stop(a.rtol, bb, rr);
   double rzc = acc[0] + coarse(), rzp = rzc;
   for (; it < a.max_iter; ++it) {
-    if (rr <= tol2) break;
+    if (stop.done(rr, it)) break;
     const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
     const double* p_old = (it & 1) ? a.p1 : a.p0;
     double* p_new = (it & 1) ? a.p0 : a.p1;
@@ -1573,9 +1588,9 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
     }
     double rzc = acc[0], rzp = acc[0], rr = acc[1];
     const double bb = acc[2];
-    const double tol2 = a.rtol * a.rtol * bb;
+    PcgStop stop(a.rtol, bb, rr);
     for (; it < a.max_iter; ++it) {
-      if (rr <= tol2) break;
+      if (stop.done(rr, it)) break;
       const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
       const double* p_old = (it & 1) ? a.p1 : a.p0;
       double* p_new = (it & 1) ? a.p0 : a.p1;
@@ -1630,7 +1645,9 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double tol2 = a.rtol * a.rtol * bb_final;
-    a.scal[0] = tol2; a.scal[1] = (rr_final <= tol2) ? 1.0 : 0.0; a.scal[2] = (double)it;
+    const bool conv = rr_final <= tol2 || (bb_final == 0.0 && it < a.max_iter);
+    a.scal[0] = tol2; a.scal[1] = conv ? 1.0 : 0.0; a.scal[2] = (double)it;
+    if (!conv) a.scal[24] += 1.0;                 // sticky: solves since the last gnx_schur_unconverged() that did not converge
     a.scal[3] = rr_final; a.scal[4] = bb_final;
     a.scal[5] = (double)(tick[0] - tick0);        // wait for peers + phase 0 + wide rake levels
     a.scal[6] = (double)(tick[1] - tick[0]);      // top part: prologue (plan + edge scalars -> shared memory)
@@ -1801,6 +1818,20 @@ static int schur_report(const SchurArgs& a, int want, double* resid_host, int32_
   return GNX_OK;
 }
 
+// number of solves on this work buffer that ended without convergence since the last call (asynchronous solves do not
+// report per call); reads one double back and resets it.  work: the buffer of gnx_schur_solve, sized for `plan`.
+extern "C" int gnx_schur_unconverged(const gnx_schur_plan_t* plan, double* work, void* stream) {
+  if (!plan || !work) return 0;
+  const int64_t nval = plan->ell_w > 0 ? (int64_t)plan->ell_w * plan->nc : 0;
+  double* scal = work + 2 * (int64_t)plan->B + 7 * (int64_t)plan->nc + (plan->nnzc > nval ? plan->nnzc : nval) + 5 * 2048;
+  double v = 0.0, zero = 0.0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(&v, scal + 24, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  if (v != 0.0) cudaMemcpyAsync(scal + 24, &zero, sizeof(double), cudaMemcpyHostToDevice, st);
+  return (int)v;
+}
+
 // P holds the initial guess of the core unknowns on entry when warm != 0.
 extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, double sigma,
                                const double* cond, const double* rsrc, const double* ftot,
@@ -1825,14 +1856,15 @@ extern "C" int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t*
     gnx_set_error("plan asks for a cluster-resident tree sweep but 16-CTA clusters are unavailable");
     return GNX_ERR_CUDA;
   }
-  if (plan->na > 0) {
+  static_assert(SCH_T == 1024 && GNX_AGG_MAX == 128 && SCH_T / GNX_AGG_MAX * 16 == GNX_AGG_MAX,
+                "core_pcg_twolevel: RSTEP, the 16-column chunks of coarse() and the part8 offsets assume these sizes");
+  if (plan->na > 0 && plan->na <= g_sch_sms) {
     // two-level PCG: one CTA per aggregate on the cooperative grid (every phase before it is grid-stride)
-    if (plan->na > g_sch_sms) {
-      gnx_set_error("two-level PCG needs %d co-resident CTAs, the device runs %d", plan->na, g_sch_sms);
-      return GNX_ERR_CUDA;
-    }
     want = plan->na;
     GNX_CUDA(launch_coop<SCH_GRID_TL>(a, want, TL_SMEM, st));
+  } else if (plan->na > 0) {
+    // fewer SMs than aggregates (a partitioned GPU): the aggregates are ignored, plain Jacobi-PCG on the grid
+    GNX_CUDA(launch_coop<SCH_GRID>(a, want, SCH_SMEM, st));
   } else if (want <= 2 && !cluster_top) {
     GNX_CUDA(gnx_launch_dependent(schur_solve_kernel<SCH_SINGLE>, dim3(1), dim3(SCH_T), SCH_SMEM, st, a));
     GNX_LAUNCH_CHECK();

@@ -329,9 +329,17 @@ class MixedSystem:
                 t = dev(arr if len(arr) else np.zeros(1, dtype=np.int32))
                 keep[name] = t
                 setattr(s, name, t.data_ptr())
-            work = self._f64(int(self.lib.gnx_schur_work_doubles(C.byref(s))))
+            work = torch.zeros(int(self.lib.gnx_schur_work_doubles(C.byref(s))), dtype=torch.float64, device=self.dev)
             self._plan = (s, keep, work, hp)
         return self._plan
+
+    def unconverged(self):
+        """solves since the last call whose Krylov part did not converge (asynchronous solves -- sync=False -- cannot
+        raise themselves): one small device -> host read"""
+        if self._plan is None or self.dn.B == 0:
+            return 0
+        plan, _, work, _ = self._plan
+        return int(self.lib.gnx_schur_unconverged(C.byref(plan), ptr(work), current_stream()))
 
     def _p2p_setup(self):
         """two symmetric all-gather buffers (alternating per solve: a fast rank may already be writing

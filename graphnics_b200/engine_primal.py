@@ -231,6 +231,10 @@ class PrimalSystem:
             self._plan = MixedSystem.schur_plan(self)
         return self._plan
 
+    def unconverged(self):
+        from .engine import MixedSystem
+        return MixedSystem.unconverged(self)
+
     def eliminate(self, co, b):
         d = self._bufs()
         check(self.lib.gnx_edge_eliminate_primal(self.dn.net_ref(), co.ref(), ptr(b), ptr(d["cond"]), ptr(d["rsrc"]),

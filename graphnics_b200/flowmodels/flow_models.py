@@ -136,11 +136,17 @@ def _cached(ms, slot, cc, make):
 # form handles
 # ------------------------------------------------------------------------------------------
 class _MixedAForm:
-    def __init__(self, model, sigma=1.0, mass=0.0):
-        self.model, self.sigma, self.mass = model, sigma, mass
+    """a_form handle; zero=True is init_a_form (flow_models.py:266-280): the zero-weighted diagonal forms that only
+    fix the shape of the block system -- it assembles to the pattern with all-zero values"""
+
+    def __init__(self, model, sigma=1.0, mass=0.0, zero=False):
+        self.model, self.sigma, self.mass, self.zero = model, sigma, mass, zero
 
     def assemble(self):
         ms = self.model._system()
+        if self.zero:
+            ms.build_pattern()
+            return AssembledMatrix(ms, torch.zeros(ms.nnz, dtype=torch.float64, device=ms.dev), None, "mixed")
         co = self.model._coeffs(self.sigma, self.mass)
         return AssembledMatrix(ms, ms.assemble(co), co, "mixed")
 
@@ -252,10 +258,14 @@ class MixedHydraulicNetwork:
 
     # -- reference API ---------------------------------------------------------------------------
     def a_form(self, a=None):
+        """the bilinear form (flow_models.py:200-264).  `a`: the form to add to -- the reference passes init_a_form()'s
+        zero form or nothing; any other handle is refused rather than silently dropped"""
+        if a is not None and not (isinstance(a, _MixedAForm) and a.zero):
+            raise NotImplementedError("a_form(a): `a` must be None or the zero form returned by init_a_form()")
         return _MixedAForm(self)
 
     def init_a_form(self):
-        return _MixedAForm(self)
+        return _MixedAForm(self, zero=True)
 
     def init_L_form(self):
         return _MixedLForm(self, zero=True)

@@ -196,4 +196,11 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
         a_n, Ln = a_n1, Ln1                                           # :214-215
         sys_.mass_apply(model._mass_coeff(ainv), x0, out=DDn)         # :216
         L = model.L_form()                                            # :218-219
+    # steps are enqueued without waiting for the solver's status; a step of a cyclic network whose Krylov part did not
+    # converge leaves its mark on the device and is reported here, once, instead of passing silently
+    bad = sys_.unconverged()
+    if bad:
+        from .._lib import GnxError
+        raise GnxError(f"time_stepping_stokes: the Schur-complement CG did not converge in {bad} of {t_steps - 1} steps "
+                       f"(check_every=k reports the first one earlier)")
     return qps

@@ -315,8 +315,33 @@ class ExactFunction:
 
 
 def project(v, V, **kw):
+    """dolfin.project(v, V) for the spaces of the network models:
+      * DG0 on the network mesh: the L2 projection = cell means (Simpson per cell), on the device;
+      * CG1 on the submesh of one edge (the flux spaces W[i] of the mixed model): the consistent-mass L2 projection
+        the model's L_form uses for f, g, p_bc (flow_models.py:315-317), computed by the same kernel;
+      * CG1 on the whole network mesh: the nodal interpolant (the L2 projection there couples the edges through the
+        junction vertices and is not implemented; the two agree to O(h^2));
+      * anything of higher order (CG2 / CG3 in the reference's tests hold exact solutions): the expression itself,
+        evaluated exactly where it is used (ExactFunction)."""
     if isinstance(v, Function) and v.function_space() is V:
         return v
+    mesh = V.mesh()
+    dn = getattr(mesh, "_dn", None)
+    if dn is None or isinstance(v, (Function, ExactFunction)):
+        return ExactFunction(v, V)
+    if V.family == "DG" and V.degree == 0 and isinstance(mesh, Mesh1D):
+        from .flowmodels.time_stepping import _cell_means
+        return Function(V, _cell_means(dn, as_coefficient(v)).contiguous(), net=dn, role="cell")
+    if V.family == "CG" and V.degree == 1 and isinstance(mesh, SubMesh):
+        from .engine import MixedSystem
+        ms = dn.__dict__.get("_proj_system")
+        if ms is None:
+            ms = dn.__dict__["_proj_system"] = MixedSystem(dn)
+        i, m = mesh.i, dn.m
+        whole = ms.project_coefficient(as_coefficient(v))
+        return Function(V, whole[i * (m + 1):(i + 1) * (m + 1)].clone(), net=dn, role="q_edge", edge=i)
+    if V.family == "CG" and V.degree == 1 and isinstance(mesh, Mesh1D):
+        return interpolate(v, V)
     return ExactFunction(v, V)
 
 

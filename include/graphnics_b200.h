@@ -351,6 +351,11 @@ int gnx_schur_solve(const gnx_network_t* net, const gnx_schur_plan_t* plan, doub
                     int32_t warm, int32_t chunk, int32_t rank_stride, const gnx_exchange_t* ex, double* resid_host, int32_t* info_host,
                     void* stream);
 
+/* How many solves on `work` ended without convergence since the last call of this function (asynchronous solves --
+ * resid_host = info_host = NULL, e.g. the steps of a time loop -- cannot say so themselves); resets the count.
+ * Synchronises the stream.  Negative: CUDA error. */
+int gnx_schur_unconverged(const gnx_schur_plan_t* plan, double* work, void* stream);
+
 /* Phase 2: back-substitution, the q and p blocks of x [N] (dof order) from the multipliers P [B]
  * (= sigma*lambda; the lambda block itself is written by gnx_schur_solve). */
 int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,

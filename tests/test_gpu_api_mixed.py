@@ -223,3 +223,29 @@ def test_time_stepping_initial_state_given_as_a_list_of_components():
     for k in range(t_steps):
         xg = qps[k].vector().get_local()
         assert np.linalg.norm(xg - xs[k]) <= 1e-8 * np.linalg.norm(xs[k]), k
+
+
+def test_zero_shape_form_and_real_projections():
+    """init_a_form() assembles to the pattern with zero values (flow_models.py:266-280); project() onto the
+    lowest-order spaces really projects (DG0: cell means, per-edge CG1: consistent-mass L2 projection)"""
+    from graphnics_b200 import (Y_bifurcation, MixedHydraulicNetwork, Expression, FunctionSpace, project, ii_assemble)
+    G = Y_bifurcation()
+    G.make_mesh(4)
+    G.make_submeshes()
+    model = MixedHydraulicNetwork(G, p_bc=Expression("x[1]", degree=2))
+    Z = ii_assemble(model.init_a_form()).tocsr()
+    A = ii_assemble(model.a_form(model.init_a_form())).tocsr()
+    assert np.array_equal(Z.indptr, A.indptr) and np.array_equal(Z.indices, A.indices) and not Z.data.any() and A.data.any()
+    with pytest.raises(NotImplementedError):
+        model.a_form(ii_assemble(model.a_form()))
+    pos = np.array([[0, 0], [0, .5], [-.5, 1], [.5, 1]], dtype=np.float64)
+    om = oracle.build_mesh(pos, np.array([[0, 1], [1, 2], [1, 3]]), 4)
+    f = Expression("sin(3*x[0]) + x[1]*x[1]", degree=2)
+    fo = oracle.Coef(lambda x: np.sin(3 * x[..., 0]) + x[..., 1] ** 2, 2)
+    p0 = project(f, FunctionSpace(G.mesh, "DG", 0)).vector().get_local()
+    xa, xb = om.coords[om.cells[:, 0]], om.coords[om.cells[:, 1]]
+    np.testing.assert_allclose(p0, (fo(xa) + 4 * fo(0.5 * (xa + xb)) + fo(xb)) / 6.0, rtol=1e-13)
+    ref = oracle.project_p1_edges(om, fo)
+    for i in range(3):
+        qi = project(f, model.W[i]).vector().get_local()
+        np.testing.assert_allclose(qi, ref[i], rtol=1e-11, atol=1e-13)
