@@ -2383,22 +2383,20 @@ __device__ __forceinline__ void rs_backsub_tile(const StepArgs& s, int32_t tile,
   }
   const double inclD = rs_seg_incl_scan(sumD, segT, sh, &totD, ltid, bid);
   double cd = Pu + (inclD - sumD);
-  if (ZFG) {
-    // the flux is constant along an edge: fill the edge's q range, no numbering lookups
-    for (int32_t le = 0; le < c.nE; ++le) {
-      const double qe = rec[le].q0;
-      double* const dst = sG + le * (m + 1) + c.shq;
-      for (int32_t t = ltid; t <= m; t += ET_T) dst[t] = qe;
-    }
-  }
   if (c.active) {
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
       cd += D[i];
-      if (!ZFG) sG[qb + sloc[c.flip ? m - (c.kk0 + i) : c.kk0 + i]] = q[i];
+      // (f = 0: the flux is the same number at every node of the edge -- any slot of the edge's range will do,
+      //  no numbering lookup)
+      if (ZFG) sG[qb + c.kk0 + i] = q0;
+      else sG[qb + sloc[c.flip ? m - (c.kk0 + i) : c.kk0 + i]] = q[i];
       sF[ps[i]] = __dmul_rn(cd, inv_sigma);
     }
-    if (!ZFG && c.kk0 + CPT == m) sG[qb + sloc[c.flip ? 0 : m]] = __dadd_rn(q0, totF);
+    if (c.kk0 + CPT == m) {
+      if (ZFG) sG[qb + m] = q0;
+      else sG[qb + sloc[c.flip ? 0 : m]] = __dadd_rn(q0, totF);
+    }
   }
   rs_tile_store(c, sF, sG, s.x, ltid, bid);
 }

@@ -45,10 +45,8 @@ def mixed_case(name, pos, edges, n, pcol):
     del xq
     ms._xq = None
 
-    def step():
-        ms.assemble(co, out=vals)
-        ms.rhs(None, None, pbc_out, pbc_node, out=b)
-        ms.solve(co, b, x=x, sync=False)
+    def step():                                   # the one-call step, as bench.py and model.solve() run it
+        ms.assemble_rhs_solve(co, vals, b, x, dict(pbc_out=pbc_out, pbc_node=pbc_node), sync=False)
     t = timed(step)
     _, info = ms.solve(co, b, x=x)
     rr, bb = ms.residual(vals, x, b).cpu().tolist()
@@ -132,8 +130,55 @@ def c5():
     mixed_case("C5 tree 19 generations n=7 on ONE GPU", pos, edges, 7, 1)
 
 
+def c3mg(n=5):
+    """C3 edge-partitioned (BASELINE.json configs[2]) under torchrun: honeycomb(200,200), mixed model, N ranks.  The
+    lattice has no rakeable bifurcation, so every multiplier is replicated: the ranks split the edge work (assembly,
+    elimination, back-substitution) and each runs the whole multilevel PCG -- the time is the PCG's, whatever N."""
+    import torch.distributed as dist
+    from graphnics_b200.generators import honeycomb
+    from graphnics_b200.parallel import PartitionedMixed, global_residual
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    pos, edges = honeycomb(200, 200, mesh=False)._graph_arrays()
+    if world > 1:
+        pm = PartitionedMixed(pos, edges, n)
+        dn, ms = pm.dn, pm.ms
+    else:
+        dn = DeviceNetwork(pos, edges, n)
+        ms = MixedSystem(dn)
+    ms.build_pattern(); ms.schur_plan()
+    co = ms.coeffs(np.ones(dn.E))
+    vals = torch.empty(ms.nnz, dtype=torch.float64, device="cuda")
+    b = torch.empty(ms.N, dtype=torch.float64, device="cuda")
+    x = torch.zeros(ms.N, dtype=torch.float64, device="cuda")
+    xq, _ = ms.dof_coordinates(False)
+    kw = dict(pbc_out=ms.end_values(xq[:, 0].contiguous()), pbc_node=dn.pos[:, 0].contiguous())
+    del xq
+    ms._xq = None
+
+    def step():
+        ms.assemble_rhs_solve(co, vals, b, x, kw, sync=False)
+    t = timed(step)
+    tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    _, info = ms.assemble_rhs_solve(co, vals, b, x, kw, sync=True)
+    resid = global_residual(ms, vals, x, b) if world > 1 else float(np.sqrt(np.divide(*ms.residual(vals, x, b).cpu().tolist())))
+    N = (len(edges) * (2 * (1 << n) + 1) + dn.B)
+    if world == 1 or dist.get_rank() == 0:
+        print(json.dumps({"case": f"C3 honeycomb(200,200) n={n} edge-partitioned", "world": world, "N": N, "edges_per_rank": dn.E,
+                          "ms_per_step_max_over_ranks": float(tt[0]), "MDOF_per_s": N / float(tt[0]) / 1e3,
+                          "cg_iterations": info.cg_iterations, "rel_residual": resid,
+                          "exchange": ms.exchange_mode if world > 1 else None}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4", "c5"]
     for w in which:
-        {"c3": c3, "c4": c4, "c5": c5}[w]()
+        {"c3": c3, "c4": c4, "c5": c5, "c3mg": c3mg}[w]()
         torch.cuda.empty_cache()
