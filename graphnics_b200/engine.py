@@ -89,8 +89,9 @@ class MixedSystem:
         E = self.dn.E
         if torch.is_tensor(value):
             return value.to(device=self.dev, dtype=torch.float64).contiguous().reshape(E)
-        # host data: through a pinned staging buffer, asynchronous on the current stream (two buffers
-        # alternate; a buffer is reused only once the upload that last read it has run)
+        # host data: uploaded on EVERY call (a user may have changed the attributes; and an end-to-end step includes
+        # the host -> device copy of its inputs) through a pinned staging buffer, asynchronous on the current
+        # stream (two buffers alternate; a buffer is reused only once the upload that last read it has run)
         st = self.__dict__.get("_edge_stage")
         if st is None:
             st = self._edge_stage = {"bufs": [torch.empty(E, dtype=torch.float64).pin_memory() for _ in range(2)],

@@ -6,6 +6,8 @@ Same attributes after `make_mesh(n)`: geom_dim, num_edges, mesh, mf, bifurcation
 num_bifurcations, boundary_ixs, tangents, tangent, edges[e]['tangent']; after
 `make_submeshes()`: edges[e]['submesh'], edges[e]['vf'].
 """
+from operator import itemgetter
+
 import networkx as nx
 import numpy as np
 
@@ -268,7 +270,10 @@ class FenicsGraph(nx.DiGraph):
             if getattr(self, "local_edges", None) is not None:          # partitioned: this rank's edges only
                 dicts = [dicts[i] for i in self.local_edges]
             self.__dict__["_edge_dicts"] = dicts
-        vals = [d.get(key, default) for d in dicts]           # (values are re-read on every solve: a user may change them)
+        try:                                                  # (values are re-read on every solve: a user may change them)
+            vals = list(map(itemgetter(key), dicts))
+        except KeyError:                                      # some edge lacks the attribute: flow_models.py:228-231 default
+            vals = [d.get(key, default) for d in dicts]
         if vals and vals.count(vals[0]) == len(vals):                     # one shared object / one value
             vals, rep = vals[:1], len(vals)
         else:
