@@ -31,7 +31,7 @@ class gnx_network_t(C.Structure):
 
 
 class gnx_mixed_coeffs_t(C.Structure):
-    _fields_ = [("a_edge", C.c_void_p), ("k_edge", C.c_void_p), ("sigma", C.c_double)]
+    _fields_ = [("a_edge", C.c_void_p), ("k_edge", C.c_void_p), ("sigma", C.c_double), ("a_cell", C.c_void_p)]
 
 
 MAX_LEVELS = 64

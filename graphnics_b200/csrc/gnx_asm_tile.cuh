@@ -15,6 +15,7 @@ template <int CPT> constexpr int asm_stage_doubles() { return (5 * ASM_T * CPT +
 // STIFF = false compiles the stiffness term k/h (NetworkStokes; two fp64 divisions per row) out.
 struct AsmEdge {
   const double* he;          // cell lengths of the edge (u -> v order)
+  const double* ac;          // per-cell mass coefficient of the edge (same order), or NULL: `a` for every cell
   double a, kk, sgn;         // mass coefficient, stiffness coefficient, +-sigma (orientation of the lo frame)
   int32_t ebase, blo1, bhi1; // staged offset of the edge's range, 1 if the lo / hi end carries a multiplier
   bool flip;                 // u > v: the lo frame runs against the edge
@@ -31,14 +32,16 @@ __device__ __forceinline__ int32_t asm_qrow(double* stage, const int2* __restric
   double kl = 0.0, kr = 0.0;
   if (STIFF) { if (hasl) kl = E.kk / hl; if (hasr) kr = E.kk / hr; }
   double diag = 0.0;
+  const double al = (E.ac && hasl) ? E.ac[E.flip ? m - t : t - 1] : E.a;
+  const double ar = (E.ac && hasr) ? E.ac[E.flip ? m - 1 - t : t] : E.a;
   if (hasl) {
-    diag += E.a * hl * (2.0 / 6.0) + kl;
-    stage[off + ((f >> 2) & 7)] = E.a * hl * (1.0 / 6.0) - kl;
+    diag += al * hl * (2.0 / 6.0) + kl;
+    stage[off + ((f >> 2) & 7)] = al * hl * (1.0 / 6.0) - kl;
     stage[off + ((f >> 11) & 7)] = -E.sgn;                           // p column of cell t-1
   }
   if (hasr) {
-    diag += E.a * hr * (2.0 / 6.0) + kr;
-    stage[off + ((f >> 8) & 7)] = E.a * hr * (1.0 / 6.0) - kr;
+    diag += ar * hr * (2.0 / 6.0) + kr;
+    stage[off + ((f >> 8) & 7)] = ar * hr * (1.0 / 6.0) - kr;
     stage[off + ((f >> 14) & 7)] = E.sgn;                            // p column of cell t
   }
   stage[off + ((f >> 5) & 7)] = diag;

@@ -87,8 +87,8 @@ __device__ __forceinline__ void stream_out(const double* stage, double* __restri
 template <int CPT, bool BULK, bool STIFF>
 __global__ void __launch_bounds__(ASM_T)
 mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
-                         const double* __restrict__ k_edge, double a_const, double sg, int32_t nb_tiles,
-                         double* __restrict__ vals) {
+                         const double* __restrict__ k_edge, const double* __restrict__ a_cell, double a_const, double sg,
+                         int32_t nb_tiles, double* __restrict__ vals) {
   constexpr int TILE = ASM_T * CPT;
   // staging buffer, 16-byte aligned; the block's CSR range is staged SHIFTED by the parity of its first
   // slot so that shared and global addresses are 16-byte congruent and the stream-out uses bulk copies
@@ -129,6 +129,7 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
       E.kk = (STIFF && k_edge) ? k_edge[e] : 0.0;
       E.sgn = E.flip ? -sg : sg;
       E.he = net.h + (int64_t)e * m;
+      E.ac = a_cell ? a_cell + (int64_t)e * m : nullptr;
       E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
     }
     const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
@@ -155,7 +156,8 @@ mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
 
 template <int CPT, bool BULK, bool STIFF>
 static void launch_values_tile3(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
-                                const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+                                const double* k_edge, const double* a_cell, double a_const, double sg, double* vals,
+                                cudaStream_t st) {
   const int G = (ASM_T * CPT) >> net->n;
   const int nb_tiles = gnx_blocks(net->E, G);
   const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
@@ -165,37 +167,40 @@ static void launch_values_tile3(const gnx_network_t* net, const GnxMixedDims& d,
     cudaFuncSetAttribute(mixed_values_tile_kernel<CPT, BULK, STIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  mixed_values_tile_kernel<CPT, BULK, STIFF><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_const,
-                                                                                    sg, nb_tiles, vals);
+  mixed_values_tile_kernel<CPT, BULK, STIFF><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_cell,
+                                                                                    a_const, sg, nb_tiles, vals);
 }
 
 template <int CPT>
 static void launch_values_tile(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
-                               const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+                               const double* k_edge, const double* a_cell, double a_const, double sg, double* vals,
+                               cudaStream_t st) {
   static int bulk = -1;
   if (bulk < 0) { const char* e = getenv("GNX_ASM_BULK"); bulk = e ? atoi(e) : 1; }    // tuning knob
   if (bulk) {
-    if (k_edge) launch_values_tile3<CPT, true, true>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else launch_values_tile3<CPT, true, false>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    if (k_edge) launch_values_tile3<CPT, true, true>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
+    else launch_values_tile3<CPT, true, false>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
   } else {
-    if (k_edge) launch_values_tile3<CPT, false, true>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else launch_values_tile3<CPT, false, false>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    if (k_edge) launch_values_tile3<CPT, false, true>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
+    else launch_values_tile3<CPT, false, false>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
   }
 }
 
 static int launch_values(const gnx_network_t* net, const GnxMixedDims& d, const double* a_edge,
-                         const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st) {
+                         const double* k_edge, double a_const, double sg, double* vals, cudaStream_t st,
+                         const double* a_cell = nullptr) {
   if (net->n <= 10 && net->rowtab && ((uintptr_t)vals & 15) == 0) {
     static int cpt = -1;
     if (cpt < 0) { const char* e = getenv("GNX_ASM_CPT"); cpt = e ? atoi(e) : 2; }     // tuning knob
     // a tile (256 * CPT cells) holds whole edges: CPT >= m / 256
     const int c = net->n >= 10 ? 4 : (net->n == 9 && cpt < 2) ? 2 : cpt;
-    if (net->n == 0 || c == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else if (net->n == 1 || c == 2) launch_values_tile<2>(net, d, a_edge, k_edge, a_const, sg, vals, st);
-    else launch_values_tile<4>(net, d, a_edge, k_edge, a_const, sg, vals, st);
+    if (net->n == 0 || c == 1) launch_values_tile<1>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
+    else if (net->n == 1 || c == 2) launch_values_tile<2>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
+    else launch_values_tile<4>(net, d, a_edge, k_edge, a_cell, a_const, sg, vals, st);
     GNX_LAUNCH_CHECK();
     return GNX_OK;
   }
+  if (a_cell) { gnx_set_error("per-cell mass coefficients need the edge-tile assembly (n <= 10, 16-byte aligned values)"); return GNX_ERR_ARG; }
   const int nb_qp = gnx_blocks(d.lam_off, ASM_T);
   const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
   mixed_values_kernel<<<nb_qp + nb_lam, ASM_T, 0, st>>>(*net, d, a_edge, k_edge, a_const, sg, nb_qp, vals);
@@ -231,7 +236,7 @@ extern "C" int gnx_assemble_mixed(const gnx_network_t* net, const gnx_mixed_coef
   GNX_CHECK_ARG(co && co->a_edge && vals && net->h);
   (void)rowptr;  // row starts are closed-form; kept in the ABI for pattern-agnostic callers
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  return launch_values(net, d, co->a_edge, co->k_edge, 1.0, co->sigma, vals, (cudaStream_t)stream);
+  return launch_values(net, d, co->a_edge, co->k_edge, 1.0, co->sigma, vals, (cudaStream_t)stream, co->a_cell);
 }
 
 extern "C" int gnx_assemble_mass_q_mixed(const gnx_network_t* net, double coeff,

@@ -312,7 +312,7 @@ template <int CPT, bool FUSED_RHS, bool BULK>
 __global__ void __launch_bounds__(ET_T)
 edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                            double inv_sigma, const double* __restrict__ b, EdgeOut out, ConstRhs rhs,
-                           int32_t nb_tiles) {
+                           int32_t nb_tiles, const double* __restrict__ a_cell) {
   __shared__ TileSmem<CPT> ts;
   __shared__ double sh[3 * 32];
   if (FUSED_RHS && (int32_t)blockIdx.x >= nb_tiles) {
@@ -381,11 +381,24 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
   double cum = incl - sumF;                       // cumF at the first cell of this thread
   double s2 = 0.0;
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) { s2 = gnx_s2_step(s2, H[i], cum, F[i]); cum = __dadd_rn(cum, F[i]); }
+  if (a_cell) {
+    // mass coefficient per cell: the weights a_k h_k take the place of h_k, the edge coefficient is 1
+    const double* ac = a_cell + (int64_t)c.e * m + c.kk0;
+    sumH = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const double ah = __dmul_rn(c.active ? ac[i] : 0.0, H[i]);
+      s2 = gnx_s2_step(s2, ah, cum, F[i]); cum = __dadd_rn(cum, F[i]);
+      sumH += ah;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { s2 = gnx_s2_step(s2, H[i], cum, F[i]); cum = __dadd_rn(cum, F[i]); }
+  }
   double acc[3] = {s2, sumG, sumH};
   gnx_seg_sum<3>(acc, segT, sh);
   if (c.active && c.kk0 == 0) {
-    const double a = a_edge[c.e];
+    const double a = a_cell ? 1.0 : a_edge[c.e];
     out.put(c.e, gnx_edge_cond(a, acc[2]), gnx_edge_rsrc(a, acc[1], acc[0]), tot);
   }
   if (FUSED_RHS) tile_store_done<BULK>();
@@ -407,11 +420,11 @@ static void launch_eliminate_tile2(const gnx_network_t* net, const GnxMixedDims&
   if (rhs) {
     const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ET_T) : 0;
     edge_eliminate_tile_kernel<CPT, true, BULK><<<nb_tiles + nb_lam, ET_T, 0, st>>>(
-        *net, d, co->a_edge, 1.0 / co->sigma, nullptr, out, *rhs, nb_tiles);
+        *net, d, co->a_edge, 1.0 / co->sigma, nullptr, out, *rhs, nb_tiles, co->a_cell);
   } else {
     ConstRhs none = {0.0, 0.0, nullptr, nullptr, nullptr};
     edge_eliminate_tile_kernel<CPT, false, BULK><<<nb_tiles, ET_T, 0, st>>>(*net, d, co->a_edge, 1.0 / co->sigma, b,
-                                                                             out, none, nb_tiles);
+                                                                             out, none, nb_tiles, co->a_cell);
   }
 }
 template <int CPT>
@@ -434,7 +447,8 @@ static int launch_eliminate_const(const gnx_network_t* net, const gnx_mixed_coef
 static int launch_eliminate(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const double* b,
                             const EdgeOut& out, cudaStream_t st, const ConstRhs* rhs = nullptr) {
   const GnxMixedDims d = gnx_mixed_dims(*net);
-  if (rhs && const_tiles_apply(net, rhs->b)) return launch_eliminate_const(net, co, out, *rhs, st);
+  if (rhs && !co->a_cell && const_tiles_apply(net, rhs->b)) return launch_eliminate_const(net, co, out, *rhs, st);
+  if (co->a_cell && net->n > 10) { gnx_set_error("per-cell mass coefficients need n <= 10"); return GNX_ERR_ARG; }
   if (net->n == 0) launch_eliminate_tile<1>(net, d, co, b, out, rhs, st);
   else if (net->n == 1 || (edge_cpt() == 2 && net->n <= 9)) launch_eliminate_tile<2>(net, d, co, b, out, rhs, st);
   else if (net->n <= 10) launch_eliminate_tile<4>(net, d, co, b, out, rhs, st);
@@ -1954,7 +1968,7 @@ __global__ void __launch_bounds__(ET_T, 4)
 edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                          const double* __restrict__ k_edge, double inv_sigma, const double* __restrict__ b,
                          const double* __restrict__ cond, const double* __restrict__ rsrc,
-                         const double* __restrict__ P, double* __restrict__ x) {
+                         const double* __restrict__ P, double* __restrict__ x, const double* __restrict__ a_cell) {
   __shared__ TileSmem<CPT> ts;
   __shared__ double sh[32];
   const TileCtx c = tile_ctx<CPT, BULK>(net, d);
@@ -2001,10 +2015,16 @@ edge_backsub_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __rest
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     q[i] = __dadd_rn(q0, cum);
-    double mq = gnx_mq_right(a, H[i], q[i], F[i]);                                 // h_j (2 q_j + q_{j+1})/6
     const bool has_left = (i > 0) || (c.kk0 > 0);
     const double fl = i > 0 ? F[i - 1] : Fl, hl = i > 0 ? H[i - 1] : Hl;
-    if (has_left) mq = gnx_mq_left(mq, a, hl, q[i], fl);                           // h_{j-1}(q_{j-1} + 2 q_j)/6
+    double ar = a, al = a;                                                         // mass coefficient of the right / left cell
+    if (a_cell) {
+      const double* ac = a_cell + (int64_t)c.e * m + c.kk0 + i;
+      ar = c.active ? ac[0] : 0.0;
+      al = (c.active && has_left) ? ac[-1] : 0.0;
+    }
+    double mq = gnx_mq_right(ar, H[i], q[i], F[i]);                                // h_j (2 q_j + q_{j+1})/6
+    if (has_left) mq = gnx_mq_left(mq, al, hl, q[i], fl);                          // h_{j-1}(q_{j-1} + 2 q_j)/6
     if (kv != 0.0) {                                                               // stiffness (NetworkStokes)
       mq = __dsub_rn(mq, __ddiv_rn(__dmul_rn(kv, F[i]), H[i]));
       if (has_left) mq = __dadd_rn(mq, __ddiv_rn(__dmul_rn(kv, fl), hl));
@@ -2036,10 +2056,10 @@ static void launch_backsub_tile(const gnx_network_t* net, const GnxMixedDims& d,
   const int G = (ET_T * CPT) >> net->n;
   if (edge_bulk(net->h, b, x))
     gnx_launch_dependent(edge_backsub_tile_kernel<CPT, true>, dim3(gnx_blocks(net->E, G)), dim3(ET_T), 0, st,
-                         *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+                         *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x, co->a_cell);
   else
     edge_backsub_tile_kernel<CPT, false><<<gnx_blocks(net->E, G), ET_T, 0, st>>>(
-        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x);
+        *net, d, co->a_edge, co->k_edge, 1.0 / co->sigma, b, cond, rsrc, P, x, co->a_cell);
 }
 
 extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co,
@@ -2052,6 +2072,7 @@ extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_
   if (net->n == 0) launch_backsub_tile<1>(net, d, co, b, cond, rsrc, P, x, st);
   else if (net->n == 1 || (edge_cpt() == 2 && net->n <= 9)) launch_backsub_tile<2>(net, d, co, b, cond, rsrc, P, x, st);
   else if (net->n <= 10) launch_backsub_tile<4>(net, d, co, b, cond, rsrc, P, x, st);
+  else if (co->a_cell) { gnx_set_error("per-cell mass coefficients need n <= 10"); return GNX_ERR_ARG; }
   else {
     const EdgeTiling t = edge_tiling(net->n);
     edge_backsub_kernel<<<gnx_blocks(net->E, t.edges_per_block), t.threads, 0, st>>>(
@@ -2439,6 +2460,7 @@ __device__ __forceinline__ void rs_assemble_tile(const StepArgs& s, int32_t atil
       E.kk = (STIFF && s.k_edge) ? s.k_edge[e] : 0.0;
       E.sgn = E.flip ? -sg : sg;
       E.he = net.h + (int64_t)e * m;
+      E.ac = nullptr;
       E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
     }
     const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
@@ -2721,7 +2743,7 @@ extern "C" int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_
                                             void* stream) {
   GNX_CHECK_ARG(net && co && co->a_edge && cond && rsrc && x && net->h && co->sigma != 0.0);
   GNX_CHECK_ARG(net->B == 0 || P);
-  if (net->B == 0 || !const_tiles_apply(net, x)) {
+  if (net->B == 0 || co->a_cell || !const_tiles_apply(net, x)) {
     GNX_CHECK_ARG(b != nullptr);
     return gnx_edge_backsub_mixed(net, co, b, cond, rsrc, P, x, stream);
   }

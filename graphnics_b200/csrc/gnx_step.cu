@@ -30,7 +30,7 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
   GNX_CHECK_ARG(!ex || ex->mode == 0 || (cond && rsrc));
   GNX_CHECK_ARG(net->B == 0 || (schur_net && plan && P && work));
   cudaStream_t main_st = (cudaStream_t)stream;
-  if (sync && epoch > 0 && net->B > 0 && (!vals || (net->rowtab && ((uintptr_t)vals & 15) == 0)) &&
+  if (sync && epoch > 0 && net->B > 0 && !co->a_cell && (!vals || (net->rowtab && ((uintptr_t)vals & 15) == 0)) &&
       gnx_step_resident_applies(net, plan, b, x, reinterpret_cast<const unsigned long long*>(sync))) {
     // small enough for the cell lengths to stay in shared memory: the whole step -- assembly included -- is ONE
     // persistent kernel on the caller's stream (no second stream, no events)

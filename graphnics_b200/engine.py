@@ -35,12 +35,13 @@ class SolveInfo:
 class _Coeffs:
     """gnx_mixed_coeffs_t + the tensors it points to."""
 
-    def __init__(self, a_edge, k_edge, sigma):
-        self.a_edge, self.k_edge, self.sigma = a_edge, k_edge, float(sigma)
+    def __init__(self, a_edge, k_edge, sigma, a_cell=None):
+        self.a_edge, self.k_edge, self.sigma, self.a_cell = a_edge, k_edge, float(sigma), a_cell
         self.c = _lib.gnx_mixed_coeffs_t()
         self.c.a_edge = a_edge.data_ptr()
         self.c.k_edge = k_edge.data_ptr() if k_edge is not None else None
         self.c.sigma = float(sigma)
+        self.c.a_cell = a_cell.data_ptr() if a_cell is not None else None
 
     def ref(self):
         return C.byref(self.c)
@@ -104,10 +105,49 @@ class MixedSystem:
         st["evs"][k].record()
         return out
 
-    def coeffs(self, a_edge, k_edge=None, sigma=1.0):
+    def coeffs(self, a_edge, k_edge=None, sigma=1.0, a_cell=None):
+        """a_cell: [E*m] device tensor, mass coefficient per cell in edge-local order (overrides a_edge)"""
         a = self.edge_array(a_edge)
         k = None if k_edge is None else self.edge_array(k_edge)
-        return _Coeffs(a, k, sigma)
+        if a_cell is not None:
+            a_cell = a_cell.to(device=self.dev, dtype=torch.float64).contiguous().reshape(self.dn.E * self.dn.m)
+        return _Coeffs(a, k, sigma, a_cell)
+
+    def cell_midpoints_edge_local(self):
+        """[E*m, gdim] midpoints of the cells in EDGE-LOCAL order (cell k of edge e at e*m + k, u -> v) -- where a
+        position-dependent edge coefficient is sampled"""
+        if getattr(self, "_xmid_el", None) is None:
+            dn = self.dn
+            m, n = dn.m, dn.n
+            k = np.arange(m, dtype=np.int64)
+            edges = dn.edges_host()
+            flip = edges[:, 0] > edges[:, 1]
+            s_lo = np.where(flip[:, None], m - 1 - k[None, :], k[None, :])           # lo-frame position of cell k
+            gcell = (np.arange(dn.E, dtype=np.int64)[:, None] * m + (s_lo ^ (s_lo >> 1))).ravel()
+            c = dn.cells.long()[torch.from_numpy(gcell).to(self.dev)]
+            self._xmid_el = (0.5 * (dn.coords[c[:, 0]] + dn.coords[c[:, 1]])).contiguous()
+        return self._xmid_el
+
+    def cell_values(self, per_edge):
+        """per-edge coefficient objects (numbers, Constants, Expressions / UFL in x and parameters) -> [E*m] tensor of
+        their values at the cell midpoints, edge-local order; one device evaluation per DISTINCT object"""
+        from .coefficients import as_coefficient
+        dn = self.dn
+        out = self._f64(dn.E, dn.m)
+        groups = {}
+        for e, obj in enumerate(per_edge):
+            groups.setdefault(id(obj), (obj, []))[1].append(e)
+        xm = None
+        for obj, es in groups.values():
+            cc = as_coefficient(obj)
+            idx = torch.as_tensor(es, device=self.dev)
+            if cc.is_constant:
+                out[idx] = cc.const_value()
+                continue
+            xm = self.cell_midpoints_edge_local() if xm is None else xm
+            vals = cc.eval_device(xm, pts_per_edge=dn.m, tangents=dn.tangents).reshape(dn.E, dn.m)
+            out[idx] = vals[idx]
+        return out.reshape(-1)
 
     # ---- pattern (built once) ----------------------------------------------------------------
     def build_pattern(self):

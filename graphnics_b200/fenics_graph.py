@@ -11,13 +11,22 @@ from operator import itemgetter
 import networkx as nx
 import numpy as np
 
-from .coefficients import (UserExpression, UFLExpr, Constant, dot, grad, tangent_components,
+from .coefficients import (UserExpression, UFLExpr, Constant, Expression, dot, grad, tangent_components,
                            as_coefficient)
 from .device import DeviceNetwork
 from .mesh import Mesh1D, SubMesh, CellMarker, VertexMarker
 
 __all__ = ["BIF_IN", "BIF_OUT", "BOUN_IN", "BOUN_OUT", "FenicsGraph", "GlobalFlux",
            "GlobalCrossectionFlux", "TangentFunction", "copy_from_nx_graph", "nxgraph_attribute_to_dolfin"]
+
+class VaryingEdgeAttribute(Exception):
+    """an edge attribute that is a function of position (and parameters) rather than one number per edge; carries the
+    per-edge objects, in device edge order, for whoever can sample them"""
+
+    def __init__(self, key, per_edge):
+        super().__init__(f"edge attribute '{key}' varies along the edge")
+        self.key, self.per_edge = key, per_edge
+
 
 # Marker tags (graphnics/fenics_graph.py:22-25)
 BIF_IN = 1
@@ -286,9 +295,10 @@ class FenicsGraph(nx.DiGraph):
             if f is None:
                 if isinstance(v, UFLExpr):
                     if v.expr.free_symbols - set(v.params):
-                        raise NotImplementedError(
-                            f"edge attribute '{key}' varies along the edge; only per-edge constants are supported")
+                        raise VaryingEdgeAttribute(key, list(np.repeat(np.asarray(vals, dtype=object), rep)) if rep > 1 else vals)
                     f = float(v.expr.subs({s: float(c) for s, c in v.params.items()}))
+                elif isinstance(v, Expression):
+                    raise VaryingEdgeAttribute(key, list(np.repeat(np.asarray(vals, dtype=object), rep)) if rep > 1 else vals)
                 else:
                     f = float(v)
                 conv[k] = f

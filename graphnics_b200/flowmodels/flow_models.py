@@ -14,6 +14,7 @@ from .. import _lib
 from ..coefficients import Constant, as_coefficient
 from ..device import current_stream
 from ..engine import MixedSystem
+from ..fenics_graph import VaryingEdgeAttribute
 from ..function import FunctionSpace, TrialFunction, TestFunction, ii_Function
 from ..la import AssembledMatrix, AssembledVector, ii_assemble, apply_bc
 from ..mesh import SubMesh
@@ -252,9 +253,15 @@ class MixedHydraulicNetwork:
     def _coeffs(self, sigma=1.0, mass=0.0):
         """operator  mass*M + sigma*(Res M + visc K)  with couplings scaled by sigma"""
         ms = self._system()
-        res = self.G.edge_attribute_array("Res", 1.0)
         visc = self._visc_edge()
-        return ms.coeffs(self._mass_coeff(mass) + sigma * res, None if visc is None else sigma * visc, sigma)
+        kv = None if visc is None else sigma * visc
+        try:
+            res = self.G.edge_attribute_array("Res", 1.0)
+        except VaryingEdgeAttribute as var:
+            # "Res" as a function of position / time (flow_models.py:228-233, the vasomotion demo): sampled per cell
+            a_cell = self._mass_coeff(mass) + sigma * ms.cell_values(var.per_edge)
+            return ms.coeffs(np.ones(ms.dn.E), kv, sigma, a_cell=a_cell)
+        return ms.coeffs(self._mass_coeff(mass) + sigma * res, kv, sigma)
 
     # -- reference API ---------------------------------------------------------------------------
     def a_form(self, a=None):
@@ -307,7 +314,11 @@ class NetworkStokes(MixedHydraulicNetwork):
         super().__init__(G=G, f=f, g=g, p_bc=p_bc, space=space)
 
     def _visc_edge(self):
-        return float(self.mu) / self.G.edge_attribute_array("Ainv", 1.0)
+        try:
+            return float(self.mu) / self.G.edge_attribute_array("Ainv", 1.0)
+        except VaryingEdgeAttribute:
+            raise NotImplementedError('NetworkStokes: the edge attribute "Ainv" must be one number per edge '
+                                      '(a position-dependent "Res" is supported)')
 
 
 class HydraulicNetwork:

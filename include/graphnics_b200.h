@@ -72,6 +72,12 @@ typedef struct gnx_mixed_coeffs {
   const double* a_edge;       /* [E] mass coefficient */
   const double* k_edge;       /* [E] stiffness coefficient, or NULL */
   double sigma;               /* coupling scale s */
+  /* [E*m] mass coefficient per CELL in edge-local order (cell k of edge e at e*m + k, u -> v, like gnx_network_t.h), or
+   * NULL: edge attribute "Res" given as a function of position / time (flow_models.py:228-233,
+   * demo/Vasomotion in arterial trees.ipynb:222-289), sampled at the cell midpoints -- the element mass matrix is
+   * a_cell h/6 [[2,1],[1,2]], exact for cell-wise constant data.  Overrides a_edge where given; the chain kernels of
+   * the solve handle it (2^0..2^10 cells per edge), the persistent / Constant-data fast paths step aside. */
+  const double* a_cell;
 } gnx_mixed_coeffs_t;
 
 const char* gnx_last_error(void);

@@ -142,18 +142,19 @@ def assemble_mixed(om, Res=1.0, visc=None):
     """Monolithic matrix of MixedHydraulicNetwork.a_form (flow_models.py:200-264),
     ii_assemble + ii_convert (:343-344), canonical numbering/sparsity.
 
-    Res  : scalar or [E] (edge attribute "Res", default Constant(1), :228-231)
+    Res  : scalar or [E] (edge attribute "Res", default Constant(1), :228-231); or [E, m]: one value per cell of
+           every submesh (submesh cell order) -- a resistance given as a function of position, sampled cell-wise
     visc : None, or scalar/[E] = mu/Ainv_e -> adds NetworkStokes' (mu/Ainv) dds(q) dds(v)
            (flow_models.py:399; the reference reads self.mu which its ctor never sets)
     """
     lay = mixed_layout(om)
     E, m, N = om.E, om.m, lay["N"]
-    Res = np.broadcast_to(np.asarray(Res, dtype=np.float64), (E,))
+    Res = np.asarray(Res, dtype=np.float64)
     h, dsb = _edge_geom(om)
     a = om.sub_cells[:, :, 0] + lay["q_off"][:, None]
     b = om.sub_cells[:, :, 1] + lay["q_off"][:, None]
     pc = lay["p_off"] + om.parent_cell          # Restriction(p, submesh_i): parent cell dof
-    R = Res[:, None]
+    R = Res if Res.ndim == 2 else np.broadcast_to(Res, (E,))[:, None]
     rows, cols, vals = [], [], []
 
     def add(r, c, v):

@@ -249,3 +249,52 @@ def test_zero_shape_form_and_real_projections():
     for i in range(3):
         qi = project(f, model.W[i]).vector().get_local()
         np.testing.assert_allclose(qi, ref[i], rtol=1e-11, atol=1e-13)
+
+
+def test_resistance_given_as_a_function_of_position():
+    """edge attribute "Res" as an Expression / UFL of x (flow_models.py:228-233, demo/Vasomotion in arterial
+    trees.ipynb:222-289): sampled at the cell midpoints; matrix entries 1e-12 and solution 1e-8 against the oracle with
+    the same cell-wise resistances, through model.solve() and through the explicit assemble / LUSolver idiom"""
+    from graphnics_b200 import (Y_bifurcation, MixedHydraulicNetwork, Expression, Constant, SpatialCoordinate, ii_assemble,
+                                ii_convert, ii_Function, LUSolver)
+    n = 5
+    G = Y_bifurcation()
+    G.make_mesh(n)
+    G.make_submeshes()
+    r0 = Expression("1 + x[0]*x[0] + 0.5*x[1]", degree=2)
+    xx = SpatialCoordinate(G.mesh)
+    G.edges[0, 1]["Res"] = r0
+    G.edges[1, 2]["Res"] = 2.0 + xx[1] * xx[1]          # UFL
+    G.edges[1, 3]["Res"] = Constant(3.0)
+    model = MixedHydraulicNetwork(G, f=Constant(0.3), g=Constant(-0.2), p_bc=Expression("x[1]", degree=2))
+    qp = model.solve()
+    pos = np.array([[0, 0], [0, .5], [-.5, 1], [.5, 1]], dtype=np.float64)
+    om = oracle.build_mesh(pos, np.array([[0, 1], [1, 2], [1, 3]]), n)
+    mid = 0.5 * (om.sub_coords[np.arange(3)[:, None], om.sub_cells[:, :, 0]] + om.sub_coords[np.arange(3)[:, None], om.sub_cells[:, :, 1]])
+    R = np.stack([1 + mid[0, :, 0] ** 2 + 0.5 * mid[0, :, 1], 2.0 + mid[1, :, 1] ** 2, np.full(om.m, 3.0)])
+    A = oracle.assemble_mixed(om, R)
+    b = oracle.assemble_mixed_rhs(om, f=0.3, g=-0.2, p_bc=oracle.Coef(lambda x: x[..., 1], 2), project=True)
+    x_ref = oracle.lu_solve(A, b)
+    Ag = model.A.tocsr()
+    assert np.array_equal(Ag.indptr, A.indptr) and np.array_equal(Ag.indices, A.indices)
+    np.testing.assert_allclose(Ag.data, A.data, rtol=1e-12, atol=1e-300)
+    xg = qp.vector().get_local()
+    assert np.linalg.norm(xg - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    Am, bm = map(ii_assemble, (model.a_form(), model.L_form()))
+    Am, bm = map(ii_convert, (Am, bm))
+    qp2 = ii_Function(model.W)
+    LUSolver(Am, "mumps").solve(qp2.vector(), bm)
+    assert np.linalg.norm(qp2.vector().get_local() - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    # a time-dependent resistance: the operator follows `t` when it is re-assembled
+    r0.t = 0.0
+    rt = Expression("1 + t + x[0]*x[0]", degree=2, t=0.0)
+    for e in G.edges():
+        G.edges[e]["Res"] = rt
+    x0 = MixedHydraulicNetwork(G, p_bc=Expression("x[1]", degree=2)).solve().vector().get_local()
+    rt.t = 2.0
+    x1 = MixedHydraulicNetwork(G, p_bc=Expression("x[1]", degree=2)).solve().vector().get_local()
+    Rt = lambda t: 1 + t + mid[:, :, 0] ** 2
+    b0 = oracle.assemble_mixed_rhs(om, p_bc=oracle.Coef(lambda x: x[..., 1], 2), project=True)
+    for xg, t in ((x0, 0.0), (x1, 2.0)):
+        xr = oracle.lu_solve(oracle.assemble_mixed(om, Rt(t)), b0)
+        assert np.linalg.norm(xg - xr) <= 1e-8 * np.linalg.norm(xr)
