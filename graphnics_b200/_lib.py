@@ -108,6 +108,10 @@ PROTOTYPES = {
     "gnx_step_mixed": (_I, [_NET, _CO, _P, _P, _D, _D, _P, _P, _P, _P, _NET, _PLAN, _P, _P, _P, _P, _P, _D, _I, _I,
                             _EX, c_f64p, c_i32p, _P, _P, _P, _P, _L, _P]),
     "gnx_step_is_resident": (_I, []),
+    "gnx_timestep_mixed": (_I, [_NET, _CO, _PLAN, _P, _P, _D, _D, _P, _P, _D, _D, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P,
+                                _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
+    "gnx_timestep_primal": (_I, [_NET, _PCO, _PLAN, _P, _P, _I, _D, _P, _I, _D, _P, _D, _D, _P, _P, _P, _P, _P, _PCO, _P, _P,
+                                 _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, c_f64p, c_i32p, _P]),
     "gnx_schur_build": (_I, [_NET, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnx_schur_work_doubles": (_L, [_PLAN]),
     "gnx_schur_unconverged": (_I, [_PLAN, _P, _P]),

@@ -87,3 +87,75 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
   }
   return GNX_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// One theta-scheme time step (graphnics/flowmodels/time_stepping.py:179-216) behind ONE call:
+//   Ln1 = L^{n+1}                                    right-hand-side kernel
+//   b   = DDn + w1 Ln1 - w0 A x^n + w0 Ln             w1 = theta dt, w0 = (1 - theta) dt; implicit Euler: w0 = 0, no SpMV
+//   x1  = (D + w1 A)^-1 b                             elimination -> Schur solve -> back-substitution
+//   DDn = D x1                                        mass apply (the next step's first term)
+// The kernels are those of the separate entry points (identical results); what this saves is the host: seven
+// Python / ctypes round trips per step cost more than the ~70 us the GPU needs for a step on a tree.
+// ------------------------------------------------------------------------------------
+static int theta_rhs(int64_t N, double w1, double w0, const int32_t* rowptr, const int32_t* colidx, const double* vals_n,
+                     const double* x0, const double* DDn, const double* Ln1, const double* Ln, double* ax, double* b,
+                     void* stream) {
+  double coefs[4] = {1.0, w1, 0.0, 0.0};
+  const double* vecs[4] = {DDn, Ln1, nullptr, nullptr};
+  int k = 2;
+  if (w0 != 0.0) {
+    GNX_CHECK_ARG(rowptr && colidx && vals_n && x0 && Ln && ax);
+    if (int rc = gnx_spmv_csr_f64((int32_t)N, rowptr, colidx, vals_n, x0, ax, stream)) return rc;
+    coefs[2] = -w0; vecs[2] = ax;
+    coefs[3] = w0; vecs[3] = Ln;
+    k = 4;
+  }
+  return gnx_lincomb(N, k, coefs, vecs, b, stream);
+}
+
+extern "C" int gnx_timestep_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const gnx_schur_plan_t* plan,
+                                  const double* f_nodal, const double* g_nodal, double f_const, double g_const,
+                                  const double* pbc_out, const double* pbc_node, double w1, double w0,
+                                  const int32_t* rowptr, const int32_t* colidx, const double* vals_n, const double* x0,
+                                  const double* Ln, double mass_coeff, double* DDn, double* Ln1, double* b, double* ax,
+                                  double* x1, double* cond, double* rsrc, double* ftot, double* P, double* work,
+                                  double rtol, int32_t max_iter, int32_t warm, double* resid_host, int32_t* info_host,
+                                  void* stream) {
+  GNX_CHECK_ARG(net && co && DDn && Ln1 && b && x1 && cond && rsrc && ftot);
+  GNX_CHECK_ARG(net->B == 0 || (plan && P && work));
+  const GnxMixedDims d = gnx_mixed_dims(*net);
+  if (int rc = gnx_assemble_rhs_mixed(net, f_nodal, g_nodal, f_const, g_const, pbc_out, pbc_node, Ln1, stream)) return rc;
+  if (int rc = theta_rhs(d.N, w1, w0, rowptr, colidx, vals_n, x0, DDn, Ln1, Ln, ax, b, stream)) return rc;
+  if (int rc = gnx_edge_eliminate_mixed(net, co, b, cond, rsrc, ftot, stream)) return rc;
+  if (net->B > 0)
+    if (int rc = gnx_schur_solve(net, plan, co->sigma, cond, rsrc, ftot, b + d.lam_off, nullptr, P, x1 + d.lam_off, work,
+                                 rtol, max_iter, warm, 0, 0, nullptr, resid_host, info_host, stream)) return rc;
+  if (int rc = gnx_edge_backsub_mixed(net, co, b, cond, rsrc, net->B > 0 ? P : nullptr, x1, stream)) return rc;
+  return gnx_mass_apply_q_mixed(net, mass_coeff, x1, DDn, stream);
+}
+
+// The same for the primal model (TimeDepHydraulicNetwork): f_cell / g_cell as in gnx_assemble_rhs_primal, the Dirichlet
+// data bc_node [V] applied to b (xii.apply_bc, time_stepping.py:188), co_mass the coefficient of the q mass term.
+extern "C" int gnx_timestep_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, const gnx_schur_plan_t* plan,
+                                   const int32_t* cells, const double* f_cell, int32_t f_lin, double f_const,
+                                   const double* g_cell, int32_t g_lin, double g_const, const double* bc_node, double w1,
+                                   double w0, const int32_t* rowptr, const int32_t* colidx, const double* vals_n,
+                                   const double* x0, const double* Ln, const gnx_primal_coeffs_t* co_mass, double* DDn,
+                                   double* Ln1, double* b, double* ax, double* x1, double* cond, double* rsrc, double* ftot,
+                                   double* P, double* work, double rtol, int32_t max_iter, int32_t warm,
+                                   double* resid_host, int32_t* info_host, void* stream) {
+  GNX_CHECK_ARG(net && co && co_mass && cells && DDn && Ln1 && b && x1 && cond && rsrc && ftot);
+  GNX_CHECK_ARG(net->B == 0 || (plan && P && work));
+  const int64_t N = gnx_primal_ndofs(net);
+  const int64_t NC = (int64_t)net->E << net->n;
+  if (int rc = gnx_assemble_rhs_primal(net, cells, f_cell, f_lin, f_const, g_cell, g_lin, g_const, Ln1, stream)) return rc;
+  if (int rc = theta_rhs(N, w1, w0, rowptr, colidx, vals_n, x0, DDn, Ln1, Ln, ax, b, stream)) return rc;
+  if (bc_node)
+    if (int rc = gnx_apply_bc_primal(net, co->sigma, bc_node, nullptr, b, stream)) return rc;
+  if (int rc = gnx_edge_eliminate_primal(net, co, b, cond, rsrc, ftot, stream)) return rc;
+  if (net->B > 0)
+    if (int rc = gnx_schur_solve(net, plan, co->sigma, cond, rsrc, ftot, nullptr, b + NC, P, nullptr, work, rtol, max_iter,
+                                 warm, 0, 0, nullptr, resid_host, info_host, stream)) return rc;
+  if (int rc = gnx_edge_backsub_primal(net, co, b, cond, rsrc, net->B > 0 ? P : nullptr, x1, stream)) return rc;
+  return gnx_mass_apply_q_primal(net, co_mass, x1, DDn, stream);
+}

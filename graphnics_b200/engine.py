@@ -777,6 +777,39 @@ class MixedSystem:
             info.cg_rel_resid = float(resid.value)
         return x, info
 
+    def timestep(self, model, L, co, w1, w0, a_n, x0, Ln, mass_coeff, DDn, Ln1, b, ax, x1, bcs=None, warm_start=False,
+                 sync=False, info=None, rtol=1e-13, max_iter=100000):
+        """one theta-scheme step behind ONE library call (gnx_timestep_mixed): L^{n+1} -> b -> solve -> D x^{n+1};
+        `L`: the model's L_form handle, `a_n`: the assembled operator of step n (Crank-Nicolson) or None"""
+        dn = self.dn
+        d = self._bufs()
+        info = info if info is not None else SolveInfo()
+        kw = L.rhs_kwargs()
+        plan = work = None
+        if dn.B > 0:
+            plan, _, work, _ = self.schur_plan()
+        resid = inf = None
+        if sync and dn.B > 0:
+            resid = C.c_double(0.0)
+            inf = (C.c_int32 * 3)()
+        cn = w0 != 0.0
+        if cn:
+            self.build_pattern()
+        check(self.lib.gnx_timestep_mixed(
+            dn.net_ref(), co.ref(), C.byref(plan) if plan is not None else None, ptr(kw.get("f_nodal")), ptr(kw.get("g_nodal")),
+            float(kw.get("f_const", 0.0)), float(kw.get("g_const", 0.0)), ptr(kw.get("pbc_out")), ptr(kw.get("pbc_node")),
+            float(w1), float(w0), ptr(self.rowptr) if cn else None, ptr(self.colidx) if cn else None,
+            ptr(a_n.vals) if cn else None, ptr(x0) if cn else None, ptr(Ln) if cn else None, float(mass_coeff), ptr(DDn),
+            ptr(Ln1), ptr(b), ptr(ax) if cn else None, ptr(x1), ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]),
+            ptr(d["P"]) if dn.B > 0 else None, ptr(work), float(rtol), int(max_iter), 1 if warm_start else 0,
+            C.byref(resid) if resid is not None else None, inf, current_stream()))
+        if resid is not None:
+            info.cg_iterations += int(inf[0])
+            info.cg_converged = bool(inf[1])
+            info.cg_batches += int(inf[2])
+            info.cg_rel_resid = float(resid.value)
+        return info
+
     def solve_bc(self, co, b, x, bcs=None, **kw):
         """solve with the model's Dirichlet data applied (the mixed model has none, flow_models.py:334)"""
         return self.solve(co, b, x=x, **kw)

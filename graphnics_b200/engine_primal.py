@@ -280,6 +280,49 @@ class PrimalSystem:
                                                ptr(d["P"]) if dn.B > 0 else None, ptr(x), st))
         return x, info
 
+    def timestep(self, model, L, co, w1, w0, a_n, x0, Ln, mass_coeff, DDn, Ln1, b, ax, x1, bcs=None, warm_start=False,
+                 sync=False, info=None, rtol=1e-13, max_iter=100000):
+        """one theta-scheme step behind ONE library call (gnx_timestep_primal); f, g and the Dirichlet data are
+        evaluated (device kernels) here, at assembly time, like PrimalLForm.assemble / solve_bc do"""
+        dn = self.dn
+        d = self._bufs()
+        info = info if info is not None else SolveInfo()
+        f, g = as_coefficient(model.f), as_coefficient(model.g)
+
+        def prep(c, slot):
+            if c.is_constant:
+                return None, 0, c.const_value()
+            return self.eval_cellwise(c, slot), int(c.degree <= 1), 0.0
+        fc, fl, f0 = prep(f, "f")
+        gc, gl, g0 = prep(g, "g")
+        flat = [bc for row in (bcs or []) for bc in (row if isinstance(row, (list, tuple)) else [row])]
+        g_node = self.bc_node_values(flat[0].value) if flat else None
+        co_mass = mass_coeff if isinstance(mass_coeff, _PCoeffs) else self.coeffs(mass_coeff, 1.0)
+        plan = work = None
+        if dn.B > 0:
+            plan, _, work, _ = self.schur_plan()
+        resid = inf = None
+        if sync and dn.B > 0:
+            resid = C.c_double(0.0)
+            inf = (C.c_int32 * 3)()
+        cn = w0 != 0.0
+        if cn:
+            self.build_pattern()
+        check(self.lib.gnx_timestep_primal(
+            dn.net_ref(), co.ref(), C.byref(plan) if plan is not None else None, ptr(dn.cells), ptr(fc), fl, float(f0),
+            ptr(gc), gl, float(g0), ptr(g_node), float(w1), float(w0), ptr(self.rowptr) if cn else None,
+            ptr(self.colidx) if cn else None, ptr(a_n.vals) if cn else None, ptr(x0) if cn else None,
+            ptr(Ln) if cn else None, co_mass.ref(), ptr(DDn), ptr(Ln1), ptr(b), ptr(ax) if cn else None, ptr(x1),
+            ptr(d["cond"]), ptr(d["rsrc"]), ptr(d["ftot"]), ptr(d["P"]) if dn.B > 0 else None, ptr(work), float(rtol),
+            int(max_iter), 1 if warm_start else 0, C.byref(resid) if resid is not None else None, inf, current_stream()))
+        self._keep = (fc, gc, co_mass)
+        if resid is not None:
+            info.cg_iterations += int(inf[0])
+            info.cg_converged = bool(inf[1])
+            info.cg_batches += int(inf[2])
+            info.cg_rel_resid = float(resid.value)
+        return info
+
     def solve_bc(self, co, b, x, bcs=None, **kw):
         """apply the model's Dirichlet data to b (in place), then solve (time_stepping.py:188-192)"""
         flat = [bc for row in (bcs or []) for bc in (row if isinstance(row, (list, tuple)) else [row])]

@@ -15,6 +15,8 @@ t_steps states; the loop variable is np.linspace(dt, T, t_steps-1) while the sch
 for the mixed model, the L2 projections inside L_form) are rebuilt at the END of each iteration,
 so projected data lag the inlet term by one step.
 """
+import os
+
 import numpy as np
 
 from ..coefficients import Constant
@@ -171,19 +173,28 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
     if progress:
         from tqdm import tqdm
         steps = tqdm(steps)
+    one_call = sys_.dn.part is None and os.environ.get("GNX_TIMESTEP_ONE_CALL", "1") != "0"
+    Ln_bufs = [x0.new_empty(N), x0.new_empty(N)] if one_call else None
     for k, t_val in enumerate(steps):
-        Ln1 = L.assemble().tensor                                     # :179
         if reassemble_lhs:                                            # :180-181
             co_eff = model._coeffs(sigma=cn1 * dt, mass=ainv)
             if cn != 0:
                 a_n1 = model.a_form().assemble()
-        if cn != 0:                                                   # :185
-            sys_.spmv(a_n.vals, x0, ax0)
-        sys_.lincomb([1.0, cn1 * dt, -dt * cn, dt * cn], [DDn, Ln1, ax0, Ln if cn != 0 else None], out=b)
         sol = ii_Function(model.W, data=hist[k + 1])                  # :194-198
         last = k == len(steps) - 1
         check = last or (check_every > 0 and (k + 1) % check_every == 0)
-        _, info = sys_.solve_bc(co_eff, b, sol.tensor(), bcs, warm_start=warm_start and k > 0, sync=check)   # :187-192
+        if one_call:
+            # :179-192 and :216 behind ONE library call (gnx_timestep_*): L^{n+1}, the scheme's right-hand side, the
+            # solve and the mass term of the next step
+            Ln1 = Ln_bufs[k & 1]
+            info = sys_.timestep(model, L, co_eff, cn1 * dt, cn * dt, a_n, x0, Ln, model._mass_coeff(ainv), DDn, Ln1, b, ax0,
+                                 sol.tensor(), bcs, warm_start=warm_start and k > 0, sync=check)
+        else:
+            Ln1 = L.assemble().tensor                                 # :179
+            if cn != 0:                                               # :185
+                sys_.spmv(a_n.vals, x0, ax0)
+            sys_.lincomb([1.0, cn1 * dt, -dt * cn, dt * cn], [DDn, Ln1, ax0, Ln if cn != 0 else None], out=b)
+            _, info = sys_.solve_bc(co_eff, b, sol.tensor(), bcs, warm_start=warm_start and k > 0, sync=check)   # :187-192
         model.solve_info = info
         qps.append(sol)
         x0 = sol.tensor()                                             # :201
@@ -194,7 +205,8 @@ def time_stepping_stokes(model, t=Constant(0), t_steps=10, T=1, qp0=None, t_step
             except AttributeError:
                 pass
         a_n, Ln = a_n1, Ln1                                           # :214-215
-        sys_.mass_apply(model._mass_coeff(ainv), x0, out=DDn)         # :216
+        if not one_call:
+            sys_.mass_apply(model._mass_coeff(ainv), x0, out=DDn)     # :216
         L = model.L_form()                                            # :218-219
     # steps are enqueued without waiting for the solver's status; a step of a cyclic network whose Krylov part did not
     # converge leaves its mark on the device and is reported here, once, instead of passing silently

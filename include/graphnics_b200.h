@@ -460,6 +460,30 @@ int gnx_axpby_dot(int64_t n, double alpha, const double* x, double beta, double*
 int gnx_lincomb(int64_t n, int32_t nterms, const double* coefs_host, const double* const* vecs_host,
                 double* out, void* stream);
 
+/* One theta-scheme time step of time_stepping_stokes (graphnics/flowmodels/time_stepping.py:179-216) behind ONE call:
+ *   Ln1 = L^{n+1};  b = DDn + w1 Ln1 - w0 A x0 + w0 Ln  (w1 = theta dt, w0 = (1-theta) dt; w0 = 0: implicit Euler -- vals_n,
+ *   x0, Ln, ax, rowptr, colidx may then be NULL);  x1 = (D + w1 A)^-1 b  (co: a = Ainv + w1 Res, sigma = w1);  DDn = D x1.
+ * Same kernels and results as gnx_assemble_rhs_* + gnx_spmv_csr_f64 + gnx_lincomb + the solve + gnx_mass_apply_q_*; it
+ * exists because seven host round trips per step cost more than the GPU needs on a tree.  Single GPU.
+ *   mixed: f_nodal / g_nodal / f_const / g_const / pbc_out / pbc_node as in gnx_assemble_rhs_mixed; DDn [N] in/out;
+ *   Ln1, b, ax, x1 [N] out / scratch; cond, rsrc, ftot, P, work as in the separate solve calls.
+ *   primal: f_cell / g_cell as in gnx_assemble_rhs_primal, bc_node [V] Dirichlet data (NULL: none), co_mass the
+ *   coefficient of the q mass term. */
+int gnx_timestep_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, const gnx_schur_plan_t* plan,
+                       const double* f_nodal, const double* g_nodal, double f_const, double g_const,
+                       const double* pbc_out, const double* pbc_node, double w1, double w0, const int32_t* rowptr,
+                       const int32_t* colidx, const double* vals_n, const double* x0, const double* Ln, double mass_coeff,
+                       double* DDn, double* Ln1, double* b, double* ax, double* x1, double* cond, double* rsrc,
+                       double* ftot, double* P, double* work, double rtol, int32_t max_iter, int32_t warm,
+                       double* resid_host, int32_t* info_host, void* stream);
+int gnx_timestep_primal(const gnx_network_t* net, const gnx_primal_coeffs_t* co, const gnx_schur_plan_t* plan,
+                        const int32_t* cells, const double* f_cell, int32_t f_lin, double f_const, const double* g_cell,
+                        int32_t g_lin, double g_const, const double* bc_node, double w1, double w0, const int32_t* rowptr,
+                        const int32_t* colidx, const double* vals_n, const double* x0, const double* Ln,
+                        const gnx_primal_coeffs_t* co_mass, double* DDn, double* Ln1, double* b, double* ax, double* x1,
+                        double* cond, double* rsrc, double* ftot, double* P, double* work, double rtol, int32_t max_iter,
+                        int32_t warm, double* resid_host, int32_t* info_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

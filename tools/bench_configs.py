@@ -124,6 +124,33 @@ def c4(steps=1000):
                       "MDOF_per_s": N * (steps - 1) / dt / 1e6, "final_norm": qn}), flush=True)
 
 
+def ts_tree(steps=200):
+    """pulsatile loop on the C2 tree (no Krylov part: a step is ~70 us of kernels, so the HOST decides): wall time per
+    step with the one-call step (gnx_timestep_mixed) and with the separate calls (GNX_TIMESTEP_ONE_CALL=0)"""
+    import graphnics_b200 as gn
+    from graphnics_b200.synthetic import murray_tree
+    pos, edges, _, _ = murray_tree(11, radius0=0.1, gam=0.9, L0=10.0, gdim=2)
+    G = gn.FenicsGraph()
+    G.add_nodes_from((i, {"pos": p}) for i, p in enumerate(pos.tolist()))
+    G.add_edges_from(map(tuple, edges.tolist()))
+    G.make_mesh(9)
+    for mode in ("1", "0"):
+        os.environ["GNX_TIMESTEP_ONE_CALL"] = mode
+        t = gn.Constant(0)
+        p_bc = gn.Expression("x[1]*(1 + 0.1*sin(6.28*t))", degree=2, t=0.0)
+        model = gn.TimeDepMixedHydraulicNetwork(G, p_bc=p_bc, Ainv=gn.Constant(1.0))
+        gn.time_stepping_stokes(model, t=t, t_steps=10, T=0.01, reassemble_lhs=False)          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sols = gn.time_stepping_stokes(model, t=t, t_steps=steps, T=0.2, reassemble_lhs=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        N = sols[-1].vector().size()
+        print(json.dumps({"case": "pulsatile loop on the C2 tree (TimeDepMixedHydraulicNetwork, IE, operator reused)",
+                          "one_call_step": mode == "1", "N": N, "steps": steps, "ms_per_step": dt / (steps - 1) * 1e3,
+                          "MDOF_per_s": N * (steps - 1) / dt / 1e6}), flush=True)
+
+
 def c5():
     from graphnics_b200.synthetic import murray_tree
     pos, edges, _, _ = murray_tree(19, gdim=2)
@@ -180,5 +207,5 @@ def c3mg(n=5):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4", "c5"]
     for w in which:
-        {"c3": c3, "c4": c4, "c5": c5, "c3mg": c3mg}[w]()
+        {"c3": c3, "c4": c4, "c5": c5, "c3mg": c3mg, "ts_tree": ts_tree}[w]()
         torch.cuda.empty_cache()
