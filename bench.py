@@ -625,15 +625,18 @@ def partitioned_case(torch, dist, dev, levels, n, args, flush, reps, warm):
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    ts, host_us = [], []
+    # All K steps (and the L2 flushes between them) are enqueued without a host wait in between: the ranks meet inside
+    # every step (the exchange), so their queues stay aligned on the device.  A host wait per step (r1/r2k) let the
+    # ranks' wake-up jitter -- tens of microseconds, more than the exchange itself -- skew the next step's start.
+    host_us, evs = [], []
     for _ in range(reps):
         if flush is not None:
             flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); t0 = time.perf_counter(); step(); host_us.append((time.perf_counter() - t0) * 1e6); e1.record()
-        e1.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        evs.append((e0, e1))
     torch.cuda.synchronize()
+    ts = [e0.elapsed_time(e1) for e0, e1 in evs]
     dist.barrier()
     t = torch.tensor(ts, dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # per step: the slowest rank
@@ -745,7 +748,9 @@ def run_partitioned(args, dev):
                    "exchange": "peer stores over NVLink + flag words inside the kernel" if sms.exchange_mode == "p2p"
                                else f"NCCL all-gather between two launches ({getattr(sms, '_p2p_error', '')})",
                    "edges_per_rank": rec["edges_per_rank"], "ndofs_per_rank": rec["ndofs_per_rank"],
-                   "bifurcations": rec["bifurcations"]}),
+                   "bifurcations": rec["bifurcations"],
+                   "timing": "CUDA events around every step on every rank, per step the max over ranks; the K steps and the "
+                             "L2 flushes between them are enqueued back to back (no host wait between steps)"}),
                "ms_per_step_stats": rec["ms_per_step_stats"], "built_once_ms": {"total_ms": rec["built_once_ms"]},
                "rel_residual": rec["rel_residual"], "gpu_launches": launches, "gpu_launches_per_step": launch_names,
                "gpu_launches_how": "CUPTI (torch.profiler) kernel records of a replay of the same K steps on rank 0",

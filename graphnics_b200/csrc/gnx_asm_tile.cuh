@@ -20,13 +20,14 @@ struct AsmEdge {
   int32_t ebase, blo1, bhi1; // staged offset of the edge's range, 1 if the lo / hi end carries a multiplier
   bool flip;                 // u > v: the lo frame runs against the edge
 };
-template <bool STIFF>
+// TAB_GLOBAL = false: `tab` (and usually E.he) point into shared memory (persistent step kernel).
+template <bool STIFF, bool TAB_GLOBAL = true>
 __device__ __forceinline__ int32_t asm_qrow(double* stage, const int2* __restrict__ tab, const AsmEdge& E, int32_t t,
                                             int32_t m, double sg) {
   const bool hasl = t > 0, hasr = t < m;
   const double hl = hasl ? E.he[E.flip ? m - t : t - 1] : 0.0;       // lo-frame cell t-1
   const double hr = hasr ? E.he[E.flip ? m - 1 - t : t] : 0.0;       // lo-frame cell t
-  const int2 tb = __ldg(tab + t);                                    // row offset + packed slot order (device.row_table)
+  const int2 tb = TAB_GLOBAL ? __ldg(tab + t) : tab[t];              // row offset + packed slot order (device.row_table)
   const int32_t f = tb.y;
   const int32_t off = E.ebase + tb.x + ((f & 1) ? E.blo1 : 0) + ((f & 2) ? E.bhi1 : 0);
   double kl = 0.0, kr = 0.0;

@@ -753,6 +753,9 @@ __device__ __forceinline__ void sch_export_roots(const SchurArgs& a, bool do_sen
   const gnx_schur_plan_t& pl = a.plan;
   const int q = threadIdx.x;
   if (q >= a.wait_world) return;
+  // diagnostic stamps of the thread that talks to the first OTHER rank: scal[18] roots sent | [19] flag released | [20] flag seen
+  const bool dbg = a.xbuf[q] && (q == 0 || (q == 1 && !a.xbuf[0]));
+  auto stamp = [&](int k) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[k] = (double)(t & 0xffffffffffull); } };
   if (do_send && a.xbuf[q]) {
     for (int32_t k = 0; k < pl.nxl; ++k) {
       const int32_t node = pl.xlist[k];
@@ -761,8 +764,10 @@ __device__ __forceinline__ void sch_export_roots(const SchurArgs& a, bool do_sen
     }
     if (!do_flags) __threadfence_system();
   }
+  stamp(18);
   if (do_flags) {
     asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[q]), "l"(a.wait_epoch) : "memory");
+    stamp(19);
     const long long* f = a.wait_flags + q;
     long long v;
     unsigned spins = 0;
@@ -772,6 +777,7 @@ __device__ __forceinline__ void sch_export_roots(const SchurArgs& a, bool do_sen
       __nanosleep(spins < 4096 ? 32 : 2000);
       if (++spins > (1u << 25)) __trap();
     }
+    stamp(20);
   }
 }
 
@@ -796,8 +802,13 @@ constexpr size_t SCH_SMEM = 3 * GNX_TOP_MAX * sizeof(double);
 // node folds its local children -- mine or another rank's, all the same -- from global memory and keeps only
 // replicated children in registers, so every rank performs the same operations on the same bits.
 // Returns true when the solve stops at the exchange (a.phase == 1).
-template <bool CLUSTER, int ROWS>
-__device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double* sr, double* sw, long long* tick = nullptr) {
+// wait_fn(): called once, after the rows' STATIC plan data are in registers and before anything the step produces
+// is read -- the persistent step kernel's solver CTA waits for the workers' edge scalars there (its plan loads then
+// overlap the elimination phase instead of following it); a no-op everywhere else.
+struct SchNoWait { __device__ __forceinline__ void operator()() const {} };
+template <bool CLUSTER, int ROWS, class WaitFn = SchNoWait>
+__device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double* sr, double* sw, long long* tick = nullptr,
+                                          WaitFn wait_fn = WaitFn()) {
   const gnx_schur_plan_t& pl = a.plan;
   const int tid = threadIdx.x, T = blockDim.x;
   cg::cluster_group cluster = cg::this_cluster();
@@ -830,10 +841,15 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   const int4* const trec = CLUSTER ? nullptr : reinterpret_cast<const int4*>(pl.top_rec);
   if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[16] = (double)(t & 0xffffffffffull); }
   // the same from the row's packed record (plan.top_rec): one 64-byte load, then every scalar it names at once
+  int4 keep[ROWS == 1 ? 4 : 1];                                // one row per thread: its record stays in registers
   auto numeric_rec = [&](int q) {
     const int32_t li = tid + q * T;
-    const int4 r0 = __ldg(trec + 4 * (base + li)), r1 = __ldg(trec + 4 * (base + li) + 1);
-    const int4 r2 = __ldg(trec + 4 * (base + li) + 2), r3 = __ldg(trec + 4 * (base + li) + 3);
+    int4 r0, r1, r2, r3;
+    if (ROWS == 1) { r0 = keep[0]; r1 = keep[1 % (ROWS == 1 ? 4 : 1)]; r2 = keep[2 % (ROWS == 1 ? 4 : 1)]; r3 = keep[3 % (ROWS == 1 ? 4 : 1)]; }
+    else {
+      r0 = __ldg(trec + 4 * (base + li)); r1 = __ldg(trec + 4 * (base + li) + 1);
+      r2 = __ldg(trec + 4 * (base + li) + 2); r3 = __ldg(trec + 4 * (base + li) + 3);
+    }
     const int32_t i = r0.x;
     w[q] = r0.w >= 0 ? -a.cond[a.eidx(r0.w)] : 0.0;
     double di = 0.0;
@@ -899,11 +915,14 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     if (li < S && ti < pl.nt) {
       if (trec) {
         const int4 r0 = __ldg(trec + 4 * ti), r1 = __ldg(trec + 4 * ti + 1);
+        if (ROWS == 1) {
+          keep[0] = r0; keep[1 % (ROWS == 1 ? 4 : 1)] = r1;
+          keep[2 % (ROWS == 1 ? 4 : 1)] = __ldg(trec + 4 * ti + 2); keep[3 % (ROWS == 1 ? 4 : 1)] = __ldg(trec + 4 * ti + 3);
+        }
         node[q] = r0.x; lev[q] = r0.y; ptop[q] = r0.z;
         nct[q] = r1.z;                                       // (bit 30: numeric() takes the generic path for this row)
         repl[q] = ncls && (ncls[r0.x] & 1);
         if (r1.z & (1 << 30)) { k0[q] = pl.ch_ptr[r0.x]; k1[q] = pl.ch_ptr[r0.x + 1]; }
-        if (!repl[q]) numeric(q);
       } else {
         const int32_t i = pl.top_nodes[ti];
         node[q] = i;
@@ -912,8 +931,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
         const int32_t par = pl.parent[i];
         if (par >= 0) ptop[q] = pl.top_of[par];
         k0[q] = pl.ch_ptr[i]; k1[q] = pl.ch_ptr[i + 1];
-        if (!repl[q]) numeric(q);
-        else {                                             // warm the index data of the row built after the exchange
+        if (repl[q]) {                                     // warm the index data of the row built after the exchange
           int32_t acc = schur_row_warm(a, i) ^ (par >= 0 ? pl.pedge[i] : 0);
           for (int32_t k = k0[q]; k < k1[q]; ++k) { const int32_t c = pl.ch_idx[k]; acc ^= pl.top_of[c] ^ ncls[c] ^ pl.pedge[c]; }
           if (acc == 0x7fffffff) sw[li] = 0.0;             // (never true in practice: keeps the loads alive)
@@ -921,6 +939,11 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
       }
     }
   }
+  wait_fn();                                               // ---- from here on: data of this step
+  if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[25] = (double)(t & 0xffffffffffull); }
+#pragma unroll
+  for (int q = 0; q < ROWS; ++q)
+    if (lev[q] >= 0 && !repl[q]) numeric(q);
   if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[17] = (double)(t & 0xffffffffffull); }
   lsync();
   if (tick) tick[0] = clock64();
@@ -929,18 +952,35 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   // the exchange, between the last local and the first replicated level
   auto exchange = [&]() -> bool {
     stamp(2);
+    // my exported roots' final (d, r): into my own arrays and -- in-kernel exchange -- straight into every other
+    // rank's, by the thread that holds them (the flag threads' release below is cumulative over the barrier)
+    const bool direct = a.phase == 0;
 #pragma unroll
     for (int q = 0; q < ROWS; ++q)
-      if (lev[q] >= 0 && !repl[q] && (ncls[node[q]] & 4)) { a.d[node[q]] = d[q]; a.r[node[q]] = r[q]; }
+      if (lev[q] >= 0 && !repl[q] && (ncls[node[q]] & 4)) {
+        a.d[node[q]] = d[q]; a.r[node[q]] = r[q];
+        if (direct) {
+#pragma unroll
+          for (int k = 0; k < GNX_MAX_PEERS; ++k)
+            if (k < a.wait_world && a.xbuf[k]) { a.xbuf[k][a.xd_off + node[q]] = d[q]; a.xbuf[k][a.xr_off + node[q]] = r[q]; }
+        }
+      }
     lsync();
     stamp(3);
-    sch_export_roots(a, a.phase != 2, a.phase == 0);
+    sch_export_roots(a, a.phase == 1, a.phase == 0);
     lsync();
     if (a.phase == 1) return true;
     stamp(4);
 #pragma unroll
     for (int q = 0; q < ROWS; ++q)
-      if (lev[q] >= 0 && repl[q]) numeric(q);
+      if (lev[q] >= 0 && repl[q]) {
+        // (diagnostic: scal[22] / [23] around the first replicated row's set-up, read after the loads it depends on)
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0) : "r"(lev[q]));
+        numeric(q);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1) : "d"(d[q]), "d"(r[q]));
+        if (!CLUSTER && lev[q] == l_sync) { a.scal[22] = (double)(t0 & 0xffffffffffull); a.scal[23] = (double)(t1 & 0xffffffffffull); }
+      }
     lsync();
     stamp(5);
     return false;
@@ -971,6 +1011,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
         sd[li] = gnx_rcp(d[q]); sr[li] = r[q];
       }
     }
+    if (ncls && l == l_sync) stamp(13);                     // (diagnostic: scal[21], first replicated level folded)
     lsync();
   }
   if (ncls && l_sync >= pl.nl) { if (exchange()) return true; }     // (no replicated raked node)
@@ -1450,9 +1491,14 @@ template <> struct SchThreads<SCH_CLUSTER> { static constexpr int value = CL_T; 
 // The whole Schur solve as a device function: the body of schur_solve_kernel<MODE>, and -- MODE == SCH_SINGLE,
 // executed by CTA 0 -- the middle phase of the persistent step kernel (step_resident_kernel below).
 // top_sh: 3 * GNX_TOP_MAX doubles of shared memory, red: 2 x 96 doubles.
-template <int MODE>
-__device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, double (*red)[3 * 32]) {
+template <int MODE, class WaitFn = SchNoWait>
+__device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, double (*red)[3 * 32], WaitFn wait_fn = WaitFn()) {
   const gnx_schur_plan_t& pl = a.plan;
+  // wait_fn (see top_solve): deferred into the top sweep when nothing before it reads data of this step -- a tree
+  // that fits the one-CTA sweep whole -- and called right here otherwise
+  const bool defer_wait = MODE == SCH_SINGLE && pl.top_rec != nullptr && pl.nc == 0 && pl.nb == 0 && pl.l_split == 0 &&
+                          pl.nt > 0 && a.phase != 2 && !(a.wait_flags && !pl.ncls);
+  if (!defer_wait) wait_fn();
   const int nblk = MODE == SCH_SINGLE ? 1 : gridDim.x;       // (one CTA of a larger grid in the persistent step kernel)
   const int32_t stride = nblk * blockDim.x;
   const int32_t t0 = (MODE == SCH_SINGLE ? 0 : blockIdx.x * blockDim.x) + threadIdx.x;
@@ -1564,8 +1610,13 @@ __device__ __forceinline__ void schur_body(const SchurArgs& a, double* top_sh, d
       // (one row per thread when the top part fits: half the per-thread state of the general two-row sweep --
       //  at 64 registers per thread that is the difference between spilling and not)
       if (blockIdx.x == 0 && pl.nt > 0) {
-        if (pl.nt <= SCH_T) top_solve<false, 1>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
-        else top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+        if (defer_wait) {
+          if (pl.nt <= SCH_T) top_solve<false, 1>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1, wait_fn);
+          else top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1, wait_fn);
+        } else {
+          if (pl.nt <= SCH_T) top_solve<false, 1>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+          else top_solve<false, TOP_ROWS>(a, top_sh, top_sh + GNX_TOP_MAX, top_sh + 2 * GNX_TOP_MAX, tick + 1);
+        }
       }
       tick[3] = clock64();
       if (a.phase == 1) return;                  // (partitioned, emulated ranks / NCCL: stop at the exchange)
@@ -2083,29 +2134,34 @@ extern "C" int gnx_edge_backsub_mixed(const gnx_network_t* net, const gnx_mixed_
 }
 
 // ------------------------------------------------------------------------------------
-// Persistent step kernel: right-hand side + elimination -> Schur solve -> back-substitution in ONE
-// cooperative launch, one CTA per SM, for networks whose cell lengths fit the GPU's shared memory
-// (<= RS_MAX_TILES tiles of 1024 cells per SM: 1.2 M cells on 148 SMs -- the C2 benchmark size).
+// Persistent step kernel: right-hand side + elimination -> Schur solve -> back-substitution (and the CSR assembly)
+// in ONE cooperative launch, one CTA per SM, for networks whose cell lengths fit the GPU's shared memory
+// (<= RS_MAX_TILES tiles of 1024 cells per worker SM: 1.2 M cells on 148 SMs -- the C2 benchmark size).
 //
 // The three-kernel chain above is latency-bound at that size: every kernel boundary costs a launch and a
 // fresh round of global loads, and the back-substitution re-reads what the elimination just had in shared
-// memory.  Here a CTA (4 sub-blocks of 256 threads, each working on one tile at a time with its own
-// named barrier) keeps the cell lengths of ITS tiles resident in shared memory for the whole solve:
-//   phase 1  all tiles' lengths requested from the copy engine at once (one mbarrier per tile); per tile the
-//            right-hand side is produced in shared memory, leaves as b (two bulk stores) and is eliminated
-//            -> three scalars per edge;  the CTA then arrives on a global counter (release);
-//   phase 2  CTA 0 waits for the counter (acquire) and runs the Schur solve (schur_body<SCH_SINGLE>: the
-//            flag exchange with the other ranks of a partitioned network, rake / core PCG, multipliers);
-//            every other CTA meanwhile ASSEMBLES the CSR values (the solver never reads them: a_form /
-//            ii_assemble of the step, flow_models.py:343) -- the row code of mixed_values_tile_kernel, 512-cell
-//            tiles dealt round-robin to the sub-blocks, each range leaving as one bulk store -- and then parks
-//            on a flag word: the latency-bound graph-level solve hides under the step's largest stream of bytes;
-//   phase 3  back-substitution out of the resident lengths (Constant data: the right-hand side entries are
+// memory.  Here CTA 0 is the SOLVER and does nothing but the graph-level solve; CTAs 1.. are WORKERS (4 sub-blocks
+// of 256 threads, each working on one tile at a time with its own named barrier) that keep the cell lengths of
+// THEIR tiles resident in shared memory for the whole step:
+//   phase 1  worker: all tiles' lengths requested from the copy engine at once (one mbarrier per tile), what the
+//            tiles need to know about their edges gathered into shared-memory records; per tile ONLY the reductions
+//            that give the three scalars per edge (nothing is staged or stored: the graph-level solve waits for
+//            nothing else), then the CTA arrives on a global counter (release);
+//            solver: meanwhile loads the STATIC part of its rows (plan records -> registers; prefetches, argument
+//            lines) and only then waits for the counter (acquire) -- schur_body's wait_fn;
+//   phase 2  solver: the Schur solve (schur_body<SCH_SINGLE>: rake sweeps out of shared memory, the exchange with the
+//            other ranks of a partitioned network, multipliers), then releases an epoch flag;
+//            worker: ASSEMBLES the CSR values of its own tiles' edges (the solver never reads them: a_form /
+//            ii_assemble of the step, flow_models.py:343) out of the resident lengths and records -- no global load
+//            at all; two groups of 512 threads, each double-buffering its bulk stores (rs_assemble) -- then produces
+//            and stores its tiles of b, then parks on the epoch flag: the latency-bound graph-level solve hides under
+//            the step's largest stream of bytes;
+//   phase 3  worker: back-substitution out of the resident lengths (Constant data: the right-hand side entries are
 //            recomputed, not re-read), the solution tile leaves as two bulk stores.
 // Per-thread arithmetic is that of edge_eliminate_tile_kernel<4,true,true>, edge_backsub_tile_kernel<4,true>
 // and mixed_values_tile_kernel<2,true,STIFF>, operation for operation: b, x and the CSR values are
-// bit-identical to the chain's.  HBM traffic of the step: h once (8 B/cell; the assembly's second look at it
-// is an L2 hit) + b, x (16 B/dof) and the values (64 B/cell) written, nothing re-read.
+// bit-identical to the chain's.  HBM traffic of the step: h once (8 B/cell) + b, x (16 B/dof) and the values
+// (64 B/cell) written, nothing re-read.
 // ------------------------------------------------------------------------------------
 constexpr int RS_T = 1024;                       // threads per CTA
 constexpr int RS_SUB = RS_T / ET_T;              // sub-blocks per CTA
@@ -2132,7 +2188,8 @@ static_assert((RS_HSLOT % 2) == 0 && (RS_FSLOT % 2) == 0 && (RS_STAGE % 2) == 0 
 struct __align__(16) RsEdge {
   double a, pin, pout;                           // mass coefficient; boundary data at the u / v end (flags say whether they apply)
   double q0, Pu;                                 // phase 3: flux at node 0, pressure at node u
-  int32_t bu, bv, flags, pad;                    // bifurcation index of the ends (-1: boundary); bit 0 flip, 1 pin, 2 pout
+  int32_t bu, bv, flags, ebp;                    // bifurcation index of the ends (-1: boundary); bit 0 flip, 1 pin, 2 pout;
+                                                 // ebp: bifurcation ends of the edges before this one (net.ebif_prefix)
 };
 
 struct StepArgs {
@@ -2159,6 +2216,12 @@ __device__ __forceinline__ unsigned long long rs_now() {
   return t;
 }
 __device__ __forceinline__ int32_t gnx_blocks_dev(int64_t n, int t) { return (int32_t)((n + t - 1) / t); }
+// [p, p + bytes) into L2, one request per 128-byte line, by the CTA's threads (p == NULL: nothing)
+__device__ __forceinline__ void rs_prefetch_l2(const void* p, int64_t bytes, int tid) {
+  if (!p) return;
+  const char* c = static_cast<const char*>(p);
+  for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)RS_T * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(c + o));
+}
 __device__ __forceinline__ void rs_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(ET_T) : "memory"); }
 
 // gnx_seg_incl_scan / gnx_seg_sum for a 256-thread sub-block (same combination order, named barrier)
@@ -2278,10 +2341,14 @@ __device__ __forceinline__ double rs_rhs_node(const StepArgs& s, const RsEdge& r
 // ZFG: f = g = 0 (boundary data only, the common steady case): every F is +0, every q-row entry of b is +0 except
 // at boundary ends; the general code then adds and multiplies zeros -- the fast path skips exactly those
 // operations (x + 0 = x, x * 0 = +0 for the positive lengths and finite data involved), so it yields the same bits.
-template <bool ZFG>
+// PART: bit 0 the edge scalars (reductions over the tile -> EdgeOut), bit 1 the tile of b (staged, bulk-stored).  The
+// streaming kernel does both at once; the persistent kernel computes the scalars in phase 1 -- the graph-level solve
+// waits for nothing else -- and writes b in phase 2, out of the same resident lengths (same operations, same bits).
+template <bool ZFG, int PART = 3>
 __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t tile, int ltid, int bid, const double* sH,
                                                   double* sF, double* sG, double* sh, const RsEdge* rec, const int32_t* sloc) {
   constexpr int CPT = RS_CPT;
+  constexpr bool RHS = (PART & 2) != 0, SCAL = (PART & 1) != 0;
   const TileCtx c = rs_tile_ctx(s.net, s.d, tile, ltid, rec);
   const RsEdge& r = rec[c.le];
   const int32_t m = c.m;
@@ -2289,17 +2356,27 @@ __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t til
   double F[CPT], H[CPT];
   double sumF = 0.0, sumG = 0.0, sumH = 0.0;
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) { H[i] = sH[cbH + c.kk0 + i]; F[i] = 0.0; }
+  for (int i = 0; i < CPT; ++i) { H[i] = (SCAL || !ZFG) ? sH[cbH + c.kk0 + i] : 0.0; F[i] = 0.0; }
   if (ZFG) {
     // b tile: zeros, then the boundary ends
+    if (RHS) {
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) sF[RS_FSLOT - 1 - (ltid + i * ET_T)] = 0.0;     // (covers [2, RS_FSLOT); slots 0, 1 below)
+      for (int i = 0; i < CPT; ++i) sF[RS_FSLOT - 1 - (ltid + i * ET_T)] = 0.0;     // (covers [2, RS_FSLOT); slots 0, 1 below)
 #pragma unroll
-    for (int i = 0; i < CPT + 1; ++i) sG[ltid + i * ET_T] = 0.0;
-    if (ltid < 2) { sF[ltid] = 0.0; sG[RS_GSLOT - 1 - ltid] = 0.0; }
-    rs_bar(bid);
-    if (c.active && c.kk0 == 0 && (r.flags & 2)) { const double v0 = __dadd_rn(0.0, r.pin); sG[qb + sloc[c.flip ? m : 0]] = v0; sumG += v0; }
-    if (c.active && c.kk0 + CPT == m && (r.flags & 4)) { const double vm = __dsub_rn(0.0, r.pout); sG[qb + sloc[c.flip ? 0 : m]] = vm; sumG += vm; }
+      for (int i = 0; i < CPT + 1; ++i) sG[ltid + i * ET_T] = 0.0;
+      if (ltid < 2) { sF[ltid] = 0.0; sG[RS_GSLOT - 1 - ltid] = 0.0; }
+      rs_bar(bid);
+    }
+    if (c.active && c.kk0 == 0 && (r.flags & 2)) {
+      const double v0 = __dadd_rn(0.0, r.pin);
+      if (RHS) sG[qb + sloc[c.flip ? m : 0]] = v0;
+      sumG += v0;
+    }
+    if (c.active && c.kk0 + CPT == m && (r.flags & 4)) {
+      const double vm = __dsub_rn(0.0, r.pout);
+      if (RHS) sG[qb + sloc[c.flip ? 0 : m]] = vm;
+      sumG += vm;
+    }
   } else if (c.active) {
     double hl = c.kk0 > 0 ? sH[cbH + c.kk0 - 1] : 0.0;
 #pragma unroll
@@ -2307,9 +2384,9 @@ __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t til
       const int32_t j = c.kk0 + i;
       const double hr = H[i];
       const double val = rs_rhs_node(s, r, j, hl, hr);
-      sG[qb + sloc[c.flip ? m - j : j]] = val;
+      if (RHS) sG[qb + sloc[c.flip ? m - j : j]] = val;
       const double fv = __dmul_rn(s.rhs.fc, hr);
-      sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = fv;
+      if (RHS) sF[cbF + gnx_gray(c.flip ? m - 1 - j : j)] = fv;
       F[i] = __dmul_rn(fv, s.inv_sigma);
       sumG += val;
       hl = hr;
@@ -2317,13 +2394,14 @@ __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t til
     if (c.kk0 + CPT == m) {
       double val = __dmul_rn(__dmul_rn(s.rhs.gc, __dadd_rn(hl, 0.0)), 0.5);
       if (r.flags & 4) val = __dsub_rn(val, r.pout);
-      sG[qb + sloc[c.flip ? 0 : m]] = val;
+      if (RHS) sG[qb + sloc[c.flip ? 0 : m]] = val;
       sumG += val;
     }
   }
 #pragma unroll
   for (int i = 0; i < CPT; ++i) { sumF += F[i]; sumH += H[i]; }
-  rs_tile_store(c, sF, sG, s.rhs.b, ltid, bid);
+  if (RHS) rs_tile_store(c, sF, sG, s.rhs.b, ltid, bid);
+  if (!SCAL) return;
   const int segT = m / CPT;
   if (ZFG) {
     double acc[2] = {sumG, sumH};
@@ -2422,49 +2500,56 @@ __device__ __forceinline__ void rs_backsub_tile(const StepArgs& s, int32_t tile,
   rs_tile_store(c, sF, sG, s.x, ltid, bid);
 }
 
-// CSR values of assembly tile `atile` (RS_ATILE cells = whole edges): mixed_values_tile_kernel<2,true,STIFF> for a
-// 256-thread sub-block
+// CSR values of one half (hsel = 0 / 1: RS_ATILE cells = whole edges) of the CTA's resident solve tile `stile`:
+// the row code of mixed_values_tile_kernel for a group of RS_AT threads (one cell per thread), fed from shared memory
+// only -- the cell lengths are the resident ones (Hslot), what it needs to know about an edge sits in the tile's
+// records (orientation, multiplier ends, position of its rows in the CSR arrays), the row table is a shared-memory
+// copy (stab).  The stand-alone kernel starts every tile with three dependent trips to device memory (ebif_prefix ->
+// edges -> bix, then the lengths: 60 % of its stall samples, profiles/r2j); here a tile starts computing at once.
+// The caller owns the staging buffer's life cycle (rs_assemble): this function stages the two ranges and commits
+// their bulk stores as one group of the group's first thread.
+constexpr int RS_AT = 512;                       // threads of an assembling group (two per CTA)
+constexpr int RS_AGRP = RS_T / RS_AT;
+static_assert(RS_AT == RS_ATILE && RS_AGRP * 2 == RS_SUB, "one cell per thread; a group uses the staging areas of two sub-blocks");
+__device__ __forceinline__ void rs_abar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(RS_AT) : "memory"); }
+
 template <bool STIFF>
-__device__ __forceinline__ void rs_assemble_tile(const StepArgs& s, int32_t atile, int ltid, int bid, double* stage) {
-  constexpr int CPT = RS_ACPT;
-  constexpr int TILE = RS_ATILE;
+__device__ __forceinline__ void rs_assemble_tile(const StepArgs& s, int32_t stile, int32_t hsel, const double* Hslot,
+                                                 const RsEdge* rec, const int2* stab, int gtid, int bid, double* stage) {
   const gnx_network_t& net = s.net;
   double* const stage_p = stage + RS_AQ;
   const int32_t m = s.d.m, n = net.n;
-  const int32_t G = TILE >> n;
-  const int32_t e0 = atile * G;
-  const int32_t nE = min(G, net.E - e0);
-  const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + net.ebif_prefix[e0];
-  const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + net.ebif_prefix[e0 + nE];
+  const int32_t Ga = RS_ATILE >> n;
+  const int32_t e0s = stile * (RS_TILE >> n);
+  const int32_t le0 = hsel * Ga;
+  const int32_t e0 = e0s + le0;
+  if (e0 >= net.E) return;                          // (the network's last solve tile may be half empty)
+  const int32_t nE = min(Ga, net.E - e0);
+  const RsEdge& rl = rec[le0 + nE - 1];
+  const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + rec[le0].ebp;
+  const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + rl.ebp + (rl.bu >= 0 ? 1 : 0) + (rl.bv >= 0 ? 1 : 0);
   const int64_t pbase = s.d.p_nnz_off + 3 * (int64_t)e0 * m;
   const int32_t psh = (int32_t)(pbase & 1);
-  const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
-  const int32_t k0 = (ltid >> 5) * (32 * CPT) + (ltid & 31);
+  const int32_t shh = (int32_t)(((int64_t)e0s * m) & 1);             // parity shift of the resident tile (rs_tile_ctx)
   const double sg = s.sigma;
-  AsmEdge E;
-  int32_t cur = -1;
-#pragma unroll
-  for (int i = 0; i < CPT; ++i) {
-    const int32_t k = k0 + 32 * i;
-    const int32_t le = k >> n;
-    if (le >= nE) break;
+  const int32_t k = gtid;                            // cell of the tile
+  const int32_t le = k >> n;
+  if (le < nE) {
     const int32_t t = k & (m - 1);
-    if (le != cur) {
-      cur = le;
-      const int32_t e = e0 + le;
-      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-      E.flip = u > v;
-      E.blo1 = net.bix[E.flip ? v : u] >= 0;
-      E.bhi1 = net.bix[E.flip ? u : v] >= 0;
-      E.a = s.a_edge[e];
-      E.kk = (STIFF && s.k_edge) ? s.k_edge[e] : 0.0;
-      E.sgn = E.flip ? -sg : sg;
-      E.he = net.h + (int64_t)e * m;
-      E.ac = nullptr;
-      E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + net.ebif_prefix[e] - base) + (int32_t)(base & 1);
-    }
-    const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
-    if (t == m - 1) asm_qrow<STIFF>(stage, tab, E, m, m, sg);
+    const RsEdge& r = rec[le0 + le];
+    const int32_t e = e0 + le;
+    AsmEdge E;
+    E.flip = r.flags & 1;
+    E.blo1 = (E.flip ? r.bv : r.bu) >= 0;
+    E.bhi1 = (E.flip ? r.bu : r.bv) >= 0;
+    E.a = r.a;
+    E.kk = (STIFF && s.k_edge) ? s.k_edge[e] : 0.0;
+    E.sgn = E.flip ? -sg : sg;
+    E.he = Hslot + shh + (le0 + le) * m;
+    E.ac = nullptr;
+    E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + r.ebp - base) + (int32_t)(base & 1);
+    const int32_t f = asm_qrow<STIFF, false>(stage, stab, E, t, m, sg);
+    if (t == m - 1) asm_qrow<STIFF, false>(stage, stab, E, m, m, sg);
     const int32_t slot = psh + 3 * (le * m + gnx_gray(t));
     const bool up = (f >> 17) & 1;
     stage_p[slot] = up ? -E.sgn : E.sgn;
@@ -2472,27 +2557,38 @@ __device__ __forceinline__ void rs_assemble_tile(const StepArgs& s, int32_t atil
     stage_p[slot + 2] = 0.0;
   }
   gnx_fence_async_smem();
-  rs_bar(bid);
-  rs_put(stage, s.vals, base, (int32_t)(end - base), ltid);
-  rs_put(stage_p, s.vals, pbase, 3 * nE * m, ltid);
-  if (ltid == 0) { gnx_bulk_commit(); gnx_bulk_wait_read(); }
-  rs_bar(bid);                                      // the staging area is free again
+  rs_abar(bid);
+  rs_put(stage, s.vals, base, (int32_t)(end - base), gtid);
+  rs_put(stage_p, s.vals, pbase, 3 * nE * m, gtid);
+  if (gtid == 0) gnx_bulk_commit();
 }
 
-// phase 2 of a CTA that does not run the Schur solve: assembly tiles and lambda rows, dealt round-robin over the
-// `nsub` assembling sub-blocks of the grid (this one is number g)
-__device__ __forceinline__ void rs_assemble(const StepArgs& s, int32_t g, int32_t nsub, int ltid, int bid, double* stage) {
-  const int32_t Ga = RS_ATILE >> s.net.n;
-  const int32_t nb_asm = gnx_blocks_dev(s.net.E, Ga);
-  const int32_t nb_lam = s.net.B > 0 ? gnx_blocks_dev(s.net.B, ASM_T) : 0;
-  for (int32_t t = g; t < nb_asm + nb_lam; t += nsub) {
-    if (t < nb_asm) {
-      if (s.k_edge) rs_assemble_tile<true>(s, t, ltid, bid, stage);
-      else rs_assemble_tile<false>(s, t, ltid, bid, stage);
-    } else {
-      const int64_t r = s.d.lam_off + (int64_t)(t - nb_asm) * ASM_T + ltid;
-      if (r < s.d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(s.net, s.d, r, s.a_edge, s.k_edge, 1.0, s.sigma, nullptr, nullptr, s.vals);
+// phase 2 of a worker: the CSR values of ITS tiles' edges -- two assembly tiles per resident solve tile, dealt to two
+// groups of 512 threads.  A group alternates between the staging areas of its two sub-blocks: while the copy engine
+// reads one tile out of shared memory (2 us for 32 KB with four stores in flight per SM -- longer than computing it,
+// 1.6 us), the group computes the next into the other.  Then the worker's share of the lambda rows (blocks of ASM_T
+// rows, dealt round-robin over the grid's sub-blocks).
+__device__ __forceinline__ void rs_assemble(const StepArgs& s, int32_t w, int32_t W, int32_t nmine, int tid,
+                                            const double* Hres, const RsEdge* recs, const int2* stab, double* stage) {
+  const int grp = tid / RS_AT, gtid = tid % RS_AT, bid = 5 + grp;
+  int32_t it = 0;
+  for (int32_t j = grp; j < 2 * nmine; j += RS_AGRP, ++it) {
+    const int32_t k = j >> 1, hsel = j & 1;
+    double* const buf = stage + (size_t)(2 * grp + (it & 1)) * RS_STAGE;
+    if (it >= 2) {                                   // the store that last used this buffer has read it
+      if (gtid == 0) gnx_bulk_wait_read_1();
+      rs_abar(bid);
     }
+    if (s.k_edge) rs_assemble_tile<true>(s, w + k * W, hsel, Hres + (size_t)k * RS_HSLOT, recs + k * RS_MAX_G, stab, gtid, bid, buf);
+    else rs_assemble_tile<false>(s, w + k * W, hsel, Hres + (size_t)k * RS_HSLOT, recs + k * RS_MAX_G, stab, gtid, bid, buf);
+  }
+  if (gtid == 0) gnx_bulk_wait_read();
+  rs_abar(bid);                                      // both staging areas of the group are free again
+  const int sub = tid / ET_T, ltid = tid % ET_T;
+  const int32_t nb_lam = s.net.B > 0 ? gnx_blocks_dev(s.net.B, ASM_T) : 0;
+  for (int32_t t = w * RS_SUB + sub; t < nb_lam; t += W * RS_SUB) {
+    const int64_t r = s.d.lam_off + (int64_t)t * ASM_T + ltid;
+    if (r < s.d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(s.net, s.d, r, s.a_edge, s.k_edge, 1.0, s.sigma, nullptr, nullptr, s.vals);
   }
 }
 
@@ -2507,6 +2603,25 @@ __device__ __forceinline__ void rs_spin_ge(const unsigned long long* p, unsigned
   }
 }
 
+// a few words of every 64-byte line of the Schur arguments, read through the constant bank: CTA 0 first needs them on
+// the step's critical path, and a parameter line nobody has touched yet costs a trip to device memory
+__device__ __forceinline__ int32_t rs_touch_args(const SchurArgs& a) {
+  const gnx_schur_plan_t& pl = a.plan;
+  int32_t acc = a.net.E ^ a.net.B ^ (int32_t)(intptr_t)a.net.inc_ptr ^ (int32_t)(intptr_t)a.net.bif_nodes;
+  acc ^= pl.B ^ pl.nl ^ pl.l_split ^ pl.nt ^ pl.nb ^ pl.l_sync ^ pl.nxl ^ pl.lvl_ptr[0] ^ pl.lvl_ptr[16] ^ pl.lvl_ptr[32];
+  acc ^= (int32_t)(intptr_t)pl.top_rec ^ (int32_t)(intptr_t)pl.ncls ^ (int32_t)(intptr_t)pl.xlist ^ (int32_t)(intptr_t)pl.parent ^
+         (int32_t)(intptr_t)pl.ch_ptr ^ (int32_t)(intptr_t)pl.top_of ^ (int32_t)(intptr_t)pl.pedge;
+  acc ^= (int32_t)(intptr_t)a.cond ^ (int32_t)(intptr_t)a.rsrc ^ (int32_t)(intptr_t)a.ftot ^ (int32_t)(intptr_t)a.b_lam ^
+         (int32_t)(intptr_t)a.P ^ (int32_t)(intptr_t)a.lam_out ^ (int32_t)(intptr_t)a.d ^ (int32_t)(intptr_t)a.r ^
+         (int32_t)(intptr_t)a.scal ^ a.max_iter ^ a.chunk ^ (int32_t)(intptr_t)a.wait_flags ^ (int32_t)a.wait_epoch ^
+         a.wait_world ^ (int32_t)(intptr_t)a.sig_flags[0] ^ (int32_t)(intptr_t)a.sig_flags[GNX_MAX_PEERS - 1] ^
+         (int32_t)(intptr_t)a.xbuf[0] ^ (int32_t)(intptr_t)a.xbuf[GNX_MAX_PEERS - 1] ^ (int32_t)a.xd_off ^ a.phase ^
+         (int32_t)__double2loint(a.inv_sigma) ^ (int32_t)__double2loint(a.rtol);
+  return acc;
+}
+
+// CTA 0 runs the graph-level solve and nothing else (gridDim.x >= 2); CTAs 1.. are the workers: worker w owns the
+// tiles w, w + W, w + 2W, ... (W = gridDim.x - 1) for the whole kernel.
 __global__ void __launch_bounds__(RS_T, 1)
 step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ SchurArgs a) {
   extern __shared__ __align__(16) double rs_sm[];
@@ -2520,18 +2635,49 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
   double* const Hres = rs_sm;
   double* const stage = rs_sm + (size_t)s.tiles_per_cta * RS_HSLOT;
   RsEdge* const recs = reinterpret_cast<RsEdge*>(stage + RS_SUB * RS_STAGE);
-  int32_t* const sloc = reinterpret_cast<int32_t*>(recs + s.tiles_per_cta * RS_MAX_G);
+  int2* const stab = reinterpret_cast<int2*>(recs + s.tiles_per_cta * RS_MAX_G);      // (RsEdge is 16-byte aligned)
+  int32_t* const sloc = reinterpret_cast<int32_t*>(stab + (m + 2));
   double* const sF = stage + sub * RS_STAGE;
   double* const sG = sF + RS_FSLOT;
   const int32_t G = RS_TILE >> net.n;
   const bool zfg = s.rhs.fc == 0.0 && s.rhs.gc == 0.0 && !s.k_edge;
+  const int32_t W = (int32_t)gridDim.x - 1, w = (int32_t)blockIdx.x - 1;
+  // lambda rows of b (every CTA helps)
+  for (int64_t r = s.d.lam_off + (int64_t)blockIdx.x * RS_T + tid; r < s.d.N; r += (int64_t)gridDim.x * RS_T) s.rhs.b[r] = 0.0;
+
+  if (blockIdx.x == 0) {
+    // ---- the solver CTA.  While the workers eliminate: the rows' plan records (64 B per row) and node classes --
+    // static data, cold in a flushed L2 -- are asked for now and are L2 hits when the solve needs them; so are the
+    // kernel arguments it will read.
+    if (tid == 0) s.sync[2] = rs_now();
+    rs_prefetch_l2(a.plan.top_rec, (int64_t)a.plan.nt * 64, tid);
+    rs_prefetch_l2(a.plan.ncls, (int64_t)a.plan.B * 4, tid);
+    if (tid == 32) { const int32_t t = rs_touch_args(a); if (t == 0x5a5a5a5b) s.sync[31] = (unsigned long long)t; }
+    auto wait_workers = [&]() {                    // all workers' edge scalars are in global memory
+      if (tid == 0) {
+        s.sync[8] = s.sync[3] = rs_now();
+        rs_spin_ge(s.sync, (unsigned long long)W);
+        s.sync[0] = 0ull;                          // nobody touches the counter again in this launch
+        s.sync[4] = rs_now();
+      }
+      __syncthreads();
+    };
+    schur_body<SCH_SINGLE>(a, stage, red, wait_workers);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(s.sync + 1), "l"(s.epoch) : "memory");
+      s.sync[5] = s.sync[6] = s.sync[7] = rs_now();
+    }
+    return;
+  }
+
+  // ---- the workers, phase 1: every tile's cell lengths in flight at once ...
   int32_t nmine = 0;
-  for (int32_t t = blockIdx.x; t < s.nb_tiles; t += gridDim.x) ++nmine;
-  // ---- phase 1: every tile's cell lengths in flight at once ...
+  for (int32_t t = w; t < s.nb_tiles; t += W) ++nmine;
   if (tid == 0) {
-    if (blockIdx.x == 0) s.sync[2] = rs_now();
     for (int32_t k = 0; k < nmine; ++k) {
-      const int32_t tile = blockIdx.x + k * gridDim.x;
+      const int32_t tile = w + k * W;
       const int32_t e0 = tile * G, nE = min(G, net.E - e0);
       const int64_t hbase = (int64_t)e0 * m;
       gnx_mbar_init(&hbar[k], 1);
@@ -2543,7 +2689,7 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
   // loads edges -> bix -> boundary data run for all edges of the CTA at once) and the numbering table
   for (int32_t idx = tid; idx < nmine * G; idx += RS_T) {
     const int32_t k = idx / G, le = idx - k * G;
-    const int32_t e = (blockIdx.x + k * gridDim.x) * G + le;
+    const int32_t e = (w + k * W) * G + le;
     if (e < net.E) {
       RsEdge r;
       const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
@@ -2552,70 +2698,55 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
       r.a = s.a_edge[e];
       r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
       r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
-      r.q0 = 0.0; r.Pu = 0.0; r.pad = 0;
+      r.q0 = 0.0; r.Pu = 0.0; r.ebp = net.ebif_prefix[e];
       recs[k * RS_MAX_G + le] = r;
     }
   }
   for (int32_t i = tid; i <= m; i += RS_T) sloc[i] = net.loc[i];
-  for (int64_t r = s.d.lam_off + (int64_t)blockIdx.x * RS_T + tid; r < s.d.N; r += (int64_t)gridDim.x * RS_T) s.rhs.b[r] = 0.0;
+  if (s.vals) for (int32_t i = tid; i <= m; i += RS_T) stab[i] = reinterpret_cast<const int2*>(net.rowtab)[i];
   __syncthreads();
-  if (blockIdx.x == 0 && tid == 0) s.sync[8] = rs_now();
-  const bool dbg = blockIdx.x == 1 && tid == 0;    // diagnostic stamps of an ordinary CTA: sync[16..]
+  const bool dbg = blockIdx.x == 1 && tid == 0;    // diagnostic stamps of a worker: sync[16..]
   if (dbg) s.sync[16] = rs_now();
+  // the edge scalars: all the graph-level solve waits for (the tile of b is written in phase 2)
   for (int32_t k = sub; k < nmine; k += RS_SUB) {
     gnx_mbar_wait(&hbar[k], 0);
     if (dbg) s.sync[17 + (k >= RS_SUB ? 2 : 0)] = rs_now();
-    if (k >= RS_SUB) {                             // the staging area still feeds the bulk stores of my previous tile
-      if (ltid == 0) gnx_bulk_wait_read();
-      rs_bar(bid);
-    }
-    if (zfg) rs_eliminate_tile<true>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
-                                     recs + k * RS_MAX_G, sloc);
-    else rs_eliminate_tile<false>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
-                                  recs + k * RS_MAX_G, sloc);
+    if (zfg) rs_eliminate_tile<true, 1>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub], recs + k * RS_MAX_G, sloc);
+    else rs_eliminate_tile<false, 1>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub], recs + k * RS_MAX_G, sloc);
     if (dbg) s.sync[18 + (k >= RS_SUB ? 2 : 0)] = rs_now();
   }
-  if (ltid == 0) gnx_bulk_wait_read();
   if (dbg) s.sync[21] = rs_now();
   // (scalars stored into other ranks' buffers were followed by a system-scope fence of the storing thread, EdgeOut::put;
   //  the gathered layout of mode 0 stores ALL of them remotely: one fence per thread there)
   if (s.out.n > 1 && !s.out.egl) __threadfence_system();
   __syncthreads();
+  if (dbg) s.sync[29] = rs_now();
   if (tid == 0) {
     __threadfence();
     atomicAdd(s.sync, 1ull);
   }
-  // ---- phase 2: the graph-level solve on CTA 0, the CSR values on all the others
-  double* const astage = stage + sub * RS_STAGE;
-  if (blockIdx.x == 0) {
-    if (tid == 0) {
-      s.sync[3] = rs_now();
-      rs_spin_ge(s.sync, gridDim.x);
-      s.sync[0] = 0ull;                            // nobody touches the counter again in this launch
-      s.sync[4] = rs_now();
+  // ---- phase 2, while CTA 0 solves: the CSR values (the solver never reads them: a_form / ii_assemble of the step,
+  // flow_models.py:343), then the tiles of b
+  if (dbg) s.sync[22] = rs_now();
+  if (s.vals) rs_assemble(s, w, W, nmine, tid, Hres, recs, stab, stage);
+  if (dbg) s.sync[23] = rs_now();
+  for (int32_t k = sub; k < nmine; k += RS_SUB) {
+    if (k >= RS_SUB) {                             // the staging area still feeds the bulk stores of my previous tile
+      if (ltid == 0) gnx_bulk_wait_read();
+      rs_bar(bid);
     }
-    __syncthreads();
-    schur_body<SCH_SINGLE>(a, stage, red);
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(s.sync + 1), "l"(s.epoch) : "memory");
-      s.sync[5] = rs_now();
-    }
-    if (s.vals && gridDim.x == 1) rs_assemble(s, sub, RS_SUB, ltid, bid, astage);     // (a one-CTA grid has nobody else)
-  } else {
-    if (dbg) s.sync[22] = rs_now();
-    if (s.vals) rs_assemble(s, (blockIdx.x - 1) * RS_SUB + sub, (gridDim.x - 1) * RS_SUB, ltid, bid, astage);
-    if (dbg) s.sync[23] = rs_now();
-    if (tid == 0) rs_spin_ge(s.sync + 1, s.epoch);
-    if (dbg) s.sync[24] = rs_now();
+    if (zfg) rs_eliminate_tile<true, 2>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub], recs + k * RS_MAX_G, sloc);
+    else rs_eliminate_tile<false, 2>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub], recs + k * RS_MAX_G, sloc);
   }
+  if (ltid == 0) gnx_bulk_wait_read();
+  if (dbg) s.sync[30] = rs_now();
+  if (tid == 0) rs_spin_ge(s.sync + 1, s.epoch);
+  if (dbg) s.sync[24] = rs_now();
   __syncthreads();
-  if (blockIdx.x == 0 && tid == 0) s.sync[6] = rs_now();
   // ---- phase 3: back-substitution out of the resident lengths; first the edges' end pressures (one thread per edge)
   for (int32_t idx = tid; idx < nmine * G; idx += RS_T) {
     const int32_t k = idx / G, le = idx - k * G;
-    const int32_t e = (blockIdx.x + k * gridDim.x) * G + le;
+    const int32_t e = (w + k * W) * G + le;
     if (e < net.E) {
       RsEdge& r = recs[k * RS_MAX_G + le];
       const double Pu = r.bu >= 0 ? __ldcg(s.P + r.bu) : 0.0;
@@ -2631,20 +2762,20 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
       if (ltid == 0) gnx_bulk_wait_read();
       rs_bar(bid);
     }
-    if (zfg) rs_backsub_tile<true>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+    if (zfg) rs_backsub_tile<true>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
                                    recs + k * RS_MAX_G, sloc);
-    else rs_backsub_tile<false>(s, blockIdx.x + k * gridDim.x, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
+    else rs_backsub_tile<false>(s, w + k * W, ltid, bid, Hres + (size_t)k * RS_HSLOT, sF, sG, sh_sub[sub],
                                 recs + k * RS_MAX_G, sloc);
     if (dbg) s.sync[26 + (k >= RS_SUB ? 1 : 0)] = rs_now();
   }
   if (ltid == 0) gnx_bulk_wait_read();
   if (dbg) s.sync[28] = rs_now();
-  if (blockIdx.x == 0 && tid == 0) s.sync[7] = rs_now();
 }
 
 static size_t rs_smem_bytes(int tiles_per_cta, int m) {
   return ((size_t)tiles_per_cta * RS_HSLOT + (size_t)RS_SUB * RS_STAGE) * sizeof(double) +
-         (size_t)tiles_per_cta * RS_MAX_G * sizeof(RsEdge) + (((size_t)m + 1 + 3) & ~(size_t)3) * sizeof(int32_t);
+         (size_t)tiles_per_cta * RS_MAX_G * sizeof(RsEdge) + ((size_t)m + 2) * sizeof(int2) +
+         (((size_t)m + 1 + 3) & ~(size_t)3) * sizeof(int32_t);
 }
 
 // ------------------------------------------------------------------------------------
@@ -2690,7 +2821,7 @@ edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
     r.a = s.a_edge[e];
     r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
     r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
-    r.q0 = 0.0; r.Pu = 0.0; r.pad = 0;
+    r.q0 = 0.0; r.Pu = 0.0; r.ebp = 0;
     if (BACKSUB) {
       const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
       const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
@@ -2775,8 +2906,8 @@ int gnx_step_resident_applies(const gnx_network_t* net, const gnx_schur_plan_t* 
   if (sch_init() != GNX_OK) return 0;
   const int G = RS_TILE >> net->n;
   const int nb_tiles = gnx_blocks(net->E, G);
-  const int grid = nb_tiles < g_sch_sms ? nb_tiles : g_sch_sms;
-  return gnx_blocks(nb_tiles, grid) <= RS_MAX_TILES;
+  const int grid = nb_tiles + 1 < g_sch_sms ? nb_tiles + 1 : g_sch_sms;     // CTA 0 solves, the others own the tiles
+  return grid >= 2 && gnx_blocks(nb_tiles, grid - 1) <= RS_MAX_TILES;
 }
 
 int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const, double g_const,
@@ -2813,8 +2944,9 @@ int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t*
   s.P = P; s.x = x; s.vals = vals; s.sigma = co->sigma;
   const int G = RS_TILE >> net->n;
   s.nb_tiles = gnx_blocks(net->E, G);
-  const int grid = s.nb_tiles < g_sch_sms ? s.nb_tiles : g_sch_sms;
-  s.tiles_per_cta = gnx_blocks(s.nb_tiles, grid);
+  const int grid = s.nb_tiles + 1 < g_sch_sms ? s.nb_tiles + 1 : g_sch_sms;
+  GNX_CHECK_ARG(grid >= 2);
+  s.tiles_per_cta = gnx_blocks(s.nb_tiles, grid - 1);
   GNX_CHECK_ARG(s.tiles_per_cta <= RS_MAX_TILES);
   s.sync = sync; s.epoch = epoch;
   SchurArgs a;

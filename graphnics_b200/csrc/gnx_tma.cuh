@@ -31,6 +31,8 @@ __device__ __forceinline__ void gnx_bulk_s2g(void* gdst, const void* ssrc, uint3
 __device__ __forceinline__ void gnx_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread: all of its committed bulk stores have finished READING shared memory
 __device__ __forceinline__ void gnx_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent group (double-buffered staging: the buffer of the store before last is free)
+__device__ __forceinline__ void gnx_bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Block-wide: g[base .. base+len) <- stage[sh .. sh+len), sh = base & 1.  `stage` is 16-byte aligned,
 // `g` points to a 16-byte aligned array.  Every writer of `stage` has run gnx_fence_async_smem() and the

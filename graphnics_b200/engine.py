@@ -748,7 +748,7 @@ class MixedSystem:
         if dn.B > 0:
             plan, _, work, _ = self.schur_plan()
         if getattr(self, "_step_sync", None) is None:      # arrival counter + epoch word of the persistent step kernel
-            self._step_sync = torch.zeros(32, dtype=torch.int64, device=self.dev)
+            self._step_sync = torch.zeros(64, dtype=torch.int64, device=self.dev)
             self._step_epoch = 0
         self._step_epoch += 1
         resid = inf = None

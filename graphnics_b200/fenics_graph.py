@@ -58,6 +58,47 @@ class _TangentField:
         return np.asarray(out)
 
 
+class _StampedAttrs(dict):
+    """Edge attribute dictionary that counts its mutations in a stamp shared by all edges of one graph
+    (`_stamp`, set on the per-graph subclass made in FenicsGraph.__init__): edge_attribute_array() walks the E
+    dictionaries again only when some attribute was written since its last walk."""
+    __slots__ = ()
+    _stamp = None
+
+    def __setitem__(self, k, v):
+        self._stamp[0] += 1
+        dict.__setitem__(self, k, v)
+
+    def __delitem__(self, k):
+        self._stamp[0] += 1
+        dict.__delitem__(self, k)
+
+    def __ior__(self, other):
+        self._stamp[0] += 1
+        dict.update(self, other)
+        return self
+
+    def update(self, *a, **kw):
+        self._stamp[0] += 1
+        dict.update(self, *a, **kw)
+
+    def setdefault(self, k, default=None):
+        self._stamp[0] += 1
+        return dict.setdefault(self, k, default)
+
+    def pop(self, *a):
+        self._stamp[0] += 1
+        return dict.pop(self, *a)
+
+    def popitem(self):
+        self._stamp[0] += 1
+        return dict.popitem(self)
+
+    def clear(self):
+        self._stamp[0] += 1
+        dict.clear(self)
+
+
 class FenicsGraph(nx.DiGraph):
     """Class for constructing meshes and associated functions from networkx directed graphs.
     Node attribute "pos" (2 or 3 coordinates) is required; node labels must be 0..V-1 in
@@ -65,7 +106,11 @@ class FenicsGraph(nx.DiGraph):
     otherwise, fenics_graph.py:71-72 -- we raise)."""
 
     def __init__(self):
+        stamp = [0]
+        # (networkx calls self.edge_attr_dict_factory() for every new edge: an instance attribute overrides the class's)
+        self.edge_attr_dict_factory = type("_EdgeAttrs", (_StampedAttrs,), {"__slots__": (), "_stamp": stamp})
         nx.DiGraph.__init__(self)
+        self._attr_stamp = stamp
         self._dn = None
         self._systems = {}
 
@@ -90,6 +135,7 @@ class FenicsGraph(nx.DiGraph):
     # edge-structure mutators drop the cached list of edge attribute dictionaries (edge_attribute_array)
     def _drop_edge_cache(self):
         self.__dict__["_edge_dicts"] = None
+        self.__dict__["_edge_attr_cache"] = {}
 
     def add_edge(self, u, v, **attr):
         self._drop_edge_cache()
@@ -271,6 +317,21 @@ class FenicsGraph(nx.DiGraph):
         """[E] float array of a (constant-per-edge) attribute; Constants / floats / constant UFL.
         Objects shared by many edges (one `Constant` for the whole graph is the common case) are
         converted once."""
+        # Nothing written to any edge attribute since the last walk for this key (the dictionaries count their
+        # mutations, _StampedAttrs) and every mutable value found then (Constant) still holds the number it held:
+        # the same array again.  2047 edges: 60-90 us of dictionary walk per solve otherwise.
+        cache = self.__dict__.setdefault("_edge_attr_cache", {})
+        hit = cache.get(key)
+        if hit is not None and hit[0] == self._attr_stamp[0] and hit[1] == default and all(c._value == v for c, v in hit[2]):
+            return hit[3]
+        out = self._edge_attribute_walk(key, default)
+        guards = self.__dict__.pop("_edge_attr_guards", None)
+        if guards is not None:
+            out.setflags(write=False)
+            cache[key] = (self._attr_stamp[0], default, guards, out)
+        return out
+
+    def _edge_attribute_walk(self, key, default):
         # same order as self.edges(): by source node, then successor insertion order.  The attribute
         # dictionaries themselves are stable objects: the list of them is kept while the edge count stands.
         dicts = self.__dict__.get("_edge_dicts")
@@ -288,11 +349,17 @@ class FenicsGraph(nx.DiGraph):
         else:
             rep = 1
         conv = {}
+        guards = []                  # (Constant, value) pairs the cached array depends on; None: do not cache
         out = np.empty(len(vals))
         for i, v in enumerate(vals):
             k = id(v)
             f = conv.get(k)
             if f is None:
+                if isinstance(v, Constant):
+                    if guards is not None:
+                        guards.append((v, v._value))
+                elif not isinstance(v, (int, float, np.integer, np.floating)):
+                    guards = None                          # (a UFL expression of parameters: re-evaluated every time)
                 if isinstance(v, UFLExpr):
                     if v.expr.free_symbols - set(v.params):
                         raise VaryingEdgeAttribute(key, list(np.repeat(np.asarray(vals, dtype=object), rep)) if rep > 1 else vals)
@@ -303,6 +370,7 @@ class FenicsGraph(nx.DiGraph):
                     f = float(v)
                 conv[k] = f
             out[i] = f
+        self.__dict__["_edge_attr_guards"] = guards
         return np.repeat(out, rep) if rep > 1 else out
 
 

@@ -88,3 +88,42 @@ def test_make_arterial_tree_matches_reference_run():
         counts.append(len(edges))
         assert len(signs) < 400 or N == 1          # `directions` is consumed, like the reference (:127)
     assert counts == [1, 3, 7, 15, 31, 62, 119]
+
+
+def test_edge_attribute_cache_follows_every_way_of_writing_an_attribute():
+    """edge_attribute_array() keeps its result while no edge attribute was written (the per-graph mutation stamp of the
+    attribute dictionaries) and no Constant it found changed value; every networkx way of writing must invalidate it"""
+    import networkx as nx
+    import graphnics_b200 as gn
+    G = gn.FenicsGraph()
+    G.add_nodes_from((i, {"pos": [float(i), 0.0]}) for i in range(5))
+    G.add_edges_from([(0, 1), (1, 2), (1, 3), (3, 4)])
+    c = gn.Constant(2.0)
+    for e in G.edges():
+        G.edges[e]["Res"] = c
+    a = G.edge_attribute_array("Res", 1.0)
+    assert a.tolist() == [2.0] * 4
+    assert G.edge_attribute_array("Res", 1.0) is a                     # cached
+    c.assign(3.0)                                                      # a Constant changed under the cache
+    assert G.edge_attribute_array("Res", 1.0).tolist() == [3.0] * 4
+    G.edges[1, 2]["Res"] = 5.0                                         # __setitem__
+    assert G.edge_attribute_array("Res", 1.0).tolist() == [3.0, 5.0, 3.0, 3.0]
+    nx.set_edge_attributes(G, {(0, 1): 7.0}, "Res")                    # networkx helper
+    assert G.edge_attribute_array("Res", 1.0).tolist() == [7.0, 5.0, 3.0, 3.0]
+    G[3][4].update(Res=9.0)                                            # dict.update through the adjacency view
+    assert G.edge_attribute_array("Res", 1.0).tolist() == [7.0, 5.0, 3.0, 9.0]
+    del G.edges[1, 3]["Res"]                                           # missing attribute -> default
+    assert G.edge_attribute_array("Res", 1.0).tolist() == [7.0, 5.0, 1.0, 9.0]
+    G.add_edge(2, 4, Res=11.0)                                         # structure change
+    assert sorted(G.edge_attribute_array("Res", 1.0).tolist()) == [1.0, 5.0, 7.0, 9.0, 11.0]
+    H = G.copy()                                                       # a copy has its own stamp
+    assert isinstance(H, gn.FenicsGraph) and H._attr_stamp is not G._attr_stamp
+    H.edges[0, 1]["Res"] = 13.0
+    assert 13.0 in H.edge_attribute_array("Res", 1.0).tolist() and 13.0 not in G.edge_attribute_array("Res", 1.0).tolist()
+    x = gn.Constant(1.0)                                               # a UFL expression of parameters is never cached
+    u = 2.0 * x
+    for e in G.edges():
+        G.edges[e]["Ainv"] = u
+    assert set(G.edge_attribute_array("Ainv", 1.0).tolist()) == {2.0}
+    x.assign(4.0)
+    assert set(G.edge_attribute_array("Ainv", 1.0).tolist()) == {8.0}

@@ -49,20 +49,22 @@ def step():
 for _ in range(5):
     step()
 torch.cuda.synchronize()
-ts, stamps, stamps1, stamps2 = [], [], [], []
+ts, stamps, stamps1, stamps2, stamps3 = [], [], [], [], []
 for _ in range(30):
-    if "--no-flush" not in sys.argv:
+    if "--read-flush" in sys.argv:                  # L2 full of CLEAN foreign lines (a write flush leaves dirty ones)
+        flush_sink = flush.view(torch.int64).sum()
+    elif "--no-flush" not in sys.argv:
         flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); step(); e1.record(); e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
     s = ms._step_sync.cpu().numpy()
     stamps.append((s[[8, 3, 4, 5, 6, 7]] - s[2]) / 1e3)
-    stamps1.append((s[16:29] - s[2]) / 1e3)
+    stamps1.append((s[16:31] - s[2]) / 1e3)
     if ms.dn.B > 0:
         w = ms.schur_plan()[2]
         sc = w[-32 - ((ms.schur_plan()[0].na ** 2 + ms.schur_plan()[0].na + 2 * 1024) if ms.schur_plan()[0].na else 0):][:32].cpu().numpy()
-        stamps2.append((np.concatenate([sc[16:18], sc[9:16]]) - sc[8]) / 1e3)
+        stamps2.append((np.concatenate([sc[16:18], sc[9:16], sc[18:24], sc[25:26]]) - sc[8]) / 1e3)
 out = {"levels": levels, "n": n, "N": ms.N, "resident": os.environ.get("GNX_STEP_RESIDENT", "1"), "vals": vals is not None,
        "us_per_step": {"min": float(np.min(ts)), "median": float(np.median(ts)), "max": float(np.max(ts))}}
 if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
@@ -70,9 +72,10 @@ if os.environ.get("GNX_STEP_RESIDENT", "1") != "0":
     out["cta0_stamps_us"] = dict(zip(["prefetched", "own_tiles_done", "all_arrived", "schur_done", "released", "end"], st.round(2).tolist()))
     st1 = np.median(np.asarray(stamps1), axis=0)
     out["cta1_stamps_us"] = dict(zip(["prefetched", "H0_arrived", "elim0_done", "H4_arrived", "elim4_done", "b_stores_read", "asm_start",
-                                      "asm_done", "released", "p3_prefetched", "bs0_done", "bs4_done", "end"], st1.round(2).tolist()))
+                                      "asm_done", "released", "p3_prefetched", "bs0_done", "bs4_done", "end", "phase1_barrier", "b_tiles_done"], st1.round(2).tolist()))
 if stamps2:
-    out["schur_stamps_us"] = dict(zip(["top_solve_entry", "rows_ready_thread0", "prologue", "local_up", "exported", "flags", "repl_rows", "up_done", "down_done"],
+    out["schur_stamps_us"] = dict(zip(["top_solve_entry", "rows_ready_thread0", "prologue", "local_up", "exported", "flags", "repl_rows", "up_done", "down_done",
+                                       "x_roots_sent", "x_flag_released", "x_flag_seen", "first_repl_level_folded", "repl_row_begin", "repl_row_end", "workers_arrived"],
                                       np.median(np.asarray(stamps2), axis=0).round(2).tolist()))
 if vals is not None and world == 1:
     rr, bb = ms.residual(vals, x, b).cpu().tolist()
