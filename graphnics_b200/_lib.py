@@ -26,7 +26,7 @@ class gnx_network_t(C.Structure):
         ("pos", C.c_void_p), ("edges", C.c_void_p), ("h", C.c_void_p), ("bix", C.c_void_p),
         ("bif_nodes", C.c_void_p), ("inc_ptr", C.c_void_p), ("inc_edge", C.c_void_p),
         ("lam_ptr", C.c_void_p), ("ebif_prefix", C.c_void_p), ("loc", C.c_void_p),
-        ("tloc", C.c_void_p), ("rowtab", C.c_void_p),
+        ("tloc", C.c_void_p), ("rowtab", C.c_void_p), ("erec", C.c_void_p),
     ]
 
 

@@ -84,12 +84,90 @@ __device__ __forceinline__ void stream_out(const double* stage, double* __restri
 // Cells are dealt to the lanes of a warp round-robin (cell = 32 * CPT * warp + 32 * round + lane): in every
 // round a warp touches 32 neighbouring rows, i.e. shared-memory addresses 5 (q) / 3 (p) doubles apart --
 // conflict-free, where a thread owning CPT consecutive cells hit every bank 4 times.
-template <int CPT, bool BULK, bool STIFF>
+// FAST (bulk copies, net.erec present, 16-byte aligned cell lengths): a tile used to open with three dependent trips to
+// device memory -- ebif_prefix[e0], then edges -> bix per edge, then the cell lengths: 60 % of the kernel's stall
+// samples (profiles/r2j, ncu source view) -- while a block's useful work is about one such trip long.  Now thread 0
+// hands the tile's range of h to the copy engine first thing (completion on an mbarrier), every thread fetches its
+// edge's 16-byte record (net.erec) and coefficient beside it, and the row code reads the lengths from shared memory:
+// ONE round trip before the arithmetic starts.  Same operations on the same numbers: bit-identical values.
+template <int CPT, bool BULK, bool STIFF, bool FAST>
 __global__ void __launch_bounds__(ASM_T)
 mixed_values_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __restrict__ a_edge,
                          const double* __restrict__ k_edge, const double* __restrict__ a_cell, double a_const, double sg,
                          int32_t nb_tiles, double* __restrict__ vals) {
   constexpr int TILE = ASM_T * CPT;
+  if (FAST) {
+    extern __shared__ __align__(16) double stage[];
+    double* const stage_p = stage + 5 * TILE + 3 * ASM_T + 4;
+    double* const sH = stage_p + 3 * TILE + 4;                          // [TILE + 2] cell lengths of the tile (parity-shifted)
+    __shared__ __align__(8) uint64_t hbar;
+    if ((int32_t)blockIdx.x >= nb_tiles) {
+      const int64_t r = d.lam_off + (int64_t)(blockIdx.x - nb_tiles) * ASM_T + threadIdx.x;
+      if (r < d.N) gnx_mixed_row_emit<GNX_MODE_VALUES>(net, d, r, a_edge, k_edge, a_const, sg, nullptr, nullptr, vals);
+      return;
+    }
+    const int32_t m = d.m, n = net.n;
+    const int32_t G = TILE >> n;
+    const int32_t e0 = blockIdx.x * G;
+    const int32_t nE = min(G, net.E - e0);
+    const int64_t hbase = (int64_t)e0 * m;
+    if (threadIdx.x == 0) {
+      gnx_mbar_init(&hbar, 1);
+      gnx_mbar_expect_tx(&hbar, gnx_bulk_body_bytes(hbase, nE * m));
+      gnx_bulk_stream_in(sH, net.h, hbase, nE * m, &hbar);
+    }
+    const int4* __restrict__ erec = reinterpret_cast<const int4*>(net.erec);
+    const int32_t k0 = (threadIdx.x >> 5) * (32 * CPT) + (threadIdx.x & 31);
+    // everything a thread needs from device memory, requested at once
+    const int4 rf = __ldg(erec + e0), rl = __ldg(erec + e0 + nE - 1);
+    int4 rc[CPT];
+    double ac[CPT], kc[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int32_t le = min((k0 + 32 * i) >> n, nE - 1);
+      rc[i] = __ldg(erec + e0 + le);
+      ac[i] = a_edge ? a_edge[e0 + le] : a_const;
+      kc[i] = (STIFF && k_edge) ? k_edge[e0 + le] : 0.0;
+    }
+    const int64_t base = (int64_t)e0 * (5 * (int64_t)m + 1) + rf.z;
+    const int64_t end = (int64_t)(e0 + nE) * (5 * (int64_t)m + 1) + rl.z + (rl.x >= 0 ? 1 : 0) + (rl.y >= 0 ? 1 : 0);
+    const int64_t pbase = d.p_nnz_off + 3 * (int64_t)e0 * m;
+    const int32_t psh = (int32_t)(pbase & 1), shh = (int32_t)(hbase & 1);
+    const int2* __restrict__ tab = reinterpret_cast<const int2*>(net.rowtab);
+    __syncthreads();                                                    // (the barrier's initialisation, thread 0's odd ends)
+    gnx_mbar_wait(&hbar, 0);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int32_t k = k0 + 32 * i;
+      const int32_t le = k >> n;
+      if (le >= nE) continue;
+      const int32_t t = k & (m - 1);
+      const int32_t e = e0 + le;
+      AsmEdge E;
+      E.flip = rc[i].w < 0;
+      E.blo1 = (E.flip ? rc[i].y : rc[i].x) >= 0;
+      E.bhi1 = (E.flip ? rc[i].x : rc[i].y) >= 0;
+      E.a = ac[i];
+      E.kk = kc[i];
+      E.sgn = E.flip ? -sg : sg;
+      E.he = sH + shh + le * m;
+      E.ac = nullptr;
+      E.ebase = (int32_t)((int64_t)e * (5 * (int64_t)m + 1) + rc[i].z - base) + (int32_t)(base & 1);
+      const int32_t f = asm_qrow<STIFF>(stage, tab, E, t, m, sg);
+      if (t == m - 1) asm_qrow<STIFF>(stage, tab, E, m, m, sg);
+      const int32_t slot = psh + 3 * (le * m + gnx_gray(t));
+      const bool up = (f >> 17) & 1;
+      stage_p[slot] = up ? -E.sgn : E.sgn;
+      stage_p[slot + 1] = up ? E.sgn : -E.sgn;
+      stage_p[slot + 2] = 0.0;
+    }
+    gnx_fence_async_smem();
+    __syncthreads();
+    gnx_bulk_stream_out(stage, vals, base, (int32_t)(end - base));
+    gnx_bulk_stream_out(stage_p, vals, pbase, 3 * nE * m);
+    if (threadIdx.x == 0) { gnx_bulk_commit(); gnx_bulk_wait_read(); }
+    return;
+  }
   // staging buffer, 16-byte aligned; the block's CSR range is staged SHIFTED by the parity of its first
   // slot so that shared and global addresses are 16-byte congruent and the stream-out uses bulk copies
   // or 128-bit loads/stores
@@ -161,14 +239,27 @@ static void launch_values_tile3(const gnx_network_t* net, const GnxMixedDims& d,
   const int G = (ASM_T * CPT) >> net->n;
   const int nb_tiles = gnx_blocks(net->E, G);
   const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ASM_T) : 0;
+  static int fast_on = -1;
+  if (fast_on < 0) { const char* e = getenv("GNX_ASM_FAST"); fast_on = e ? atoi(e) : 1; }                // A-B knob
+  if (BULK && fast_on && net->erec && !a_cell && ((uintptr_t)net->h & 15) == 0) {
+    constexpr int smem = (asm_stage_doubles<CPT>() + ASM_T * CPT + 2) * (int)sizeof(double);
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+      cudaFuncSetAttribute(mixed_values_tile_kernel<CPT, BULK, STIFF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr = true;
+    }
+    mixed_values_tile_kernel<CPT, BULK, STIFF, true><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_cell,
+                                                                                            a_const, sg, nb_tiles, vals);
+    return;
+  }
   constexpr int smem = asm_stage_doubles<CPT>() * (int)sizeof(double);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(mixed_values_tile_kernel<CPT, BULK, STIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(mixed_values_tile_kernel<CPT, BULK, STIFF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  mixed_values_tile_kernel<CPT, BULK, STIFF><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_cell,
-                                                                                    a_const, sg, nb_tiles, vals);
+  mixed_values_tile_kernel<CPT, BULK, STIFF, false><<<nb_tiles + nb_lam, ASM_T, smem, st>>>(*net, d, a_edge, k_edge, a_cell,
+                                                                                           a_const, sg, nb_tiles, vals);
 }
 
 template <int CPT>

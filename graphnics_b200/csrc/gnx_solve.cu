@@ -620,6 +620,7 @@ struct SchurArgs {
   int32_t nx;
   int64_t xd_off, xr_off;
   int32_t phase;                              // 0: whole solve, flags in the kernel; 1: up to the exchange; 2: after it
+  int32_t xpoll;                              // 1: exported roots validate themselves (GNX_XSENT); 0: flag after the data
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
     if (chunk == 2147483647) return e;          // (uniform: everything but the gathered layout -- no integer division)
     const int32_t r = e / chunk;
@@ -744,6 +745,46 @@ __device__ __forceinline__ void sch_flag_exchange(const SchurArgs& a) {
   }
 }
 
+// In-kernel exchange of the exported roots without a flag round trip: a root's final (d, r) travel as two plain
+// 8-byte peer stores and VALIDATE THEMSELVES -- the slot holds GNX_XSENT (a NaN no computation produces) until the
+// value lands, the reader polls the word itself and puts the sentinel back once it has the value.  (A flag would need
+// a release after the data: the storing SM waits for the NVLink acknowledgement of its data stores -- 2-4 us measured
+// -- before the flag may even leave.)  The two exchange buffers alternate per solve and a rank cannot run two solves
+// ahead of a peer, so a slot is never rewritten before its reader has reset it; engine.py fills the (d, r) region
+// with the sentinel when it creates the buffers.
+#define GNX_XSENT 0x7FF85EA71E550001ull
+__device__ __forceinline__ double sch_poll_word(double* p) {
+  unsigned long long v;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v != GNX_XSENT) break;
+    __nanosleep(spins < 4096 ? 20 : 2000);
+    if (++spins > (1u << 25)) __trap();         // about a minute: a rank is missing -- fail instead of hanging the GPU
+  }
+  return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void sch_take_root(const SchurArgs& a, int32_t c, double& dc, double& rc) {
+  dc = sch_poll_word(a.d + c);
+  rc = sch_poll_word(a.r + c);
+  *reinterpret_cast<volatile unsigned long long*>(a.d + c) = GNX_XSENT;
+  *reinterpret_cast<volatile unsigned long long*>(a.r + c) = GNX_XSENT;
+}
+
+__device__ __forceinline__ void sch_wait_flags(const SchurArgs& a) {
+  if ((int)threadIdx.x < a.wait_world) {
+    const long long* f = a.wait_flags + threadIdx.x;
+    long long v;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= a.wait_epoch) break;
+      __nanosleep(spins < 4096 ? 32 : 2000);
+      if (++spins > (1u << 25)) __trap();
+    }
+  }
+}
+
 // The exchange of a subtree-partitioned solve, run by the first `world` threads of ONE CTA after a barrier that
 // made my roots' final (d, r) visible in MY global arrays: thread q stores them into rank q's buffer and then
 // RELEASES its flag word there (st.release.sys orders the thread's own stores before the flag: no separate
@@ -839,6 +880,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   // numeric part of a row's set-up: row (from global memory, or built here for a replicated node), link weight,
   // children below the top part folded in
   const int4* const trec = CLUSTER ? nullptr : reinterpret_cast<const int4*>(pl.top_rec);
+  const bool xin = !CLUSTER && ncls && a.phase == 0 && a.wait_flags && a.xpoll;   // partitioned solve, exchange in this kernel
   if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[16] = (double)(t & 0xffffffffffull); }
   // the same from the row's packed record (plan.top_rec): one 64-byte load, then every scalar it names at once
   int4 keep[ROWS == 1 ? 4 : 1];                                // one row per thread: its record stays in registers
@@ -869,9 +911,12 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     for (int k = 0; k < 2; ++k) {
       if (bc[k] >= 0) {                                     // child below the top part: final in global memory
         const double wc = -a.cond[a.eidx(be[k])];
-        const double t = wc / __ldcg(a.d + bc[k]);
+        double dc, rc;
+        if (xin && repl[q] && (ncls[bc[k]] & 2)) sch_take_root(a, bc[k], dc, rc);     // another rank's subtree root
+        else { dc = __ldcg(a.d + bc[k]); rc = __ldcg(a.r + bc[k]); }
+        const double t = wc / dc;
         di -= wc * t;
-        ri -= t * __ldcg(a.r + bc[k]);
+        ri -= t * rc;
       }
     }
     c0[q] = r1.x; c1[q] = r1.y; nct[q] = r1.z;
@@ -894,9 +939,12 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
       const int32_t tc = top_child(q, c);
       if (tc < 0) {                                        // child below the top part: final in global memory
         const double wc = -a.cond[a.eidx(pl.pedge[c])];
-        const double t = wc / __ldcg(a.d + c);
+        double dc, rc;
+        if (xin && repl[q] && (ncls[c] & 2)) sch_take_root(a, c, dc, rc);
+        else { dc = __ldcg(a.d + c); rc = __ldcg(a.r + c); }
+        const double t = wc / dc;
         di -= wc * t;
-        ri -= t * __ldcg(a.r + c);
+        ri -= t * rc;
       } else {
         if (nct[q] == 0) c0[q] = tc; else if (nct[q] == 1) c1[q] = tc;
         ++nct[q];
@@ -940,6 +988,10 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
     }
   }
   wait_fn();                                               // ---- from here on: data of this step
+  // my edge scalars have landed in every rank's buffer (their senders fenced them at system scope, and this CTA runs
+  // after they all arrived): tell the ranks NOW -- the flags then cross NVLink under the local sweep
+  if (xin && tid < a.wait_world)
+    asm volatile("st.release.sys.global.s64 [%0], %1;" :: "l"(a.sig_flags[tid]), "l"(a.wait_epoch) : "memory");
   if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[25] = (double)(t & 0xffffffffffull); }
 #pragma unroll
   for (int q = 0; q < ROWS; ++q)
@@ -967,7 +1019,8 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
       }
     lsync();
     stamp(3);
-    sch_export_roots(a, a.phase == 1, a.phase == 0);
+    if (xin) sch_wait_flags(a);                                      // (released long ago: the edge scalars are here)
+    else sch_export_roots(a, a.phase == 1, a.phase == 0);            // (phase 0: the flag threads' release covers the roots)
     lsync();
     if (a.phase == 1) return true;
     stamp(4);
@@ -1827,6 +1880,9 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   a.chunk = chunk > 0 ? chunk : 2147483647; a.rank_stride = chunk > 0 ? rank_stride : 0;
   a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_world = 0;
   a.nx = 0; a.xd_off = a.xr_off = 0; a.phase = 0;
+  static int xpoll = -1;                        // A-B knob: GNX_XCHG_FLAGS=1 keeps the data-then-flag exchange of the roots
+  if (xpoll < 0) { const char* e = getenv("GNX_XCHG_FLAGS"); xpoll = (e && atoi(e)) ? 0 : 1; }
+  a.xpoll = xpoll;
   for (int k = 0; k < GNX_MAX_PEERS; ++k) a.xbuf[k] = nullptr;
   const bool subtree = ex && ex->mode == 1;
   GNX_CHECK_ARG(subtree == (plan->ncls != nullptr));
@@ -2191,6 +2247,25 @@ struct __align__(16) RsEdge {
   int32_t bu, bv, flags, ebp;                    // bifurcation index of the ends (-1: boundary); bit 0 flip, 1 pin, 2 pout;
                                                  // ebp: bifurcation ends of the edges before this one (net.ebif_prefix)
 };
+
+// bu, bv, flip bit, ebp and the node u of edge e: from the edge's 16-byte record when the network has one
+// (gnx_network_t.erec), else by walking edges -> bix (one more dependent trip to device memory)
+__device__ __forceinline__ int32_t rs_edge_static(const gnx_network_t& net, int32_t e, RsEdge& r) {
+  int32_t u;
+  if (net.erec) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(net.erec) + e);
+    r.bu = q.x; r.bv = q.y; r.ebp = q.z;
+    u = q.w & 0x7fffffff;
+    r.flags = q.w < 0 ? 1 : 0;
+  } else {
+    u = net.edges[2 * e];
+    const int32_t v = net.edges[2 * e + 1];
+    r.bu = net.bix[u]; r.bv = net.bix[v];
+    r.ebp = net.ebif_prefix[e];
+    r.flags = u > v ? 1 : 0;
+  }
+  return u;
+}
 
 struct StepArgs {
   gnx_network_t net;
@@ -2692,13 +2767,12 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
     const int32_t e = (w + k * W) * G + le;
     if (e < net.E) {
       RsEdge r;
-      const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-      r.bu = net.bix[u]; r.bv = net.bix[v];
-      r.flags = (u > v ? 1 : 0) | ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
+      const int32_t u = rs_edge_static(net, e, r);
+      r.flags |= ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
       r.a = s.a_edge[e];
       r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
       r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
-      r.q0 = 0.0; r.Pu = 0.0; r.ebp = net.ebif_prefix[e];
+      r.q0 = 0.0; r.Pu = 0.0;
       recs[k * RS_MAX_G + le] = r;
     }
   }
@@ -2815,13 +2889,12 @@ edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
   if (tid < nE) {
     const int32_t e = e0 + tid;
     RsEdge r;
-    const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-    r.bu = net.bix[u]; r.bv = net.bix[v];
-    r.flags = (u > v ? 1 : 0) | ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
+    const int32_t u = rs_edge_static(net, e, r);
+    r.flags |= ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
     r.a = s.a_edge[e];
     r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
     r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
-    r.q0 = 0.0; r.Pu = 0.0; r.ebp = 0;
+    r.q0 = 0.0; r.Pu = 0.0;
     if (BACKSUB) {
       const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
       const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;

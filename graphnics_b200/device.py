@@ -186,6 +186,11 @@ class DeviceNetwork:
             self.loc = torch.from_numpy(loc).to(dev, non_blocking=True)
             self.tloc = torch.from_numpy(tloc).to(dev, non_blocking=True)
             self.rowtab = torch.from_numpy(row_table(self.n)).to(dev, non_blocking=True) if self.n <= 10 else None
+            # per-edge record of the tile kernels (gnx_network_t.erec): one 16-byte load instead of edges -> bix
+            eu, ev = self.edges[:, 0].long(), self.edges[:, 1].long()
+            flipbit = torch.where(eu > ev, torch.full_like(eu, -(1 << 31)), torch.zeros_like(eu))
+            self.erec = torch.stack([self.bix[eu].long(), self.bix[ev].long(), self.ebif_prefix[:E].long(),
+                                     eu + flipbit], dim=1).to(torch.int32).contiguous()
             cnt = t.counts()
             if self.glob is not None:
                 gcnt = self.glob.counts()
@@ -208,6 +213,7 @@ class DeviceNetwork:
                 setattr(s, name, getattr(self, name).data_ptr())
             s.bif_nodes = self._bif_nodes.data_ptr()
             s.rowtab = self.rowtab.data_ptr() if self.rowtab is not None else None
+            s.erec = self.erec.data_ptr() if getattr(self, "erec", None) is not None else None
             self._net = s
         return self._net
 

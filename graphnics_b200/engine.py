@@ -460,6 +460,8 @@ class MixedSystem:
             for _ in range(2):
                 t = symm.empty(nw, dtype=torch.float64, device=self.dev)
                 t.zero_()
+                # the (d, r) slots of exported subtree roots validate themselves (GNX_XSENT, gnx_solve.cu)
+                t[3 * dn.E_glob: 3 * dn.E_glob + 2 * dn.B].view(torch.int64).fill_(0x7FF85EA71E550001)
                 torch.cuda.synchronize(self.dev)           # flags are zero before any peer can reach them
                 h = symm.rendezvous(t, group)
                 bufs.append(t); hdls.append(h)

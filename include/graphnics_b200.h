@@ -59,6 +59,10 @@ typedef struct gnx_network {
                                  its q-row (same for every edge; built once by the host, device.row_table); the
                                  edge-tile assembly kernel needs it, every other entry point ignores it (may be NULL
                                  for n > 10) */
+  const int32_t* erec;        /* [E*4] or NULL: what the edge-tile kernels need to know about an edge in ONE 16-byte
+                                 load instead of the chain edges -> bix: bix[u], bix[v], ebif_prefix[e],
+                                 u | (u > v ? 1 << 31 : 0).  Built once by the host (device.py) from the tables above;
+                                 kernels walk the tables themselves when it is NULL */
 } gnx_network_t;
 
 /* Edge-wise operator coefficients of the (generalised) mixed system
