@@ -142,60 +142,74 @@ extern "C" int gnx_project_p1_edges(const gnx_network_t* net, const double* c_no
 // ------------------------------------------------------------------------------------
 // projected value at the v-end of every edge (only edges whose head is a boundary node matter)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// One WARP per edge.  (One thread per edge walked the window serially: 65 nodes x (vertex id -> coordinates from
+// device memory -> two expression evaluations) -- a chain of dependent loads with E threads on the whole GPU, 230 us
+// on the C2 tree and 3/4 of a pulsatile time step.)  The lanes fetch the window's node coordinates and evaluate the
+// expression at nodes and midpoints in parallel (two rounds of independent work through shared memory); lane 0 then
+// runs the Thomas forward sweep -- the same recurrence in the same order -- out of shared memory.
+constexpr int PE_WARPS = 4;
+constexpr int PE_MAXW = 64;                                  // window nodes (the host passes <= 64)
+__global__ void __launch_bounds__(32 * PE_WARPS)
 project_end_kernel(gnx_network_t net, const double* __restrict__ coords, gnx_program_t P, int degree,
                    int window, double* __restrict__ out) {
-  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sx[PE_WARPS][PE_MAXW + 2][3];
+  __shared__ double sf[PE_WARPS][PE_MAXW + 2], sfm[PE_WARPS][PE_MAXW + 2], shh[PE_WARPS][PE_MAXW + 2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t e = blockIdx.x * PE_WARPS + w;
   if (e >= net.E) return;
   const int32_t u = net.edges[2 * e], v = net.edges[2 * e + 1];
-  if (net.bix[v] >= 0) { out[e] = 0.0; return; }           // head is a bifurcation: value unused
+  if (net.bix[v] >= 0) { if (lane == 0) out[e] = 0.0; return; }   // head is a bifurcation: value unused
   const int32_t m = 1 << net.n, gd = net.gdim;
   const int32_t lo = min(u, v), hi = max(u, v);
   const bool flip = u > v;
-  const int32_t K = min(window, m);
+  const int32_t K = min(min(window, PE_MAXW), m);
   const double* he = net.h + (int64_t)e * m;
-  // walk edge-local nodes j = m-K .. m (node m is the head v)
-  auto node_x = [&](int32_t j, double* xo) {
+  const int32_t j0 = m - K;
+  const int32_t jb = j0 > 0 ? j0 - 1 : j0;                   // first node needed (left neighbour of the window)
+  const int32_t nn = m - jb + 1;                             // nodes jb .. m  (<= K + 2)
+  // round 1: node coordinates and values
+  for (int32_t i = lane; i < nn; i += 32) {
+    const int32_t j = jb + i;
     const int32_t t = flip ? m - j : j;
     const int32_t vid = gnx_vertex_id(net.V, net.E, net.n, e, lo, hi, t);
-    for (int k = 0; k < 3; ++k) xo[k] = k < gd ? coords[(int64_t)vid * gd + k] : 0.0;
-  };
-  auto mid_f = [&](const double* xa, const double* xb, double fa, double fb) {
-    if (degree < 2) return 0.5 * (fa + fb);
-    double xm[3];
-    for (int k = 0; k < 3; ++k) xm[k] = 0.5 * (xa[k] + xb[k]);
-    return gnx_rpn_eval(P, xm, gd, nullptr, 0.0);
-  };
-  const int32_t j0 = m - K;
-  double xp[3], xc[3], xn[3];
-  double fp = 0.0, fc, fn_;
-  node_x(j0, xc);
-  fc = gnx_rpn_eval(P, xc, gd, nullptr, 0.0);
-  double hl = 0.0, fml = 0.0;
-  if (j0 > 0) {                                              // left cell of the first window node
-    node_x(j0 - 1, xp);
-    fp = gnx_rpn_eval(P, xp, gd, nullptr, 0.0);
-    hl = he[j0 - 1];
-    fml = mid_f(xp, xc, fp, fc);
+    double x[3];
+    for (int k = 0; k < 3; ++k) x[k] = k < gd ? coords[(int64_t)vid * gd + k] : 0.0;
+    for (int k = 0; k < 3; ++k) sx[w][i][k] = x[k];
+    sf[w][i] = gnx_rpn_eval(P, x, gd, nullptr, 0.0);
   }
-  double cprev = 0.0, dprev = 0.0;                           // Thomas forward sweep
-  for (int32_t j = j0; j <= m; ++j) {
-    double hr = 0.0, fmr = 0.0;
-    if (j < m) {
-      node_x(j + 1, xn);
-      fn_ = gnx_rpn_eval(P, xn, gd, nullptr, 0.0);
-      hr = he[j];
-      fmr = mid_f(xc, xn, fc, fn_);
+  __syncwarp();
+  // round 2: cells jb .. m-1 (between nodes i and i+1): length and midpoint value
+  for (int32_t i = lane; i < nn - 1; i += 32) {
+    shh[w][i] = he[jb + i];
+    double fm;
+    if (degree < 2) fm = 0.5 * (sf[w][i] + sf[w][i + 1]);
+    else {
+      double xm[3];
+      for (int k = 0; k < 3; ++k) xm[k] = 0.5 * (sx[w][i][k] + sx[w][i + 1][k]);
+      fm = gnx_rpn_eval(P, xm, gd, nullptr, 0.0);
     }
+    sfm[w][i] = fm;
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  // Thomas forward sweep over the window nodes j = j0 .. m
+  const int32_t o = j0 - jb;                                 // index of node j0
+  double hl = 0.0, fml = 0.0;
+  if (j0 > 0) { hl = shh[w][0]; fml = sfm[w][0]; }
+  double cprev = 0.0, dprev = 0.0;
+  for (int32_t j = j0; j <= m; ++j) {
+    const int32_t i = o + (j - j0);
+    const double fc = sf[w][i];
+    double hr = 0.0, fmr = 0.0;
+    if (j < m) { hr = shh[w][i]; fmr = sfm[w][i]; }
     const double a = (j > j0) ? hl * (1.0 / 6.0) : 0.0;     // coupling to j0-1 dropped (decays 0.268^K)
     const double b = (hl + hr) * (1.0 / 3.0);
     const double c = hr * (1.0 / 6.0);
     const double d = hl * (2.0 * fml + fc) * (1.0 / 6.0) + hr * (fc + 2.0 * fmr) * (1.0 / 6.0);
-    const double den = b - a * cprev;
-    cprev = c / den;
-    dprev = (d - a * dprev) / den;
-    hl = hr; fml = fmr; fc = fn_;
-    for (int k = 0; k < 3; ++k) xc[k] = xn[k];
+    const double inv = 1.0 / (b - a * cprev);               // (one division per node on the serial chain)
+    cprev = c * inv;
+    dprev = (d - a * dprev) * inv;
+    hl = hr; fml = fmr;
   }
   out[e] = dprev;
 }
@@ -205,7 +219,8 @@ extern "C" int gnx_project_end_values(const gnx_network_t* net, const double* co
                                       double* out, void* stream) {
   if (int rc = check_prog(prog)) return rc;
   GNX_CHECK_ARG(net && coords && out && window >= 1 && net->h && net->bix && net->edges);
-  project_end_kernel<<<gnx_blocks(net->E, 128), 128, 0, (cudaStream_t)stream>>>(*net, coords, *prog, degree, window, out);
+  GNX_CHECK_ARG(window <= PE_MAXW);
+  project_end_kernel<<<gnx_blocks(net->E, PE_WARPS), 32 * PE_WARPS, 0, (cudaStream_t)stream>>>(*net, coords, *prog, degree, window, out);
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }

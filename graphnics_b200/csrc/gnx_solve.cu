@@ -2419,7 +2419,9 @@ __device__ __forceinline__ double rs_rhs_node(const StepArgs& s, const RsEdge& r
 // PART: bit 0 the edge scalars (reductions over the tile -> EdgeOut), bit 1 the tile of b (staged, bulk-stored).  The
 // streaming kernel does both at once; the persistent kernel computes the scalars in phase 1 -- the graph-level solve
 // waits for nothing else -- and writes b in phase 2, out of the same resident lengths (same operations, same bits).
-template <bool ZFG, int PART = 3>
+// ENDS: `sloc` holds only loc[0] and loc[m] (all the f = g = 0 path looks up -- the streaming kernel then needs no
+// 4 KB numbering table in shared memory: 6 -> 8 resident blocks per SM).
+template <bool ZFG, int PART = 3, bool ENDS = false>
 __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t tile, int ltid, int bid, const double* sH,
                                                   double* sF, double* sG, double* sh, const RsEdge* rec, const int32_t* sloc) {
   constexpr int CPT = RS_CPT;
@@ -2444,12 +2446,12 @@ __device__ __forceinline__ void rs_eliminate_tile(const StepArgs& s, int32_t til
     }
     if (c.active && c.kk0 == 0 && (r.flags & 2)) {
       const double v0 = __dadd_rn(0.0, r.pin);
-      if (RHS) sG[qb + sloc[c.flip ? m : 0]] = v0;
+      if (RHS) sG[qb + (ENDS ? sloc[c.flip ? 1 : 0] : sloc[c.flip ? m : 0])] = v0;
       sumG += v0;
     }
     if (c.active && c.kk0 + CPT == m && (r.flags & 4)) {
       const double vm = __dsub_rn(0.0, r.pout);
-      if (RHS) sG[qb + sloc[c.flip ? 0 : m]] = vm;
+      if (RHS) sG[qb + (ENDS ? sloc[c.flip ? 0 : 1] : sloc[c.flip ? 0 : m])] = vm;
       sumG += vm;
     }
   } else if (c.active) {
@@ -2859,13 +2861,13 @@ static size_t rs_smem_bytes(int tiles_per_cta, int m) {
 // What a tile needs to know about its edges is gathered into shared memory by one thread per edge first.
 // ------------------------------------------------------------------------------------
 template <bool ZFG, bool BACKSUB>
-__global__ void __launch_bounds__(ET_T, 4)
+__global__ void __launch_bounds__(ET_T, (ZFG && !BACKSUB) ? 8 : 4)      // (a 32-register cap costs the back-substitution 8 %)
 edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
   __shared__ __align__(16) double sH[RS_HSLOT];
   __shared__ __align__(16) double sFG[RS_FSLOT + RS_GSLOT];
   __shared__ double sh[3 * 32];
   __shared__ RsEdge rec[RS_MAX_G];
-  __shared__ int32_t sloc[1024 + 4];
+  __shared__ int32_t sloc[ZFG ? 4 : 1024 + 4];                        // (f = g = 0: loc[0] and loc[m] only)
   __shared__ __align__(8) uint64_t hbar;
   const gnx_network_t& net = s.net;
   const int tid = threadIdx.x;
@@ -2884,7 +2886,8 @@ edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
     gnx_mbar_expect_tx(&hbar, gnx_bulk_body_bytes(hbase, nE * m));
     gnx_bulk_stream_in(sH, net.h, hbase, nE * m, &hbar);
   }
-  for (int32_t i = tid; i <= m; i += ET_T) sloc[i] = net.loc[i];
+  if (ZFG) { if (tid < 2) sloc[tid] = net.loc[tid ? m : 0]; }
+  else for (int32_t i = tid; i <= m; i += ET_T) sloc[i] = net.loc[i];
   if (BACKSUB) gnx_pdl_wait();                                      // P and the edge scalars come from the kernels before
   if (tid < nE) {
     const int32_t e = e0 + tid;
@@ -2906,7 +2909,7 @@ edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
   __syncthreads();
   gnx_mbar_wait(&hbar, 0);
   if (BACKSUB) rs_backsub_tile<ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
-  else rs_eliminate_tile<ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
+  else rs_eliminate_tile<ZFG, 3, ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
   if (tid == 0) gnx_bulk_wait_read();
 }
 

@@ -224,7 +224,7 @@ class MixedSystem:
             self._lv = torch.from_numpy(lv + np.arange(dn.E, dtype=np.int64) * (dn.m + 1)).to(self.dev)
         return nodal.reshape(-1)[self._lv].contiguous()
 
-    def project_end_values(self, coef, window=64):
+    def project_end_values(self, coef, window=40):
         """projected coefficient at the v-end of every edge (the BOUN_OUT term, flow_models.py:324)"""
         dn = self.dn
         out = self._f64(dn.E)
