@@ -621,6 +621,7 @@ struct SchurArgs {
   int64_t xd_off, xr_off;
   int32_t phase;                              // 0: whole solve, flags in the kernel; 1: up to the exchange; 2: after it
   int32_t xpoll;                              // 1: exported roots validate themselves (GNX_XSENT); 0: flag after the data
+  int32_t fast_bar;                           // 1: epoch-flag barriers in the multilevel PCG; 0: grid.sync()
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
     if (chunk == 2147483647) return e;          // (uniform: everything but the gathered layout -- no integer division)
     const int32_t r = e / chunk;
@@ -667,6 +668,28 @@ __device__ __forceinline__ void sch_sync() {
   if (MODE == SCH_SINGLE) __syncthreads();
   else if (MODE == SCH_CLUSTER) cg::this_cluster().sync();
   else cg::this_grid().sync();                  // SCH_GRID, SCH_GRID_TL
+}
+
+// Barrier of a co-resident grid by epoch flags: CTA b releases flags[b] = seq (cumulative over its __syncthreads: all
+// the CTA wrote before is visible to whoever acquires the flag), the first nblk threads of every CTA wait until every
+// flag has reached seq.  The flags only grow (no reset, reusable across launches: a CTA reads its own flag to learn
+// the last epoch).  An experiment (GNX_PCG_FLAG_BARRIER=1): no faster than cooperative_groups' grid.sync() on 128 CTAs.
+__device__ __forceinline__ void sch_flag_barrier(long long* flags, int nblk, long long seq) {
+  // (a flag per 128-byte line: 128 CTAs polling 128 words packed into eight lines serialise on a few L2 slices --
+  //  measured 1.5x SLOWER than grid.sync())
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("st.release.gpu.global.s64 [%0], %1;" :: "l"(flags + 16 * blockIdx.x), "l"(seq) : "memory");
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    long long v;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(flags + 16 * i) : "memory");
+      if (v >= seq) break;
+      if (++spins > (1u << 28)) __trap();       // a CTA is missing: fail instead of hanging the GPU
+    }
+  }
+  __syncthreads();
 }
 
 // partials of every block are re-reduced by every block in the same order -> identical bits
@@ -1485,6 +1508,10 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   const double bb = acc[2];
   PcgStop stop(a.rtol, bb, rr);
   double rzc = acc[0] + coarse(), rzp = rzc;
+  // the two barriers of an iteration: epoch flags (part[4], zero when the work buffer was created)
+  long long* const bar_flags = reinterpret_cast<long long*>(a.part[4]);
+  long long bar_seq = bar_flags[16 * J];          // (my own last epoch; equal in every CTA)
+  const bool fast_bar = a.fast_bar != 0;
   for (; it < a.max_iter; ++it) {
     if (stop.done(rr, it)) break;
     const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
@@ -1506,9 +1533,15 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
       a.wc[i] = wi;
       pw[0] += pi * wi;
     }
+    block_allreduce<1>(pw, red[1]);
+    if (tid == 0) a.part[3][J] = pw[0];
+    if (fast_bar) sch_flag_barrier(bar_flags, na, ++bar_seq); else grid.sync();
     {
-      double* const part[1] = {a.part[3]};
-      grid_allreduce<SCH_GRID, 1>(pw, part, na, red[1]);
+      double t = 0.0;
+      for (int i = tid; i < na; i += T) t += __ldcg(a.part[3] + i);
+      pw[0] = t;
+      __syncthreads();                            // red[1] reuse
+      block_allreduce<1>(pw, red[1]);
     }
     const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
     double v3[2] = {0.0, 0.0};                    // r.D^-1 r, r.r
@@ -1522,7 +1555,7 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
     block_allreduce<2>(v3, red[0]);
     if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; }
     sub_sums(false);
-    grid.sync();
+    if (fast_bar) sch_flag_barrier(bar_flags, na, ++bar_seq); else grid.sync();
     double t2[2] = {0.0, 0.0};
     for (int i = tid; i < na; i += T) { t2[0] += __ldcg(a.part[0] + i); t2[1] += __ldcg(a.part[1] + i); }
     __syncthreads();                              // red[0] reuse
@@ -1883,6 +1916,12 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   static int xpoll = -1;                        // A-B knob: GNX_XCHG_FLAGS=1 keeps the data-then-flag exchange of the roots
   if (xpoll < 0) { const char* e = getenv("GNX_XCHG_FLAGS"); xpoll = (e && atoi(e)) ? 0 : 1; }
   a.xpoll = xpoll;
+  // A-B knob: GNX_PCG_FLAG_BARRIER=1 replaces cooperative_groups' grid barrier in the multilevel PCG by epoch flags
+  // (sch_flag_barrier).  Measured on B200 (tools/time_two_level.py, honeycomb 200x200, 322 iterations): 4.73 ms
+  // against 4.61 ms with grid.sync() -- the barrier is not what an iteration waits for; off by default.
+  static int fast_bar = -1;
+  if (fast_bar < 0) { const char* e = getenv("GNX_PCG_FLAG_BARRIER"); fast_bar = (e && atoi(e)) ? 1 : 0; }
+  a.fast_bar = fast_bar;
   for (int k = 0; k < GNX_MAX_PEERS; ++k) a.xbuf[k] = nullptr;
   const bool subtree = ex && ex->mode == 1;
   GNX_CHECK_ARG(subtree == (plan->ncls != nullptr));
