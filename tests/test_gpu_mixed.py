@@ -327,3 +327,39 @@ def test_fused_rhs_elimination_and_overlapped_step(eng, name, n):
         assert np.array_equal(b.cpu().numpy().view(np.int64), b_ref.cpu().numpy().view(np.int64))
         assert np.array_equal(vals.cpu().numpy().view(np.int64), vals_ref.cpu().numpy().view(np.int64))
         assert np.array_equal(x.cpu().numpy().view(np.int64), x_ref.cpu().numpy().view(np.int64))
+
+
+@pytest.mark.parametrize("name,n", [("Y", 6), ("honeycomb_4_4", 5), ("arterial_tree_N7", 6), ("arterial_tree_N7", 9)])
+def test_edge_records_change_no_bit(eng, name, n):
+    """gnx_network_t.erec (one 16-byte record per edge instead of the chain edges -> bix -> ebif_prefix) and the
+    copy-engine staging of the cell lengths in the streaming assembly are a faster way to the SAME numbers: values, b
+    and x with and without the records are identical bit for bit (persistent kernel and kernel chain alike)"""
+    import torch
+    DeviceNetwork, MixedSystem = eng
+    pos, edges = graph(name)
+    rng = np.random.default_rng(11)
+    res = rng.uniform(0.5, 2.0, size=len(edges))
+    pbc_o, pbc_n = rng.normal(size=len(edges)), rng.normal(size=len(pos))
+    out = []
+    for with_records in (True, False):
+        dn = DeviceNetwork(pos, edges, n)
+        if not with_records:
+            dn.erec = None
+            dn._net = None
+            assert not dn.net.erec
+        else:
+            assert dn.net.erec
+        ms = MixedSystem(dn)
+        co = ms.coeffs(res)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        kw = dict(pbc_out=dev(pbc_o), pbc_node=dev(pbc_n))
+        vals_a = ms.assemble(co)
+        vals = torch.full((ms.nnz,), np.nan, dtype=torch.float64, device="cuda")
+        b = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+        x = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+        ms.assemble_rhs_solve(co, vals, b, x, kw)
+        torch.cuda.synchronize()
+        out.append([t.cpu().numpy().view(np.int64) for t in (vals_a, vals, b, x)])
+    for a, c in zip(*out):
+        assert np.array_equal(a, c)
+    assert np.array_equal(out[0][0], out[0][1])            # stand-alone assembly == the step's
