@@ -2768,6 +2768,8 @@ step_resident_kernel(const __grid_constant__ StepArgs s, const __grid_constant__
     if (tid == 0) s.sync[2] = rs_now();
     rs_prefetch_l2(a.plan.top_rec, (int64_t)a.plan.nt * 64, tid);
     rs_prefetch_l2(a.plan.ncls, (int64_t)a.plan.B * 4, tid);
+    // (the workers' second dependent trip: boundary data at the node an edge record names)
+    if (net.V <= (1 << 16)) rs_prefetch_l2(s.rhs.pbc_node, (int64_t)net.V * 8, tid);
     if (tid == 32) { const int32_t t = rs_touch_args(a); if (t == 0x5a5a5a5b) s.sync[31] = (unsigned long long)t; }
     auto wait_workers = [&]() {                    // all workers' edge scalars are in global memory
       if (tid == 0) {
@@ -2899,57 +2901,80 @@ static size_t rs_smem_bytes(int tiles_per_cta, int m) {
 // re-reading b (16 B/dof of traffic less than edge_backsub_tile_kernel), and f = g = 0 takes the fast path.
 // What a tile needs to know about its edges is gathered into shared memory by one thread per edge first.
 // ------------------------------------------------------------------------------------
-template <bool ZFG, bool BACKSUB>
-__global__ void __launch_bounds__(ET_T, (ZFG && !BACKSUB) ? 8 : 4)      // (a 32-register cap costs the back-substitution 8 %)
-edge_const_tile_kernel(const __grid_constant__ StepArgs s) {
-  __shared__ __align__(16) double sH[RS_HSLOT];
+// TPB tiles per block: the cell lengths and edge records of ALL of them are requested when the block starts, so only the
+// first tile waits for device memory -- the second one's data land while the first is swept, and its sweep overlaps
+// the first one's bulk stores.  (One tile per block spends more time waiting -- two dependent trips for the records
+// beside the bulk load -- than computing, and 6-8 resident blocks per SM do not cover that.)
+template <bool ZFG, bool BACKSUB, int TPB>
+__global__ void __launch_bounds__(ET_T, (ZFG && !BACKSUB) ? 6 : 4)
+edge_const_tile_kernel(const __grid_constant__ StepArgs s, int32_t nb_blocks) {
+  __shared__ __align__(16) double sH[TPB][RS_HSLOT];
   __shared__ __align__(16) double sFG[RS_FSLOT + RS_GSLOT];
   __shared__ double sh[3 * 32];
-  __shared__ RsEdge rec[RS_MAX_G];
+  __shared__ RsEdge rec[TPB][RS_MAX_G];
   __shared__ int32_t sloc[ZFG ? 4 : 1024 + 4];                        // (f = g = 0: loc[0] and loc[m] only)
-  __shared__ __align__(8) uint64_t hbar;
+  __shared__ __align__(8) uint64_t hbar[TPB];
   const gnx_network_t& net = s.net;
   const int tid = threadIdx.x;
   const int32_t m = s.d.m;
-  if (!BACKSUB && (int32_t)blockIdx.x >= s.nb_tiles) {              // blocks past the tiles zero the lambda rows of b
-    const int64_t r = s.d.lam_off + (int64_t)(blockIdx.x - s.nb_tiles) * ET_T + tid;
+  if (!BACKSUB && (int32_t)blockIdx.x >= nb_blocks) {               // blocks past the tiles zero the lambda rows of b
+    const int64_t r = s.d.lam_off + (int64_t)(blockIdx.x - nb_blocks) * ET_T + tid;
     if (r < s.d.N) s.rhs.b[r] = 0.0;
     return;
   }
   if (!BACKSUB) gnx_pdl_trigger();
   const int32_t G = RS_TILE >> net.n;
-  const int32_t e0 = blockIdx.x * G, nE = min(G, net.E - e0);
+  const int32_t t0 = blockIdx.x * TPB;
+  const int32_t nt = min(TPB, s.nb_tiles - t0);
   if (tid == 0) {                                                   // static data: in flight before the dependency wait
-    const int64_t hbase = (int64_t)e0 * m;
-    gnx_mbar_init(&hbar, 1);
-    gnx_mbar_expect_tx(&hbar, gnx_bulk_body_bytes(hbase, nE * m));
-    gnx_bulk_stream_in(sH, net.h, hbase, nE * m, &hbar);
+    for (int j = 0; j < nt; ++j) {
+      const int32_t e0 = (t0 + j) * G, nE = min(G, net.E - e0);
+      const int64_t hbase = (int64_t)e0 * m;
+      gnx_mbar_init(&hbar[j], 1);
+      gnx_mbar_expect_tx(&hbar[j], gnx_bulk_body_bytes(hbase, nE * m));
+      gnx_bulk_stream_in(sH[j], net.h, hbase, nE * m, &hbar[j]);
+    }
   }
   if (ZFG) { if (tid < 2) sloc[tid] = net.loc[tid ? m : 0]; }
   else for (int32_t i = tid; i <= m; i += ET_T) sloc[i] = net.loc[i];
   if (BACKSUB) gnx_pdl_wait();                                      // P and the edge scalars come from the kernels before
-  if (tid < nE) {
-    const int32_t e = e0 + tid;
-    RsEdge r;
-    const int32_t u = rs_edge_static(net, e, r);
-    r.flags |= ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
-    r.a = s.a_edge[e];
-    r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
-    r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
-    r.q0 = 0.0; r.Pu = 0.0;
-    if (BACKSUB) {
-      const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
-      const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
-      r.Pu = Pu;
-      r.q0 = __dmul_rn(s.cond[e], __dadd_rn(__dsub_rn(Pu, Pv), s.rsrc[e]));
+  for (int32_t idx = tid; idx < nt * G; idx += ET_T) {
+    const int32_t j = idx / G, le = idx - j * G;
+    const int32_t e = (t0 + j) * G + le;
+    if (e < net.E) {
+      RsEdge r;
+      const int32_t u = rs_edge_static(net, e, r);
+      r.flags |= ((r.bu < 0 && s.rhs.pbc_node) ? 2 : 0) | ((r.bv < 0 && s.rhs.pbc_out) ? 4 : 0);
+      r.a = s.a_edge[e];
+      r.pin = (r.flags & 2) ? s.rhs.pbc_node[u] : 0.0;
+      r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
+      r.q0 = 0.0; r.Pu = 0.0;
+      if (BACKSUB) {
+        const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
+        const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
+        r.Pu = Pu;
+        r.q0 = __dmul_rn(s.cond[e], __dadd_rn(__dsub_rn(Pu, Pv), s.rsrc[e]));
+      }
+      rec[j][le] = r;
     }
-    rec[tid] = r;
   }
   __syncthreads();
-  gnx_mbar_wait(&hbar, 0);
-  if (BACKSUB) rs_backsub_tile<ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
-  else rs_eliminate_tile<ZFG, 3, ZFG>(s, blockIdx.x, tid, 0, sH, sFG, sFG + RS_FSLOT, sh, rec, sloc);
+  for (int j = 0; j < nt; ++j) {
+    if (j > 0) {                                                    // the staging area still feeds the previous tile's stores
+      if (tid == 0) gnx_bulk_wait_read();
+      __syncthreads();
+    }
+    gnx_mbar_wait(&hbar[j], 0);
+    if (BACKSUB) rs_backsub_tile<ZFG>(s, t0 + j, tid, 0, sH[j], sFG, sFG + RS_FSLOT, sh, rec[j], sloc);
+    else rs_eliminate_tile<ZFG, 3, ZFG>(s, t0 + j, tid, 0, sH[j], sFG, sFG + RS_FSLOT, sh, rec[j], sloc);
+  }
   if (tid == 0) gnx_bulk_wait_read();
+}
+
+static int const_tpb() {              // tuning knob: tiles per block of the streaming Constant-data kernels (1 or 2)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GNX_CONST_TPB"); v = e ? atoi(e) : 2; if (v != 1) v = 2; }
+  return v;
 }
 
 static bool const_tiles_apply(const gnx_network_t* net, const void* b_or_x) {
@@ -2975,8 +3000,12 @@ static int launch_eliminate_const(const gnx_network_t* net, const gnx_mixed_coef
   s.out = out;
   const int nb_lam = net->B > 0 ? gnx_blocks(net->B, ET_T) : 0;
   const bool zfg = rhs.fc == 0.0 && rhs.gc == 0.0 && !co->k_edge;
-  if (zfg) edge_const_tile_kernel<true, false><<<s.nb_tiles + nb_lam, ET_T, 0, st>>>(s);
-  else edge_const_tile_kernel<false, false><<<s.nb_tiles + nb_lam, ET_T, 0, st>>>(s);
+  const int tpb = const_tpb();
+  const int nbk = gnx_blocks(s.nb_tiles, tpb);
+#define GNX_ELIM_LAUNCH(Z, T) edge_const_tile_kernel<Z, false, T><<<nbk + nb_lam, ET_T, 0, st>>>(s, nbk)
+  if (zfg) { if (tpb == 1) GNX_ELIM_LAUNCH(true, 1); else GNX_ELIM_LAUNCH(true, 2); }
+  else { if (tpb == 1) GNX_ELIM_LAUNCH(false, 1); else GNX_ELIM_LAUNCH(false, 2); }
+#undef GNX_ELIM_LAUNCH
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
@@ -2999,8 +3028,12 @@ extern "C" int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_
   s.cond = cond; s.rsrc = rsrc; s.P = P; s.x = x;
   const bool zfg = f_const == 0.0 && g_const == 0.0 && !co->k_edge;
   cudaStream_t st = (cudaStream_t)stream;
-  if (zfg) GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<true, true>, dim3(s.nb_tiles), dim3(ET_T), 0, st, s));
-  else GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<false, true>, dim3(s.nb_tiles), dim3(ET_T), 0, st, s));
+  const int tpb = const_tpb();
+  const int32_t nbk = gnx_blocks(s.nb_tiles, tpb);
+#define GNX_BS_LAUNCH(Z, T) GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<Z, true, T>, dim3(nbk), dim3(ET_T), 0, st, s, nbk))
+  if (zfg) { if (tpb == 1) GNX_BS_LAUNCH(true, 1); else GNX_BS_LAUNCH(true, 2); }
+  else { if (tpb == 1) GNX_BS_LAUNCH(false, 1); else GNX_BS_LAUNCH(false, 2); }
+#undef GNX_BS_LAUNCH
   GNX_LAUNCH_CHECK();
   return GNX_OK;
 }
