@@ -621,7 +621,7 @@ struct SchurArgs {
   int64_t xd_off, xr_off;
   int32_t phase;                              // 0: whole solve, flags in the kernel; 1: up to the exchange; 2: after it
   int32_t xpoll;                              // 1: exported roots validate themselves (GNX_XSENT); 0: flag after the data
-  int32_t fast_bar;                           // 1: epoch-flag barriers in the multilevel PCG; 0: grid.sync()
+  int32_t pcg_grid_sync;                      // multilevel PCG: 0 tagged all-reduce (tl_allreduce), 1 grid.sync() + partials
   __device__ __forceinline__ int64_t eidx(int32_t e) const {
     if (chunk == 2147483647) return e;          // (uniform: everything but the gathered layout -- no integer division)
     const int32_t r = e / chunk;
@@ -668,28 +668,6 @@ __device__ __forceinline__ void sch_sync() {
   if (MODE == SCH_SINGLE) __syncthreads();
   else if (MODE == SCH_CLUSTER) cg::this_cluster().sync();
   else cg::this_grid().sync();                  // SCH_GRID, SCH_GRID_TL
-}
-
-// Barrier of a co-resident grid by epoch flags: CTA b releases flags[b] = seq (cumulative over its __syncthreads: all
-// the CTA wrote before is visible to whoever acquires the flag), the first nblk threads of every CTA wait until every
-// flag has reached seq.  The flags only grow (no reset, reusable across launches: a CTA reads its own flag to learn
-// the last epoch).  An experiment (GNX_PCG_FLAG_BARRIER=1): no faster than cooperative_groups' grid.sync() on 128 CTAs.
-__device__ __forceinline__ void sch_flag_barrier(long long* flags, int nblk, long long seq) {
-  // (a flag per 128-byte line: 128 CTAs polling 128 words packed into eight lines serialise on a few L2 slices --
-  //  measured 1.5x SLOWER than grid.sync())
-  __syncthreads();
-  if (threadIdx.x == 0)
-    asm volatile("st.release.gpu.global.s64 [%0], %1;" :: "l"(flags + 16 * blockIdx.x), "l"(seq) : "memory");
-  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
-    long long v;
-    unsigned spins = 0;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(flags + 16 * i) : "memory");
-      if (v >= seq) break;
-      if (++spins > (1u << 28)) __trap();       // a CTA is missing: fail instead of hanging the GPU
-    }
-  }
-  __syncthreads();
 }
 
 // partials of every block are re-reduced by every block in the same order -> identical bits
@@ -1344,7 +1322,59 @@ __device__ __forceinline__ void core_pcg_cluster(const SchurArgs& a, double* sm,
 // Shared memory: E^-1 [na][na+1] | s2 | y2 | pivot row | pivot column | 8 x na partials | y1 | 1/dE.
 // ------------------------------------------------------------------------------------
 constexpr int AGG_LD = GNX_AGG_MAX + 1;          // odd leading dimension: column walks are conflict-free
-constexpr size_t TL_SMEM = ((size_t)GNX_AGG_MAX * AGG_LD + 12 * GNX_AGG_MAX + 2 * GNX_SUB_MAX) * sizeof(double);
+constexpr int TL_RSH = 2048;                     // rows of an aggregate whose residual is also kept in shared memory
+constexpr size_t TL_SMEM = ((size_t)GNX_AGG_MAX * AGG_LD + 12 * GNX_AGG_MAX + 2 * GNX_SUB_MAX + TL_RSH) * sizeof(double);
+
+// All-reduce over the co-resident CTAs of the multilevel PCG WITHOUT a grid barrier: every CTA publishes its K partials
+// in its own 128-byte line and reads everybody's; a word says by itself whether it is the one a reader is waiting
+// for -- the two low mantissa bits of partial 0 carry a tag (call / 2 mod 3; 3 = never published) -- so there is no
+// flag, no counter and no reset, and the data arrive with the synchronisation instead of one L2 round trip after it
+// (grid.sync() + reading the partials: 2.8 us of a 13 us iteration at CTA 0).  Two sets of lines alternate:
+// to publish call c + 2 a CTA must have finished call c + 1, which needs everyone's c + 1 partial, published after
+// its owner finished reading call c.  The tag perturbs a dot product by <= 3 ulp, the same in every CTA (all read the
+// same words: control flow stays grid-uniform).  RELEASE: everything the CTA wrote before (vectors its neighbours read
+// next, partials 1..K-1, aggregate sums) is visible to whoever sees partial 0 -- the barrier semantics the second
+// reduction point of an iteration needs; the first one publishes nothing but its number.  Measured gain: 2 % (honeycomb
+// 200x200: 4.65 against 4.74 ms) -- most of the "barrier time" is waiting for the slowest CTA.  (An epoch-flag barrier in
+// place of grid.sync(), partials read afterwards, was tried first: no gain -- and 1.5x SLOWER with the 128 flags packed
+// into eight cache lines, the polls serialise on a few L2 slices; hence one line per CTA here.)
+template <int K, bool RELEASE>
+__device__ __forceinline__ void tl_allreduce(double (&v)[K], double* arena, int nblk, unsigned& call, double* sh) {
+  static_assert(RELEASE || K == 1, "without release semantics only the tagged word itself is ordered");
+  block_allreduce<K>(v, sh);
+  const unsigned set = call & 1u;
+  const unsigned long long tag = (call >> 1) % 3u;
+  if (threadIdx.x == 0) {
+    double* const p = arena + ((size_t)set * GNX_AGG_MAX + blockIdx.x) * 16;
+#pragma unroll
+    for (int k = 1; k < K; ++k) p[k] = v[k];
+    const unsigned long long w = ((unsigned long long)__double_as_longlong(v[0]) & ~3ull) | tag;
+    if (RELEASE) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory");
+    else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory");
+  }
+  double t[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    double* const p = arena + ((size_t)set * GNX_AGG_MAX + i) * 16;
+    unsigned long long w;
+    unsigned spins = 0;
+    for (;;) {
+      if (RELEASE) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      if ((w & 3ull) == tag) break;
+      if (++spins > (1u << 28)) __trap();       // a CTA is missing: fail instead of hanging the GPU
+    }
+    t[0] += __longlong_as_double((long long)(w & ~3ull));
+#pragma unroll
+    for (int k = 1; k < K; ++k) t[k] += __ldcg(p + k);
+  }
+  __syncthreads();                              // sh reuse; and: the whole CTA is behind thread i's acquire
+  block_allreduce<K>(t, sh);
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = t[k];
+  ++call;
+}
 
 template <class Gather>
 __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm, double (*red)[3 * 32], Gather gather,
@@ -1359,7 +1389,18 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   double* const part8 = ck + GNX_AGG_MAX;
   double* const y1_sh = part8 + 8 * GNX_AGG_MAX;
   double* const dEi_sh = y1_sh + GNX_SUB_MAX;
+  double* const rsh = dEi_sh + GNX_SUB_MAX;       // [TL_RSH] my rows' residual (when they fit: no re-read from L2)
   const int32_t r0 = pl.agg_ptr[J], r1 = pl.agg_ptr[J + 1];
+  const bool r_in_smem = r1 - r0 <= TL_RSH;
+  // tagged all-reduce (tl_allreduce): my two lines start as "never published"; the grid barrier of the first
+  // (cooperative-groups) all-reduce below orders this before anybody's first poll
+  double* const arena = a.part[3];                // part[3], part[4]: 2 sets x GNX_AGG_MAX lines of 16 doubles
+  const bool tagged = a.pcg_grid_sync == 0 && na <= GNX_AGG_MAX;
+  if (tagged && tid < 2) {
+    const unsigned long long never = 3ull;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(arena + ((size_t)tid * GNX_AGG_MAX + J) * 16), "l"(never) : "memory");
+  }
+  unsigned arc = 0;
   const int ns = pl.ns > 1 ? pl.ns : 1, nf = na * ns, lg = __ffs(ns) - 1;       // fine aggregates per coarse one
   cg::grid_group grid = cg::this_grid();
   // sums of r over my fine aggregates and their total -> a.s1, a.sE; with_dE: also the fine diagonal of
@@ -1374,7 +1415,7 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
       const int32_t i0 = ns > 1 ? pl.sub_ptr[f] : r0, i1 = ns > 1 ? pl.sub_ptr[f + 1] : r1;
       double sr = 0.0, sd = 0.0;
       for (int32_t i = i0 + (w % wps) * 32 + lane; i < i1; i += 32 * wps) {
-        sr += __ldcg(a.rc + i);
+        sr += (r_in_smem && !with_dE) ? rsh[i - r0] : __ldcg(a.rc + i);
         if (with_dE) {
           double t = __ldcg(a.dg + i);
           for (int32_t k = pl.crp[i]; k < pl.crp[i + 1]; ++k)
@@ -1508,10 +1549,6 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
   const double bb = acc[2];
   PcgStop stop(a.rtol, bb, rr);
   double rzc = acc[0] + coarse(), rzp = rzc;
-  // the two barriers of an iteration: epoch flags (part[4], zero when the work buffer was created)
-  long long* const bar_flags = reinterpret_cast<long long*>(a.part[4]);
-  long long bar_seq = bar_flags[16 * J];          // (my own last epoch; equal in every CTA)
-  const bool fast_bar = a.fast_bar != 0;
   for (; it < a.max_iter; ++it) {
     if (stop.done(rr, it)) break;
     const double beta = (it == 0 || rzp == 0.0) ? 0.0 : rzc / rzp;
@@ -1533,15 +1570,10 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
       a.wc[i] = wi;
       pw[0] += pi * wi;
     }
-    block_allreduce<1>(pw, red[1]);
-    if (tid == 0) a.part[3][J] = pw[0];
-    if (fast_bar) sch_flag_barrier(bar_flags, na, ++bar_seq); else grid.sync();
-    {
-      double t = 0.0;
-      for (int i = tid; i < na; i += T) t += __ldcg(a.part[3] + i);
-      pw[0] = t;
-      __syncthreads();                            // red[1] reuse
-      block_allreduce<1>(pw, red[1]);
+    if (tagged) tl_allreduce<1, false>(pw, arena, na, arc, red[1]);
+    else {
+      double* const part[1] = {a.part[3]};      // (the arena of the tagged path: unused in this mode)
+      grid_allreduce<SCH_GRID, 1>(pw, part, na, red[1]);
     }
     const double alpha = (pw[0] != 0.0) ? rzc / pw[0] : 0.0;
     double v3[2] = {0.0, 0.0};                    // r.D^-1 r, r.r
@@ -1550,16 +1582,23 @@ __device__ __forceinline__ void core_pcg_twolevel(const SchurArgs& a, double* sm
       const double ri = a.rc[i] - alpha * a.wc[i];
       const double zi = ri / a.dg[i];
       a.rc[i] = ri; a.zc[i] = zi;
+      if (r_in_smem) rsh[i - r0] = ri;
       v3[0] += ri * zi; v3[1] += ri * ri;
     }
-    block_allreduce<2>(v3, red[0]);
-    if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; }
-    sub_sums(false);
-    if (fast_bar) sch_flag_barrier(bar_flags, na, ++bar_seq); else grid.sync();
-    double t2[2] = {0.0, 0.0};
-    for (int i = tid; i < na; i += T) { t2[0] += __ldcg(a.part[0] + i); t2[1] += __ldcg(a.part[1] + i); }
-    __syncthreads();                              // red[0] reuse
-    block_allreduce<2>(t2, red[0]);
+    double t2[2] = {v3[0], v3[1]};
+    if (tagged) {
+      sub_sums(false);                            // (a.s1, a.sE: published by the release of the all-reduce below)
+      tl_allreduce<2, true>(t2, arena, na, arc, red[0]);
+    } else {
+      block_allreduce<2>(v3, red[0]);
+      if (tid == 0) { a.part[0][J] = v3[0]; a.part[1][J] = v3[1]; }
+      sub_sums(false);
+      grid.sync();
+      t2[0] = t2[1] = 0.0;
+      for (int i = tid; i < na; i += T) { t2[0] += __ldcg(a.part[0] + i); t2[1] += __ldcg(a.part[1] + i); }
+      __syncthreads();                            // red[0] reuse
+      block_allreduce<2>(t2, red[0]);
+    }
     rzp = rzc; rzc = t2[0] + coarse(); rr = t2[1];
   }
   rr_final = rr; bb_final = bb;
@@ -1916,12 +1955,9 @@ static int schur_args_fill(SchurArgs& a, const gnx_network_t* net, const gnx_sch
   static int xpoll = -1;                        // A-B knob: GNX_XCHG_FLAGS=1 keeps the data-then-flag exchange of the roots
   if (xpoll < 0) { const char* e = getenv("GNX_XCHG_FLAGS"); xpoll = (e && atoi(e)) ? 0 : 1; }
   a.xpoll = xpoll;
-  // A-B knob: GNX_PCG_FLAG_BARRIER=1 replaces cooperative_groups' grid barrier in the multilevel PCG by epoch flags
-  // (sch_flag_barrier).  Measured on B200 (tools/time_two_level.py, honeycomb 200x200, 322 iterations): 4.73 ms
-  // against 4.61 ms with grid.sync() -- the barrier is not what an iteration waits for; off by default.
-  static int fast_bar = -1;
-  if (fast_bar < 0) { const char* e = getenv("GNX_PCG_FLAG_BARRIER"); fast_bar = (e && atoi(e)) ? 1 : 0; }
-  a.fast_bar = fast_bar;
+  static int pcg_gs = -1;                       // A-B knob: GNX_PCG_GRID_SYNC=1 keeps cooperative_groups' grid barrier
+  if (pcg_gs < 0) { const char* e = getenv("GNX_PCG_GRID_SYNC"); pcg_gs = (e && atoi(e)) ? 1 : 0; }
+  a.pcg_grid_sync = pcg_gs;
   for (int k = 0; k < GNX_MAX_PEERS; ++k) a.xbuf[k] = nullptr;
   const bool subtree = ex && ex->mode == 1;
   GNX_CHECK_ARG(subtree == (plan->ncls != nullptr));
