@@ -6,6 +6,7 @@ Same attributes after `make_mesh(n)`: geom_dim, num_edges, mesh, mf, bifurcation
 num_bifurcations, boundary_ixs, tangents, tangent, edges[e]['tangent']; after
 `make_submeshes()`: edges[e]['submesh'], edges[e]['vf'].
 """
+from functools import partial
 from operator import itemgetter
 
 import networkx as nx
@@ -59,43 +60,52 @@ class _TangentField:
 
 
 class _StampedAttrs(dict):
-    """Edge attribute dictionary that counts its mutations in a stamp shared by all edges of one graph
-    (`_stamp`, set on the per-graph subclass made in FenicsGraph.__init__): edge_attribute_array() walks the E
-    dictionaries again only when some attribute was written since its last walk."""
-    __slots__ = ()
-    _stamp = None
+    """Edge attribute dictionary that counts its mutations in a stamp shared by all edges of one graph (`_stamp`: the
+    graph's one-element list, handed over by the factory FenicsGraph.__init__ installs): edge_attribute_array() walks
+    the E dictionaries again only when some attribute was written since its last walk.  The stamp is held per instance
+    (not per class), so copy.deepcopy / pickle of a graph give the copy its own stamp, shared by its own dictionaries."""
+    __slots__ = ("_stamp",)
+
+    def __init__(self, stamp=None):
+        dict.__init__(self)
+        self._stamp = stamp
+
+    def _bump(self):
+        st = getattr(self, "_stamp", None)
+        if st is not None:
+            st[0] += 1
 
     def __setitem__(self, k, v):
-        self._stamp[0] += 1
+        self._bump()
         dict.__setitem__(self, k, v)
 
     def __delitem__(self, k):
-        self._stamp[0] += 1
+        self._bump()
         dict.__delitem__(self, k)
 
     def __ior__(self, other):
-        self._stamp[0] += 1
+        self._bump()
         dict.update(self, other)
         return self
 
     def update(self, *a, **kw):
-        self._stamp[0] += 1
+        self._bump()
         dict.update(self, *a, **kw)
 
     def setdefault(self, k, default=None):
-        self._stamp[0] += 1
+        self._bump()
         return dict.setdefault(self, k, default)
 
     def pop(self, *a):
-        self._stamp[0] += 1
+        self._bump()
         return dict.pop(self, *a)
 
     def popitem(self):
-        self._stamp[0] += 1
+        self._bump()
         return dict.popitem(self)
 
     def clear(self):
-        self._stamp[0] += 1
+        self._bump()
         dict.clear(self)
 
 
@@ -108,7 +118,7 @@ class FenicsGraph(nx.DiGraph):
     def __init__(self):
         stamp = [0]
         # (networkx calls self.edge_attr_dict_factory() for every new edge: an instance attribute overrides the class's)
-        self.edge_attr_dict_factory = type("_EdgeAttrs", (_StampedAttrs,), {"__slots__": (), "_stamp": stamp})
+        self.edge_attr_dict_factory = partial(_StampedAttrs, stamp)
         nx.DiGraph.__init__(self)
         self._attr_stamp = stamp
         self._dn = None

@@ -127,3 +127,24 @@ def test_edge_attribute_cache_follows_every_way_of_writing_an_attribute():
     assert set(G.edge_attribute_array("Ainv", 1.0).tolist()) == {2.0}
     x.assign(4.0)
     assert set(G.edge_attribute_array("Ainv", 1.0).tolist()) == {8.0}
+
+
+def test_edge_attribute_cache_survives_deepcopy_and_pickle():
+    """a copied graph (copy.deepcopy, pickle, G.copy()) has its OWN mutation stamp, shared by its own attribute
+    dictionaries: writing to the copy invalidates the copy's cache and only the copy's"""
+    import copy
+    import pickle
+    import graphnics_b200 as gn
+    G = gn.FenicsGraph()
+    G.add_nodes_from((i, {"pos": [float(i), 0.0]}) for i in range(3))
+    G.add_edges_from([(0, 1), (1, 2)])
+    G.edges[0, 1]["Res"] = 2.0
+    assert G.edge_attribute_array("Res").tolist() == [2.0, 1.0]
+    for H in (copy.deepcopy(G), pickle.loads(pickle.dumps(G)), G.copy()):
+        assert isinstance(H, gn.FenicsGraph) and H._attr_stamp is not G._attr_stamp
+        assert H.edges[0, 1]._stamp is H._attr_stamp
+        assert H.edge_attribute_array("Res").tolist() == [2.0, 1.0]
+        H.edges[0, 1]["Res"] = 5.0
+        H.add_edge(2, 0, Res=7.0)
+        assert H.edge_attribute_array("Res").tolist() == [5.0, 1.0, 7.0]
+        assert G.edge_attribute_array("Res").tolist() == [2.0, 1.0]
