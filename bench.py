@@ -437,8 +437,8 @@ def run_gpu(args):
            "gpu_launches_how": "CUPTI (torch.profiler) kernel records of a replay of the same K steps after the timed region",
            "host_enqueue_us_per_step": float(np.median(host_us)),
            "schur": {"rake_levels": len(hp.levels), "core": hp.nc},
-           "step_path": ("ONE persistent cooperative kernel (cell lengths resident in shared memory; CSR assembly on the SMs "
-                         "that wait for the one-CTA Schur phase)" if resident else
+           "step_path": ("ONE persistent cooperative kernel (cell lengths resident in shared memory; CTA 0 runs the graph-level "
+                         "solve while the other SMs assemble the CSR values of their own edges)" if resident else
                          ("kernel chain on one stream" if args.no_overlap else
                           "kernel chain: CSR assembly on the caller's stream overlaps rhs -> eliminate -> Schur -> back-substitute "
                           "on a high-priority stream")),
