@@ -554,6 +554,15 @@ def kernels_at_scale(hbm, timed, levels=17, n=7):
     k("edge_const_tile_kernel<backsub> (Constant data: b recomputed, not read)", lambda: ms.lib.gnx_edge_backsub_mixed_const(
         dn.net_ref(), co.ref(), 0.0, 0.0, pbc_out.data_ptr(), pbc_node.data_ptr(), b.data_ptr(), bufs["cond"].data_ptr(),
         bufs["rsrc"].data_ptr(), bufs["P"].data_ptr(), x.data_ptr(), st()), 8 * N + 8 * NC)
+    # ... and what the one-call step runs on a network this large: the edges' end flux / pressure gathered once
+    q0e = torch.empty(dn.E, dtype=torch.float64, device=dn.device)
+    pue = torch.empty(dn.E, dtype=torch.float64, device=dn.device)
+    k("edge_flux_kernel (end flux and pressure of every edge, once per solve)", lambda: ms.lib.gnx_edge_flux_mixed(
+        dn.net_ref(), bufs["cond"].data_ptr(), bufs["rsrc"].data_ptr(), bufs["P"].data_ptr(), q0e.data_ptr(), pue.data_ptr(), st()),
+      8 * 5 * dn.E + 16 * dn.E)
+    k("edge_const_tile_kernel<backsub> given the end fluxes (as in the one-call step)", lambda: ms.lib.gnx_edge_backsub_mixed_flux(
+        dn.net_ref(), co.ref(), 0.0, 0.0, pbc_out.data_ptr(), pbc_node.data_ptr(), q0e.data_ptr(), pue.data_ptr(),
+        x.data_ptr(), st()), 8 * N + 8 * NC)
     k("spmv_kernel (CSR, fp64 values, int32 indices)", lambda: ms.spmv(vals, x, y), 12 * nnz + 4 * (N + 1) + 16 * N)
     # what plain library kernels reach on the same buffers: a pure write stream is bounded well below the
     # copy figure MEASURED_PEAKS.json quotes, which is the ceiling for the write-dominated assembly / rhs kernels

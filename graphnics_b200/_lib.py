@@ -127,6 +127,8 @@ PROTOTYPES = {
     "gnx_edge_backsub_primal": (_I, [_NET, _PCO, _P, _P, _P, _P, _P, _P]),
     "gnx_edge_backsub_mixed": (_I, [_NET, _CO, _P, _P, _P, _P, _P, _P]),
     "gnx_edge_backsub_mixed_const": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnx_edge_flux_mixed": (_I, [_NET, _P, _P, _P, _P, _P, _P]),
+    "gnx_edge_backsub_mixed_flux": (_I, [_NET, _CO, _D, _D, _P, _P, _P, _P, _P, _P]),
     "gnx_spmv_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "gnx_reduce_work_doubles": (_L, [_L]),
     "gnx_residual_csr_f64": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -2351,6 +2351,8 @@ struct StepArgs {
   ConstRhs rhs;
   EdgeOut out;
   const double *cond, *rsrc;                     // this rank's edge scalars where the back-substitution finds them
+  const double *q0_in, *Pu_in;                   // or, streaming back-substitution: the edges' end flux and pressure ready
+                                                 // made (gnx_edge_flux_mixed); NULL: gathered from P by every block
   const double* P;
   double* x;
   double* vals;                                  // CSR values (NULL: no assembly)
@@ -2986,10 +2988,15 @@ edge_const_tile_kernel(const __grid_constant__ StepArgs s, int32_t nb_blocks) {
       r.pout = (r.flags & 4) ? s.rhs.pbc_out[e] : 0.0;
       r.q0 = 0.0; r.Pu = 0.0;
       if (BACKSUB) {
-        const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
-        const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
-        r.Pu = Pu;
-        r.q0 = __dmul_rn(s.cond[e], __dadd_rn(__dsub_rn(Pu, Pv), s.rsrc[e]));
+        if (s.q0_in) {                                              // (no second dependent trip: P gathered once, per edge)
+          r.Pu = s.Pu_in[e];
+          r.q0 = s.q0_in[e];
+        } else {
+          const double Pu = r.bu >= 0 ? s.P[r.bu] : 0.0;
+          const double Pv = r.bv >= 0 ? s.P[r.bv] : 0.0;
+          r.Pu = Pu;
+          r.q0 = __dmul_rn(s.cond[e], __dadd_rn(__dsub_rn(Pu, Pv), s.rsrc[e]));
+        }
       }
       rec[j][le] = r;
     }
@@ -3023,7 +3030,7 @@ static void const_tiles_args(StepArgs& s, const gnx_network_t* net, const gnx_mi
   s.net = *net; s.d = gnx_mixed_dims(*net);
   s.a_edge = co->a_edge; s.k_edge = co->k_edge; s.inv_sigma = 1.0 / co->sigma; s.sigma = co->sigma;
   s.rhs = rhs;
-  s.cond = s.rsrc = nullptr; s.P = nullptr; s.x = nullptr; s.vals = nullptr;
+  s.cond = s.rsrc = nullptr; s.q0_in = s.Pu_in = nullptr; s.P = nullptr; s.x = nullptr; s.vals = nullptr;
   s.nb_tiles = gnx_blocks(net->E, RS_TILE >> net->n);
   s.tiles_per_cta = 1; s.sync = nullptr; s.epoch = 0;
 }
@@ -3062,6 +3069,67 @@ extern "C" int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_
   const_tiles_args(s, net, co, ConstRhs{f_const, g_const, pbc_out, pbc_node, nullptr});
   edge_out_local(s.out, nullptr, nullptr, nullptr);
   s.cond = cond; s.rsrc = rsrc; s.P = P; s.x = x;
+  const bool zfg = f_const == 0.0 && g_const == 0.0 && !co->k_edge;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tpb = const_tpb();
+  const int32_t nbk = gnx_blocks(s.nb_tiles, tpb);
+#define GNX_BS_LAUNCH(Z, T) GNX_CUDA(gnx_launch_dependent(edge_const_tile_kernel<Z, true, T>, dim3(nbk), dim3(ET_T), 0, st, s, nbk))
+  if (zfg) { if (tpb == 1) GNX_BS_LAUNCH(true, 1); else GNX_BS_LAUNCH(true, 2); }
+  else { if (tpb == 1) GNX_BS_LAUNCH(false, 1); else GNX_BS_LAUNCH(false, 2); }
+#undef GNX_BS_LAUNCH
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// End flux and end pressure of every edge from the multipliers, ONCE per solve (one thread per edge):
+//   Pu[e] = P at the tail node (0 at a boundary node),  q0[e] = cond[e] (P_u - P_v + rsrc[e])
+// -- what every block of the streaming back-substitution otherwise gathers for its own edges through a second dependent
+// trip to device memory (edge record -> P), behind which its eight warps wait at a barrier (ncu: 10 warps stalled per
+// issue).  q0 may alias ftot and Pu may alias rsrc (a thread reads its edge's entries before it writes them).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+edge_flux_kernel(gnx_network_t net, const double* __restrict__ cond, const double* rsrc, const double* __restrict__ P,
+                 double* q0, double* Pu_out) {
+  gnx_pdl_trigger();
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t bu = -1, bv = -1;
+  if (e < net.E) {                                  // static data before the dependency wait
+    if (net.erec) { const int4 q = __ldg(reinterpret_cast<const int4*>(net.erec) + e); bu = q.x; bv = q.y; }
+    else { bu = net.bix[net.edges[2 * e]]; bv = net.bix[net.edges[2 * e + 1]]; }
+  }
+  gnx_pdl_wait();                                   // P comes from the Schur kernel
+  if (e >= net.E) return;
+  const double Pu = bu >= 0 ? P[bu] : 0.0;
+  const double Pv = bv >= 0 ? P[bv] : 0.0;
+  const double q = __dmul_rn(cond[e], __dadd_rn(__dsub_rn(Pu, Pv), rsrc[e]));
+  q0[e] = q;
+  Pu_out[e] = Pu;
+}
+
+extern "C" int gnx_edge_flux_mixed(const gnx_network_t* net, const double* cond, const double* rsrc, const double* P,
+                                   double* q0, double* Pu, void* stream) {
+  GNX_CHECK_ARG(net && cond && rsrc && q0 && Pu && (net->B == 0 || P) && net->edges && net->bix);
+  GNX_CUDA(gnx_launch_dependent(edge_flux_kernel, dim3(gnx_blocks(net->E, 256)), dim3(256), 0, (cudaStream_t)stream, *net, cond,
+                                rsrc, P, q0, Pu));
+  GNX_LAUNCH_CHECK();
+  return GNX_OK;
+}
+
+// gnx_edge_backsub_mixed_const with the edges' end flux q0 [E] and end pressure Pu [E] given (gnx_edge_flux_mixed)
+// instead of cond / rsrc / P: x bit-identical.  Needs the tile path (2^6 .. 2^10 cells per edge, per-edge coefficients).
+extern "C" int gnx_edge_backsub_mixed_flux(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const,
+                                           double g_const, const double* pbc_out, const double* pbc_node, const double* q0,
+                                           const double* Pu, double* x, void* stream) {
+  GNX_CHECK_ARG(net && co && co->a_edge && q0 && Pu && x && net->h && co->sigma != 0.0);
+  if (co->a_cell || !const_tiles_apply(net, x)) {
+    gnx_set_error("gnx_edge_backsub_mixed_flux needs the edge-tile path (2^6..2^10 cells per edge, per-edge coefficients)");
+    return GNX_ERR_ARG;
+  }
+  StepArgs s;
+  const_tiles_args(s, net, co, ConstRhs{f_const, g_const, pbc_out, pbc_node, nullptr});
+  edge_out_local(s.out, nullptr, nullptr, nullptr);
+  s.q0_in = q0; s.Pu_in = Pu; s.x = x;
   const bool zfg = f_const == 0.0 && g_const == 0.0 && !co->k_edge;
   cudaStream_t st = (cudaStream_t)stream;
   const int tpb = const_tpb();
@@ -3126,6 +3194,7 @@ int gnx_step_resident_launch(const gnx_network_t* net, const gnx_mixed_coeffs_t*
     s.cond = cond; s.rsrc = rsrc;
   }
   s.P = P; s.x = x; s.vals = vals; s.sigma = co->sigma;
+  s.q0_in = s.Pu_in = nullptr;
   const int G = RS_TILE >> net->n;
   s.nb_tiles = gnx_blocks(net->E, G);
   const int grid = s.nb_tiles + 1 < g_sch_sms ? s.nb_tiles + 1 : g_sch_sms;

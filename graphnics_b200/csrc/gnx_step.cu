@@ -78,8 +78,18 @@ extern "C" int gnx_step_mixed(const gnx_network_t* net, const gnx_mixed_coeffs_t
     if (int rc = gnx_schur_solve(schur_net, plan, co->sigma, cond, rsrc, ftot, b + gnx_mixed_dims(*net).lam_off, nullptr,
                                  P, lam, work, rtol, max_iter, warm, 0, 0, nullptr, resid_host, info_host, solve_st)) return rc;
   }
-  if (int rc = gnx_edge_backsub_mixed_const(net, co, f_const, g_const, pbc_out, pbc_node, b, cond, rsrc,
-                                            net->B > 0 ? P : nullptr, x, solve_st)) return rc;
+  // Large networks: the edges' end flux and end pressure are gathered from the multipliers ONCE (one thread per edge,
+  // written over the scratch arrays ftot / rsrc, dead by now) instead of by every back-substitution block for itself.
+  static int flux_on = -1;
+  if (flux_on < 0) { const char* e = getenv("GNX_EDGE_FLUX"); flux_on = e ? atoi(e) : 1; }              // A-B knob
+  if (flux_on && net->B > 0 && ftot && (!ex || ex->mode == 1) && !co->a_cell && net->n >= 6 && net->n <= 10 &&
+      net->E >= 4096 && ((uintptr_t)net->h & 15) == 0 && ((uintptr_t)x & 15) == 0) {
+    double* q0 = ftot;
+    double* Pu = const_cast<double*>(rsrc);
+    if (int rc = gnx_edge_flux_mixed(net, cond, rsrc, P, q0, Pu, solve_st)) return rc;
+    if (int rc = gnx_edge_backsub_mixed_flux(net, co, f_const, g_const, pbc_out, pbc_node, q0, Pu, x, solve_st)) return rc;
+  } else if (int rc = gnx_edge_backsub_mixed_const(net, co, f_const, g_const, pbc_out, pbc_node, b, cond, rsrc,
+                                                   net->B > 0 ? P : nullptr, x, solve_st)) return rc;
   if (fork) {
     GNX_CUDA(cudaEventRecord((cudaEvent_t)ev_join, solve_st));
     if (int rc = gnx_assemble_mixed(net, co, rowptr, vals, main_st)) return rc;

@@ -380,6 +380,19 @@ int gnx_edge_backsub_mixed_const(const gnx_network_t* net, const gnx_mixed_coeff
                                  const double* pbc_out, const double* pbc_node, const double* b, const double* cond,
                                  const double* rsrc, const double* P, double* x, void* stream);
 
+/* End flux and end pressure of every edge from the multipliers (one thread per edge; the last step of
+ * LUSolver.solve, flow_models.py:347-350, seen from an edge):  Pu [E] = P at the tail node (0 at a boundary node),
+ * q0 [E] = cond (P_u - P_v + rsrc).  q0 may alias ftot and Pu may alias rsrc of the elimination. */
+int gnx_edge_flux_mixed(const gnx_network_t* net, const double* cond, const double* rsrc, const double* P,
+                        double* q0, double* Pu, void* stream);
+
+/* gnx_edge_backsub_mixed_const given q0 / Pu (gnx_edge_flux_mixed) instead of cond / rsrc / P: the blocks of a large
+ * network then reach their edge data in ONE trip to device memory; x is bit-identical.  Edge-tile path only
+ * (2^6 .. 2^10 cells per edge, per-edge coefficients), GNX_ERR_ARG otherwise. */
+int gnx_edge_backsub_mixed_flux(const gnx_network_t* net, const gnx_mixed_coeffs_t* co, double f_const, double g_const,
+                                const double* pbc_out, const double* pbc_node, const double* q0, const double* Pu,
+                                double* x, void* stream);
+
 /* One MixedHydraulicNetwork.solve() (flow_models.py:337-350: ii_assemble(a), ii_assemble(L) with Constant f, g,
  * ii_convert, LUSolver.solve) behind ONE call -- the same kernels as gnx_assemble_mixed +
  * gnx_rhs_eliminate_mixed + gnx_schur_solve + gnx_edge_backsub_mixed with bit-identical results; it exists

@@ -363,3 +363,41 @@ def test_edge_records_change_no_bit(eng, name, n):
     for a, c in zip(*out):
         assert np.array_equal(a, c)
     assert np.array_equal(out[0][0], out[0][1])            # stand-alone assembly == the step's
+
+
+def test_edge_flux_path_of_large_networks_changes_no_bit(eng):
+    """networks too large for the persistent kernel: the one-call step gathers the edges' end flux / end pressure once
+    (gnx_edge_flux_mixed) and back-substitutes from them (gnx_edge_backsub_mixed_flux); the separate entry points
+    gather per block (gnx_edge_backsub_mixed_const) or read b (gnx_edge_backsub_mixed) -- same x bit for bit"""
+    import ctypes as C
+    import torch
+    from graphnics_b200.synthetic import murray_tree
+    DeviceNetwork, MixedSystem = eng
+    pos, edges, _, _ = murray_tree(15, gdim=2)
+    dn = DeviceNetwork(pos, edges, 6)
+    ms = MixedSystem(dn)
+    rng = np.random.default_rng(5)
+    co = ms.coeffs(rng.uniform(0.5, 2.0, size=len(edges)))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    kw = dict(pbc_out=dev(rng.normal(size=len(edges))), pbc_node=dev(rng.normal(size=len(pos))), f_const=0.5, g_const=-0.25)
+    b_ref = ms.rhs(**kw)
+    x_ref, _ = ms.solve(co, b_ref)                       # elimination of a given b, generic back-substitution
+    vals = torch.empty(ms.nnz, dtype=torch.float64, device="cuda")
+    b = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+    x = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+    ms.assemble_rhs_solve(co, vals, b, x, kw)            # one-call step: kernel chain with the flux path
+    torch.cuda.synchronize()
+    assert not int(ms.lib.gnx_step_is_resident())
+    assert np.array_equal(b.cpu().numpy().view(np.int64), b_ref.cpu().numpy().view(np.int64))
+    assert np.array_equal(x.cpu().numpy().view(np.int64), x_ref.cpu().numpy().view(np.int64))
+    # the two entry points on their own, from the step's scratch arrays (cond is intact; rsrc / ftot now hold Pu / q0)
+    d = ms._bufs()
+    x2 = torch.full((ms.N,), np.nan, dtype=torch.float64, device="cuda")
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    st = torch.cuda.current_stream().cuda_stream
+    rc = ms.lib.gnx_edge_backsub_mixed_flux(dn.net_ref(), co.ref(), 0.5, -0.25, ptr(kw["pbc_out"]), ptr(kw["pbc_node"]),
+                                            ptr(d["ftot"]), ptr(d["rsrc"]), ptr(x2), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    q_p = slice(0, dn.lam_off)
+    assert np.array_equal(x2[q_p].cpu().numpy().view(np.int64), x_ref[q_p].cpu().numpy().view(np.int64))
