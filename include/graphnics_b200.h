@@ -235,11 +235,15 @@ typedef struct gnx_exchange {
    * A rank eliminates, builds the Schur rows of and rakes the bifurcations whose whole subtree it owns WITHOUT any
    * communication; only the scalars of edges at replicated bifurcations (bit 31) and the final (d, r) pair of every
    * local subtree root under a replicated parent (gnx_schur_plan_t.xlist) are stored into all buffers over NVLink.  The
-   * ONE flag exchange of a solve then happens inside the Schur kernel at rake level plan.l_sync; the replicated
+   * ONE exchange of a solve then happens inside the Schur kernel at rake level plan.l_sync; the replicated
    * bifurcations (the top of the tree: 2^k - 1 for a binary tree on 2^k ranks) are processed redundantly, bit-identically.
-   * phase: 0 = the whole solve in one kernel, flags inside (epoch > 0); 1 = up to the exchange (stores to the peers
-   * done, no flags); 2 = from the exchange on -- 1 and 2 let a caller put its own collective / barrier in between
-   * (NCCL fallback, ranks emulated in one process). */
+   * phase: 0 = the whole solve in one kernel (epoch > 0): the flag words tell that a rank's EDGE SCALARS have landed
+   * (released as soon as its elimination is complete), the (d, r) words of the subtree roots VALIDATE THEMSELVES -- the
+   * caller creates both buffers with the whole (d, r) region filled with the 64-bit pattern 0x7FF85EA71E550001 (a NaN
+   * no computation produces), the owner of a root stores its pair with plain peer stores, a reader polls the word until
+   * it differs from the pattern and writes the pattern back (GNX_XCHG_FLAGS=1: data first, flag after, no pattern
+   * needed); 1 = up to the exchange (stores to the peers done, no flags); 2 = from the exchange on -- 1 and 2 let a
+   * caller put its own collective / barrier in between (NCCL fallback, ranks emulated in one process). */
   const int32_t* egl;
   int32_t E_glob, B_glob, phase, reserved;
 } gnx_exchange_t;
