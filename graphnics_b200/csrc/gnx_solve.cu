@@ -380,7 +380,6 @@ edge_eliminate_tile_kernel(gnx_network_t net, GnxMixedDims d, const double* __re
   const double incl = gnx_seg_incl_scan(sumF, segT, sh, &tot);
   double cum = incl - sumF;                       // cumF at the first cell of this thread
   double s2 = 0.0;
-#pragma unroll
   if (a_cell) {
     // mass coefficient per cell: the weights a_k h_k take the place of h_k, the edge coefficient is 1
     const double* ac = a_cell + (int64_t)c.e * m + c.kk0;
@@ -869,9 +868,10 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   // sw[] the link weight to the parent.  The first two top children of a node sit in registers (a binary
   // tree has no more), further ones are re-read from the plan: a level of the up-sweep then costs shared
   // memory reads, a handful of FMAs, ONE reciprocal and a barrier -- no global load, no second division.
-  int32_t node[ROWS], lev[ROWS], ptop[ROWS], k0[ROWS], k1[ROWS], c0[ROWS], c1[ROWS], nct[ROWS];
-  double d[ROWS], r[ROWS], w[ROWS];
-  bool repl[ROWS];
+  // (zero-initialised for the compiler's sake: the lambdas below capture them before the set-up loop fills them)
+  int32_t node[ROWS] = {}, lev[ROWS] = {}, ptop[ROWS] = {}, k0[ROWS] = {}, k1[ROWS] = {}, c0[ROWS] = {}, c1[ROWS] = {}, nct[ROWS] = {};
+  double d[ROWS] = {}, r[ROWS] = {}, w[ROWS] = {};
+  bool repl[ROWS] = {};
   // is child c of row q kept in registers / shared memory (else: final in global memory)?
   auto top_child = [&](int q, int32_t c) -> int32_t {
     const int32_t tc = pl.top_of[c];
@@ -884,7 +884,7 @@ __device__ __forceinline__ bool top_solve(const SchurArgs& a, double* sd, double
   const bool xin = !CLUSTER && ncls && a.phase == 0 && a.wait_flags && a.xpoll;   // partitioned solve, exchange in this kernel
   if (!CLUSTER && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.scal[16] = (double)(t & 0xffffffffffull); }
   // the same from the row's packed record (plan.top_rec): one 64-byte load, then every scalar it names at once
-  int4 keep[ROWS == 1 ? 4 : 1];                                // one row per thread: its record stays in registers
+  int4 keep[ROWS == 1 ? 4 : 1] = {};                           // one row per thread: its record stays in registers
   auto numeric_rec = [&](int q) {
     const int32_t li = tid + q * T;
     int4 r0, r1, r2, r3;
